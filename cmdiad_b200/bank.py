@@ -1,0 +1,221 @@
+"""Python handle around one device-resident memory bank (cmdb_bank) -- thin marshalling only, all compute is in the
+CUDA library.  torch is used for host/device buffers and streams, never for the arithmetic of the path."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
+def _as_f32(x):
+    """contiguous float32 torch tensor (host or device) without copying when already so"""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+class ScoreResult:
+    """Outputs of one scoring call; field names follow compute_single_s_s_map (features.py:225-297)."""
+    __slots__ = ("s", "s_star", "s_idx", "min_val", "min_idx", "nn_idx", "m_star_knn", "w", "s_map", "s_map_pre",
+                 "s_map_u8")
+
+
+class Bank:
+    """One memory bank (patch_rgb_lib / patch_xyz_lib / patch_fusion_lib) resident in HBM on one GPU."""
+
+    def __init__(self, dim, capacity_rows, device=0, row_offset=0):
+        self._lib = L.load()
+        self._h = ctypes.c_void_p()
+        L.check(self._lib.cmdb_bank_create(int(device), int(dim), int(capacity_rows), ctypes.byref(self._h)))
+        self.dim = int(dim)
+        self.device = int(device)
+        self.capacity = int(capacity_rows)
+        if row_offset:
+            self.set_row_offset(row_offset)
+
+    # ---- lifecycle -------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cmdb_bank_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def rows(self):
+        n = ctypes.c_int64()
+        L.check(self._lib.cmdb_bank_rows(self._h, ctypes.byref(n)))
+        return n.value
+
+    def set_row_offset(self, off):
+        L.check(self._lib.cmdb_bank_set_row_offset(self._h, int(off)))
+
+    def set_score_impl(self, impl):
+        L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_SCORE_IMPL, int(impl)))
+
+    def stream(self):
+        """torch view of the handle's CUDA stream (for event timing on the stream the kernels run on)"""
+        p = ctypes.c_void_p()
+        L.check(self._lib.cmdb_bank_stream(self._h, ctypes.byref(p)))
+        return torch.cuda.ExternalStream(p.value, device=torch.device("cuda", self.device))
+
+    # ---- storage ---------------------------------------------------------------------------------------------
+    def append(self, rows):
+        rows = _as_f32(rows)
+        assert rows.dim() == 2 and rows.shape[1] == self.dim, f"expected [n,{self.dim}], got {tuple(rows.shape)}"
+        L.check(self._lib.cmdb_bank_append(self._h, _ptr(rows), rows.shape[0], int(rows.is_cuda)))
+
+    def stats(self):
+        """(mean, unbiased std, sum, sum of squares) over all elements, float64"""
+        m, s, sm, sq = (ctypes.c_double() for _ in range(4))
+        L.check(self._lib.cmdb_bank_stats(self._h, ctypes.byref(m), ctypes.byref(s), ctypes.byref(sm), ctypes.byref(sq)))
+        return m.value, s.value, sm.value, sq.value
+
+    def normalize(self, mean, std):
+        L.check(self._lib.cmdb_bank_normalize(self._h, float(mean), float(std)))
+
+    def gather(self, idx):
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int64))
+        L.check(self._lib.cmdb_bank_gather(self._h, _ptr(idx), idx.shape[0]))
+
+    def read(self, row0=0, n_rows=None):
+        n_rows = self.rows - row0 if n_rows is None else n_rows
+        out = torch.empty((n_rows, self.dim), dtype=torch.float32)
+        L.check(self._lib.cmdb_bank_read(self._h, int(row0), int(n_rows), _ptr(out)))
+        return out
+
+    def finalize(self):
+        L.check(self._lib.cmdb_bank_finalize(self._h))
+
+    # ---- coreset ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _csr(csr):
+        if csr is None:
+            return None, None, None, 0
+        indptr, indices, data, d_proj = csr
+        return (np.ascontiguousarray(indptr, dtype=np.int32), np.ascontiguousarray(indices, dtype=np.int32),
+                np.ascontiguousarray(data, dtype=np.float64), int(d_proj))
+
+    def coreset_select(self, n_select, csr, dtype_mode=L.CORESET_FP16, force_idx=None, return_min=False):
+        """Greedy k-center selection on the projected bank; csr = (indptr, indices, data, d_proj) or None."""
+        indptr, indices, data, d_proj = self._csr(csr)
+        out = np.zeros(int(n_select), dtype=np.int64)
+        if force_idx is None and not return_min:
+            L.check(self._lib.cmdb_coreset_select(self._h, int(n_select), _ptr(indptr), _ptr(indices), _ptr(data), d_proj,
+                                                  int(dtype_mode), _ptr(out)))
+            return out
+        fi = None if force_idx is None else np.ascontiguousarray(force_idx, dtype=np.int64)
+        mn = np.zeros(self.rows, dtype=np.float16 if dtype_mode == L.CORESET_FP16 else np.float64)
+        L.check(self._lib.cmdb_coreset_select_debug(self._h, int(n_select), _ptr(indptr), _ptr(indices), _ptr(data),
+                                                    d_proj, int(dtype_mode), _ptr(out), _ptr(fi), _ptr(mn)))
+        return (out, mn) if return_min else out
+
+    def project(self, csr, row0=0, n_rows=None):
+        indptr, indices, data, d_proj = self._csr(csr)
+        n_rows = self.rows - row0 if n_rows is None else n_rows
+        out = np.zeros((n_rows, d_proj), dtype=np.float64)
+        L.check(self._lib.cmdb_project(self._h, _ptr(indptr), _ptr(indices), _ptr(data), d_proj, int(row0), int(n_rows),
+                                       _ptr(out)))
+        return out
+
+    # ---- scoring ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _alloc_out(P, out_hw, full):
+        r = ScoreResult()
+        r.s = np.zeros(1, np.float32)
+        r.s_star = np.zeros(1, np.float32)
+        r.s_idx = np.zeros(1, np.int64)
+        r.min_val = np.zeros(P, np.float32)
+        r.min_idx = np.zeros(P, np.int64)
+        r.nn_idx = np.zeros(3, np.int64)
+        r.m_star_knn = np.zeros(2, np.float32)
+        r.w = np.zeros(1, np.float32)
+        r.s_map = np.zeros((out_hw, out_hw), np.float32)
+        r.s_map_pre = np.zeros((out_hw, out_hw), np.float32) if full else None
+        r.s_map_u8 = np.zeros((out_hw, out_hw), np.uint8) if full else None
+        so = L.ScoreOut()
+        for name, ctype in (("s", L.c_f32_p), ("s_star", L.c_f32_p), ("s_idx", L.c_i64_p), ("min_val", L.c_f32_p),
+                            ("min_idx", L.c_i64_p), ("nn_idx", L.c_i64_p), ("m_star_knn", L.c_f32_p), ("w", L.c_f32_p),
+                            ("s_map", L.c_f32_p), ("s_map_pre", L.c_f32_p), ("s_map_u8", L.c_u8_p)):
+            a = getattr(r, name)
+            setattr(so, name, a.ctypes.data_as(ctype) if a is not None else ctype())
+        return r, so
+
+    def score(self, patch, feature_map_dims, out_hw=224, full=False):
+        """calculate_dist + compute_single_s_s_map for one image; patch [P,dim] float32, already normalised."""
+        patch = _as_f32(patch)
+        P = patch.shape[0]
+        fh, fw = feature_map_dims
+        r, so = self._alloc_out(P, out_hw, full)
+        L.check(self._lib.cmdb_score(self._h, _ptr(patch), P, int(fh), int(fw), int(out_hw), int(patch.is_cuda),
+                                     ctypes.byref(so)))
+        return r
+
+    def score_sharded(self, patch, feature_map_dims, out_hw=224, full=False, group=None):
+        """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; the five phases
+        of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between."""
+        import torch.distributed as dist
+        patch = _as_f32(patch)
+        P = patch.shape[0]
+        fh, fw = feature_map_dims
+        dev = torch.device("cuda", self.device)
+        world = dist.get_world_size(group)
+        keys = torch.empty(P, dtype=torch.int64, device=dev)
+        L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(patch), P, int(patch.is_cuda), _ptr(keys)))
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+        m_star = torch.empty(self.dim, dtype=torch.float32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        L.check(self._lib.cmdb_score_shard_select(self._h, _ptr(keys), P, _ptr(m_star)))
+        dist.all_reduce(m_star, op=dist.ReduceOp.SUM, group=group)
+        top = torch.empty(3, dtype=torch.int64, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        L.check(self._lib.cmdb_score_shard_topk(self._h, _ptr(m_star), _ptr(top)))
+        gathered = torch.empty(3 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, top, group=group)
+        nn_rows = torch.empty(3 * self.dim, dtype=torch.float32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), 3 * world, _ptr(nn_rows)))
+        dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream(dev).synchronize()
+        r, so = self._alloc_out(P, out_hw, full)
+        L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), P, int(fh), int(fw), int(out_hw),
+                                                  ctypes.byref(so)))
+        return r
+
+
+def upsample_blur(s_map, out_hw=224, device=0):
+    """F.interpolate(bilinear) + KNNGaussianBlur(4) of a [fh,fw] float32 map (features.py:293-295)."""
+    lib = L.load()
+    m = np.ascontiguousarray(np.asarray(s_map, dtype=np.float32))
+    fh, fw = m.shape
+    out = np.zeros((out_hw, out_hw), np.float32)
+    pre = np.zeros((out_hw, out_hw), np.float32)
+    u8 = np.zeros((out_hw, out_hw), np.uint8)
+    L.check(lib.cmdb_upsample_blur(int(device), _ptr(m), fh, fw, int(out_hw), _ptr(out), _ptr(pre), _ptr(u8)))
+    return out, pre, u8
+
+
+def coreset_rownorms(z, last, device=0):
+    """One canonical-order distance pass ||z - last||_2 (float16 or float64 arrays), for parity pinning."""
+    lib = L.load()
+    z = np.ascontiguousarray(z)
+    mode = L.CORESET_FP16 if z.dtype == np.float16 else L.CORESET_FP64
+    last = np.ascontiguousarray(np.asarray(last, dtype=z.dtype).reshape(-1))
+    out = np.zeros(z.shape[0], dtype=z.dtype)
+    L.check(lib.cmdb_coreset_rownorms(int(device), _ptr(z), _ptr(last), z.shape[0], z.shape[1], mode, _ptr(out)))
+    return out

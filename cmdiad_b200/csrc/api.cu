@@ -1,0 +1,281 @@
+// extern "C" entry points that orchestrate the kernels: coreset selection, projection, scoring (single GPU and the
+// row-sharded phases), stand-alone upsample+blur.  Declarations and reference citations: include/cmdiad_b200.h.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cmdb {
+
+int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
+                       int64_t *out_idx_host, const int64_t *force_idx_host, void *out_min_last_host);
+
+__global__ void __launch_bounds__(512) f32_to_f64_kernel(const float *__restrict__ x, long long n, double *__restrict__ z) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        z[i] = (double)x[i];
+}
+
+// keys[p] = (float_bits(min_val[p]) << 32) | global_row ; and the inverse
+__global__ void pack_keys_kernel(const float *__restrict__ min_val, const long long *__restrict__ min_idx, int P,
+                                 long long *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) {
+        const long long g = min_idx[i];
+        keys[i] = g < 0 ? 0x7fffffffffffffffLL
+                        : (long long)(((unsigned long long)__float_as_uint(min_val[i]) << 32) | (unsigned long long)g);
+    }
+}
+__global__ void unpack_keys_kernel(const long long *__restrict__ keys, int P, float *__restrict__ min_val,
+                                   long long *__restrict__ min_idx, unsigned long long *s_key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) {
+        const unsigned long long k = (unsigned long long)keys[i];
+        const float v = __uint_as_float((unsigned int)(k >> 32));
+        min_val[i] = v;
+        min_idx[i] = (long long)(k & 0xffffffffULL);
+        atomicMax(s_key, ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - (unsigned int)i));
+    }
+}
+// out[c] = bank[global_row - offset][c] if this shard owns the row, else 0
+__global__ void contrib_rows_kernel(const float *__restrict__ bank, long long rows, long long row_offset, int dim,
+                                    const long long *__restrict__ global_rows, const unsigned long long *__restrict__ keys,
+                                    int n, float *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * dim; i += gridDim.x * blockDim.x) {
+        const int r = i / dim, c = i - r * dim;
+        long long g = global_rows ? global_rows[r] : (keys[r] == ~0ULL ? -1 : (long long)(keys[r] & 0xffffffffULL));
+        const long long l = g - row_offset;
+        out[i] = (g >= 0 && l >= 0 && l < rows) ? bank[(size_t)l * dim + c] : 0.f;
+    }
+}
+__global__ void m_star_row_kernel(const void *tail, long long *out) { *out = reinterpret_cast<const TailResult *>(tail)->m_star_row; }
+
+static int check_score_args(cmdb_bank *b, const void *patch, int P, const char *fn) {
+    CMDB_REQUIRE(b && patch, CMDB_ERR_INVALID, "%s: NULL argument", fn);
+    CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "%s: call cmdb_bank_finalize first", fn);
+    CMDB_REQUIRE(P >= 1 && P <= (1 << 20), CMDB_ERR_INVALID, "%s: P=%d out of range", fn, P);
+    return CMDB_OK;
+}
+
+static int stage_patch(cmdb_bank *b, const float *patch, int P, int is_device, int out_hw) {
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CHECK(score_scratch_alloc(b, P, out_hw));
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.q_f32, patch, sizeof(float) * (size_t)P * b->dim,
+                              is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
+    return CMDB_OK;
+}
+
+static int local_min(cmdb_bank *b, int P) {
+    int n_cand = 0;
+    if (b->score_impl == CMDB_SCORE_TCGEN05) CMDB_CHECK(score_gemm_candidates(b, P, &n_cand));
+    else CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
+    return score_refine(b, P, n_cand);
+}
+
+static int copy_outputs(cmdb_bank *b, int P, int out_hw, cmdb_score_out *out) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    TailResult tr;
+    CMDB_CUDA(cudaMemcpyAsync(&tr, s.tail, sizeof(tr), cudaMemcpyDeviceToHost, st));
+    if (out->min_val) CMDB_CUDA(cudaMemcpyAsync(out->min_val, s.min_val, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
+    if (out->min_idx) CMDB_CUDA(cudaMemcpyAsync(out->min_idx, s.min_idx, sizeof(long long) * P, cudaMemcpyDeviceToHost, st));
+    const size_t npix = (size_t)out_hw * out_hw;
+    if (out->s_map) CMDB_CUDA(cudaMemcpyAsync(out->s_map, s.map_out, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
+    if (out->s_map_pre) CMDB_CUDA(cudaMemcpyAsync(out->s_map_pre, s.map_pre, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
+    if (out->s_map_u8) CMDB_CUDA(cudaMemcpyAsync(out->s_map_u8, s.map_u8, npix, cudaMemcpyDeviceToHost, st));
+    CMDB_CUDA(cudaStreamSynchronize(st));
+    if (out->s) *out->s = tr.s;
+    if (out->s_star) *out->s_star = tr.s_star;
+    if (out->s_idx) *out->s_idx = tr.s_idx;
+    if (out->w) *out->w = tr.w;
+    if (out->m_star_knn) out->m_star_knn[0] = tr.knn0, out->m_star_knn[1] = tr.knn1;
+    if (out->nn_idx)
+        for (int k = 0; k < 3; ++k) out->nn_idx[k] = tr.nn_idx[k];
+    return CMDB_OK;
+}
+
+}  // namespace cmdb
+
+using namespace cmdb;
+
+extern "C" {
+
+int cmdb_project(cmdb_bank *b, const int32_t *indptr, const int32_t *indices, const double *data, int d_proj, int64_t row0,
+                 int64_t n_rows, double *out_host) {
+    CMDB_REQUIRE(b && out_host && row0 >= 0 && n_rows > 0 && row0 + n_rows <= b->rows, CMDB_ERR_INVALID,
+                 "cmdb_project: bad row range");
+    CMDB_REQUIRE(d_proj > 0, CMDB_ERR_INVALID, "cmdb_project: d_proj must be positive");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    double *z = nullptr;
+    CMDB_CUDA(cudaMalloc(&z, sizeof(double) * (size_t)n_rows * d_proj));
+    int rc = project_rows(b, b->data + row0 * b->dim, n_rows, b->dim, indptr, indices, data, d_proj, z);
+    cudaError_t e = cudaSuccess;
+    if (rc == CMDB_OK) e = cudaMemcpy(out_host, z, sizeof(double) * (size_t)n_rows * d_proj, cudaMemcpyDeviceToHost);
+    cudaFree(z);
+    if (rc != CMDB_OK) return rc;
+    CMDB_CUDA(e);
+    return CMDB_OK;
+}
+
+static int coreset_impl(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices, const double *data,
+                        int d_proj, int dtype_mode, int64_t *out_idx_host, const int64_t *force_idx, void *out_min_last) {
+    CMDB_REQUIRE(b && out_idx_host, CMDB_ERR_INVALID, "cmdb_coreset_select: NULL argument");
+    CMDB_REQUIRE(b->rows > 0, CMDB_ERR_STATE, "cmdb_coreset_select: bank is empty");
+    CMDB_REQUIRE(n_select >= 1 && n_select <= b->rows, CMDB_ERR_INVALID, "cmdb_coreset_select: n_select=%lld not in [1,%lld]",
+                 (long long)n_select, (long long)b->rows);
+    CMDB_REQUIRE(d_proj >= 0 && d_proj <= b->dim, CMDB_ERR_INVALID,
+                 "cmdb_coreset_select: d_proj=%d exceeds dim=%d (sklearn raises ValueError here; pass 0 to skip the projection)",
+                 d_proj, b->dim);
+    CMDB_CUDA(cudaSetDevice(b->device));
+    const int d = d_proj > 0 ? d_proj : b->dim;
+    double *z = nullptr;
+    CMDB_CUDA(cudaMalloc(&z, sizeof(double) * (size_t)b->rows * d));
+    int rc;
+    if (d_proj > 0) {
+        rc = project_rows(b, b->data, b->rows, b->dim, indptr, indices, data, d_proj, z);
+    } else {
+        // features.py:369-370: projection skipped, the float32 bank itself is used
+        f32_to_f64_kernel<<<b->num_sms * 4, 512, 0, b->stream>>>(b->data, (long long)b->rows * d, z);
+        rc = cudaGetLastError() == cudaSuccess ? CMDB_OK : CMDB_ERR_CUDA;
+    }
+    if (rc == CMDB_OK) rc = coreset_greedy_dev(b, z, b->rows, d, n_select, dtype_mode, out_idx_host, force_idx, out_min_last);
+    cudaFree(z);
+    return rc;
+}
+
+int cmdb_coreset_select(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices, const double *data,
+                        int d_proj, int dtype_mode, int64_t *out_idx_host) {
+    return coreset_impl(b, n_select, indptr, indices, data, d_proj, dtype_mode, out_idx_host, nullptr, nullptr);
+}
+
+// test hook (not in the public header): teacher forcing and the final min-distance vector
+int cmdb_coreset_select_debug(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices,
+                              const double *data, int d_proj, int dtype_mode, int64_t *out_idx_host,
+                              const int64_t *force_idx_host, void *out_min_last_host) {
+    return coreset_impl(b, n_select, indptr, indices, data, d_proj, dtype_mode, out_idx_host, force_idx_host,
+                        out_min_last_host);
+}
+
+int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,
+                          void *out_host) {
+    return coreset_rownorms(device, z_host, last_host, n_rows, d, dtype_mode, out_host);
+}
+
+int cmdb_score(cmdb_bank *b, const float *patch, int P, int fh, int fw, int out_hw, int patch_is_device,
+               cmdb_score_out *out) {
+    CMDB_CHECK(check_score_args(b, patch, P, "cmdb_score"));
+    CMDB_REQUIRE(out, CMDB_ERR_INVALID, "cmdb_score: out is NULL");
+    CMDB_REQUIRE(fh > 0 && fw > 0 && fh * fw == P, CMDB_ERR_INVALID, "cmdb_score: feature_map_dims %dx%d != P=%d", fh, fw, P);
+    CMDB_CHECK(stage_patch(b, patch, P, patch_is_device, out_hw));
+    CMDB_CHECK(local_min(b, P));
+    CMDB_CHECK(score_select(b, true));
+    CMDB_CHECK(score_wdist_topk(b));
+    CMDB_CHECK(score_merge_top3(b));
+    CMDB_CHECK(score_final(b, false));
+    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8));
+    return copy_outputs(b, P, out_hw, out);
+}
+
+int cmdb_score_shard_min(cmdb_bank *b, const float *patch, int P, int patch_is_device, int64_t *keys_device) {
+    CMDB_CHECK(check_score_args(b, patch, P, "cmdb_score_shard_min"));
+    CMDB_REQUIRE(keys_device, CMDB_ERR_INVALID, "cmdb_score_shard_min: keys_device is NULL");
+    CMDB_CHECK(stage_patch(b, patch, P, patch_is_device, 224));
+    CMDB_CHECK(local_min(b, P));
+    pack_keys_kernel<<<(P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, P, (long long *)keys_device);
+    CMDB_CUDA(cudaGetLastError());
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));  // the caller's collective runs on another stream
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_select(cmdb_bank *b, const int64_t *reduced_keys_device, int P, float *m_star_contrib_device) {
+    CMDB_CHECK(check_score_args(b, reduced_keys_device, P, "cmdb_score_shard_select"));
+    CMDB_REQUIRE(m_star_contrib_device && P <= b->ss.cap_p, CMDB_ERR_INVALID, "cmdb_score_shard_select: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long), st));
+    unpack_keys_kernel<<<(P + 255) / 256, 256, 0, st>>>((const long long *)reduced_keys_device, P, b->ss.min_val,
+                                                        b->ss.min_idx, b->ss.s_key);
+    CMDB_CHECK(score_select(b, false));
+    long long *row_dev = reinterpret_cast<long long *>(b->ss.top3);  // scratch, overwritten later by the merge
+    m_star_row_kernel<<<1, 1, 0, st>>>(b->ss.tail, row_dev);
+    contrib_rows_kernel<<<4, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, row_dev, nullptr, 1,
+                                           m_star_contrib_device);
+    CMDB_CUDA(cudaGetLastError());
+    CMDB_CUDA(cudaStreamSynchronize(st));
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_topk(cmdb_bank *b, const float *m_star_device, int64_t *topk_keys_device) {
+    CMDB_CHECK(check_score_args(b, m_star_device, 1, "cmdb_score_shard_topk"));
+    CMDB_REQUIRE(topk_keys_device && b->ss.cap_p > 0, CMDB_ERR_INVALID, "cmdb_score_shard_topk: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.m_star, m_star_device, sizeof(float) * b->dim, cudaMemcpyDeviceToDevice, st));
+    CMDB_CHECK(score_wdist_topk(b));
+    CMDB_CHECK(score_merge_top3(b));
+    CMDB_CUDA(cudaMemcpyAsync(topk_keys_device, b->ss.top3, sizeof(long long) * 3, cudaMemcpyDeviceToDevice, st));
+    CMDB_CUDA(cudaStreamSynchronize(st));
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_nn(cmdb_bank *b, const int64_t *gathered_keys_device, int n_keys, float *nn_rows_contrib_device) {
+    CMDB_CHECK(check_score_args(b, gathered_keys_device, 1, "cmdb_score_shard_nn"));
+    CMDB_REQUIRE(nn_rows_contrib_device && n_keys >= 3 && n_keys <= 3 * b->ss.n_topk_blocks, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_nn: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.topk_keys, gathered_keys_device, sizeof(long long) * n_keys, cudaMemcpyDeviceToDevice, st));
+    const int saved = b->ss.n_topk_blocks;
+    b->ss.n_topk_blocks = n_keys / 3;
+    int rc = score_merge_top3(b);
+    b->ss.n_topk_blocks = saved;
+    CMDB_CHECK(rc);
+    contrib_rows_kernel<<<8, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, nullptr, b->ss.top3, 3,
+                                           nn_rows_contrib_device);
+    CMDB_CUDA(cudaGetLastError());
+    CMDB_CUDA(cudaStreamSynchronize(st));
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int P, int fh, int fw, int out_hw,
+                            cmdb_score_out *out) {
+    CMDB_CHECK(check_score_args(b, nn_rows_device, P, "cmdb_score_shard_finish"));
+    CMDB_REQUIRE(out && fh > 0 && fw > 0 && fh * fw == P && P <= b->ss.cap_p, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_finish: bad arguments");
+    CMDB_REQUIRE(out_hw * out_hw <= b->ss.map_cap, CMDB_ERR_INVALID, "cmdb_score_shard_finish: out_hw larger than in phase 1");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.nn_rows, nn_rows_device, sizeof(float) * 3 * b->dim, cudaMemcpyDeviceToDevice, b->stream));
+    CMDB_CHECK(score_final(b, true));
+    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8));
+    return copy_outputs(b, P, out_hw, out);
+}
+
+int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host, float *out_pre_host,
+                       uint8_t *out_u8_host) {
+    CMDB_REQUIRE(map_host && out_host && fh > 0 && fw > 0, CMDB_ERR_INVALID, "cmdb_upsample_blur: bad arguments");
+    CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_upsample_blur: out_hw=%d not in [8,256]", out_hw);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        set_error("cmdb_upsample_blur: no CUDA device; this library has no CPU fallback");
+        return CMDB_ERR_CUDA;
+    }
+    CMDB_CUDA(cudaSetDevice(device));
+    const size_t npix = (size_t)out_hw * out_hw;
+    float *in = nullptr, *pre = nullptr, *o = nullptr;
+    unsigned char *u8 = nullptr;
+    cudaError_t e = cudaMalloc(&in, sizeof(float) * fh * fw);
+    if (e == cudaSuccess) e = cudaMalloc(&pre, sizeof(float) * npix);
+    if (e == cudaSuccess) e = cudaMalloc(&o, sizeof(float) * npix);
+    if (e == cudaSuccess) e = cudaMalloc(&u8, npix);
+    if (e == cudaSuccess) e = cudaMemcpy(in, map_host, sizeof(float) * fh * fw, cudaMemcpyHostToDevice);
+    int rc = CMDB_OK;
+    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, in, fh, fw, out_hw, pre, o, u8);
+    if (e == cudaSuccess && rc == CMDB_OK) e = cudaMemcpy(out_host, o, sizeof(float) * npix, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == CMDB_OK && out_pre_host) e = cudaMemcpy(out_pre_host, pre, sizeof(float) * npix, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == CMDB_OK && out_u8_host) e = cudaMemcpy(out_u8_host, u8, npix, cudaMemcpyDeviceToHost);
+    cudaFree(in), cudaFree(pre), cudaFree(o), cudaFree(u8);
+    if (rc != CMDB_OK) return rc;
+    CMDB_CUDA(e);
+    return CMDB_OK;
+}
+
+}  // extern "C"

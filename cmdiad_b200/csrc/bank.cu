@@ -1,0 +1,424 @@
+// Memory-bank storage: pre-allocated row-major float32 bank in HBM, statistics, normalisation, gather and the
+// split-fp16 scoring layout.  Replaces the Python-list banks + torch.cat + mean/std/normalise/index-select of
+// run_coreset (reference multiple_features.py:37-48 and the five other variants).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cmdb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// statistics: sum and sum of squares in float64 (one pass, float4 loads), grid sized to the SM count
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) stats_kernel(const float *__restrict__ x, int64_t n, double *__restrict__ out) {
+    double s = 0.0, ss = 0.0;
+    const int64_t n4 = n >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(x4 + i);
+        // per-vector partial in float64 keeps the dependent chain short
+        double a = (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        double b = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        s += a;
+        ss += b;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        double v = x[(n4 << 2) + threadIdx.x];
+        s += v;
+        ss += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    __shared__ double sh[2][16];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh[0][w] = s;
+        sh[1][w] = ss;
+    }
+    __syncthreads();
+    if (w == 0) {
+        s = l < (blockDim.x >> 5) ? sh[0][l] : 0.0;
+        ss = l < (blockDim.x >> 5) ? sh[1][l] : 0.0;
+        for (int o = 8; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (l == 0) {
+            atomicAdd(out, s);
+            atomicAdd(out + 1, ss);
+        }
+    }
+}
+
+// (x - mean) / std with one IEEE subtract and one IEEE divide per element == torch's float32 CPU result
+__global__ void __launch_bounds__(512) normalize_kernel(float *__restrict__ x, int64_t n, float mean, float stdv) {
+    const int64_t n4 = n >> 2;
+    float4 *x4 = reinterpret_cast<float4 *>(x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = x4[i];
+        v.x = __fdiv_rn(__fsub_rn(v.x, mean), stdv);
+        v.y = __fdiv_rn(__fsub_rn(v.y, mean), stdv);
+        v.z = __fdiv_rn(__fsub_rn(v.z, mean), stdv);
+        v.w = __fdiv_rn(__fsub_rn(v.w, mean), stdv);
+        x4[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        int64_t i = (n4 << 2) + threadIdx.x;
+        x[i] = __fdiv_rn(__fsub_rn(x[i], mean), stdv);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                          const long long *__restrict__ idx, int64_t n, int dim4) {
+    // one warp per destination row, float4 copies
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n;
+         r += (int64_t)gridDim.x * warps_per_block) {
+        const float4 *s = reinterpret_cast<const float4 *>(src) + idx[r] * dim4;
+        float4 *d = reinterpret_cast<float4 *>(dst) + r * dim4;
+        for (int c = lane; c < dim4; c += 32) d[c] = __ldg(s + c);
+    }
+}
+
+__global__ void __launch_bounds__(512) absmax_kernel(const float *__restrict__ x, int64_t n, unsigned int *out) {
+    float m = 0.f;
+    const int64_t n4 = n >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(x4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[(n4 << 2) + threadIdx.x]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like uints
+}
+
+// Split x*2^e into fp16 hi + fp16 lo (hi + lo carries ~22 significand bits) and compute ||x||^2 (true units) per row.
+// One warp per row; rows >= n_rows (padding up to the GEMM tile) are zero with norm = +inf so they never win a min.
+__global__ void __launch_bounds__(256) split_rows_kernel_impl(const float *__restrict__ x, int64_t n_rows, int64_t n_pad,
+                                                         int dim, float scale, __half *__restrict__ hi,
+                                                         __half *__restrict__ lo, float *__restrict__ norm,
+                                                         float pad_norm) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int dim4 = dim >> 2;
+    for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_pad;
+         r += (int64_t)gridDim.x * warps_per_block) {
+        uint2 *h = reinterpret_cast<uint2 *>(hi + r * dim);
+        uint2 *l = reinterpret_cast<uint2 *>(lo + r * dim);
+        if (r >= n_rows) {
+            for (int c = lane; c < dim4; c += 32) {
+                h[c] = make_uint2(0u, 0u);
+                l[c] = make_uint2(0u, 0u);
+            }
+            if (lane == 0) norm[r] = pad_norm;
+            continue;
+        }
+        const float4 *s = reinterpret_cast<const float4 *>(x + r * dim);
+        double acc = 0.0;
+        for (int c = lane; c < dim4; c += 32) {
+            float4 v = __ldg(s + c);
+            acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;  // true units
+            v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;  // power of two: exact
+            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            h[c] = make_uint2(*reinterpret_cast<unsigned int *>(&h0), *reinterpret_cast<unsigned int *>(&h1));
+            l[c] = make_uint2(*reinterpret_cast<unsigned int *>(&l0), *reinterpret_cast<unsigned int *>(&l1));
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) norm[r] = (float)acc;
+    }
+}
+
+void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t n_rows, int64_t n_pad, int dim,
+                       int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm) {
+    int grid = (int)std::min<int64_t>((n_pad + 7) / 8, (int64_t)num_sms * 8);
+    split_rows_kernel_impl<<<grid, 256, 0, stream>>>(x, n_rows, n_pad, dim, ldexpf(1.f, scale_exp), hi, lo, norm, pad_norm);
+}
+
+int bank_max_abs(cmdb_bank *b, const float *x, int64_t n, float *out_host) {
+    CMDB_CUDA(cudaMemsetAsync(b->absmax_buf, 0, sizeof(unsigned int), b->stream));
+    int grid = (int)std::min<int64_t>((n / 4 + 511) / 512 + 1, (int64_t)b->num_sms * 4);
+    absmax_kernel<<<grid, 512, 0, b->stream>>>(x, n, b->absmax_buf);
+    CMDB_CUDA(cudaGetLastError());
+    unsigned int bits = 0;
+    CMDB_CUDA(cudaMemcpyAsync(&bits, b->absmax_buf, sizeof(bits), cudaMemcpyDeviceToHost, b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    memcpy(out_host, &bits, sizeof(float));
+    return CMDB_OK;
+}
+
+// scale exponent e such that max|x| * 2^e lands in [2^12, 2^13): far from fp16 overflow (65504) after the
+// query-side scaling is applied too, and keeps the lo parts of all but negligible elements in fp16's normal range
+int pick_scale_exp(float absmax) {
+    if (!(absmax > 0.f) || !isfinite(absmax)) return 0;
+    int e;
+    frexpf(absmax, &e);  // absmax = m * 2^e, m in [0.5, 1)
+    return 13 - e;
+}
+
+}  // namespace cmdb
+
+using namespace cmdb;
+
+extern "C" {
+
+int cmdb_version(void) { return 100; }
+
+const char *cmdb_last_error(void) { return cmdb::g_err; }
+
+int cmdb_device_count(int *out_n) {
+    CMDB_REQUIRE(out_n != nullptr, CMDB_ERR_INVALID, "cmdb_device_count: out_n is NULL");
+    int n = 0;
+    *out_n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return CMDB_OK;  // no driver / no device: zero devices, not an error
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    *out_n = ok;
+    return CMDB_OK;
+}
+
+int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out) {
+    CMDB_REQUIRE(out != nullptr, CMDB_ERR_INVALID, "cmdb_bank_create: out is NULL");
+    *out = nullptr;
+    CMDB_REQUIRE(dim > 0 && dim % 64 == 0, CMDB_ERR_INVALID, "cmdb_bank_create: dim=%d must be a positive multiple of 64",
+                 dim);
+    CMDB_REQUIRE(capacity_rows > 0, CMDB_ERR_INVALID, "cmdb_bank_create: capacity_rows=%lld must be positive",
+                 (long long)capacity_rows);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        set_error("cmdb_bank_create: no CUDA device (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return CMDB_ERR_CUDA;
+    }
+    CMDB_REQUIRE(device >= 0 && device < ndev, CMDB_ERR_INVALID, "cmdb_bank_create: device %d out of range [0,%d)", device,
+                 ndev);
+    int major = 0;
+    CMDB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CMDB_REQUIRE(major == 10, CMDB_ERR_CUDA, "cmdb_bank_create: device %d is sm_%d0, this library is sm_100a only", device,
+                 major);
+    CMDB_CUDA(cudaSetDevice(device));
+    cmdb_bank *b = new cmdb_bank();
+    b->device = device;
+    b->dim = dim;
+    b->capacity = capacity_rows;
+    cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t err = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&b->data, sizeof(float) * (size_t)capacity_rows * dim);
+    if (err == cudaSuccess) err = cudaMalloc(&b->stats_buf, 2 * sizeof(double));
+    if (err == cudaSuccess) err = cudaMalloc(&b->absmax_buf, sizeof(unsigned int));
+    if (err != cudaSuccess) {
+        set_error("cmdb_bank_create: allocation of %lld x %d floats failed: %s", (long long)capacity_rows, dim,
+                  cudaGetErrorString(err));
+        (void)cudaGetLastError();
+        cmdb_bank_destroy(b);
+        return CMDB_ERR_CUDA;
+    }
+    *out = b;
+    return CMDB_OK;
+}
+
+static void free_scoring_layout(cmdb_bank *b) {
+    cudaFree(b->hi);
+    cudaFree(b->lo);
+    cudaFree(b->norm);
+    b->hi = b->lo = nullptr;
+    b->norm = nullptr;
+    free(b->tmap_hi);
+    free(b->tmap_lo);
+    b->tmap_hi = b->tmap_lo = nullptr;
+    score_scratch_free(b);
+    b->finalized = false;
+}
+
+void cmdb_bank_destroy(cmdb_bank *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    free_scoring_layout(b);
+    cudaFree(b->data);
+    cudaFree(b->stats_buf);
+    cudaFree(b->absmax_buf);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int cmdb_bank_append(cmdb_bank *b, const float *rows, int64_t n_rows, int rows_is_device) {
+    CMDB_REQUIRE(b && rows && n_rows >= 0, CMDB_ERR_INVALID, "cmdb_bank_append: bad arguments");
+    CMDB_REQUIRE(b->rows + n_rows <= b->capacity, CMDB_ERR_CAPACITY, "cmdb_bank_append: %lld + %lld rows exceed capacity %lld",
+                 (long long)b->rows, (long long)n_rows, (long long)b->capacity);
+    if (n_rows == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaMemcpyAsync(b->data + b->rows * b->dim, rows, sizeof(float) * (size_t)n_rows * b->dim,
+                              rows_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
+    // the caller may reuse / free its buffer as soon as we return (pageable host memory is staged synchronously anyway)
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    b->rows += n_rows;
+    b->finalized = false;
+    return CMDB_OK;
+}
+
+int cmdb_bank_rows(const cmdb_bank *b, int64_t *out_rows) {
+    CMDB_REQUIRE(b && out_rows, CMDB_ERR_INVALID, "cmdb_bank_rows: bad arguments");
+    *out_rows = b->rows;
+    return CMDB_OK;
+}
+
+int cmdb_bank_dim(const cmdb_bank *b, int *out_dim) {
+    CMDB_REQUIRE(b && out_dim, CMDB_ERR_INVALID, "cmdb_bank_dim: bad arguments");
+    *out_dim = b->dim;
+    return CMDB_OK;
+}
+
+int cmdb_bank_set_row_offset(cmdb_bank *b, int64_t row_offset) {
+    CMDB_REQUIRE(b && row_offset >= 0, CMDB_ERR_INVALID, "cmdb_bank_set_row_offset: bad arguments");
+    b->row_offset = row_offset;
+    return CMDB_OK;
+}
+
+int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_set_option: bank is NULL");
+    if (option == CMDB_OPT_SCORE_IMPL) {
+        CMDB_REQUIRE(value == CMDB_SCORE_TCGEN05 || value == CMDB_SCORE_SIMT, CMDB_ERR_INVALID,
+                     "cmdb_bank_set_option: unknown scoring implementation %d", value);
+        b->score_impl = value;
+        return CMDB_OK;
+    }
+    set_error("cmdb_bank_set_option: unknown option %d", option);
+    return CMDB_ERR_INVALID;
+}
+
+int cmdb_bank_stream(cmdb_bank *b, void **out_stream) {
+    CMDB_REQUIRE(b && out_stream, CMDB_ERR_INVALID, "cmdb_bank_stream: bad arguments");
+    *out_stream = (void *)b->stream;
+    return CMDB_OK;
+}
+
+int cmdb_bank_stats(cmdb_bank *b, double *out_mean, double *out_std, double *out_sum, double *out_sumsq) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_stats: bank is NULL");
+    CMDB_REQUIRE(b->rows > 0, CMDB_ERR_STATE, "cmdb_bank_stats: bank is empty");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    const int64_t n = b->rows * b->dim;
+    CMDB_CUDA(cudaMemsetAsync(b->stats_buf, 0, 2 * sizeof(double), b->stream));
+    int grid = (int)std::min<int64_t>((n / 4 + 511) / 512 + 1, (int64_t)b->num_sms * 4);
+    stats_kernel<<<grid, 512, 0, b->stream>>>(b->data, n, b->stats_buf);
+    CMDB_CUDA(cudaGetLastError());
+    double h[2];
+    CMDB_CUDA(cudaMemcpyAsync(h, b->stats_buf, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    const double mean = h[0] / (double)n;
+    double var = n > 1 ? (h[1] - h[0] * mean) / (double)(n - 1) : NAN;  // unbiased, like torch.std
+    if (var < 0) var = 0;
+    if (out_mean) *out_mean = mean;
+    if (out_std) *out_std = sqrt(var);
+    if (out_sum) *out_sum = h[0];
+    if (out_sumsq) *out_sumsq = h[1];
+    return CMDB_OK;
+}
+
+int cmdb_bank_normalize(cmdb_bank *b, float mean, float stdv) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_normalize: bank is NULL");
+    if (b->rows == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    const int64_t n = b->rows * b->dim;
+    int grid = (int)std::min<int64_t>((n / 4 + 511) / 512 + 1, (int64_t)b->num_sms * 4);
+    normalize_kernel<<<grid, 512, 0, b->stream>>>(b->data, n, mean, stdv);
+    CMDB_CUDA(cudaGetLastError());
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    b->finalized = false;
+    return CMDB_OK;
+}
+
+int cmdb_bank_gather(cmdb_bank *b, const int64_t *idx_host, int64_t n) {
+    CMDB_REQUIRE(b && idx_host && n > 0, CMDB_ERR_INVALID, "cmdb_bank_gather: bad arguments");
+    CMDB_REQUIRE(n <= b->capacity, CMDB_ERR_CAPACITY, "cmdb_bank_gather: n exceeds capacity");
+    for (int64_t i = 0; i < n; ++i)
+        CMDB_REQUIRE(idx_host[i] >= 0 && idx_host[i] < b->rows, CMDB_ERR_INVALID,
+                     "cmdb_bank_gather: idx[%lld]=%lld out of range [0,%lld)", (long long)i, (long long)idx_host[i],
+                     (long long)b->rows);
+    CMDB_CUDA(cudaSetDevice(b->device));
+    long long *idx_dev = nullptr;
+    float *tmp = nullptr;
+    CMDB_CUDA(cudaMalloc(&idx_dev, sizeof(long long) * (size_t)n));
+    cudaError_t e = cudaMalloc(&tmp, sizeof(float) * (size_t)n * b->dim);
+    if (e != cudaSuccess) {
+        cudaFree(idx_dev);
+        CMDB_CUDA(e);
+    }
+    e = cudaMemcpyAsync(idx_dev, idx_host, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) {
+        int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)b->num_sms * 8);
+        gather_rows_kernel<<<grid, 256, 0, b->stream>>>(b->data, tmp, idx_dev, n, b->dim / 4);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(b->data, tmp, sizeof(float) * (size_t)n * b->dim, cudaMemcpyDeviceToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(idx_dev);
+    cudaFree(tmp);
+    CMDB_CUDA(e);
+    b->rows = n;
+    b->finalized = false;
+    return CMDB_OK;
+}
+
+int cmdb_bank_read(cmdb_bank *b, int64_t row0, int64_t n_rows, float *out_host) {
+    CMDB_REQUIRE(b && out_host && row0 >= 0 && n_rows >= 0 && row0 + n_rows <= b->rows, CMDB_ERR_INVALID,
+                 "cmdb_bank_read: rows [%lld,%lld) outside [0,%lld)", (long long)row0, (long long)(row0 + n_rows),
+                 b ? (long long)b->rows : 0LL);
+    if (n_rows == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaMemcpyAsync(out_host, b->data + row0 * b->dim, sizeof(float) * (size_t)n_rows * b->dim,
+                              cudaMemcpyDeviceToHost, b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    return CMDB_OK;
+}
+
+int cmdb_bank_finalize(cmdb_bank *b) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_finalize: bank is NULL");
+    CMDB_REQUIRE(b->rows > 0, CMDB_ERR_STATE, "cmdb_bank_finalize: bank is empty");
+    CMDB_REQUIRE(b->rows + b->row_offset < (1LL << 31), CMDB_ERR_UNSUPPORTED,
+                 "cmdb_bank_finalize: global row numbers must fit 31 bits for the packed (distance,row) keys");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    free_scoring_layout(b);
+    const int64_t pad = (b->rows + kScoreBN - 1) / kScoreBN * kScoreBN;
+    CMDB_CUDA(cudaMalloc(&b->hi, sizeof(__half) * (size_t)pad * b->dim));
+    CMDB_CUDA(cudaMalloc(&b->lo, sizeof(__half) * (size_t)pad * b->dim));
+    CMDB_CUDA(cudaMalloc(&b->norm, sizeof(float) * (size_t)pad));
+    float absmax = 0.f;
+    CMDB_CHECK(bank_max_abs(b, b->data, b->rows * b->dim, &absmax));
+    CMDB_REQUIRE(isfinite(absmax), CMDB_ERR_INVALID, "cmdb_bank_finalize: bank contains non-finite values");
+    b->scale_exp = pick_scale_exp(absmax);
+    launch_split_rows(b->stream, b->num_sms, b->data, b->rows, pad, b->dim, b->scale_exp, b->hi, b->lo, b->norm, INFINITY);
+    CMDB_CUDA(cudaGetLastError());
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    b->fin_rows = b->rows;
+    b->fin_rows_pad = pad;
+    CMDB_CHECK(score_make_tensor_maps(b));
+    b->finalized = true;
+    return CMDB_OK;
+}
+
+}  // extern "C"

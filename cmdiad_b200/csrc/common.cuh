@@ -1,0 +1,142 @@
+// Shared declarations of the cmdiad_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cmdiad_b200.h"
+
+namespace cmdb {
+
+void set_error(const char *fmt, ...);
+
+#define CMDB_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            cmdb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            (void)cudaGetLastError();                                                                \
+            return CMDB_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define CMDB_CHECK(expr)           \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != CMDB_OK) return _s; \
+    } while (0)
+
+#define CMDB_REQUIRE(cond, status, ...)   \
+    do {                                  \
+        if (!(cond)) {                    \
+            cmdb::set_error(__VA_ARGS__); \
+            return status;                \
+        }                                 \
+    } while (0)
+
+constexpr int kNumSMsDefault = 148;
+constexpr int kMaxQueryRows = 1024;  // query rows per GEMM launch (8 M-tiles of 128)
+constexpr int kScoreBN = 256;        // bank rows per GEMM tile
+constexpr int kScoreBM = 128;        // query rows per GEMM tile
+constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 128-byte swizzle row)
+
+// device scratch of one scoring call, sized at finalize time
+struct ScoreScratch {
+    int cap_p = 0;                  // padded query capacity (multiple of 128)
+    float *q_f32 = nullptr;         // [cap_p, D]  normalised query patches
+    __half *q_hi = nullptr;         // [cap_p, D]  split-fp16 query operand
+    __half *q_lo = nullptr;
+    float *q_norm = nullptr;        // [cap_p]     ||q||^2
+    unsigned int *q_absmax = nullptr;  // float bits of max|q|
+    int *q_scale_exp = nullptr;     // device: exponent e_q with q_hi + q_lo = q * 2^e_q
+    void *tmap_qhi = nullptr;       // host CUtensorMap objects for q_hi / q_lo
+    void *tmap_qlo = nullptr;
+    float *m_test = nullptr;        // [D] patch[s_idx]
+    float *m_star = nullptr;        // [D] bank[min_idx[s_idx]]
+    float *nn_rows = nullptr;       // [3, D] rows of the 3 nearest neighbours (sharded mode)
+    unsigned long long *top3 = nullptr;  // merged 3 smallest w_dist keys
+    int n_topk_blocks = 0;
+    float4 *cand = nullptr;         // [cap_p, n_ctas] per-CTA top-2 (val1, idx1, val2, idx2) of the GEMM epilogue
+    float *min_val = nullptr;       // [cap_p]
+    long long *min_idx = nullptr;   // [cap_p]
+    unsigned long long *s_key = nullptr;    // packed argmax key of min_val
+    unsigned long long *topk_keys = nullptr;  // [n_blocks*3] per-block w_dist top-3 packed keys
+    void *tail = nullptr;           // TailResult
+    float *map_pre = nullptr;       // [out_hw^2]
+    float *map_out = nullptr;
+    unsigned char *map_u8 = nullptr;
+    int map_cap = 0;
+};
+
+}  // namespace cmdb
+
+struct cmdb_bank {
+    int device = 0;
+    int dim = 0;
+    int num_sms = cmdb::kNumSMsDefault;
+    int64_t capacity = 0;
+    int64_t rows = 0;
+    int64_t row_offset = 0;
+    int score_impl = CMDB_SCORE_TCGEN05;
+    cudaStream_t stream = nullptr;
+    float *data = nullptr;  // [capacity, dim] float32 row-major
+    // scoring layout (cmdb_bank_finalize)
+    bool finalized = false;
+    int64_t fin_rows = 0;
+    int64_t fin_rows_pad = 0;  // multiple of kScoreBN
+    __half *hi = nullptr;      // [fin_rows_pad, dim] fp16(x * 2^scale_exp)
+    __half *lo = nullptr;      // [fin_rows_pad, dim] fp16(x * 2^scale_exp - hi)
+    float *norm = nullptr;     // [fin_rows_pad] ||x * 2^scale_exp||^2 ; +inf on padding rows
+    int scale_exp = 0;
+    void *tmap_hi = nullptr;  // host copies of the CUtensorMap objects (128 B each)
+    void *tmap_lo = nullptr;
+    cmdb::ScoreScratch ss;
+    double *stats_buf = nullptr;  // 2 doubles on device
+    unsigned int *absmax_buf = nullptr;
+};
+
+namespace cmdb {
+
+// bank.cu
+int bank_max_abs(cmdb_bank *b, const float *x, int64_t n, float *out_host);
+int pick_scale_exp(float absmax);
+void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t n_rows, int64_t n_pad, int dim,
+                       int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm);
+
+// project.cu
+int project_rows(cmdb_bank *b, const float *x_dev, int64_t n_rows, int D, const int32_t *indptr_h,
+                 const int32_t *indices_h, const double *data_h, int d_proj, double *z_dev);
+
+// coreset.cu
+int coreset_greedy(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
+                   int64_t *out_idx_host);
+int coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,
+                     void *out_host);
+
+// score_gemm.cu
+int score_scratch_alloc(cmdb_bank *b, int P, int out_hw);
+void score_scratch_free(cmdb_bank *b);
+int score_make_tensor_maps(cmdb_bank *b);
+int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out);  // q_f32 -> cand via the tcgen05 distance GEMM
+
+// score_tail.cu
+struct TailResult {  // device-side result block (ScoreScratch::tail)
+    float s, s_star, w, knn0, knn1;
+    int s_idx;
+    long long nn_idx[3];
+    long long m_star_row;  // global row of m_star
+};
+int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out);
+int score_refine(cmdb_bank *b, int P, int n_cand);
+int score_select(cmdb_bank *b, bool local_m_star);
+int score_wdist_topk(cmdb_bank *b);
+int score_merge_top3(cmdb_bank *b);
+int score_final(cmdb_bank *b, bool use_nn_rows);
+int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
+                         float *out_dev, unsigned char *u8_dev);
+
+}  // namespace cmdb

@@ -1,0 +1,605 @@
+// Greedy k-center coreset selection (reference features.py:372-425) as ONE persistent cooperative kernel.
+//
+// Per pick the reference launches >= 8 ATen kernels, materialises z - last as an [N,d'] temporary and syncs the host
+// twice.  Here the whole loop of n-1 dependent picks runs inside one kernel:
+//   * the projected bank z ([N,d'] half or double, natural row-major layout) is streamed once per pick (HBM/L2 bound:
+//     N*d'*sizeof(T) algorithmic bytes per pick); rows are statically partitioned CTA -> warp, so every warp keeps
+//     re-reading the same rows and the running min-distance vector never leaves shared memory;
+//   * the distance ||z_i - last|| is evaluated in the CANONICAL reduction order documented in
+//     oracle/coreset_oracle.c (the order of ATen's CUDA reduction for torch.linalg.norm on a contiguous [N,d'] tensor:
+//     32 lanes per row, aligned 4-element vectors round-robin over lanes, 4 accumulators per lane, fma accumulate,
+//     ((a0+a1)+a2)+a3, shfl_down-shaped tree, IEEE sqrt, one rounding to the storage type), so the selected indices
+//     are bit-identical to the torch-CUDA reference, including its lowest-index tie-break;
+//   * the 32 per-lane partials of 32 rows are transposed through shared memory so that the tree, sqrt, min and
+//     argmax bookkeeping run lane-parallel (one row per lane) instead of as 5 shuffles per row;
+//   * the per-pick grid-wide argmax is an all-gather of one (value,row) slot per CTA through L2 (release store +
+//     acquire polling, double-buffered by pick parity) -- no atomics, no host round trip, ~1 us per pick.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cmdb {
+
+namespace cg = cooperative_groups;
+
+constexpr int kCsThreads = 512;
+constexpr int kCsWarps = kCsThreads / 32;
+constexpr int kRowBatch = 4;  // rows in flight per warp
+
+struct __align__(16) PickSlot {
+    unsigned long long val;  // value bits (non-negative half/double order like unsigned integers)
+    unsigned long long tag;  // (epoch << 32) | row
+};
+
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T>
+struct Traits;
+template <>
+struct Traits<__half> {
+    using acc_t = float;
+    static __device__ __forceinline__ unsigned long long bits(__half v) { return (unsigned long long)__half_as_ushort(v); }
+    static __device__ __forceinline__ __half from_acc(float a) { return __float2half_rn(sqrtf(a)); }
+    static __device__ __forceinline__ __half zero() { return __ushort_as_half((unsigned short)0); }
+    static __device__ __forceinline__ bool lt(__half a, __half b) { return __half2float(a) < __half2float(b); }
+    static __device__ __forceinline__ bool gt(__half a, __half b) { return __half2float(a) > __half2float(b); }
+};
+template <>
+struct Traits<double> {
+    using acc_t = double;
+    static __device__ __forceinline__ unsigned long long bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+    static __device__ __forceinline__ double from_acc(double a) { return sqrt(a); }
+    static __device__ __forceinline__ double zero() { return 0.0; }
+    static __device__ __forceinline__ bool lt(double a, double b) { return a < b; }
+    static __device__ __forceinline__ bool gt(double a, double b) { return a > b; }
+};
+
+// ---- one aligned 4-element vector: load + accumulate ----
+struct HVec {
+    __half2 a, b;
+};
+__device__ __forceinline__ HVec ldvec(const __half *p) {
+    uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    HVec v;
+    v.a = *reinterpret_cast<__half2 *>(&r.x);
+    v.b = *reinterpret_cast<__half2 *>(&r.y);
+    return v;
+}
+struct DVec {
+    double2 a, b;
+};
+__device__ __forceinline__ DVec ldvec(const double *p) {
+    DVec v;
+    v.a = __ldg(reinterpret_cast<const double2 *>(p));
+    v.b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return v;
+}
+__device__ __forceinline__ HVec zero_vec(const __half *) {
+    HVec v;
+    v.a = v.b = __half2(Traits<__half>::zero(), Traits<__half>::zero());
+    return v;
+}
+__device__ __forceinline__ DVec zero_vec(const double *) {
+    DVec v;
+    v.a = v.b = make_double2(0.0, 0.0);
+    return v;
+}
+// z - last is rounded to the storage type (half: HSUB2 == float subtract + RNE), then fma-accumulated
+__device__ __forceinline__ void accum(const HVec &x, const HVec &l, float (&acc)[4]) {
+    float2 d0 = __half22float2(__hsub2(x.a, l.a)), d1 = __half22float2(__hsub2(x.b, l.b));
+    acc[0] = fmaf(d0.x, d0.x, acc[0]);
+    acc[1] = fmaf(d0.y, d0.y, acc[1]);
+    acc[2] = fmaf(d1.x, d1.x, acc[2]);
+    acc[3] = fmaf(d1.y, d1.y, acc[3]);
+}
+__device__ __forceinline__ void accum(const DVec &x, const DVec &l, double (&acc)[4]) {
+    double d;
+    d = x.a.x - l.a.x, acc[0] = fma(d, d, acc[0]);
+    d = x.a.y - l.a.y, acc[1] = fma(d, d, acc[1]);
+    d = x.b.x - l.b.x, acc[2] = fma(d, d, acc[2]);
+    d = x.b.y - l.b.y, acc[3] = fma(d, d, acc[3]);
+}
+__device__ __forceinline__ float sqdiff(__half x, __half l, float acc) {
+    float d = __half2float(__hsub(x, l));
+    return fmaf(d, d, acc);
+}
+__device__ __forceinline__ double sqdiff(double x, double l, double acc) {
+    double d = x - l;
+    return fma(d, d, acc);
+}
+__device__ __forceinline__ void set_elem(HVec &v, int j, __half x) {
+    if (j == 0) v.a.x = x;
+    else if (j == 1) v.a.y = x;
+    else if (j == 2) v.b.x = x;
+    else v.b.y = x;
+}
+__device__ __forceinline__ void set_elem(DVec &v, int j, double x) {
+    if (j == 0) v.a.x = x;
+    else if (j == 1) v.a.y = x;
+    else if (j == 2) v.b.x = x;
+    else v.b.y = x;
+}
+
+template <typename T>
+struct VecOf;
+template <>
+struct VecOf<__half> {
+    using type = HVec;
+};
+template <>
+struct VecOf<double> {
+    using type = DVec;
+};
+
+// geometry of one alignment class (shift s = (row*d) & 3) in the vectorised order
+struct ClassGeom {
+    int s, base, nfull, ntail, voff;  // voff: element offset of main vector 0 from the aligned row base (0 or 4)
+};
+__device__ __forceinline__ ClassGeom class_geom(int s, int d) {
+    ClassGeom g;
+    g.s = s;
+    g.base = s ? 4 - s : 0;
+    const int end = d - g.base;
+    g.nfull = end >> 2;
+    g.ntail = end & 3;
+    g.voff = s ? 4 : 0;
+    return g;
+}
+
+// `last` (the most recently selected row, in shared memory) arranged for one alignment class
+template <typename T, int NV>
+struct LastRegs {
+    typename VecOf<T>::type main[NV];
+    T head, tail;
+};
+template <typename T, int NV>
+__device__ __forceinline__ void load_last(LastRegs<T, NV> &L, const T *last_sh, const ClassGeom &g, int lane, int d,
+                                          bool vectorized) {
+    if (vectorized) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            const int v = lane + 32 * t;
+            L.main[t] = zero_vec((const T *)nullptr);
+            if (v < g.nfull) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) set_elem(L.main[t], j, last_sh[g.base + 4 * v + j]);
+            }
+        }
+        L.head = (g.s > 0 && lane >= g.s && lane < 4) ? last_sh[lane - g.s] : Traits<T>::zero();
+        L.tail = (lane < g.ntail) ? last_sh[g.base + 4 * g.nfull + lane] : Traits<T>::zero();
+    } else {
+        // d < 128: lane x owns elements x, x+32, x+64, x+96 -> accumulators 0..3 (kept in main[0])
+        L.main[0] = zero_vec((const T *)nullptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < d) set_elem(L.main[0], j, last_sh[lane + 32 * j]);
+        L.head = L.tail = Traits<T>::zero();
+    }
+}
+
+// per-lane partial ((a0+a1)+a2)+a3 of row `rowp` (natural layout, element 0 at rowp) in the canonical order
+template <typename T, int NV>
+struct RowLoads {
+    typename VecOf<T>::type main[NV];
+    T head, tail;
+};
+template <typename T, int NV>
+__device__ __forceinline__ void issue_loads(RowLoads<T, NV> &R, const T *rowp, const ClassGeom &g, int lane, int d,
+                                            bool vectorized) {
+    if (vectorized) {
+        const T *vb = rowp - g.s + g.voff;  // 4-element aligned
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            const int v = lane + 32 * t;
+            if (v < g.nfull) R.main[t] = ldvec(vb + 4 * v);
+            else R.main[t] = zero_vec((const T *)nullptr);
+        }
+        R.head = (g.s > 0 && lane >= g.s && lane < 4) ? __ldg(rowp + (lane - g.s)) : Traits<T>::zero();
+        R.tail = (lane < g.ntail) ? __ldg(rowp + g.base + 4 * g.nfull + lane) : Traits<T>::zero();
+    } else {
+        R.main[0] = zero_vec((const T *)nullptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < d) set_elem(R.main[0], j, __ldg(rowp + lane + 32 * j));
+        R.head = R.tail = Traits<T>::zero();
+    }
+}
+template <typename T, int NV>
+__device__ __forceinline__ typename Traits<T>::acc_t lane_partial(const RowLoads<T, NV> &R, const LastRegs<T, NV> &L,
+                                                                   bool vectorized) {
+    typename Traits<T>::acc_t acc[4] = {0, 0, 0, 0};
+    if (vectorized) {
+        acc[0] = sqdiff(R.head, L.head, acc[0]);  // lanes without a head element add fma(0,0,0) = 0
+#pragma unroll
+        for (int t = 0; t < NV; ++t) accum(R.main[t], L.main[t], acc);  // absent vectors are 0 - 0
+        acc[0] = sqdiff(R.tail, L.tail, acc[0]);
+    } else {
+        accum(R.main[0], L.main[0], acc);
+    }
+    return ((acc[0] + acc[1]) + acc[2]) + acc[3];
+}
+
+// shfl_down-shaped tree over 32 partials held by one thread: offsets 1,2,4,8,16, value of "lane 0"
+template <typename A>
+__device__ __forceinline__ A tree32(A (&v)[32]) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int l = 0; l + off < 32; l += 2 * off) v[l] = v[l] + v[l + off];
+    }
+    return v[0];
+}
+
+struct CoresetParams {
+    const void *z;               // [N,d] half or double
+    void *mind;                  // [N] running min distances (global copy; shared memory is used when it fits)
+    long long N;
+    int d;
+    long long n_select;
+    long long *out_idx;          // [n_select]
+    const long long *force_idx;  // optional teacher forcing
+    PickSlot *slots;             // [2][gridDim.x]
+    long long rows_per_cta;
+    int mind_in_smem;
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p) {
+    using acc_t = typename Traits<T>::acc_t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: tile [kCsWarps][32][33] acc_t | last_sh [d] T | red (val,row) [32] | mind [rows_per_cta] T
+    acc_t *tile_all = reinterpret_cast<acc_t *>(smem_raw);
+    T *last_sh = reinterpret_cast<T *>(tile_all + kCsWarps * 32 * 33);
+    unsigned long long *red_val = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(last_sh + p.d) + 15) & ~uintptr_t(15));
+    unsigned long long *red_row = red_val + 32;
+    T *mind_sh = reinterpret_cast<T *>(red_row + 32);
+
+    const T *z = reinterpret_cast<const T *>(p.z);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = p.d;
+    const bool vectorized = d >= 128;
+    acc_t *tile = tile_all + warp * 32 * 33;
+
+    const long long cta_row0 = (long long)blockIdx.x * p.rows_per_cta;
+    const long long cta_row1 = min(p.N, cta_row0 + p.rows_per_cta);
+    const long long cta_rows = max(0LL, cta_row1 - cta_row0);
+    T *mind = p.mind_in_smem ? mind_sh : reinterpret_cast<T *>(p.mind) + cta_row0;
+    if (p.mind_in_smem)
+        for (long long i = threadIdx.x; i < cta_rows; i += kCsThreads) mind_sh[i] = reinterpret_cast<T *>(p.mind)[cta_row0 + i];
+    // warp's contiguous chunk of the CTA's rows
+    const long long rows_per_warp = (cta_rows + kCsWarps - 1) / kCsWarps;
+    const long long w_row0 = cta_row0 + warp * rows_per_warp;
+    const long long w_row1 = min(cta_row1, w_row0 + rows_per_warp);
+
+    long long sel = 0;  // features.py:372 -- pick 0 is row 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[0] = 0;
+
+    for (long long pick = 1; pick < p.n_select; ++pick) {
+        // ---- stage `last` = z[sel] in shared memory; owner CTA zeroes min_d[sel] (features.py:418-419) ----
+        __syncthreads();
+        for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
+        if (threadIdx.x == 0 && pick > 1 && sel >= cta_row0 && sel < cta_row1) mind[sel - cta_row0] = Traits<T>::zero();
+        __syncthreads();
+
+        T best_val = Traits<T>::zero();
+        long long best_row = -1;
+        // ---- distance pass over the warp's rows, one alignment class at a time ----
+        for (int c = 0; c < 4; ++c) {
+            long long first = w_row0 + ((c - (int)(w_row0 & 3)) & 3);  // first row of the chunk with row % 4 == c
+            if (first >= w_row1) continue;
+            const int s = vectorized ? (int)(((long long)c * d) & 3) : 0;
+            const ClassGeom g = class_geom(s, d);
+            LastRegs<T, NV> L;
+            load_last<T, NV>(L, last_sh, g, lane, d, vectorized);
+            const long long n_class = (w_row1 - first + 3) >> 2;  // rows first, first+4, ...
+            for (long long g0 = 0; g0 < n_class; g0 += 32) {
+                const int n_here = (int)min(32LL, n_class - g0);
+                for (int r0 = 0; r0 < n_here; r0 += kRowBatch) {
+                    RowLoads<T, NV> R[kRowBatch];
+#pragma unroll
+                    for (int b = 0; b < kRowBatch; ++b) {
+                        const long long row = first + 4 * (g0 + min(r0 + b, n_here - 1));
+                        issue_loads<T, NV>(R[b], z + row * d, g, lane, d, vectorized);
+                    }
+#pragma unroll
+                    for (int b = 0; b < kRowBatch; ++b)
+                        if (r0 + b < n_here) tile[(r0 + b) * 33 + lane] = lane_partial<T, NV>(R[b], L, vectorized);
+                }
+                __syncwarp();
+                if (lane < n_here) {
+                    acc_t v[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = tile[lane * 33 + k];
+                    const T dist = Traits<T>::from_acc(tree32(v));
+                    const long long row = first + 4 * (g0 + lane);
+                    T m = mind[row - cta_row0];
+                    if (Traits<T>::lt(dist, m)) {  // torch.minimum (features.py:413)
+                        m = dist;
+                        mind[row - cta_row0] = m;
+                    }
+                    // argmax with lowest-index tie-break (features.py:415)
+                    if (best_row < 0 || Traits<T>::gt(m, best_val) || (!Traits<T>::lt(m, best_val) && row < best_row)) {
+                        best_val = m;
+                        best_row = row;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- CTA argmax: warp shuffle, then shared memory ----
+        unsigned long long bv = best_row < 0 ? 0ULL : Traits<T>::bits(best_val);
+        unsigned long long br = best_row < 0 ? ~0ULL : (unsigned long long)best_row;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long ov = __shfl_xor_sync(0xffffffffu, bv, o), orow = __shfl_xor_sync(0xffffffffu, br, o);
+            if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+        }
+        if (lane == 0) red_val[warp] = bv, red_row[warp] = br;
+        __syncthreads();
+        PickSlot *slots = p.slots + (pick & 1) * gridDim.x;
+        if (warp == 0) {
+            bv = lane < kCsWarps ? red_val[lane] : 0ULL;
+            br = lane < kCsWarps ? red_row[lane] : ~0ULL;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long ov = __shfl_xor_sync(0xffffffffu, bv, o), orow = __shfl_xor_sync(0xffffffffu, br, o);
+                if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+            }
+            if (lane == 0) {
+                st_relaxed_u64(&slots[blockIdx.x].val, bv);
+                st_release_u64(&slots[blockIdx.x].tag, ((unsigned long long)pick << 32) | (br & 0xffffffffULL));
+            }
+        }
+        // ---- grid all-gather of the per-CTA winners through L2 ----
+        bv = 0ULL, br = ~0ULL;
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += kCsThreads) {
+            unsigned long long tag;
+            do {
+                tag = ld_acquire_u64(&slots[c].tag);
+            } while ((tag >> 32) != (unsigned long long)pick);
+            const unsigned long long ov = ld_relaxed_u64(&slots[c].val);
+            const unsigned long long orow = (tag & 0xffffffffULL) == 0xffffffffULL ? ~0ULL : (tag & 0xffffffffULL);
+            if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long ov = __shfl_xor_sync(0xffffffffu, bv, o), orow = __shfl_xor_sync(0xffffffffu, br, o);
+            if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+        }
+        __syncthreads();  // red_* reads of the CTA stage are done
+        if (lane == 0) red_val[warp] = bv, red_row[warp] = br;
+        __syncthreads();
+        bv = red_val[0], br = red_row[0];
+#pragma unroll
+        for (int w = 1; w < kCsWarps; ++w) {
+            const unsigned long long ov = red_val[w], orow = red_row[w];
+            if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+        }
+        const long long argmax = (long long)br;
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[pick] = argmax;
+        sel = p.force_idx ? p.force_idx[pick] : argmax;
+    }
+    // final state of the min-distance vector (tests / diagnostics)
+    __syncthreads();
+    if (threadIdx.x == 0 && p.n_select > 1 && sel >= cta_row0 && sel < cta_row1) mind[sel - cta_row0] = Traits<T>::zero();
+    __syncthreads();
+    if (p.mind_in_smem)
+        for (long long i = threadIdx.x; i < cta_rows; i += kCsThreads) reinterpret_cast<T *>(p.mind)[cta_row0 + i] = mind_sh[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one distance pass (also the initial min-distance vector): out[i] = ||z_i - last||_2 in the canonical order
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) rownorm_kernel(const T *__restrict__ z, const T *__restrict__ last, long long N,
+                                                      int d, T *__restrict__ out_same, __half *__restrict__ out_half) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *last_sh = reinterpret_cast<T *>(smem_raw);
+    for (int e = threadIdx.x; e < d; e += blockDim.x) last_sh[e] = last[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const bool vectorized = d >= 128;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < N; row += warps) {
+        const int s = vectorized ? (int)((row * d) & 3) : 0;
+        const ClassGeom g = class_geom(s, d);
+        LastRegs<T, NV> L;
+        load_last<T, NV>(L, last_sh, g, lane, d, vectorized);
+        RowLoads<T, NV> R;
+        issue_loads<T, NV>(R, z + row * d, g, lane, d, vectorized);
+        typename Traits<T>::acc_t v = lane_partial<T, NV>(R, L, vectorized);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) {
+            const T r = Traits<T>::from_acc(v);
+            if (out_same) out_same[row] = r;
+            // features.py:391 min_distances.half(): torch converts double -> float -> half
+            if (out_half) out_half[row] = __float2half_rn((float)r);
+        }
+    }
+}
+
+// z64 -> half (torch .half(): double -> float -> half), natural layout
+__global__ void __launch_bounds__(512) to_half_kernel(const double *__restrict__ z, long long n, __half *__restrict__ zh) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        zh[i] = __float2half_rn((float)z[i]);
+}
+
+template <typename T>
+static int launch_rownorm(cudaStream_t st, int num_sms, const T *z, const T *last, long long N, int d, T *out_same,
+                          __half *out_half) {
+    const int nv = (d / 4 + 31) / 32;
+    const int grid = (int)std::min<long long>((N + 7) / 8, (long long)num_sms * 8);
+    const size_t smem = sizeof(T) * (size_t)d;
+#define CMDB_RN(NVV)                                                                                   \
+    case NVV:                                                                                          \
+        rownorm_kernel<T, NVV><<<grid, 256, smem, st>>>(z, last, N, d, out_same, out_half);            \
+        break;
+    switch (d >= 128 ? nv : 1) {
+        CMDB_RN(1) CMDB_RN(2) CMDB_RN(3) CMDB_RN(4) CMDB_RN(5) CMDB_RN(6) CMDB_RN(7) CMDB_RN(8)
+        default:
+            set_error("coreset: projected dim %d > 1024 is not supported", d);
+            return CMDB_ERR_UNSUPPORTED;
+    }
+#undef CMDB_RN
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
+template <typename T>
+static int launch_coreset(cmdb_bank *b, CoresetParams p) {
+    const int d = p.d;
+    const int nv = d >= 128 ? (d / 4 + 31) / 32 : 1;
+    int grid = b->num_sms;
+    const size_t fixed = sizeof(typename Traits<T>::acc_t) * kCsWarps * 32 * 33 + sizeof(T) * (size_t)d + 16 + 64 * 8;
+    auto run = [&](auto kern) -> int {
+        p.rows_per_cta = (p.N + grid - 1) / grid;
+        size_t smem = fixed + sizeof(T) * (size_t)p.rows_per_cta;
+        p.mind_in_smem = smem <= 200 * 1024;
+        if (!p.mind_in_smem) smem = fixed;
+        CMDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CMDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCsThreads, smem));
+        CMDB_REQUIRE(per_sm >= 1, CMDB_ERR_CUDA, "coreset: persistent kernel does not fit on an SM (smem %zu)", smem);
+        CMDB_CUDA(cudaMemsetAsync(p.slots, 0, sizeof(PickSlot) * 2 * grid, b->stream));
+        void *args[] = {&p};
+        CMDB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kCsThreads), args, smem, b->stream));
+        return CMDB_OK;
+    };
+#define CMDB_CS(NVV) \
+    case NVV:        \
+        return run(coreset_kernel<T, NVV>);
+    switch (nv) {
+        CMDB_CS(1) CMDB_CS(2) CMDB_CS(3) CMDB_CS(4) CMDB_CS(5) CMDB_CS(6) CMDB_CS(7) CMDB_CS(8)
+        default:
+            set_error("coreset: projected dim %d > 1024 is not supported", d);
+            return CMDB_ERR_UNSUPPORTED;
+    }
+#undef CMDB_CS
+}
+
+int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
+                       int64_t *out_idx_host, const int64_t *force_idx_host, void *out_min_last_host) {
+    CMDB_REQUIRE(N > 0 && d >= 32 && n_select >= 1 && n_select <= N, CMDB_ERR_INVALID,
+                 "coreset: need N>0, d>=32, 1<=n_select<=N (N=%lld d=%d n=%lld)", (long long)N, d, (long long)n_select);
+    CMDB_REQUIRE(N < (1LL << 32) - 1, CMDB_ERR_UNSUPPORTED, "coreset: N must fit 32 bits");
+    CMDB_REQUIRE(dtype_mode == CMDB_CORESET_FP16 || dtype_mode == CMDB_CORESET_FP64, CMDB_ERR_INVALID,
+                 "coreset: unknown dtype_mode %d", dtype_mode);
+    cudaStream_t st = b->stream;
+    long long *idx_dev = nullptr, *force_dev = nullptr;
+    PickSlot *slots = nullptr;
+    __half *zh = nullptr;
+    void *mind = nullptr;
+    int rc = CMDB_OK;
+    auto cleanup = [&]() {
+        cudaFree(idx_dev);
+        cudaFree(force_dev);
+        cudaFree(slots);
+        cudaFree(zh);
+        cudaFree(mind);
+    };
+#define CS_TRY(expr)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) {                                                                             \
+            set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));                  \
+            (void)cudaGetLastError();                                                                        \
+            cleanup();                                                                                       \
+            return CMDB_ERR_CUDA;                                                                            \
+        }                                                                                                    \
+    } while (0)
+    CS_TRY(cudaMalloc(&idx_dev, sizeof(long long) * (size_t)n_select));
+    CS_TRY(cudaMalloc(&slots, sizeof(PickSlot) * 2 * (size_t)b->num_sms));
+    if (force_idx_host) {
+        CS_TRY(cudaMalloc(&force_dev, sizeof(long long) * (size_t)n_select));
+        CS_TRY(cudaMemcpyAsync(force_dev, force_idx_host, sizeof(long long) * (size_t)n_select, cudaMemcpyHostToDevice, st));
+    }
+    CoresetParams p{};
+    p.N = N, p.d = d, p.n_select = n_select, p.out_idx = idx_dev, p.force_idx = force_dev, p.slots = slots;
+    if (dtype_mode == CMDB_CORESET_FP16) {
+        CS_TRY(cudaMalloc(&zh, sizeof(__half) * (size_t)N * d));
+        CS_TRY(cudaMalloc(&mind, sizeof(__half) * (size_t)N));
+        // features.py:378 initial distances in float64, then .half() (:389-391)
+        rc = launch_rownorm<double>(st, b->num_sms, z_dev, z_dev, N, d, nullptr, reinterpret_cast<__half *>(mind));
+        if (rc == CMDB_OK) {
+            to_half_kernel<<<b->num_sms * 4, 512, 0, st>>>(z_dev, (long long)N * d, zh);
+            CS_TRY(cudaGetLastError());
+            p.z = zh, p.mind = mind;
+            rc = launch_coreset<__half>(b, p);
+        }
+    } else {
+        CS_TRY(cudaMalloc(&mind, sizeof(double) * (size_t)N));
+        rc = launch_rownorm<double>(st, b->num_sms, z_dev, z_dev, N, d, reinterpret_cast<double *>(mind), nullptr);
+        if (rc == CMDB_OK) {
+            p.z = z_dev, p.mind = mind;
+            rc = launch_coreset<double>(b, p);
+        }
+    }
+    if (rc != CMDB_OK) {
+        cleanup();
+        return rc;
+    }
+    CS_TRY(cudaMemcpyAsync(out_idx_host, idx_dev, sizeof(long long) * (size_t)n_select, cudaMemcpyDeviceToHost, st));
+    if (out_min_last_host)
+        CS_TRY(cudaMemcpyAsync(out_min_last_host, mind,
+                               (dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double)) * (size_t)N,
+                               cudaMemcpyDeviceToHost, st));
+    CS_TRY(cudaStreamSynchronize(st));
+#undef CS_TRY
+    cleanup();
+    return CMDB_OK;
+}
+
+int coreset_greedy(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
+                   int64_t *out_idx_host) {
+    return coreset_greedy_dev(b, z_dev, N, d, n_select, dtype_mode, out_idx_host, nullptr, nullptr);
+}
+
+int coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,
+                     void *out_host) {
+    CMDB_REQUIRE(z_host && last_host && out_host && n_rows > 0 && d >= 32, CMDB_ERR_INVALID, "rownorms: bad arguments");
+    CMDB_CUDA(cudaSetDevice(device));
+    int num_sms = kNumSMsDefault;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t es = dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double);
+    void *z = nullptr, *last = nullptr, *out = nullptr;
+    cudaError_t e = cudaMalloc(&z, es * (size_t)n_rows * d);
+    if (e == cudaSuccess) e = cudaMalloc(&last, es * (size_t)d);
+    if (e == cudaSuccess) e = cudaMalloc(&out, es * (size_t)n_rows);
+    if (e == cudaSuccess) e = cudaMemcpy(z, z_host, es * (size_t)n_rows * d, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(last, last_host, es * (size_t)d, cudaMemcpyHostToDevice);
+    int rc = CMDB_OK;
+    if (e == cudaSuccess) {
+        if (dtype_mode == CMDB_CORESET_FP16)
+            rc = launch_rownorm<__half>(nullptr, num_sms, (const __half *)z, (const __half *)last, n_rows, d, (__half *)out,
+                                        nullptr);
+        else
+            rc = launch_rownorm<double>(nullptr, num_sms, (const double *)z, (const double *)last, n_rows, d, (double *)out,
+                                        nullptr);
+        if (rc == CMDB_OK) e = cudaMemcpy(out_host, out, es * (size_t)n_rows, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(z);
+    cudaFree(last);
+    cudaFree(out);
+    if (rc != CMDB_OK) return rc;
+    CMDB_CUDA(e);
+    return CMDB_OK;
+}
+
+}  // namespace cmdb

@@ -1,0 +1,439 @@
+// Patch -> bank nearest-neighbour search as a fused tcgen05 distance GEMM (reference features.py:186-190 + :227).
+//
+// torch.cdist computes d^2 = ||a||^2 + ||b||^2 - 2 a.b with a float32 GEMM and the reference then takes min/argmin over
+// the materialised [P,R] matrix.  Here the contraction runs on the 5th-generation tensor cores and the distance matrix
+// never exists:
+//   * FP32-equivalent operands: every float32 value (scaled by a power of two) is split into fp16 hi + fp16 lo
+//     (22 significand bits); a.b ~= hi.hi + hi.lo + lo.hi, three kind::f16 MMAs per K step into ONE fp32 TMEM
+//     accumulator -- 1.5x the tensor time of a plain fp16 GEMM and half that of 3xTF32;
+//   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer (SWIZZLE_128B tiles of q_hi/q_lo/b_hi/b_lo
+//     into a 2-stage ring), warp 1 = single-thread tcgen05.mma issuer (M=128 queries x N=256 bank rows, accumulators
+//     double-buffered in all 512 TMEM columns), warps 4-7 = epilogue;
+//   * epilogue: tcgen05.ld 32 columns at a time, val = ||b||^2 - 2 a.b (the per-query ||a||^2 is constant under argmin),
+//     branch-free per-thread top-2 (value, bank row) kept across all tiles of the CTA; one thread == one query row, so
+//     no cross-lane reduction is needed.  Per-CTA top-2 lists go to HBM (P x 148 x 16 B) and refine_kernel
+//     (score_tail.cu) re-checks the best candidates with exact float32 differences.
+// Algorithmic work: 2*P*R*D FLOP per image; tensor work is 3x that.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cmdb {
+
+constexpr int BM = kScoreBM;      // 128 query rows  (UMMA M)
+constexpr int BN = kScoreBN;      // 256 bank rows   (UMMA N)
+constexpr int BK = kScoreBK;      // 64 fp16 = 128 B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 2;
+constexpr int kMaxMT = kMaxQueryRows / BM;  // 8
+constexpr int kGemmThreads = 256;
+constexpr uint32_t kTileABytes = BM * BK * 2;  // 16 KB
+constexpr uint32_t kTileBBytes = BN * BK * 2;  // 32 KB
+constexpr uint32_t kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // 96 KB
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmSmem {  // offsets inside dynamic shared memory (1024-byte aligned base)
+    static constexpr uint32_t stage(int s) { return s * kStageBytes; }
+    static constexpr uint32_t a_hi(int s) { return stage(s); }
+    static constexpr uint32_t a_lo(int s) { return stage(s) + kTileABytes; }
+    static constexpr uint32_t b_hi(int s) { return stage(s) + 2 * kTileABytes; }
+    static constexpr uint32_t b_lo(int s) { return stage(s) + 2 * kTileABytes + kTileBBytes; }
+    static constexpr uint32_t bnorm = kStages * kStageBytes;              // [2][BN] float
+    static constexpr uint32_t state = bnorm + 2 * BN * 4;                 // [kMaxMT][BM] float4
+    static constexpr uint32_t bars = state + kMaxMT * BM * 16;            // mbarriers
+    static constexpr uint32_t total = bars + 128;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+        "[%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO in [16,30) (unused for a single swizzle atom along K), SBO = 8 rows * 128 B = 1024 B >> 4 in [32,46),
+// version 1 in [46,48), layout type SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((8u * BK * 2u) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B fp16 (0), both K-major,
+// N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct GemmParams {
+    int mt;             // M tiles of this launch (<= kMaxMT)
+    int m_tile_base;    // first M tile (row m_tile_base*128 of q_hi/q_lo)
+    int nt;             // N tiles (bank rows / 256)
+    int kb;             // K blocks (D / 64)
+    const float *bnorm; // [nt*256] ||b||^2, +inf on padding rows
+    const int *q_scale_exp;
+    int b_scale_exp;
+    float4 *cand;       // [P_pad][cand_stride]
+    int cand_stride;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+                  const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+    const uint32_t bar_full = sbase + GemmSmem::bars, bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + GemmSmem::bars + 8 * (2 * kStages + 4));
+    float *bnorm_s = reinterpret_cast<float *>(smem + GemmSmem::bnorm);
+    float4 *state = reinterpret_cast<float4 *>(smem + GemmSmem::state);
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    for (int i = threadIdx.x; i < p.mt * BM; i += kGemmThreads)
+        state[i] = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.mt * p.nt;
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n = t / p.mt, m = t - n * p.mt + p.m_tile_base;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_expect_tx(full, kStageBytes);
+                    tma_load_2d(sbase + GemmSmem::a_hi(stage), &tm_qhi, full, kb * BK, m * BM);
+                    tma_load_2d(sbase + GemmSmem::a_lo(stage), &tm_qlo, full, kb * BK, m * BM);
+                    tma_load_2d(sbase + GemmSmem::b_hi(stage), &tm_bhi, full, kb * BK, n * BN);
+                    tma_load_2d(sbase + GemmSmem::b_lo(stage), &tm_blo, full, kb * BK, n * BN);
+                    if (++stage == kStages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int j = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+                const int buf = j & 1;
+                mbar_wait(bar_tempty + 8 * buf, ((j >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t a_hi = make_sw128_desc(sbase + GemmSmem::a_hi(stage));
+                    const uint64_t a_lo = make_sw128_desc(sbase + GemmSmem::a_lo(stage));
+                    const uint64_t b_hi = make_sw128_desc(sbase + GemmSmem::b_hi(stage));
+                    const uint64_t b_lo = make_sw128_desc(sbase + GemmSmem::b_lo(stage));
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
+                        umma_f16(tmem_d, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) != 0);
+                        umma_f16(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1);
+                        umma_f16(tmem_d, a_lo + adv, b_hi + adv, kIdesc, 1);
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+                    if (++stage == kStages) stage = 0, phase ^= 1;
+                }
+                umma_commit(bar_tfull + 8 * buf);  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: 4 warps, thread == query row =================
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;     // row inside the M tile
+        const int et = threadIdx.x - 128;        // 0..127
+        const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp)));
+        int j = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+            const int n = t / p.mt, m_local = t - n * p.mt;
+            const int buf = j & 1;
+            float *bn = bnorm_s + buf * BN;
+            // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
+            bn[et] = __ldg(p.bnorm + (size_t)n * BN + et);
+            bn[et + 128] = __ldg(p.bnorm + (size_t)n * BN + et + 128);
+            float4 st = state[m_local * BM + row];
+            float b1 = st.x, b2 = st.z;
+            int i1 = __float_as_int(st.y), i2 = __float_as_int(st.w);
+            mbar_wait(bar_tfull + 8 * buf, (j >> 1) & 1);
+            tc_fence_after();
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // bn[] visible to the 4 epilogue warps
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
+            const int col0 = n * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(taddr + ch * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float v = fmaf(__uint_as_float(r[k]), c, bn[ch * 32 + k]);
+                    const int col = col0 + ch * 32 + k;
+                    const bool c1 = v < b1, c2 = v < b2;
+                    i2 = c1 ? i1 : (c2 ? col : i2);
+                    b2 = fminf(b2, fmaxf(b1, v));
+                    i1 = c1 ? col : i1;
+                    b1 = fminf(b1, v);
+                }
+            }
+            state[m_local * BM + row] = make_float4(b1, __int_as_float(i1), b2, __int_as_float(i2));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // per-CTA candidate lists -> HBM
+    for (int i = threadIdx.x; i < p.mt * BM; i += kGemmThreads)
+        p.cand[(size_t)(p.m_tile_base * BM + i) * p.cand_stride + blockIdx.x] = state[i];
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------- query preparation (device-side scale selection)
+__global__ void __launch_bounds__(512) q_absmax_kernel(const float *__restrict__ x, long long n, unsigned int *out) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// one warp per query row: q * 2^e -> fp16 hi/lo; rows >= P are zero.  e is derived from max|q| on the device so the
+// call never syncs with the host; block 0 publishes it for the GEMM epilogue.
+__global__ void __launch_bounds__(256) q_split_kernel(const float *__restrict__ q, int P, int P_pad, int dim,
+                                                      const unsigned int *__restrict__ absmax_bits, __half *__restrict__ hi,
+                                                      __half *__restrict__ lo, int *__restrict__ scale_exp_out) {
+    const float amax = __uint_as_float(*absmax_bits);
+    int e = 0;
+    if (amax > 0.f && amax < INFINITY) {
+        int ex;
+        frexpf(amax, &ex);
+        e = 13 - ex;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scale_exp_out = e;
+    const float scale = ldexpf(1.f, e);
+    const int lane = threadIdx.x & 31, dim4 = dim >> 2;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < P_pad; r += gridDim.x * 8) {
+        uint2 *h = reinterpret_cast<uint2 *>(hi + (size_t)r * dim), *l = reinterpret_cast<uint2 *>(lo + (size_t)r * dim);
+        for (int cc = lane; cc < dim4; cc += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < P) v = __ldg(reinterpret_cast<const float4 *>(q + (size_t)r * dim) + cc);
+            v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            h[cc] = make_uint2(*reinterpret_cast<unsigned int *>(&h0), *reinterpret_cast<unsigned int *>(&h1));
+            l[cc] = make_uint2(*reinterpret_cast<unsigned int *>(&l0), *reinterpret_cast<unsigned int *>(&l1));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp16 [rows, dim] row-major, box = [box_rows, 64] (128 B inner extent), SWIZZLE_128B
+static int make_map(void **slot, const __half *base, long long rows, int dim, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    CMDB_REQUIRE(fn != nullptr, CMDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if (!*slot) *slot = aligned_alloc(64, sizeof(CUtensorMap));
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(*slot), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, gdim, gstr, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CMDB_REQUIRE(r == CUDA_SUCCESS, CMDB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CMDB_OK;
+}
+
+int score_make_tensor_maps(cmdb_bank *b) {
+    CMDB_CHECK(make_map(&b->tmap_hi, b->hi, b->fin_rows_pad, b->dim, BN));
+    CMDB_CHECK(make_map(&b->tmap_lo, b->lo, b->fin_rows_pad, b->dim, BN));
+    return CMDB_OK;
+}
+
+void score_scratch_free(cmdb_bank *b) {
+    ScoreScratch &s = b->ss;
+    cudaFree(s.q_f32), cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_norm), cudaFree(s.q_absmax), cudaFree(s.q_scale_exp);
+    cudaFree(s.cand), cudaFree(s.min_val), cudaFree(s.min_idx), cudaFree(s.s_key), cudaFree(s.topk_keys), cudaFree(s.tail);
+    cudaFree(s.map_pre), cudaFree(s.map_out), cudaFree(s.map_u8), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
+    cudaFree(s.top3);
+    free(s.tmap_qhi), free(s.tmap_qlo);
+    s = ScoreScratch();
+}
+
+int score_scratch_alloc(cmdb_bank *b, int P, int out_hw) {
+    ScoreScratch &s = b->ss;
+    const int p_pad = (P + BM - 1) / BM * BM;
+    const int map_n = out_hw * out_hw;
+    if (s.cap_p >= p_pad && s.map_cap >= map_n) return CMDB_OK;
+    const int cap_p = std::max(p_pad, s.cap_p), map_cap = std::max(map_n, s.map_cap);
+    score_scratch_free(b);
+    const size_t D = b->dim;
+    s.n_topk_blocks = b->num_sms * 4;
+    CMDB_CUDA(cudaMalloc(&s.q_f32, sizeof(float) * cap_p * D));
+    CMDB_CUDA(cudaMalloc(&s.q_hi, sizeof(__half) * cap_p * D));
+    CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
+    CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.q_absmax, sizeof(unsigned int)));
+    CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int)));
+    CMDB_CUDA(cudaMalloc(&s.cand, sizeof(float4) * (size_t)cap_p * b->num_sms));
+    CMDB_CUDA(cudaMalloc(&s.min_val, sizeof(float) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.min_idx, sizeof(long long) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long)));
+    CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks));
+    CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3));
+    CMDB_CUDA(cudaMalloc(&s.tail, sizeof(TailResult)));
+    CMDB_CUDA(cudaMalloc(&s.map_pre, sizeof(float) * map_cap));
+    CMDB_CUDA(cudaMalloc(&s.map_out, sizeof(float) * map_cap));
+    CMDB_CUDA(cudaMalloc(&s.map_u8, map_cap));
+    CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D));
+    CMDB_CUDA(cudaMalloc(&s.m_star, sizeof(float) * D));
+    CMDB_CUDA(cudaMalloc(&s.nn_rows, sizeof(float) * 3 * D));
+    s.cap_p = cap_p, s.map_cap = map_cap;
+    CMDB_CHECK(make_map(&s.tmap_qhi, s.q_hi, cap_p, b->dim, BM));
+    CMDB_CHECK(make_map(&s.tmap_qlo, s.q_lo, cap_p, b->dim, BM));
+    return CMDB_OK;
+}
+
+int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
+    ScoreScratch &s = b->ss;
+    const int p_pad = (P + BM - 1) / BM * BM;
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaMemsetAsync(s.q_absmax, 0, sizeof(unsigned int), st));
+    q_absmax_kernel<<<std::min(b->num_sms, (int)(((long long)P * b->dim / 4 + 511) / 512)), 512, 0, st>>>(
+        s.q_f32, (long long)P * b->dim, s.q_absmax);
+    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(s.q_f32, P, p_pad, b->dim, s.q_absmax, s.q_hi,
+                                                                              s.q_lo, s.q_scale_exp);
+    CMDB_CUDA(cudaGetLastError());
+    static bool attr_set = false;
+    if (!attr_set) {
+        CMDB_CUDA(cudaFuncSetAttribute(score_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem::total + 1024));
+        attr_set = true;
+    }
+    GemmParams p{};
+    p.nt = (int)(b->fin_rows_pad / BN);
+    p.kb = b->dim / BK;
+    p.bnorm = b->norm;
+    p.q_scale_exp = s.q_scale_exp;
+    p.b_scale_exp = b->scale_exp;
+    p.cand = s.cand;
+    p.cand_stride = b->num_sms;
+    const int mt_total = p_pad / BM;
+    for (int m0 = 0; m0 < mt_total; m0 += kMaxMT) {
+        p.m_tile_base = m0;
+        p.mt = std::min(kMaxMT, mt_total - m0);
+        score_gemm_kernel<<<b->num_sms, kGemmThreads, GemmSmem::total + 1024, st>>>(
+            *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
+            *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
+        CMDB_CUDA(cudaGetLastError());
+    }
+    *n_cand_out = b->num_sms;
+    return CMDB_OK;
+}
+
+}  // namespace cmdb

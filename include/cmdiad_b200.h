@@ -1,0 +1,156 @@
+/*
+ * cmdiad_b200 -- C ABI of the B200-native (sm_100a) memory-bank anomaly-scoring path of evenrose/CMDIAD.
+ *
+ * The reference has no plugin/operator registry: the seam is a handful of Python methods on the `Features` classes
+ * (feature_extractors/features.py, feature_extractors/multiple_features.py).  Each entry point below names the
+ * reference lines it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C, no torch types: pointers + sizes.  The caller owns every input/output buffer; the library owns only the
+ *     opaque bank handle and the device memory behind it.
+ *   - every function returns 0 on success or a negative cmdb_status; nothing throws across the ABI.
+ *     cmdb_last_error() returns a thread-local, NUL-terminated description of the last failure on this thread.
+ *   - `*_is_device` flags: 0 = the pointer is host memory (pageable or pinned), 1 = device memory on the bank's GPU.
+ *   - calls on one handle are serialised by the caller (the reference is single-threaded per method object); distinct
+ *     handles may be used from different threads.  Each handle owns one CUDA stream; host-visible results are complete
+ *     when the call returns.
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute call fails with CMDB_ERR_CUDA.
+ *   - indices are int64 and GLOBAL row numbers (shard row offset + local row) so that "ties -> lowest index" survives
+ *     row-sharding across GPUs.
+ */
+#ifndef CMDIAD_B200_H
+#define CMDIAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmdb_bank cmdb_bank; /* one memory bank (patch_rgb_lib / patch_xyz_lib / patch_fusion_lib) on one GPU */
+
+typedef enum cmdb_status {
+    CMDB_OK = 0,
+    CMDB_ERR_INVALID = -1,  /* bad argument (NULL, negative size, d_proj > dim, ...) */
+    CMDB_ERR_CUDA = -2,     /* CUDA runtime/driver failure, or no sm_100 device */
+    CMDB_ERR_STATE = -3,    /* call not valid in the bank's current state (e.g. score before finalize) */
+    CMDB_ERR_CAPACITY = -4, /* append beyond capacity_rows */
+    CMDB_ERR_UNSUPPORTED = -5
+} cmdb_status;
+
+/* coreset_dtype of the reference (main.py:151, features.py:388-395) */
+#define CMDB_CORESET_FP16 0 /* 'FP16': half data, float accumulate (reference default) */
+#define CMDB_CORESET_FP64 1 /* 'TF32': the reference only flips a matmul flag, the data stays float64 */
+
+/* scoring implementation selector (cmdb_bank_set_option(CMDB_OPT_SCORE_IMPL)) */
+#define CMDB_SCORE_TCGEN05 0 /* tcgen05/TMEM split-fp16 distance GEMM (default, the product path) */
+#define CMDB_SCORE_SIMT 1    /* plain fp32 CUDA-core kernel, diagnostics only (same outputs, ~10x slower) */
+
+#define CMDB_OPT_SCORE_IMPL 1
+
+int cmdb_version(void);
+const char *cmdb_last_error(void);
+/* number of visible sm_100 devices (0 and CMDB_OK when there is none) */
+int cmdb_device_count(int *out_n);
+
+/* ---- bank storage: replaces the Python-list banks and torch.cat (multiple_features.py:35,38; features.py:49-51) ---- */
+
+/* Pre-allocates a row-major float32 [capacity_rows, dim] bank in HBM on `device`. dim must be a multiple of 64. */
+int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out);
+void cmdb_bank_destroy(cmdb_bank *bank);
+/* self.patch_*_lib.append(patch)  (multiple_features.py:35, 131, 217, 363-365, 607-609, 870-871) */
+int cmdb_bank_append(cmdb_bank *bank, const float *rows, int64_t n_rows, int rows_is_device);
+int cmdb_bank_rows(const cmdb_bank *bank, int64_t *out_rows);
+int cmdb_bank_dim(const cmdb_bank *bank, int *out_dim);
+/* Row-sharding: this handle holds global rows [row_offset, row_offset + rows). Default offset 0. */
+int cmdb_bank_set_row_offset(cmdb_bank *bank, int64_t row_offset);
+int cmdb_bank_set_option(cmdb_bank *bank, int option, int value);
+/* torch.mean / torch.std (unbiased) over ALL elements (multiple_features.py:39-40): float64 accumulation on the GPU.
+ * out_sum / out_sumsq (optional) return the raw float64 sums so that shards can be combined on the host. */
+int cmdb_bank_stats(cmdb_bank *bank, double *out_mean, double *out_std_unbiased, double *out_sum, double *out_sumsq);
+/* lib = (lib - mean) / std in float32, in place (multiple_features.py:41); one IEEE subtract and one IEEE divide. */
+int cmdb_bank_normalize(cmdb_bank *bank, float mean, float std);
+/* lib = lib[idx] (multiple_features.py:48): keeps n rows in the given order; idx are LOCAL row numbers. */
+int cmdb_bank_gather(cmdb_bank *bank, const int64_t *idx_host, int64_t n);
+/* copies rows [row0, row0+n_rows) back to the host (to refill self.patch_*_lib, which features.py:238-283 index) */
+int cmdb_bank_read(cmdb_bank *bank, int64_t row0, int64_t n_rows, float *out_host);
+/* Builds the scoring layout (fp16 hi/lo split, row norms) for the current rows. Must precede cmdb_score*. */
+int cmdb_bank_finalize(cmdb_bank *bank);
+/* the cudaStream_t every kernel of this handle is launched on (for event timing by the caller) */
+int cmdb_bank_stream(cmdb_bank *bank, void **out_stream);
+
+/* ---- coreset: replaces Features.get_coreset_idx_randomp (features.py:360-425) ---- */
+
+/*
+ * Sparse random projection (features.py:365-366) followed by the greedy k-center loop (features.py:372-420), all on
+ * the GPU in one persistent kernel.  The CSR matrix [d_proj, dim] is sklearn's SparseRandomProjection.components_
+ * (float64 data, per-row indices in STORED order), generated on the host by the caller exactly as the reference does;
+ * d_proj == 0 means "no projection" (the reference's ValueError branch, features.py:369-370).
+ * out_idx_host: int64 [n_select], out_idx_host[0] == 0 always (features.py:372).  Indices are local rows.
+ */
+int cmdb_coreset_select(cmdb_bank *bank, int64_t n_select, const int32_t *csr_indptr, const int32_t *csr_indices,
+                        const double *csr_data, int d_proj, int dtype_mode, int64_t *out_idx_host);
+
+/* Projection only: out_host float64 [n_rows, d_proj] for rows [row0, row0+n_rows) (bit-exact with sklearn). */
+int cmdb_project(cmdb_bank *bank, const int32_t *csr_indptr, const int32_t *csr_indices, const double *csr_data,
+                 int d_proj, int64_t row0, int64_t n_rows, double *out_host);
+
+/* One distance pass of the greedy loop (features.py:405) in the canonical reduction order, for parity pinning:
+ * z [n_rows, d] and last [d] are half bits (dtype_mode FP16) or float64 (FP64); out has the same type, [n_rows]. */
+int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,
+                          void *out_host);
+
+/* ---- scoring: replaces Features.calculate_dist + compute_single_s_s_map (features.py:186-190, 225-297) ---- */
+
+typedef struct cmdb_score_out {
+    /* all pointers are HOST buffers owned by the caller; NULL = not wanted */
+    float *s;            /* [1]  w * s_star                                   (features.py:290) */
+    float *s_star;       /* [1]  max_p min_r dist                             (features.py:231) */
+    int64_t *s_idx;      /* [1]  argmax_p, ties -> lowest p                   (features.py:228) */
+    float *min_val;      /* [P]  min_r ||patch_p - bank_r||_2                 (features.py:227) */
+    int64_t *min_idx;    /* [P]  argmin_r (global rows), ties -> lowest r     (features.py:227) */
+    int64_t *nn_idx;     /* [3]  3 nearest bank rows of m_star, ascending     (features.py:254) */
+    float *m_star_knn;   /* [2]  ||m_test - bank[nn_idx[1:]]||_2              (features.py:275-283) */
+    float *w;            /* [1]  re-weighting factor                          (features.py:287) */
+    float *s_map;        /* [out_hw*out_hw] upsampled + blurred map           (features.py:293-295) */
+    float *s_map_pre;    /* [out_hw*out_hw] bilinear map before the blur      (features.py:294) */
+    uint8_t *s_map_u8;   /* [out_hw*out_hw] the 8-bit image handed to the blur (utils/utils.py:82 ToPILImage) */
+} cmdb_score_out;
+
+/*
+ * Scores one image's patches against the bank: dist = cdist(patch, bank), min/argmin, s*, m*, top-3 re-weighting,
+ * bilinear upsample to out_hw x out_hw and the PIL-exact Gaussian blur (radius 4).  patch: float32 [P, dim], already
+ * normalised by the caller ((patch - mean) / std, multiple_features.py:90); P == fh*fw (feature_map_dims).
+ * The [P, R] distance matrix is never materialised.
+ */
+int cmdb_score(cmdb_bank *bank, const float *patch, int P, int fh, int fw, int out_hw, int patch_is_device,
+               cmdb_score_out *out);
+
+/*
+ * Row-sharded scoring (one process per GPU).  Every rank holds a contiguous block of bank rows
+ * (cmdb_bank_set_row_offset) and the full, replicated patch.  All buffers named *_device are device memory on the
+ * bank's GPU, owned by the caller (torch tensors), so the collectives between the phases run on them directly:
+ *   1. cmdb_score_shard_min     keys[p] = (float_bits(local min distance) << 32) | global_row   -> all-reduce MIN (int64)
+ *      (non-negative, so integer MIN == argmin with lowest-global-row tie-break)
+ *   2. cmdb_score_shard_select  decodes the reduced keys (min_val, min_idx, s_star, s_idx); writes m_star = the winning
+ *      bank row if this rank owns it, zeros otherwise                                           -> all-reduce SUM (float[dim])
+ *   3. cmdb_score_shard_topk    3 smallest local w_dist keys for the (now replicated) m_star     -> all-gather (int64[3])
+ *   4. cmdb_score_shard_nn      merges the gathered keys; writes the rows of the 3 neighbours this rank owns, zeros
+ *      otherwise                                                                                -> all-reduce SUM (float[3*dim])
+ *   5. cmdb_score_shard_finish  m_star_knn, w, s, upsample + blur; identical result on every rank.
+ */
+int cmdb_score_shard_min(cmdb_bank *bank, const float *patch, int P, int patch_is_device, int64_t *keys_device);
+int cmdb_score_shard_select(cmdb_bank *bank, const int64_t *reduced_keys_device, int P, float *m_star_contrib_device);
+int cmdb_score_shard_topk(cmdb_bank *bank, const float *m_star_device, int64_t *topk_keys_device);
+int cmdb_score_shard_nn(cmdb_bank *bank, const int64_t *gathered_keys_device, int n_keys, float *nn_rows_contrib_device);
+int cmdb_score_shard_finish(cmdb_bank *bank, const float *nn_rows_device, int P, int fh, int fw, int out_hw,
+                            cmdb_score_out *out);
+
+/* Stand-alone score-map post-processing (features.py:293-295, utils/utils.py:71-83): map [fh*fw] -> [out_hw^2]. */
+int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host,
+                       float *out_pre_host, uint8_t *out_u8_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMDIAD_B200_H */

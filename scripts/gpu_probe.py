@@ -1,0 +1,189 @@
+"""Diagnostics run on the GPU box (not a test, not a benchmark): prints mismatch statistics and rough timings for every
+kernel so one gpurun call tells as much as possible."""
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cmdiad_b200 import Bank, coreset_rownorms, synth, upsample_blur  # noqa: E402
+from cmdiad_b200 import _lib as L  # noqa: E402
+from oracle import restate as O  # noqa: E402
+
+
+def section(name):
+    def deco(fn):
+        def run():
+            print(f"\n=== {name} ===", flush=True)
+            t = time.time()
+            try:
+                fn()
+            except Exception:
+                traceback.print_exc()
+            print(f"--- {name}: {time.time() - t:.1f}s", flush=True)
+        return run
+    return deco
+
+
+def ev_time(stream, fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), float(np.median(ts))
+
+
+@section("rownorms vs oracle vs torch-cuda")
+def s_rownorms():
+    for d in (64, 100, 128, 129, 130, 131, 221, 301, 375):
+        g = np.random.Generator(np.random.PCG64(d))
+        z = (g.standard_normal((4099, d)) * 1.7).astype(np.float16)
+        got = coreset_rownorms(z, z[17])
+        orc = O.rownorms_restated(z, z[17])
+        zt = torch.from_numpy(z).cuda()
+        ref = torch.linalg.norm(zt - zt[17:18], dim=1, keepdims=True).cpu().numpy()[:, 0]
+        z64 = g.standard_normal((4099, d))
+        got64 = coreset_rownorms(z64, z64[5])
+        zt64 = torch.from_numpy(z64).cuda()
+        ref64 = torch.linalg.norm(zt64 - zt64[5:6], dim=1, keepdims=True).cpu().numpy()[:, 0]
+        print(f"d={d}: fp16 kernel!=oracle {(got.view(np.uint16) != orc.view(np.uint16)).sum()}, kernel!=torch "
+              f"{(got.view(np.uint16) != ref.view(np.uint16)).sum()}, oracle!=torch {(orc.view(np.uint16) != ref.view(np.uint16)).sum()}"
+              f" | fp64 kernel!=oracle {(got64 != O.rownorms_restated(z64, z64[5])).sum()}, kernel!=torch {(got64 != ref64).sum()}")
+
+
+@section("projection")
+def s_proj():
+    g = np.random.Generator(np.random.PCG64(1))
+    x = g.standard_normal((3000, 768), dtype=np.float32)
+    csr = O.sparse_components(3000, 768, 0.9, 0)
+    b = Bank(768, 3000)
+    b.append(x)
+    z = b.project(csr)
+    print("mismatch vs oracle:", (z != O.project_restated(x, *csr)).sum(), "of", z.size)
+    b.close()
+
+
+@section("coreset small parity")
+def s_coreset_small():
+    lib = np.concatenate(synth.image_bank(10, 784, 768, 11), 0)
+    lib = (lib - lib.mean()) / lib.std()
+    csr = O.sparse_components(lib.shape[0], 768, 0.9, 0)
+    z = O.project_restated(lib, *csr)
+    b = Bank(768, lib.shape[0])
+    b.append(lib)
+    n = 784
+    for mode, name in ((L.CORESET_FP64, "TF32"), (L.CORESET_FP16, "FP16")):
+        t = time.time()
+        idx = b.coreset_select(n, csr, mode)
+        dt = time.time() - t
+        ref = O.coreset_restated(z, n, name)
+        lit = O.coreset_torch_literal(torch.from_numpy(z), n, name, device="cuda").numpy()
+        ne, nl = np.nonzero(idx != ref)[0], np.nonzero(idx != lit)[0]
+        print(f"{name}: {dt*1e3:.1f} ms; vs oracle first-div {ne[:1]}, vs torch-cuda literal first-div {nl[:1]}, "
+              f"oracle vs literal first-div {np.nonzero(ref != lit)[0][:1]}")
+    b.close()
+
+
+@section("coreset 200k x 768 -> 301, 10% timing")
+def s_coreset_big():
+    N, D = 200_000, 768
+    cent = synth.centroids(D)
+    b = Bank(D, N)
+    for i in range(8):
+        b.append(synth.patches(N // 8, D, seed=100 + i, cent=cent))
+    mean, std, _, _ = b.stats()
+    b.normalize(mean, std)
+    csr = O.sparse_components(N, D, 0.9, 0)
+    for n in (2000, 20000):
+        torch.cuda.synchronize()
+        t = time.time()
+        idx = b.coreset_select(n, csr, L.CORESET_FP16)
+        dt = time.time() - t
+        print(f"FP16 n={n}: {dt:.3f} s total, {(dt) / (n - 1) * 1e6:.2f} us/pick incl. projection; d'={csr[3]}; "
+              f"algorithmic {(n-1)*N*csr[3]*2/dt/1e9:.0f} GB/s; unique {len(set(idx.tolist()))}")
+    t = time.time()
+    z = b.project(csr, 0, 1000)
+    print("projection of 1000 rows (incl. D2H)", time.time() - t)
+    t = time.time()
+    idx = b.coreset_select(500, csr, L.CORESET_FP64)
+    dt = time.time() - t
+    print(f"FP64 n=500: {dt:.3f} s")
+    b.close()
+
+
+@section("score small parity (both impls)")
+def s_score_small():
+    cent = synth.centroids(768, 256)
+    lib = synth.patches(5000, 768, seed=1, cent=cent)
+    patch = synth.patches(784, 768, seed=2, anomalous_frac=0.01, cent=cent)
+    ref = O.score_restated(patch, lib, (28, 28), 224)
+    for impl, name in ((L.SCORE_SIMT, "simt"), (L.SCORE_TCGEN05, "tcgen05")):
+        try:
+            b = Bank(768, 5000)
+            b.append(lib)
+            b.finalize()
+            b.set_score_impl(impl)
+            r = b.score(patch, (28, 28), 224, full=True)
+            print(f"{name}: argmin mismatches {(r.min_idx != ref['min_idx']).sum()}, min_val max rel err "
+                  f"{np.max(np.abs(r.min_val - ref['min_val']) / ref['min_val']):.2e}, s {r.s[0]:.6f} vs {ref['s']:.6f}, "
+                  f"s_idx {r.s_idx[0]} vs {ref['s_idx']}, nn {r.nn_idx} vs {ref['nn_idx']}, knn {r.m_star_knn} vs {ref['m_star_knn']}, "
+                  f"pre max rel {np.max(np.abs(r.s_map_pre - ref['s_map_pre']) / ref['s_map_pre']):.2e}, "
+                  f"u8 mismatches {(r.s_map_u8 != ref['s_map_u8']).sum()}, blur mismatches {(r.s_map != ref['s_map']).sum()}")
+            b.close()
+        except Exception:
+            traceback.print_exc()
+
+
+@section("upsample+blur")
+def s_blur():
+    g = np.random.Generator(np.random.PCG64(12))
+    m = (np.abs(g.standard_normal((28, 28))) * 7 + 3).astype(np.float32)
+    out, pre, u8 = upsample_blur(m, 224)
+    ref, ref_u8 = O.knn_blur_restated(pre)
+    print("pre mismatches", (pre != O.bilinear_restated(m, 224)).sum(), "u8", (u8 != ref_u8).sum(), "blur", (out != ref).sum())
+
+
+@section("score 200k x 768 timing")
+def s_score_big():
+    R, D, P = 200_000, 768, 784
+    cent = synth.centroids(D)
+    b = Bank(D, R)
+    for i in range(8):
+        b.append(synth.patches(R // 8, D, seed=300 + i, cent=cent))
+    t = time.time()
+    b.finalize()
+    print("finalize", time.time() - t)
+    patch = torch.from_numpy(synth.patches(P, D, seed=400, anomalous_frac=0.01, cent=cent)).cuda()
+    st = b.stream()
+    for impl, name in ((L.SCORE_TCGEN05, "tcgen05"), (L.SCORE_SIMT, "simt")):
+        b.set_score_impl(impl)
+        best, med = ev_time(st, lambda: b.score(patch, (28, 28), 224), iters=5, warm=2)
+        flop = 2.0 * P * R * D
+        print(f"{name}: whole call best {best:.3f} ms median {med:.3f} ms -> {P / med * 1e3:.0f} patches/s, "
+              f"{flop / med / 1e9:.1f} algorithmic TFLOP/s")
+    b.set_score_impl(L.SCORE_TCGEN05)
+    r1 = b.score(patch, (28, 28), 224)
+    b.set_score_impl(L.SCORE_SIMT)
+    r2 = b.score(patch, (28, 28), 224)
+    print("tcgen05 vs simt: idx mismatches", (r1.min_idx != r2.min_idx).sum(), "val mismatches", (r1.min_val != r2.min_val).sum(),
+          "s", r1.s[0], r2.s[0])
+    b.close()
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), torch.__version__)
+    which = sys.argv[1:] or ["rownorms", "proj", "blur", "score_small", "coreset_small", "score_big", "coreset_big"]
+    table = dict(rownorms=s_rownorms, proj=s_proj, coreset_small=s_coreset_small, coreset_big=s_coreset_big,
+                 score_small=s_score_small, blur=s_blur, score_big=s_score_big)
+    for w in which:
+        table[w]()

@@ -1,0 +1,203 @@
+"""GPU parity tests (through the C ABI): fused distance GEMM + min/argmin, s*/m*/top-3 re-weighting, upsample + blur,
+and the method-class mirror end to end against the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(built):
+    from cmdiad_b200 import Bank, upsample_blur
+    from cmdiad_b200 import _lib as L
+    from oracle import restate as O
+    assert torch.cuda.is_available()
+    return dict(Bank=Bank, L=L, O=O, upsample_blur=upsample_blur)
+
+
+def _bank(env, lib, impl=None):
+    b = env["Bank"](lib.shape[1], lib.shape[0])
+    b.append(lib)
+    b.finalize()
+    if impl is not None:
+        b.set_score_impl(impl)
+    return b
+
+
+def _check_against_oracle(env, r, ref, P):
+    ok, nbad = cases.tie_aware_idx_ok(r.min_idx, ref["min_idx"], ref["dist"].numpy())
+    assert ok and nbad <= max(1, P // 500), f"{nbad} argmin mismatches"
+    np.testing.assert_allclose(r.min_val, ref["min_val"], rtol=1e-4)  # north_star tolerance
+    assert int(r.s_idx[0]) == ref["s_idx"]
+    np.testing.assert_allclose(r.s_star[0], ref["s_star"], rtol=1e-4)
+    assert set(r.nn_idx[1:].tolist()) == set(ref["nn_idx"][1:].tolist())
+    np.testing.assert_allclose(np.sort(r.m_star_knn), np.sort(ref["m_star_knn"]), rtol=1e-4)
+    np.testing.assert_allclose(r.s[0], ref["s"], rtol=1e-4)
+    np.testing.assert_allclose(r.s_map_pre, ref["s_map_pre"], rtol=1e-4)
+    lsb = ref["s_map"].max() / 255.0
+    diff = np.abs(r.s_map - ref["s_map"])
+    assert diff.max() <= 1.001 * lsb and (diff > 0).mean() <= 0.01
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_score_golden_rgb_case(env, golden, impl):
+    """the reference's own outputs (frozen in tests/golden/rgb_case.npz) for 2 test images against a 784-row coreset"""
+    O, L = env["O"], env["L"]
+    g = golden["rgb_case"]
+    lib = cases.rgb_normalised_lib(golden)
+    bank_rows = lib[g["coreset_idx_TF32"]]
+    b = _bank(env, bank_rows, L.SCORE_TCGEN05 if impl == "tcgen05" else L.SCORE_SIMT)
+    for t in range(cases.RGB_CASE["n_test"]):
+        patch = ((torch.from_numpy(cases.rgb_test_patch(t)) - torch.tensor(g["rgb_mean"])) / torch.tensor(g["rgb_std"])).numpy()
+        r = b.score(patch, (28, 28), 224, full=True)
+        ref = O.score_restated(patch, bank_rows, (28, 28), 224)
+        _check_against_oracle(env, r, ref, 784)
+        assert (r.min_idx == g[f"t{t}_min_idx"]).mean() >= 0.998
+        np.testing.assert_allclose(r.min_val, g[f"t{t}_min_val"], rtol=1e-4)
+        np.testing.assert_allclose(r.s[0], g[f"t{t}_s"], rtol=1e-4)
+        gm = g[f"t{t}_s_map"][0]
+        diff = np.abs(r.s_map - gm)
+        assert diff.max() <= 1.001 * gm.max() / 255 and (diff > 0).mean() <= 0.01
+    b.close()
+
+
+@pytest.mark.parametrize("R,P,fm,D", [(1000, 784, 28, 768), (257, 3136, 56, 768), (5000, 3136, 56, 1152),
+                                      (2048, 784, 28, 1920), (3, 784, 28, 768), (70000, 784, 28, 768),
+                                      (513, 100, 10, 64)])
+def test_score_shapes_vs_oracle(env, R, P, fm, D):
+    """ragged bank sizes (not multiples of the 256-row tile), P > 1024 (several GEMM launches), all BASELINE dims"""
+    from cmdiad_b200 import synth
+    O = env["O"]
+    cent = synth.centroids(D, 256)
+    lib = synth.patches(R, D, seed=R + P, cent=cent)
+    patch = synth.patches(P, D, seed=R + P + 1, anomalous_frac=0.01, cent=cent)
+    b = _bank(env, lib)
+    r = b.score(patch, (fm, fm), 224, full=True)
+    ref = O.score_restated(patch, lib, (fm, fm), 224)
+    _check_against_oracle(env, r, ref, P)
+    b.close()
+
+
+def test_score_tcgen05_equals_simt(env):
+    """both candidate generators feed the same exact re-check, so outputs must be identical bit for bit"""
+    from cmdiad_b200 import synth
+    L = env["L"]
+    lib = synth.patches(30000, 768, seed=5, dist="G")
+    patch = synth.patches(784, 768, seed=6, dist="G")
+    b = _bank(env, lib)
+    r1 = b.score(patch, (28, 28), 224, full=True)
+    b.set_score_impl(L.SCORE_SIMT)
+    r2 = b.score(patch, (28, 28), 224, full=True)
+    assert (r1.min_idx == r2.min_idx).all() and (r1.min_val == r2.min_val).all()
+    assert r1.s[0] == r2.s[0] and (r1.s_map == r2.s_map).all()
+    b.close()
+
+
+def test_score_duplicate_rows_lowest_index(env):
+    """exact ties in the bank: argmin must be the lowest row (torch.min semantics, features.py:227)"""
+    from cmdiad_b200 import synth
+    base = synth.patches(700, 768, seed=1, dist="G")
+    lib = np.concatenate([base, base], 0)
+    patch = base[:784 // 2].repeat(2, 0) + 0.01 * synth.patches(784, 768, seed=2, dist="G")
+    b = _bank(env, lib)
+    r = b.score(patch, (28, 28), 224)
+    assert (r.min_idx < 700).all()
+    b.close()
+
+
+def test_score_large_values_are_rescaled(env):
+    """the fp16 split is scaled per bank / per image, so unnormalised magnitudes still work"""
+    from cmdiad_b200 import synth
+    O = env["O"]
+    lib = synth.patches(2000, 768, seed=3) * 3.0e4
+    patch = synth.patches(784, 768, seed=4, anomalous_frac=0.01) * 3.0e4
+    b = _bank(env, lib)
+    r = b.score(patch, (28, 28), 224, full=True)
+    ref = O.score_restated(patch, lib, (28, 28), 224)
+    assert (r.min_idx == ref["min_idx"]).mean() > 0.995
+    np.testing.assert_allclose(r.min_val, ref["min_val"], rtol=1e-4)
+    b.close()
+
+
+def test_upsample_blur_bit_exact(env):
+    """bilinear (features.py:294) + KNNGaussianBlur (utils/utils.py:71-83): identical bits given identical input"""
+    O = env["O"]
+    g = np.random.Generator(np.random.PCG64(12))
+    for h in (28, 56):
+        m = (np.abs(g.standard_normal((h, h))) * 7 + 3).astype(np.float32)
+        out, pre, u8 = env["upsample_blur"](m, 224)
+        assert (pre == O.bilinear_restated(m, 224)).all()
+        ref, ref_u8 = O.knn_blur_restated(pre)
+        assert (u8 == ref_u8).all() and (out == ref).all()
+        t = torch.nn.functional.interpolate(torch.from_numpy(m).view(1, 1, h, h), size=(224, 224), mode="bilinear")
+        assert (pre == t[0, 0].numpy()).all()
+
+
+def test_score_errors(env):
+    L = env["L"]
+    b = env["Bank"](768, 100)
+    b.append(np.ones((100, 768), np.float32))
+    with pytest.raises(L.CmdbError) as e:
+        b.score(np.ones((784, 768), np.float32), (28, 28))
+    assert e.value.status == L.CMDB_ERR_STATE  # not finalized
+    b.finalize()
+    with pytest.raises(L.CmdbError):
+        b.score(np.ones((784, 768), np.float32), (28, 27))  # dims do not match P
+    b.close()
+
+
+def test_double_bank_pipeline_matches_reference_golden(env, golden):
+    """DoubleRGBPointFeatures end to end through the mirror classes: cross-wired statistics, two coresets, late-fusion
+    head, compute_s_s_map -- against tests/golden/dual_case.npz produced by the unmodified reference"""
+    from cmdiad_b200 import DoubleRGBPointFeatures, default_args
+    g = golden["dual_case"]
+    m = DoubleRGBPointFeatures(default_args(coreset_dtype="TF32", random_state=0), parity_stats=True,
+                               bank_capacity_rows=3 * 3136)
+    xyz_train, rgb_train = cases.dual_train()
+    for x, r in zip(xyz_train, rgb_train):
+        m.add_sample_to_mem_bank({"xyz": x, "rgb": r}, class_name="synthetic")
+    m.run_coreset()
+    for k in ("xyz_mean", "xyz_std", "rgb_mean", "rgb_std"):
+        assert np.float32(getattr(m, k)) == g[k], k
+    assert m.patch_xyz_lib.shape[0] == int(g["n_xyz"]) and m.patch_rgb_lib.shape[0] == int(g["n_rgb"])
+    assert (m.coreset_idx.numpy() == g["coreset_idx_rgb"]).all()
+    assert (m.patch_xyz_lib[::53].numpy() == g["xyz_lib_sample"]).all()
+    for x, r in zip(xyz_train, rgb_train):
+        m.add_sample_to_late_fusion_mem_bank({"xyz": x, "rgb": r})
+    np.testing.assert_allclose(torch.cat(m.s_lib, 0).numpy(), g["s_lib"], rtol=1e-4)
+    m.run_late_fusion()
+    xt, rt = cases.dual_test()
+    m.predict({"xyz": xt, "rgb": rt}, torch.zeros(1, 224, 224), 0, ["synthetic/0.png"])
+    np.testing.assert_allclose(m.image_preds[0], g["image_pred"], rtol=1e-3)
+    np.testing.assert_allclose(m.predictions[0], g["prediction"], rtol=1e-3, atol=1e-3 * np.abs(g["prediction"]).max())
+    m.close()
+
+
+def test_full_size_bank_properties(env):
+    """BASELINE size (200k x 768, P = 784): parity through a GPU brute force on the same inputs (the float32 [P,R]
+    matrix the reference would build) plus size-independent properties"""
+    from cmdiad_b200 import synth
+    R, D, P = 200_000, 768, 784
+    cent = synth.centroids(D)
+    lib = np.concatenate([synth.patches(50_000, D, seed=900 + i, cent=cent) for i in range(4)], 0)
+    patch = synth.patches(P, D, seed=950, anomalous_frac=0.01, cent=cent)
+    b = _bank(env, lib)
+    r = b.score(patch, (28, 28), 224, full=True)
+    dist = torch.cdist(torch.from_numpy(patch).cuda(), torch.from_numpy(lib).cuda(), compute_mode="donot_use_mm_for_euclid_dist")
+    mv, mi = torch.min(dist, dim=1)
+    mv, mi = mv.cpu().numpy(), mi.cpu().numpy()
+    bad = np.nonzero(r.min_idx != mi)[0]
+    dist_c = dist.cpu().numpy()
+    for p in bad:
+        assert abs(dist_c[p, r.min_idx[p]] - dist_c[p, mi[p]]) <= 2e-6 * dist_c[p, mi[p]]
+    assert len(bad) <= 2
+    np.testing.assert_allclose(r.min_val, mv, rtol=1e-5)
+    # properties: a bank row scores 0 against itself; s_star is the max of min_val; appending the patch to the bank
+    # makes every min distance 0
+    assert r.s_star[0] == r.min_val.max() and r.s_idx[0] == int(np.argmax(r.min_val))
+    self_r = b.score(lib[1000:1784], (28, 28), 224)
+    assert (self_r.min_idx == np.arange(1000, 1784)).all() and (self_r.min_val == 0).all()
+    b.close()
