@@ -20,6 +20,8 @@ CORESET_FP64 = 1
 SCORE_TCGEN05 = 0
 SCORE_SIMT = 1
 OPT_SCORE_IMPL = 1
+OPT_TIMING = 2
+T_STAGES = ("stage_in", "gemm", "refine", "reweight", "map", "out")
 
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)
@@ -62,6 +64,7 @@ SYMBOLS = {
     "cmdb_bank_read": (_I, [_VP, _I64, _I64, _VP]),
     "cmdb_bank_finalize": (_I, [_VP]),
     "cmdb_bank_stream": (_I, [_VP, ctypes.POINTER(_VP)]),
+    "cmdb_bank_get_timings": (_I, [_VP, c_f32_p]),
     "cmdb_coreset_select": (_I, [_VP, _I64, _VP, _VP, _VP, _I, _I, _VP]),
     "cmdb_project": (_I, [_VP, _VP, _VP, _VP, _I, _I64, _I64, _VP]),
     "cmdb_coreset_rownorms": (_I, [_I, _VP, _VP, _I64, _I, _I, _VP]),

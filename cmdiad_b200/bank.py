@@ -68,6 +68,15 @@ class Bank:
     def set_score_impl(self, impl):
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_SCORE_IMPL, int(impl)))
 
+    def set_timing(self, on=True):
+        L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_TIMING, int(bool(on))))
+
+    def timings(self):
+        """{stage: ms} of the last score() call (CUDA events on the handle's stream); needs set_timing(True)"""
+        arr = (ctypes.c_float * len(L.T_STAGES))()
+        L.check(self._lib.cmdb_bank_get_timings(self._h, arr))
+        return dict(zip(L.T_STAGES, [float(x) for x in arr]))
+
     def stream(self):
         """torch view of the handle's CUDA stream (for event timing on the stream the kernels run on)"""
         p = ctypes.c_void_p()

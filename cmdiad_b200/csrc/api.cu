@@ -65,8 +65,12 @@ static int stage_patch(cmdb_bank *b, const float *patch, int P, int is_device, i
 
 static int local_min(cmdb_bank *b, int P) {
     int n_cand = 0;
-    if (b->score_impl == CMDB_SCORE_TCGEN05) CMDB_CHECK(score_gemm_candidates(b, P, &n_cand));
-    else CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
+    if (b->score_impl == CMDB_SCORE_TCGEN05) {
+        CMDB_CHECK(score_query_prep(b, P));
+        CMDB_CHECK(score_gemm_candidates(b, P, &n_cand));
+    } else {
+        CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
+    }
     return score_refine(b, P, n_cand);
 }
 
@@ -164,14 +168,40 @@ int cmdb_score(cmdb_bank *b, const float *patch, int P, int fh, int fw, int out_
     CMDB_CHECK(check_score_args(b, patch, P, "cmdb_score"));
     CMDB_REQUIRE(out, CMDB_ERR_INVALID, "cmdb_score: out is NULL");
     CMDB_REQUIRE(fh > 0 && fw > 0 && fh * fw == P, CMDB_ERR_INVALID, "cmdb_score: feature_map_dims %dx%d != P=%d", fh, fw, P);
+#define CMDB_MARK(i)                                                   \
+    do {                                                               \
+        if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[i], b->stream)); \
+    } while (0)
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_MARK(CMDB_T_STAGE_IN);
     CMDB_CHECK(stage_patch(b, patch, P, patch_is_device, out_hw));
-    CMDB_CHECK(local_min(b, P));
+    int n_cand = 0;
+    if (b->score_impl == CMDB_SCORE_TCGEN05) {
+        CMDB_CHECK(score_query_prep(b, P));
+        CMDB_MARK(CMDB_T_GEMM);
+        CMDB_CHECK(score_gemm_candidates(b, P, &n_cand));
+    } else {
+        CMDB_MARK(CMDB_T_GEMM);
+        CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
+    }
+    CMDB_MARK(CMDB_T_REFINE);
+    CMDB_CHECK(score_refine(b, P, n_cand));
+    CMDB_MARK(CMDB_T_REWEIGHT);
     CMDB_CHECK(score_select(b, true));
     CMDB_CHECK(score_wdist_topk(b));
     CMDB_CHECK(score_merge_top3(b));
     CMDB_CHECK(score_final(b, false));
+    CMDB_MARK(CMDB_T_MAP);
     CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8));
-    return copy_outputs(b, P, out_hw, out);
+    CMDB_MARK(CMDB_T_OUT);
+    const int rc = copy_outputs(b, P, out_hw, out);
+    if (b->timing && rc == CMDB_OK) {
+        CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->stream));
+        CMDB_CUDA(cudaEventSynchronize(b->ev[CMDB_T_COUNT]));
+        b->ev_valid = true;
+    }
+#undef CMDB_MARK
+    return rc;
 }
 
 int cmdb_score_shard_min(cmdb_bank *b, const float *patch, int P, int patch_is_device, int64_t *keys_device) {

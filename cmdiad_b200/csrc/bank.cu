@@ -261,6 +261,8 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     cudaFree(b->data);
     cudaFree(b->stats_buf);
     cudaFree(b->absmax_buf);
+    for (auto &e : b->ev)
+        if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -306,6 +308,15 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
         b->score_impl = value;
         return CMDB_OK;
     }
+    if (option == CMDB_OPT_TIMING) {
+        b->timing = value != 0;
+        if (b->timing && !b->ev[0]) {
+            CMDB_CUDA(cudaSetDevice(b->device));
+            for (auto &e : b->ev) CMDB_CUDA(cudaEventCreate(&e));
+        }
+        b->ev_valid = false;
+        return CMDB_OK;
+    }
     set_error("cmdb_bank_set_option: unknown option %d", option);
     return CMDB_ERR_INVALID;
 }
@@ -313,6 +324,13 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
 int cmdb_bank_stream(cmdb_bank *b, void **out_stream) {
     CMDB_REQUIRE(b && out_stream, CMDB_ERR_INVALID, "cmdb_bank_stream: bad arguments");
     *out_stream = (void *)b->stream;
+    return CMDB_OK;
+}
+
+int cmdb_bank_get_timings(cmdb_bank *b, float *out_ms) {
+    CMDB_REQUIRE(b && out_ms, CMDB_ERR_INVALID, "cmdb_bank_get_timings: bad arguments");
+    CMDB_REQUIRE(b->timing && b->ev_valid, CMDB_ERR_STATE, "cmdb_bank_get_timings: enable CMDB_OPT_TIMING and call cmdb_score first");
+    for (int i = 0; i < CMDB_T_COUNT; ++i) CMDB_CUDA(cudaEventElapsedTime(out_ms + i, b->ev[i], b->ev[i + 1]));
     return CMDB_OK;
 }
 

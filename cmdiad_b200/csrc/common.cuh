@@ -95,6 +95,9 @@ struct cmdb_bank {
     void *tmap_hi = nullptr;  // host copies of the CUtensorMap objects (128 B each)
     void *tmap_lo = nullptr;
     cmdb::ScoreScratch ss;
+    int timing = 0;
+    cudaEvent_t ev[CMDB_T_COUNT + 1] = {};
+    bool ev_valid = false;
     double *stats_buf = nullptr;  // 2 doubles on device
     unsigned int *absmax_buf = nullptr;
 };
@@ -121,6 +124,7 @@ int coreset_rownorms(int device, const void *z_host, const void *last_host, int6
 int score_scratch_alloc(cmdb_bank *b, int P, int out_hw);
 void score_scratch_free(cmdb_bank *b);
 int score_make_tensor_maps(cmdb_bank *b);
+int score_query_prep(cmdb_bank *b, int P);  // q_f32 -> q_hi / q_lo (device-side scale selection)
 int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out);  // q_f32 -> cand via the tcgen05 distance GEMM
 
 // score_tail.cu

@@ -140,7 +140,9 @@ struct GemmParams {
 __global__ void __launch_bounds__(kGemmThreads, 1)
 score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, GemmParams p) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this round-up
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
@@ -400,7 +402,7 @@ int score_scratch_alloc(cmdb_bank *b, int P, int out_hw) {
     return CMDB_OK;
 }
 
-int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
+int score_query_prep(cmdb_bank *b, int P) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
     cudaStream_t st = b->stream;
@@ -410,11 +412,14 @@ int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(s.q_f32, P, p_pad, b->dim, s.q_absmax, s.q_hi,
                                                                               s.q_lo, s.q_scale_exp);
     CMDB_CUDA(cudaGetLastError());
-    static bool attr_set = false;
-    if (!attr_set) {
-        CMDB_CUDA(cudaFuncSetAttribute(score_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem::total + 1024));
-        attr_set = true;
-    }
+    return CMDB_OK;
+}
+
+int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
+    ScoreScratch &s = b->ss;
+    const int p_pad = (P + BM - 1) / BM * BM;
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaFuncSetAttribute(score_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem::total + 1024));
     GemmParams p{};
     p.nt = (int)(b->fin_rows_pad / BN);
     p.kb = b->dim / BK;

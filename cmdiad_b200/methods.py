@@ -93,7 +93,9 @@ class Features(torch.nn.Module):
         self.args = args if args is not None else default_args()
         self.cuda_device = int(device)
         self.feature_fn = feature_fn
-        self.parity_stats = parity_stats  # keep host copies and use torch.mean/std bit-for-bit like the reference
+        # False: statistics on the device (float64 accumulation).  True: keep host copies and call torch.mean / torch.std
+        # exactly like the reference.  dict {modal: (mean|None, std|None)}: use these scalars (bit-parity experiments)
+        self.parity_stats = parity_stats
         self.bank_capacity_rows = bank_capacity_rows
         self.verbose = verbose
         self.class_name = None
@@ -133,7 +135,7 @@ class Features(torch.nn.Module):
             cap = self.bank_capacity_rows or int(self.args.max_sample) * patch.shape[0]
             self._banks[modal] = Bank(patch.shape[1], cap, device=self.cuda_device)
         self._banks[modal].append(patch)
-        if self.parity_stats:
+        if self.parity_stats is True:
             self._host_copies[modal].append(patch.cpu())
 
     def _lib(self, modal):
@@ -204,12 +206,16 @@ class Features(torch.nn.Module):
     def run_coreset(self):
         stats = {}
         for m in set(self.mean_from.values()) | set(self.std_from.values()):
-            if self.parity_stats:
+            if self.parity_stats is True:
                 cat = torch.cat(self._host_copies[m], 0)
                 stats[m] = (torch.mean(cat), torch.std(cat))
             else:
                 mean, std, _, _ = self._banks[m].stats()
-                stats[m] = (torch.tensor(mean, dtype=torch.float32), torch.tensor(std, dtype=torch.float32))
+                stats[m] = [torch.tensor(mean, dtype=torch.float32), torch.tensor(std, dtype=torch.float32)]
+                if isinstance(self.parity_stats, dict) and m in self.parity_stats:
+                    for i, v in enumerate(self.parity_stats[m]):
+                        if v is not None:
+                            stats[m][i] = torch.tensor(np.float32(v))
         for m in self.bank_modals:
             setattr(self, f"{m}_mean", stats[self.mean_from[m]][0])
             setattr(self, f"{m}_std", stats[self.std_from[m]][1])

@@ -47,6 +47,16 @@ typedef enum cmdb_status {
 #define CMDB_SCORE_SIMT 1    /* plain fp32 CUDA-core kernel, diagnostics only (same outputs, ~10x slower) */
 
 #define CMDB_OPT_SCORE_IMPL 1
+#define CMDB_OPT_TIMING 2 /* 1 = record CUDA events between the stages of cmdb_score (see cmdb_bank_get_timings) */
+
+/* stage indices of cmdb_bank_get_timings */
+#define CMDB_T_STAGE_IN 0   /* patch copy + fp16 split of the queries */
+#define CMDB_T_GEMM 1       /* tcgen05 distance GEMM + fused top-2 epilogue (or the SIMT diagnostics kernel) */
+#define CMDB_T_REFINE 2     /* exact re-check -> min_val / min_idx / s_star */
+#define CMDB_T_REWEIGHT 3   /* m_star selection, w_dist top-3 pass over the bank, w and s */
+#define CMDB_T_MAP 4        /* bilinear upsample + Gaussian blur */
+#define CMDB_T_OUT 5        /* device -> host copies of the results */
+#define CMDB_T_COUNT 6
 
 int cmdb_version(void);
 const char *cmdb_last_error(void);
@@ -78,6 +88,9 @@ int cmdb_bank_read(cmdb_bank *bank, int64_t row0, int64_t n_rows, float *out_hos
 int cmdb_bank_finalize(cmdb_bank *bank);
 /* the cudaStream_t every kernel of this handle is launched on (for event timing by the caller) */
 int cmdb_bank_stream(cmdb_bank *bank, void **out_stream);
+/* milliseconds of each stage (CMDB_T_*) of the last cmdb_score call on this handle; needs CMDB_OPT_TIMING = 1.
+ * out_ms: float [CMDB_T_COUNT].  Measured with CUDA events on the handle's stream. */
+int cmdb_bank_get_timings(cmdb_bank *bank, float *out_ms);
 
 /* ---- coreset: replaces Features.get_coreset_idx_randomp (features.py:360-425) ---- */
 

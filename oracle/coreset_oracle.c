@@ -229,6 +229,30 @@ int oracle_rownorms_fp16(const uint16_t *zh_bits, const uint16_t *last_bits, int
     return 0;
 }
 
+/* probe variant: multiply and add rounded separately (no fma) -- used once to pin which one torch's CUDA build does */
+int oracle_rownorms_fp64_nofma(const double *z, const double *last, int64_t N, int d, double *out) {
+    plan_t p;
+    plan_init(&p, d);
+    for (int64_t i = 0; i < N; ++i) {
+        double acc[MAXLANES][VEC];
+        memset(acc, 0, sizeof(acc));
+        int shift = (int)((i * d) % VEC);
+        const uint8_t *ln = p.lane[shift], *ac = p.acc[shift];
+        for (int e = 0; e < d; ++e) {
+            volatile double v = z[i * d + e] - last[e];
+            volatile double sq = v * v;
+            acc[ln[e]][ac[e]] = acc[ln[e]][ac[e]] + sq;
+        }
+        double lanev[MAXLANES];
+        for (int l = 0; l < p.lanes; ++l) lanev[l] = ((acc[l][0] + acc[l][1]) + acc[l][2]) + acc[l][3];
+        for (int off = 1; off < p.lanes; off <<= 1)
+            for (int l = 0; l + off < p.lanes; l += 2 * off) lanev[l] = lanev[l] + lanev[l + off];
+        out[i] = sqrt(lanev[0]);
+    }
+    plan_free(&p);
+    return 0;
+}
+
 int oracle_rownorms_fp64(const double *z, const double *last, int64_t N, int d, double *out) {
     plan_t p;
     plan_init(&p, d);

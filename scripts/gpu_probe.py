@@ -56,6 +56,11 @@ def s_rownorms():
         got64 = coreset_rownorms(z64, z64[5])
         zt64 = torch.from_numpy(z64).cuda()
         ref64 = torch.linalg.norm(zt64 - zt64[5:6], dim=1, keepdims=True).cpu().numpy()[:, 0]
+        import ctypes
+        nf = np.zeros(4099)
+        l5 = np.ascontiguousarray(z64[5])
+        O.lib().oracle_rownorms_fp64_nofma(O._p(z64), O._p(l5), ctypes.c_int64(4099), ctypes.c_int(d), O._p(nf))
+        print(f"   fp64 nofma-oracle != torch: {(nf != ref64).sum()}")
         print(f"d={d}: fp16 kernel!=oracle {(got.view(np.uint16) != orc.view(np.uint16)).sum()}, kernel!=torch "
               f"{(got.view(np.uint16) != ref.view(np.uint16)).sum()}, oracle!=torch {(orc.view(np.uint16) != ref.view(np.uint16)).sum()}"
               f" | fp64 kernel!=oracle {(got64 != O.rownorms_restated(z64, z64[5])).sum()}, kernel!=torch {(got64 != ref64).sum()}")
