@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([NVCC, "-shared", "-o", SO, *objs, "-lcudart_static" if False else "-lcudart"], check=True)
+    subprocess.run([NVCC, "-shared", "-o", SO, *objs, "-lcudart", "-Xlinker", "--no-undefined"], check=True)
     if verbose:
         print("\n".join(log))
     return SO

@@ -77,15 +77,21 @@ static int local_min(cmdb_bank *b, int P) {
 static int copy_outputs(cmdb_bank *b, int P, int out_hw, cmdb_score_out *out) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
-    TailResult tr;
-    CMDB_CUDA(cudaMemcpyAsync(&tr, s.tail, sizeof(tr), cudaMemcpyDeviceToHost, st));
-    if (out->min_val) CMDB_CUDA(cudaMemcpyAsync(out->min_val, s.min_val, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
-    if (out->min_idx) CMDB_CUDA(cudaMemcpyAsync(out->min_idx, s.min_idx, sizeof(long long) * P, cudaMemcpyDeviceToHost, st));
     const size_t npix = (size_t)out_hw * out_hw;
-    if (out->s_map) CMDB_CUDA(cudaMemcpyAsync(out->s_map, s.map_out, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
-    if (out->s_map_pre) CMDB_CUDA(cudaMemcpyAsync(out->s_map_pre, s.map_pre, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
-    if (out->s_map_u8) CMDB_CUDA(cudaMemcpyAsync(out->s_map_u8, s.map_u8, npix, cudaMemcpyDeviceToHost, st));
+    // one device->host copy of the result block (through the optional debug maps only when they are wanted)
+    size_t bytes = s.off_map_out + sizeof(float) * npix;
+    if (out->s_map_pre) bytes = s.off_map_pre + sizeof(float) * npix;
+    if (out->s_map_u8) bytes = s.off_map_u8 + npix;
+    CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, bytes, cudaMemcpyDeviceToHost, st));
     CMDB_CUDA(cudaStreamSynchronize(st));
+    const unsigned char *h = s.out_block_host;
+    TailResult tr;
+    memcpy(&tr, h, sizeof(tr));
+    if (out->min_val) memcpy(out->min_val, h + s.off_min_val, sizeof(float) * P);
+    if (out->min_idx) memcpy(out->min_idx, h + s.off_min_idx, sizeof(long long) * P);
+    if (out->s_map) memcpy(out->s_map, h + s.off_map_out, sizeof(float) * npix);
+    if (out->s_map_pre) memcpy(out->s_map_pre, h + s.off_map_pre, sizeof(float) * npix);
+    if (out->s_map_u8) memcpy(out->s_map_u8, h + s.off_map_u8, npix);
     if (out->s) *out->s = tr.s;
     if (out->s_star) *out->s_star = tr.s_star;
     if (out->s_idx) *out->s_idx = tr.s_idx;
@@ -187,12 +193,9 @@ int cmdb_score(cmdb_bank *b, const float *patch, int P, int fh, int fw, int out_
     CMDB_MARK(CMDB_T_REFINE);
     CMDB_CHECK(score_refine(b, P, n_cand));
     CMDB_MARK(CMDB_T_REWEIGHT);
-    CMDB_CHECK(score_select(b, true));
-    CMDB_CHECK(score_wdist_topk(b));
-    CMDB_CHECK(score_merge_top3(b));
-    CMDB_CHECK(score_final(b, false));
+    CMDB_CHECK(score_reweight(b, true));
     CMDB_MARK(CMDB_T_MAP);
-    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8));
+    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8, b->ss.map_tmp, b->ss.map_max));
     CMDB_MARK(CMDB_T_OUT);
     const int rc = copy_outputs(b, P, out_hw, out);
     if (b->timing && rc == CMDB_OK) {
@@ -239,8 +242,7 @@ int cmdb_score_shard_topk(cmdb_bank *b, const float *m_star_device, int64_t *top
     CMDB_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = b->stream;
     CMDB_CUDA(cudaMemcpyAsync(b->ss.m_star, m_star_device, sizeof(float) * b->dim, cudaMemcpyDeviceToDevice, st));
-    CMDB_CHECK(score_wdist_topk(b));
-    CMDB_CHECK(score_merge_top3(b));
+    CMDB_CHECK(score_reweight(b, false));
     CMDB_CUDA(cudaMemcpyAsync(topk_keys_device, b->ss.top3, sizeof(long long) * 3, cudaMemcpyDeviceToDevice, st));
     CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
@@ -253,11 +255,7 @@ int cmdb_score_shard_nn(cmdb_bank *b, const int64_t *gathered_keys_device, int n
     CMDB_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = b->stream;
     CMDB_CUDA(cudaMemcpyAsync(b->ss.topk_keys, gathered_keys_device, sizeof(long long) * n_keys, cudaMemcpyDeviceToDevice, st));
-    const int saved = b->ss.n_topk_blocks;
-    b->ss.n_topk_blocks = n_keys / 3;
-    int rc = score_merge_top3(b);
-    b->ss.n_topk_blocks = saved;
-    CMDB_CHECK(rc);
+    CMDB_CHECK(score_merge_top3(b, n_keys));
     contrib_rows_kernel<<<8, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, nullptr, b->ss.top3, 3,
                                            nn_rows_contrib_device);
     CMDB_CUDA(cudaGetLastError());
@@ -274,7 +272,7 @@ int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int P, in
     CMDB_CUDA(cudaSetDevice(b->device));
     CMDB_CUDA(cudaMemcpyAsync(b->ss.nn_rows, nn_rows_device, sizeof(float) * 3 * b->dim, cudaMemcpyDeviceToDevice, b->stream));
     CMDB_CHECK(score_final(b, true));
-    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8));
+    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8, b->ss.map_tmp, b->ss.map_max));
     return copy_outputs(b, P, out_hw, out);
 }
 
@@ -290,19 +288,21 @@ int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int ou
     }
     CMDB_CUDA(cudaSetDevice(device));
     const size_t npix = (size_t)out_hw * out_hw;
-    float *in = nullptr, *pre = nullptr, *o = nullptr;
-    unsigned char *u8 = nullptr;
+    float *in = nullptr, *pre = nullptr, *o = nullptr, *mx = nullptr;
+    unsigned char *u8 = nullptr, *tmp = nullptr;
     cudaError_t e = cudaMalloc(&in, sizeof(float) * fh * fw);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, npix);
+    if (e == cudaSuccess) e = cudaMalloc(&mx, sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&pre, sizeof(float) * npix);
     if (e == cudaSuccess) e = cudaMalloc(&o, sizeof(float) * npix);
     if (e == cudaSuccess) e = cudaMalloc(&u8, npix);
     if (e == cudaSuccess) e = cudaMemcpy(in, map_host, sizeof(float) * fh * fw, cudaMemcpyHostToDevice);
     int rc = CMDB_OK;
-    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, in, fh, fw, out_hw, pre, o, u8);
+    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, in, fh, fw, out_hw, pre, o, u8, tmp, mx);
     if (e == cudaSuccess && rc == CMDB_OK) e = cudaMemcpy(out_host, o, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_pre_host) e = cudaMemcpy(out_pre_host, pre, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_u8_host) e = cudaMemcpy(out_u8_host, u8, npix, cudaMemcpyDeviceToHost);
-    cudaFree(in), cudaFree(pre), cudaFree(o), cudaFree(u8);
+    cudaFree(in), cudaFree(pre), cudaFree(o), cudaFree(u8), cudaFree(tmp), cudaFree(mx);
     if (rc != CMDB_OK) return rc;
     CMDB_CUDA(e);
     return CMDB_OK;

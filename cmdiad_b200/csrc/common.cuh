@@ -52,7 +52,7 @@ struct ScoreScratch {
     __half *q_lo = nullptr;
     float *q_norm = nullptr;        // [cap_p]     ||q||^2
     unsigned int *q_absmax = nullptr;  // float bits of max|q|
-    int *q_scale_exp = nullptr;     // device: exponent e_q with q_hi + q_lo = q * 2^e_q
+    int *q_scale_exp = nullptr;     // device [cap_p]: per-row exponent e_q with q_hi + q_lo = q * 2^e_q
     void *tmap_qhi = nullptr;       // host CUtensorMap objects for q_hi / q_lo
     void *tmap_qlo = nullptr;
     float *m_test = nullptr;        // [D] patch[s_idx]
@@ -60,15 +60,23 @@ struct ScoreScratch {
     float *nn_rows = nullptr;       // [3, D] rows of the 3 nearest neighbours (sharded mode)
     unsigned long long *top3 = nullptr;  // merged 3 smallest w_dist keys
     int n_topk_blocks = 0;
+    unsigned int *done_counter = nullptr;  // last-block-done counter of reweight_kernel
     float4 *cand = nullptr;         // [cap_p, n_ctas] per-CTA top-2 (val1, idx1, val2, idx2) of the GEMM epilogue
     float *min_val = nullptr;       // [cap_p]
     long long *min_idx = nullptr;   // [cap_p]
     unsigned long long *s_key = nullptr;    // packed argmax key of min_val
     unsigned long long *topk_keys = nullptr;  // [n_blocks*3] per-block w_dist top-3 packed keys
     void *tail = nullptr;           // TailResult
+    // results live in ONE device block (tail | min_val | min_idx | map_out | map_pre | map_u8) mirrored by a pinned
+    // host block, so a scoring call ends with a single device->host copy
+    unsigned char *out_block = nullptr;
+    unsigned char *out_block_host = nullptr;  // cudaMallocHost
+    size_t off_min_val = 0, off_min_idx = 0, off_map_out = 0, off_map_pre = 0, off_map_u8 = 0, out_block_bytes = 0;
     float *map_pre = nullptr;       // [out_hw^2]
     float *map_out = nullptr;
     unsigned char *map_u8 = nullptr;
+    unsigned char *map_tmp = nullptr;  // horizontally blurred 8-bit image between the two blur kernels
+    float *map_max = nullptr;
     int map_cap = 0;
 };
 
@@ -137,10 +145,10 @@ struct TailResult {  // device-side result block (ScoreScratch::tail)
 int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out);
 int score_refine(cmdb_bank *b, int P, int n_cand);
 int score_select(cmdb_bank *b, bool local_m_star);
-int score_wdist_topk(cmdb_bank *b);
-int score_merge_top3(cmdb_bank *b);
+int score_reweight(cmdb_bank *b, bool fused);
+int score_merge_top3(cmdb_bank *b, int n_keys);
 int score_final(cmdb_bank *b, bool use_nn_rows);
 int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
-                         float *out_dev, unsigned char *u8_dev);
+                         float *out_dev, unsigned char *u8_dev, unsigned char *tmp_dev, float *mx_dev);
 
 }  // namespace cmdb

@@ -14,13 +14,11 @@
 //     argmax bookkeeping run lane-parallel (one row per lane) instead of as 5 shuffles per row;
 //   * the per-pick grid-wide argmax is an all-gather of one (value,row) slot per CTA through L2 (release store +
 //     acquire polling, double-buffered by pick parity) -- no atomics, no host round trip, ~1 us per pick.
-#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace cmdb {
-
-namespace cg = cooperative_groups;
 
 constexpr int kCsThreads = 512;
 constexpr int kCsWarps = kCsThreads / 32;
@@ -99,13 +97,22 @@ __device__ __forceinline__ DVec zero_vec(const double *) {
     v.a = v.b = make_double2(0.0, 0.0);
     return v;
 }
-// z - last is rounded to the storage type (half: HSUB2 == float subtract + RNE), then fma-accumulated
+// z - last is rounded to the storage type (half: HSUB2 == float subtract + RNE), then fma-accumulated.
+// fma.rn.f32.f16 (SASS FHFMA, sm_100) multiplies two halves exactly and adds in float with one rounding == fmaf on the
+// converted values, without the two conversion instructions per element.
+__device__ __forceinline__ void fhfma2(__half2 dv, float &a0, float &a1) {
+    asm("{\n"
+        ".reg .f16 lo, hi;\n"
+        "mov.b32 {lo, hi}, %2;\n"
+        "fma.rn.f32.f16 %0, lo, lo, %0;\n"
+        "fma.rn.f32.f16 %1, hi, hi, %1;\n"
+        "}"
+        : "+f"(a0), "+f"(a1)
+        : "r"(*reinterpret_cast<unsigned int *>(&dv)));
+}
 __device__ __forceinline__ void accum(const HVec &x, const HVec &l, float (&acc)[4]) {
-    float2 d0 = __half22float2(__hsub2(x.a, l.a)), d1 = __half22float2(__hsub2(x.b, l.b));
-    acc[0] = fmaf(d0.x, d0.x, acc[0]);
-    acc[1] = fmaf(d0.y, d0.y, acc[1]);
-    acc[2] = fmaf(d1.x, d1.x, acc[2]);
-    acc[3] = fmaf(d1.y, d1.y, acc[3]);
+    fhfma2(__hsub2(x.a, l.a), acc[0], acc[1]);
+    fhfma2(__hsub2(x.b, l.b), acc[2], acc[3]);
 }
 __device__ __forceinline__ void accum(const DVec &x, const DVec &l, double (&acc)[4]) {
     double d;
@@ -115,8 +122,9 @@ __device__ __forceinline__ void accum(const DVec &x, const DVec &l, double (&acc
     d = x.b.y - l.b.y, acc[3] = fma(d, d, acc[3]);
 }
 __device__ __forceinline__ float sqdiff(__half x, __half l, float acc) {
-    float d = __half2float(__hsub(x, l));
-    return fmaf(d, d, acc);
+    const unsigned short dv = __half_as_ushort(__hsub(x, l));
+    asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(acc) : "h"(dv));
+    return acc;
 }
 __device__ __forceinline__ double sqdiff(double x, double l, double acc) {
     double d = x - l;
@@ -258,9 +266,52 @@ struct CoresetParams {
     int mind_in_smem;
 };
 
+// per-warp constants of the streaming loop: every warp handles ONE alignment class (rows with row % 4 == warp % 4 of
+// its 4-warp group's chunk), so the class geometry is computed once per kernel and `last` is re-staged once per pick
+template <typename T, int NV>
+struct WarpPlan {
+    ClassGeom g;
+    int main_off;   // element offset (from the row start) of this lane's first aligned main vector
+    int head_off, tail_off;
+    bool has_head, has_tail;
+    bool vmain[NV];
+    long long first, n_rows;  // rows first, first+4, ... (n_rows of them)
+};
+
+template <typename T, int NV>
+__device__ __forceinline__ void issue_row(RowLoads<T, NV> &R, const T *rowp, const WarpPlan<T, NV> &w, int lane, int d,
+                                          bool vectorized) {
+    if (vectorized) {
+        const T *vb = rowp + w.main_off;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            if (w.vmain[t]) R.main[t] = ldvec(vb + 128 * t);
+            else R.main[t] = zero_vec((const T *)nullptr);
+        }
+        R.head = w.has_head ? __ldg(rowp + w.head_off) : Traits<T>::zero();
+        R.tail = w.has_tail ? __ldg(rowp + w.tail_off) : Traits<T>::zero();
+    } else {
+        R.main[0] = zero_vec((const T *)nullptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < d) set_elem(R.main[0], j, __ldg(rowp + lane + 32 * j));
+        R.head = R.tail = Traits<T>::zero();
+    }
+}
+
+template <typename T>
+struct Batch {
+    static constexpr int rows = 4;
+};
+template <>
+struct Batch<double> {
+    static constexpr int rows = 2;  // 32-byte vectors: keep the register footprint of two batches in flight below 128
+};
+
 template <typename T, int NV>
 __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p) {
     using acc_t = typename Traits<T>::acc_t;
+    constexpr int RB = Batch<T>::rows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: tile [kCsWarps][32][33] acc_t | last_sh [d] T | red (val,row) [32] | mind [rows_per_cta] T
     acc_t *tile_all = reinterpret_cast<acc_t *>(smem_raw);
@@ -282,10 +333,29 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     T *mind = p.mind_in_smem ? mind_sh : reinterpret_cast<T *>(p.mind) + cta_row0;
     if (p.mind_in_smem)
         for (long long i = threadIdx.x; i < cta_rows; i += kCsThreads) mind_sh[i] = reinterpret_cast<T *>(p.mind)[cta_row0 + i];
-    // warp's contiguous chunk of the CTA's rows
-    const long long rows_per_warp = (cta_rows + kCsWarps - 1) / kCsWarps;
-    const long long w_row0 = cta_row0 + warp * rows_per_warp;
-    const long long w_row1 = min(cta_row1, w_row0 + rows_per_warp);
+
+    // ---- static work split: 4-warp groups share a contiguous chunk; warp (w & 3) takes its rows with row % 4 == w & 3 ----
+    WarpPlan<T, NV> wp;
+    {
+        constexpr int kGroups = kCsWarps / 4;
+        const long long rows_per_group = (cta_rows + kGroups - 1) / kGroups;
+        const long long g_row0 = cta_row0 + (warp >> 2) * rows_per_group;
+        const long long g_row1 = min(cta_row1, g_row0 + rows_per_group);
+        const int c = warp & 3;
+        wp.first = g_row0 + ((c - (int)(g_row0 & 3)) & 3);
+        wp.n_rows = wp.first < g_row1 ? (g_row1 - wp.first + 3) >> 2 : 0;
+        const int s = vectorized ? (int)(((long long)c * d) & 3) : 0;
+        wp.g = class_geom(s, d);
+        wp.main_off = wp.g.voff - s + 4 * lane;
+        wp.has_head = s > 0 && lane >= s && lane < 4;
+        wp.head_off = lane - s;
+        wp.has_tail = lane < wp.g.ntail;
+        wp.tail_off = wp.g.base + 4 * wp.g.nfull + lane;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) wp.vmain[t] = lane + 32 * t < wp.g.nfull;
+    }
+    const long long n_batches = (wp.n_rows + RB - 1) / RB;
+    const size_t row_stride = (size_t)4 * d;  // elements between consecutive rows of this warp
 
     long long sel = 0;  // features.py:372 -- pick 0 is row 0
     if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[0] = 0;
@@ -296,51 +366,64 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
         for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
         if (threadIdx.x == 0 && pick > 1 && sel >= cta_row0 && sel < cta_row1) mind[sel - cta_row0] = Traits<T>::zero();
         __syncthreads();
+        LastRegs<T, NV> L;
+        load_last<T, NV>(L, last_sh, wp.g, lane, d, vectorized);
 
         T best_val = Traits<T>::zero();
         long long best_row = -1;
-        // ---- distance pass over the warp's rows, one alignment class at a time ----
-        for (int c = 0; c < 4; ++c) {
-            long long first = w_row0 + ((c - (int)(w_row0 & 3)) & 3);  // first row of the chunk with row % 4 == c
-            if (first >= w_row1) continue;
-            const int s = vectorized ? (int)(((long long)c * d) & 3) : 0;
-            const ClassGeom g = class_geom(s, d);
-            LastRegs<T, NV> L;
-            load_last<T, NV>(L, last_sh, g, lane, d, vectorized);
-            const long long n_class = (w_row1 - first + 3) >> 2;  // rows first, first+4, ...
-            for (long long g0 = 0; g0 < n_class; g0 += 32) {
-                const int n_here = (int)min(32LL, n_class - g0);
-                for (int r0 = 0; r0 < n_here; r0 += kRowBatch) {
-                    RowLoads<T, NV> R[kRowBatch];
+        // ---- distance pass: software-pipelined stream of RB-row batches, two batches of loads in flight ----
+        RowLoads<T, NV> A[RB], B[RB];
+        const T *base = z + wp.first * d;
+        auto issue = [&](RowLoads<T, NV>(&buf)[RB], long long bidx) {
 #pragma unroll
-                    for (int b = 0; b < kRowBatch; ++b) {
-                        const long long row = first + 4 * (g0 + min(r0 + b, n_here - 1));
-                        issue_loads<T, NV>(R[b], z + row * d, g, lane, d, vectorized);
-                    }
-#pragma unroll
-                    for (int b = 0; b < kRowBatch; ++b)
-                        if (r0 + b < n_here) tile[(r0 + b) * 33 + lane] = lane_partial<T, NV>(R[b], L, vectorized);
-                }
-                __syncwarp();
-                if (lane < n_here) {
-                    acc_t v[32];
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = tile[lane * 33 + k];
-                    const T dist = Traits<T>::from_acc(tree32(v));
-                    const long long row = first + 4 * (g0 + lane);
-                    T m = mind[row - cta_row0];
-                    if (Traits<T>::lt(dist, m)) {  // torch.minimum (features.py:413)
-                        m = dist;
-                        mind[row - cta_row0] = m;
-                    }
-                    // argmax with lowest-index tie-break (features.py:415)
-                    if (best_row < 0 || Traits<T>::gt(m, best_val) || (!Traits<T>::lt(m, best_val) && row < best_row)) {
-                        best_val = m;
-                        best_row = row;
-                    }
-                }
-                __syncwarp();
+            for (int r = 0; r < RB; ++r) {
+                const long long k = min(bidx * RB + r, wp.n_rows - 1);  // clamp: duplicates are never stored
+                issue_row<T, NV>(buf[r], base + (size_t)k * row_stride, wp, lane, d, vectorized);
             }
+        };
+        auto finalize = [&](long long grp, int n_here) {
+            __syncwarp();
+            if (lane < n_here) {
+                // shfl_down-shaped tree over the row's 32 lane partials, evaluated as 4 sub-trees of 8 to keep the
+                // register footprint small while two batches of loads are in flight (same association as tree32)
+                acc_t q4[4];
+#pragma unroll 1
+                for (int blk = 0; blk < 4; ++blk) {
+                    acc_t v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = tile[lane * 33 + blk * 8 + k];
+                    q4[blk] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                }
+                const T dist = Traits<T>::from_acc((q4[0] + q4[1]) + (q4[2] + q4[3]));
+                const long long row = wp.first + 4 * (grp * 32 + lane);
+                T m = mind[row - cta_row0];
+                if (Traits<T>::lt(dist, m)) {  // torch.minimum (features.py:413)
+                    m = dist;
+                    mind[row - cta_row0] = m;
+                }
+                // argmax, ties -> lowest index (features.py:415); rows of one lane increase, so strict > suffices
+                if (best_row < 0 || Traits<T>::gt(m, best_val)) {
+                    best_val = m;
+                    best_row = row;
+                }
+            }
+            __syncwarp();
+        };
+        auto compute = [&](RowLoads<T, NV>(&buf)[RB], long long bidx) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const long long k = bidx * RB + r;
+                if (k < wp.n_rows) tile[(int)(k & 31) * 33 + lane] = lane_partial<T, NV>(buf[r], L, vectorized);
+            }
+            const long long k_end = min(wp.n_rows, (bidx + 1) * RB);  // rows [.., k_end) are in the tile
+            if ((k_end & 31) == 0 || k_end == wp.n_rows) finalize((k_end - 1) >> 5, (int)(k_end - (((k_end - 1) >> 5) << 5)));
+        };
+        if (n_batches > 0) issue(A, 0);
+        for (long long bi = 0; bi < n_batches; bi += 2) {
+            if (bi + 1 < n_batches) issue(B, bi + 1);
+            compute(A, bi);
+            if (bi + 2 < n_batches) issue(A, bi + 2);
+            if (bi + 1 < n_batches) compute(B, bi + 1);
         }
         // ---- CTA argmax: warp shuffle, then shared memory ----
         unsigned long long bv = best_row < 0 ? 0ULL : Traits<T>::bits(best_val);
@@ -366,13 +449,14 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                 st_release_u64(&slots[blockIdx.x].tag, ((unsigned long long)pick << 32) | (br & 0xffffffffULL));
             }
         }
-        // ---- grid all-gather of the per-CTA winners through L2 ----
+        // ---- grid all-gather of the per-CTA winners through L2 (relaxed polling, one acquire fence at the end) ----
         bv = 0ULL, br = ~0ULL;
         for (int c = threadIdx.x; c < (int)gridDim.x; c += kCsThreads) {
             unsigned long long tag;
             do {
-                tag = ld_acquire_u64(&slots[c].tag);
+                tag = ld_relaxed_u64(&slots[c].tag);
             } while ((tag >> 32) != (unsigned long long)pick);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
             const unsigned long long ov = ld_relaxed_u64(&slots[c].val);
             const unsigned long long orow = (tag & 0xffffffffULL) == 0xffffffffULL ? ~0ULL : (tag & 0xffffffffULL);
             if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
@@ -478,8 +562,42 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
         CMDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCsThreads, smem));
         CMDB_REQUIRE(per_sm >= 1, CMDB_ERR_CUDA, "coreset: persistent kernel does not fit on an SM (smem %zu)", smem);
         CMDB_CUDA(cudaMemsetAsync(p.slots, 0, sizeof(PickSlot) * 2 * grid, b->stream));
+        // The projected bank is re-read once per pick.  B200's L2 (126 MB) cannot hold a 120 MB cyclic sweep under its
+        // default replacement (measured: 20 % hit rate), so pin as much of it as the persisting carve-out allows and
+        // stream the rest: DRAM traffic per pick drops to roughly (1 - hitRatio) of the bank.
+        const char *env = getenv("CMDB_CORESET_L2PERSIST");
+        const bool want_persist = !(env && env[0] == '0');
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, b->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, b->device);
+        const size_t z_bytes = sizeof(T) * (size_t)p.N * p.d;
+        bool persisting = false;
+        cudaStreamAttrValue attr{};
+        if (want_persist && max_persist > 0 && max_window > 0) {
+            const size_t carve = std::min<size_t>(z_bytes, (size_t)max_persist);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                attr.accessPolicyWindow.base_ptr = const_cast<void *>(p.z);
+                attr.accessPolicyWindow.num_bytes = std::min<size_t>(z_bytes, (size_t)max_window);
+                attr.accessPolicyWindow.hitRatio =
+                    (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                persisting = cudaStreamSetAttribute(b->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            }
+            (void)cudaGetLastError();
+        }
+        if (getenv("CMDB_TRACE"))
+            fprintf(stderr, "[cmdb] coreset: N=%lld d=%d grid=%d smem=%zu mind_in_smem=%d z=%.1f MB L2 persist=%d (max %d MB, window %d MB, hitRatio %.2f)\n",
+                    p.N, p.d, grid, smem, p.mind_in_smem, z_bytes / 1e6, (int)persisting, max_persist >> 20, max_window >> 20,
+                    persisting ? attr.accessPolicyWindow.hitRatio : 0.f);
         void *args[] = {&p};
-        CMDB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kCsThreads), args, smem, b->stream));
+        cudaError_t le = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kCsThreads), args, smem, b->stream);
+        if (persisting) {
+            attr.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(b->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            // the carve-out is released by the caller after the kernel has finished (coreset_greedy_dev)
+        }
+        CMDB_CUDA(le);
         return CMDB_OK;
     };
 #define CMDB_CS(NVV) \
@@ -561,6 +679,9 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
                                (dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double)) * (size_t)N,
                                cudaMemcpyDeviceToHost, st));
     CS_TRY(cudaStreamSynchronize(st));
+    (void)cudaCtxResetPersistingL2Cache();
+    (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    (void)cudaGetLastError();
 #undef CS_TRY
     cleanup();
     return CMDB_OK;

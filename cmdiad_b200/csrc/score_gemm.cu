@@ -227,7 +227,6 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;     // row inside the M tile
         const int et = threadIdx.x - 128;        // 0..127
-        const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp)));
         int j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
             const int n = t / p.mt, m_local = t - n * p.mt;
@@ -236,6 +235,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
             bn[et] = __ldg(p.bnorm + (size_t)n * BN + et);
             bn[et + 128] = __ldg(p.bnorm + (size_t)n * BN + et + 128);
+            // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
+            const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + (p.m_tile_base + m_local) * BM + row)));
             float4 st = state[m_local * BM + row];
             float b1 = st.x, b2 = st.z;
             int i1 = __float_as_int(st.y), i2 = __float_as_int(st.w);
@@ -277,35 +278,32 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     }
 }
 
-// ---------------------------------------------------------------- query preparation (device-side scale selection)
-__global__ void __launch_bounds__(512) q_absmax_kernel(const float *__restrict__ x, long long n, unsigned int *out) {
-    float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
-}
-
-// one warp per query row: q * 2^e -> fp16 hi/lo; rows >= P are zero.  e is derived from max|q| on the device so the
-// call never syncs with the host; block 0 publishes it for the GEMM epilogue.
+// ---------------------------------------------------------------- query preparation
+// One warp per query row: per-ROW power-of-two scale (max|q_row| -> [2^12, 2^13)), q * 2^e -> fp16 hi/lo; rows >= P are
+// zero.  A per-row scale needs no grid-wide reduction (one launch, no host sync) and is free in the GEMM epilogue,
+// where one thread owns one query row.
 __global__ void __launch_bounds__(256) q_split_kernel(const float *__restrict__ q, int P, int P_pad, int dim,
-                                                      const unsigned int *__restrict__ absmax_bits, __half *__restrict__ hi,
-                                                      __half *__restrict__ lo, int *__restrict__ scale_exp_out) {
-    const float amax = __uint_as_float(*absmax_bits);
-    int e = 0;
-    if (amax > 0.f && amax < INFINITY) {
-        int ex;
-        frexpf(amax, &ex);
-        e = 13 - ex;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *scale_exp_out = e;
-    const float scale = ldexpf(1.f, e);
+                                                      __half *__restrict__ hi, __half *__restrict__ lo,
+                                                      int *__restrict__ scale_exp_out) {
     const int lane = threadIdx.x & 31, dim4 = dim >> 2;
     for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < P_pad; r += gridDim.x * 8) {
         uint2 *h = reinterpret_cast<uint2 *>(hi + (size_t)r * dim), *l = reinterpret_cast<uint2 *>(lo + (size_t)r * dim);
+        float amax = 0.f;
+        if (r < P)
+            for (int cc = lane; cc < dim4; cc += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(q + (size_t)r * dim) + cc);
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        int e = 0;
+        if (amax > 0.f && amax < INFINITY) {
+            int ex;
+            frexpf(amax, &ex);
+            e = 13 - ex;
+        }
+        if (lane == 0) scale_exp_out[r] = e;
+        const float scale = ldexpf(1.f, e);
         for (int cc = lane; cc < dim4; cc += 32) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < P) v = __ldg(reinterpret_cast<const float4 *>(q + (size_t)r * dim) + cc);
@@ -361,9 +359,10 @@ int score_make_tensor_maps(cmdb_bank *b) {
 void score_scratch_free(cmdb_bank *b) {
     ScoreScratch &s = b->ss;
     cudaFree(s.q_f32), cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_norm), cudaFree(s.q_absmax), cudaFree(s.q_scale_exp);
-    cudaFree(s.cand), cudaFree(s.min_val), cudaFree(s.min_idx), cudaFree(s.s_key), cudaFree(s.topk_keys), cudaFree(s.tail);
-    cudaFree(s.map_pre), cudaFree(s.map_out), cudaFree(s.map_u8), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
-    cudaFree(s.top3);
+    cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys), cudaFree(s.out_block);
+    cudaFree(s.map_tmp), cudaFree(s.map_max), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
+    cudaFree(s.top3), cudaFree(s.done_counter);
+    if (s.out_block_host) cudaFreeHost(s.out_block_host);
     free(s.tmap_qhi), free(s.tmap_qlo);
     s = ScoreScratch();
 }
@@ -382,17 +381,30 @@ int score_scratch_alloc(cmdb_bank *b, int P, int out_hw) {
     CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
     CMDB_CUDA(cudaMalloc(&s.q_absmax, sizeof(unsigned int)));
-    CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int)));
+    CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.done_counter, sizeof(unsigned int)));
+    CMDB_CUDA(cudaMemset(s.done_counter, 0, sizeof(unsigned int)));
     CMDB_CUDA(cudaMalloc(&s.cand, sizeof(float4) * (size_t)cap_p * b->num_sms));
-    CMDB_CUDA(cudaMalloc(&s.min_val, sizeof(float) * cap_p));
-    CMDB_CUDA(cudaMalloc(&s.min_idx, sizeof(long long) * cap_p));
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    s.off_min_val = up(sizeof(TailResult));
+    s.off_min_idx = s.off_min_val + up(sizeof(float) * cap_p);
+    s.off_map_out = s.off_min_idx + up(sizeof(long long) * cap_p);
+    s.off_map_pre = s.off_map_out + up(sizeof(float) * map_cap);
+    s.off_map_u8 = s.off_map_pre + up(sizeof(float) * map_cap);
+    s.out_block_bytes = s.off_map_u8 + up(map_cap);
+    CMDB_CUDA(cudaMalloc(&s.out_block, s.out_block_bytes));
+    CMDB_CUDA(cudaMallocHost(&s.out_block_host, s.out_block_bytes));
+    s.tail = s.out_block;
+    s.min_val = reinterpret_cast<float *>(s.out_block + s.off_min_val);
+    s.min_idx = reinterpret_cast<long long *>(s.out_block + s.off_min_idx);
+    s.map_out = reinterpret_cast<float *>(s.out_block + s.off_map_out);
+    s.map_pre = reinterpret_cast<float *>(s.out_block + s.off_map_pre);
+    s.map_u8 = s.out_block + s.off_map_u8;
+    CMDB_CUDA(cudaMalloc(&s.map_tmp, map_cap));
+    CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float)));
     CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long)));
     CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks));
     CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3));
-    CMDB_CUDA(cudaMalloc(&s.tail, sizeof(TailResult)));
-    CMDB_CUDA(cudaMalloc(&s.map_pre, sizeof(float) * map_cap));
-    CMDB_CUDA(cudaMalloc(&s.map_out, sizeof(float) * map_cap));
-    CMDB_CUDA(cudaMalloc(&s.map_u8, map_cap));
     CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D));
     CMDB_CUDA(cudaMalloc(&s.m_star, sizeof(float) * D));
     CMDB_CUDA(cudaMalloc(&s.nn_rows, sizeof(float) * 3 * D));
@@ -406,11 +418,8 @@ int score_query_prep(cmdb_bank *b, int P) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
     cudaStream_t st = b->stream;
-    CMDB_CUDA(cudaMemsetAsync(s.q_absmax, 0, sizeof(unsigned int), st));
-    q_absmax_kernel<<<std::min(b->num_sms, (int)(((long long)P * b->dim / 4 + 511) / 512)), 512, 0, st>>>(
-        s.q_f32, (long long)P * b->dim, s.q_absmax);
-    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(s.q_f32, P, p_pad, b->dim, s.q_absmax, s.q_hi,
-                                                                              s.q_lo, s.q_scale_exp);
+    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(s.q_f32, P, p_pad, b->dim, s.q_hi, s.q_lo,
+                                                                              s.q_scale_exp);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }

@@ -2,8 +2,8 @@
 //   refine      exact float32 re-check of the GEMM epilogue's per-CTA top-2 candidates -> min_val / min_idx (:227),
 //               and the packed argmax key of min_val -> s_star / s_idx (:228-231)
 //   select      m_test = patch[s_idx], m_star = bank[min_idx[s_idx]] (:235-251)
-//   wdist_topk  w_dist = ||m_star - bank_r|| for every bank row, 3 smallest (:239-254); HBM bound, R*D*4 bytes
-//   final       m_star_knn, w, s (:275-290)
+//   reweight    w_dist = ||m_star - bank_r|| for every bank row, 3 smallest (:239-254; HBM bound, R*D*4 bytes), with
+//               the m_star selection as prologue and m_star_knn, w, s (:275-290) as last-block epilogue
 //   upsample_blur  bilinear 28^2/56^2 -> 224^2 (:293-294) + KNNGaussianBlur (utils/utils.py:71-83): /max, 8-bit
 //               truncation, Pillow's 3+3 pass integer box blur, /255, *max -- one CTA, whole image in shared memory
 #include <math.h>
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) select_kernel(const unsigned long long *s
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// wdist_topk: exact ||m_star - bank_r||^2 for every local bank row, per-block 3 smallest as packed keys
+// reweight: exact ||m_star - bank_r||^2 for every local bank row, 3 smallest as packed keys
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void top3_insert(unsigned long long (&t)[3], unsigned long long k) {
     if (k < t[2]) {
@@ -242,23 +242,68 @@ __device__ __forceinline__ void top3_insert(unsigned long long (&t)[3], unsigned
     }
 }
 
-__global__ void __launch_bounds__(256) wdist_topk_kernel(const float *__restrict__ bank, long long rows, int dim,
-                                                         long long row_offset, const float *__restrict__ m_star,
-                                                         unsigned long long *__restrict__ block_keys) {
+// block-wide 3 smallest of the per-thread sorted triples t[]: three rounds of "everyone offers its head, winner pops"
+__device__ __forceinline__ void block_top3(unsigned long long (&t)[3], unsigned long long *sh /* [8] */,
+                                           unsigned long long (&out)[3]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        unsigned long long v = t[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
+            v = ov < v ? ov : v;
+        }
+        __syncthreads();
+        if (lane == 0) sh[warp] = v;
+        __syncthreads();
+        v = sh[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) v = sh[w] < v ? sh[w] : v;
+        out[r] = v;
+        if (v != ~0ULL && t[0] == v) t[0] = t[1], t[1] = t[2], t[2] = ~0ULL;  // keys are unique (row in the low bits)
+    }
+}
+
+struct ReweightParams {
+    const float *bank;               // [rows, dim] float32 (local shard)
+    long long rows, row_offset;
+    int dim;
+    const float *q;                  // [P, dim] normalised patches
+    const unsigned long long *s_key; // packed argmax of min_val
+    const long long *min_idx;        // [P] global rows
+    const float *m_star_explicit;    // sharded mode: replicated m_star row; NULL = take it from the local bank
+    unsigned long long *block_keys;  // [gridDim.x * 3]
+    unsigned long long *top3;        // [3] merged result
+    unsigned int *done_counter;      // last-block-done counter (self resetting)
+    TailResult *res;
+    int fuse_final;                  // 1: the last block also computes m_star_knn, w, s (single-GPU path)
+};
+
+// w_dist pass (features.py:239-254): exact ||m_star - bank_r||^2 for every local bank row, 3 smallest.
+// Prologue = "select" (decode s*, s_idx, locate m_star); epilogue = last-block-done merge (+ final re-weighting), so the
+// whole re-weighting stage is one launch.  HBM bound: rows*dim*4 bytes.
+__global__ void __launch_bounds__(256) reweight_kernel(ReweightParams p) {
     extern __shared__ __align__(16) float ms[];
-    __shared__ unsigned long long wk[8][3];
-    for (int c = threadIdx.x; c < dim; c += blockDim.x) ms[c] = m_star[c];
+    __shared__ unsigned long long wk[8];
+    __shared__ bool is_last;
+    __shared__ float knn[2];
+    const unsigned long long skey = *p.s_key;
+    const int s_idx = (int)(0xffffffffu - (unsigned int)(skey & 0xffffffffu));
+    const long long g_star = p.min_idx[s_idx];
+    const float *m_star = p.m_star_explicit ? p.m_star_explicit : p.bank + (size_t)(g_star - p.row_offset) * p.dim;
+    for (int c = threadIdx.x; c < p.dim; c += blockDim.x) ms[c] = m_star[c];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int dim4 = dim >> 2;
+    const int dim = p.dim, dim4 = dim >> 2;
     unsigned long long t[3] = {~0ULL, ~0ULL, ~0ULL};
     const long long warps = (long long)gridDim.x * 8;
     // two rows in flight per warp
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += 2 * warps) {
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < p.rows; r += 2 * warps) {
         const long long r2 = r + warps;
-        const bool has2 = r2 < rows;
-        const float4 *a = reinterpret_cast<const float4 *>(bank + (size_t)r * dim);
-        const float4 *a2 = reinterpret_cast<const float4 *>(bank + (size_t)(has2 ? r2 : r) * dim);
+        const bool has2 = r2 < p.rows;
+        const float4 *a = reinterpret_cast<const float4 *>(p.bank + (size_t)r * dim);
+        const float4 *a2 = reinterpret_cast<const float4 *>(p.bank + (size_t)(has2 ? r2 : r) * dim);
         float acc = 0.f, acc2 = 0.f;
         for (int c = lane; c < dim4; c += 32) {
             const float4 x = __ldg(a + c), x2 = __ldg(a2 + c);
@@ -278,41 +323,65 @@ __global__ void __launch_bounds__(256) wdist_topk_kernel(const float *__restrict
             acc += __shfl_xor_sync(0xffffffffu, acc, o);
             acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
         }
-        top3_insert(t, pack_min_key(acc, (unsigned int)(r + row_offset)));
-        if (has2) top3_insert(t, pack_min_key(acc2, (unsigned int)(r2 + row_offset)));
+        if (lane == 0) {  // one copy per warp keeps the keys unique for block_top3
+            top3_insert(t, pack_min_key(acc, (unsigned int)(r + p.row_offset)));
+            if (has2) top3_insert(t, pack_min_key(acc2, (unsigned int)(r2 + p.row_offset)));
+        }
     }
-    if (lane == 0) wk[warp][0] = t[0], wk[warp][1] = t[1], wk[warp][2] = t[2];
+    unsigned long long f[3];
+    block_top3(t, wk, f);
+    if (threadIdx.x == 0) {
+        p.block_keys[blockIdx.x * 3 + 0] = f[0];
+        p.block_keys[blockIdx.x * 3 + 1] = f[1];
+        p.block_keys[blockIdx.x * 3 + 2] = f[2];
+        __threadfence();
+        is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    // ---- last block: merge every block's keys, then (single-GPU path) finish the re-weighting ----
+    __threadfence();
+    t[0] = t[1] = t[2] = ~0ULL;
+    for (int i = threadIdx.x; i < (int)gridDim.x * 3; i += blockDim.x) top3_insert(t, __ldcg(p.block_keys + i));
+    block_top3(t, wk, f);
+    if (threadIdx.x == 0) {
+        p.top3[0] = f[0], p.top3[1] = f[1], p.top3[2] = f[2];
+        *p.done_counter = 0;
+        p.res->s_idx = s_idx;
+        p.res->s_star = __uint_as_float((unsigned int)(skey >> 32));
+        p.res->m_star_row = g_star;
+        for (int k = 0; k < 3; ++k) p.res->nn_idx[k] = f[k] == ~0ULL ? -1 : (long long)(f[k] & 0xffffffffULL);
+    }
+    if (!p.fuse_final) return;
+    // features.py:275-283: m_star_knn = ||m_test - bank[nn_idx[1:]]||, m_test = patch[s_idx]
+    if (warp < 2) {
+        const unsigned long long key = f[1 + warp];
+        float d2 = 0.f;
+        if (key != ~0ULL)
+            d2 = warp_sqdist(p.q + (size_t)s_idx * dim, p.bank + (size_t)((long long)(key & 0xffffffffULL) - p.row_offset) * dim,
+                             dim4, lane);
+        if (lane == 0) knn[warp] = key != ~0ULL ? sqrtf(d2) : NAN;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long f[3] = {~0ULL, ~0ULL, ~0ULL};
-        for (int w = 0; w < 8; ++w)
-            for (int k = 0; k < 3; ++k) top3_insert(f, wk[w][k]);
-        block_keys[blockIdx.x * 3 + 0] = f[0];
-        block_keys[blockIdx.x * 3 + 1] = f[1];
-        block_keys[blockIdx.x * 3 + 2] = f[2];
+        const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))  (features.py:285)
+        const float s_star = __uint_as_float((unsigned int)(skey >> 32));
+        const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
+        const float w = 1.f - expf(s_star / Dn) / den;  // features.py:287
+        p.res->w = w;
+        p.res->s = w * s_star;                          // features.py:290
+        p.res->knn0 = knn[0], p.res->knn1 = knn[1];
     }
 }
 
-// merge per-block keys -> 3 smallest (one block)
-__global__ void __launch_bounds__(256) merge_top3_kernel(const unsigned long long *__restrict__ block_keys, int n_keys,
+// merge gathered keys -> 3 smallest (one block; sharded mode, after the all-gather)
+__global__ void __launch_bounds__(256) merge_top3_kernel(const unsigned long long *__restrict__ keys, int n_keys,
                                                          unsigned long long *__restrict__ out3) {
-    __shared__ unsigned long long wk[8][3];
-    unsigned long long t[3] = {~0ULL, ~0ULL, ~0ULL};
-    for (int i = threadIdx.x; i < n_keys; i += blockDim.x) top3_insert(t, block_keys[i]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // warp merge through shuffles: every lane offers its 3 keys in turn
-    unsigned long long f[3] = {~0ULL, ~0ULL, ~0ULL};
-    for (int src = 0; src < 32; ++src)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) top3_insert(f, __shfl_sync(0xffffffffu, t[k], src));
-    if (lane == 0) wk[warp][0] = f[0], wk[warp][1] = f[1], wk[warp][2] = f[2];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long g[3] = {~0ULL, ~0ULL, ~0ULL};
-        for (int w = 0; w < 8; ++w)
-            for (int k = 0; k < 3; ++k) top3_insert(g, wk[w][k]);
-        out3[0] = g[0], out3[1] = g[1], out3[2] = g[2];
-    }
+    __shared__ unsigned long long wk[8];
+    unsigned long long t[3] = {~0ULL, ~0ULL, ~0ULL}, f[3];
+    for (int i = threadIdx.x; i < n_keys; i += blockDim.x) top3_insert(t, keys[i]);
+    block_top3(t, wk, f);
+    if (threadIdx.x == 0) out3[0] = f[0], out3[1] = f[1], out3[2] = f[2];
 }
 
 // final: m_star_knn = ||m_test - bank[nn[1:]]|| (features.py:275-283), w and s (:285-290).  nn_rows: optional
@@ -345,9 +414,14 @@ __global__ void __launch_bounds__(64) final_kernel(const unsigned long long *__r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// upsample + blur, one CTA of 1024 threads
+// upsample + blur in two small multi-CTA kernels (the image is split into 16 row bands, then 16 column bands):
+//   K1  every CTA recomputes the global max of the upsampled map (needed before the 8-bit quantisation; 50k pixels, cheaper
+//       than a grid barrier), upsamples + quantises its row band and runs the 3 horizontal box passes in shared memory;
+//   K2  every CTA loads its column band of K1's result and runs the 3 vertical passes (Pillow transposes instead), then
+//       applies ToTensor (/255) and * max.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBlurThreads = 1024;
+constexpr int kBlurThreads = 512;
+constexpr int kBlurBands = 16;
 
 __device__ __forceinline__ void bilinear_coeff(int dst, float scale, int n_in, int &i0, int &i1, float &w0, float &w1) {
     // ATen area_pixel_compute_source_index (align_corners=False) + HelperInterpLinear weights
@@ -358,11 +432,23 @@ __device__ __forceinline__ void bilinear_coeff(int dst, float scale, int n_in, i
     w0 = __fsub_rn(1.f, w1);
 }
 
-// one box pass along x (stride_x) for all lines; Pillow ImagingLineBoxBlur8 as a clamped 9-tap integer FIR
+__device__ __forceinline__ float bilinear_at(const float *__restrict__ in_s, int fh, int fw_, float sh, float sw, int y, int x) {
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    bilinear_coeff(y, sh, fh, y0, y1, wy0, wy1);
+    bilinear_coeff(x, sw, fw_, x0, x1, wx0, wx1);
+    // ATen Interpolate<2,...,interp_size 2>: t0*w0 + t1*w1 contracted as fma(t0, w0, t1*w1), W inside H
+    const float t0 = __fmaf_rn(in_s[y0 * fw_ + x0], wx0, __fmul_rn(in_s[y0 * fw_ + x1], wx1));
+    const float t1 = __fmaf_rn(in_s[y1 * fw_ + x0], wx0, __fmul_rn(in_s[y1 * fw_ + x1], wx1));
+    return __fmaf_rn(t0, wy0, __fmul_rn(t1, wy1));
+}
+
+// one box pass along the `n`-long axis of an [n_lines][n] (x_stride == 1) or [n][n_lines] (x_stride == n_lines) tile;
+// Pillow ImagingLineBoxBlur8 as a clamped 9-tap integer FIR with 32-bit fixed-point weights
 __device__ __forceinline__ void box_pass(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst, int n_lines,
                                          int n, int line_stride, int x_stride, int radius, unsigned int ww, unsigned int fw) {
     for (int i = threadIdx.x; i < n_lines * n; i += kBlurThreads) {
-        // consecutive threads walk the contiguous image dimension in both orientations (bank-conflict free)
+        // consecutive threads walk the contiguous tile dimension in both orientations (bank-conflict free)
         int line, x;
         if (x_stride == 1) line = i / n, x = i - line * n;
         else x = i / n_lines, line = i - x * n_lines;
@@ -375,33 +461,22 @@ __device__ __forceinline__ void box_pass(const unsigned char *__restrict__ src, 
     }
 }
 
-__global__ void __launch_bounds__(kBlurThreads) upsample_blur_kernel(const float *__restrict__ map_in, int fh, int fw_,
-                                                                     int out_hw, float *__restrict__ pre,
-                                                                     float *__restrict__ out, unsigned char *__restrict__ u8_out,
-                                                                     int radius, unsigned int ww, unsigned int fwt) {
+__global__ void __launch_bounds__(kBlurThreads) upsample_hblur_kernel(const float *__restrict__ map_in, int fh, int fw_,
+                                                                      int out_hw, int band, float *__restrict__ pre,
+                                                                      unsigned char *__restrict__ u8_out,
+                                                                      unsigned char *__restrict__ tmp, float *__restrict__ mx_out,
+                                                                      int radius, unsigned int ww, unsigned int fwt) {
     extern __shared__ __align__(16) unsigned char sm[];
-    float *in_s = reinterpret_cast<float *>(sm);                       // [fh*fw]
-    unsigned char *A = sm + sizeof(float) * ((fh * fw_ + 3) & ~3);     // [out_hw^2]
-    unsigned char *B = A + ((out_hw * out_hw + 15) & ~15);
-    __shared__ float red[32];
+    float *in_s = reinterpret_cast<float *>(sm);                    // [fh*fw]
+    unsigned char *A = sm + sizeof(float) * ((fh * fw_ + 3) & ~3);  // [band][out_hw]
+    unsigned char *B = A + ((band * out_hw + 15) & ~15);
+    __shared__ float red[kBlurThreads / 32];
     for (int i = threadIdx.x; i < fh * fw_; i += kBlurThreads) in_s[i] = map_in[i];
     __syncthreads();
     const float sh = (float)fh / (float)out_hw, sw = (float)fw_ / (float)out_hw;
     const int npix = out_hw * out_hw;
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < npix; i += kBlurThreads) {
-        const int y = i / out_hw, x = i - y * out_hw;
-        int y0, y1, x0, x1;
-        float wy0, wy1, wx0, wx1;
-        bilinear_coeff(y, sh, fh, y0, y1, wy0, wy1);
-        bilinear_coeff(x, sw, fw_, x0, x1, wx0, wx1);
-        // ATen Interpolate<2,...,interp_size 2>: t0*w0 + t1*w1 contracted as fma(t0, w0, t1*w1), W inside H
-        const float t0 = __fmaf_rn(in_s[y0 * fw_ + x0], wx0, __fmul_rn(in_s[y0 * fw_ + x1], wx1));
-        const float t1 = __fmaf_rn(in_s[y1 * fw_ + x0], wx0, __fmul_rn(in_s[y1 * fw_ + x1], wx1));
-        const float v = __fmaf_rn(t0, wy0, __fmul_rn(t1, wy1));
-        pre[i] = v;
-        mx = fmaxf(mx, v);
-    }
+    float mx = -INFINITY;  // map_max = img.max() over the WHOLE upsampled image (utils/utils.py:81)
+    for (int i = threadIdx.x; i < npix; i += kBlurThreads) mx = fmaxf(mx, bilinear_at(in_s, fh, fw_, sh, sw, i / out_hw, i % out_hw));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -409,29 +484,53 @@ __global__ void __launch_bounds__(kBlurThreads) upsample_blur_kernel(const float
     mx = red[0];
 #pragma unroll
     for (int w = 1; w < kBlurThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *mx_out = mx;
+    const int y0 = blockIdx.x * band, rows = min(band, out_hw - y0);
+    if (rows <= 0) return;
     // KNNGaussianBlur: img / max -> ToPILImage: mul(255).byte() (truncation)
-    for (int i = threadIdx.x; i < npix; i += kBlurThreads) {
-        const float qv = __fmul_rn(__fdiv_rn(pre[i], mx), 255.f);
-        const unsigned char u = (unsigned char)(int)qv;
+    for (int i = threadIdx.x; i < rows * out_hw; i += kBlurThreads) {
+        const int y = y0 + i / out_hw, x = i % out_hw;
+        const float v = bilinear_at(in_s, fh, fw_, sh, sw, y, x);
+        if (pre) pre[y * out_hw + x] = v;
+        const unsigned char u = (unsigned char)(int)__fmul_rn(__fdiv_rn(v, mx), 255.f);
         A[i] = u;
-        if (u8_out) u8_out[i] = u;
+        if (u8_out) u8_out[y * out_hw + x] = u;
     }
     __syncthreads();
-    // Pillow ImagingBoxBlur: 3 horizontal passes, then 3 vertical ones (its transpose trick, done by indexing)
-    box_pass(A, B, out_hw, out_hw, out_hw, 1, radius, ww, fwt);
+    box_pass(A, B, rows, out_hw, out_hw, 1, radius, ww, fwt);
     __syncthreads();
-    box_pass(B, A, out_hw, out_hw, out_hw, 1, radius, ww, fwt);
+    box_pass(B, A, rows, out_hw, out_hw, 1, radius, ww, fwt);
     __syncthreads();
-    box_pass(A, B, out_hw, out_hw, out_hw, 1, radius, ww, fwt);
+    box_pass(A, B, rows, out_hw, out_hw, 1, radius, ww, fwt);
     __syncthreads();
-    box_pass(B, A, out_hw, out_hw, 1, out_hw, radius, ww, fwt);
+    for (int i = threadIdx.x; i < rows * out_hw; i += kBlurThreads) tmp[y0 * out_hw + i] = B[i];
+}
+
+__global__ void __launch_bounds__(kBlurThreads) vblur_kernel(const unsigned char *__restrict__ tmp, int out_hw, int band,
+                                                             const float *__restrict__ mx_in, float *__restrict__ out,
+                                                             int radius, unsigned int ww, unsigned int fwt) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int x0 = blockIdx.x * band, cols = min(band, out_hw - x0);
+    if (cols <= 0) return;
+    unsigned char *A = sm;  // [out_hw][cols]: column band, lines = columns (stride 1), pass axis = rows (stride cols)
+    unsigned char *B = A + ((out_hw * band + 15) & ~15);
+    for (int i = threadIdx.x; i < out_hw * cols; i += kBlurThreads) {
+        const int y = i / cols, c = i - y * cols;
+        A[i] = tmp[y * out_hw + x0 + c];
+    }
     __syncthreads();
-    box_pass(A, B, out_hw, out_hw, 1, out_hw, radius, ww, fwt);
+    box_pass(A, B, cols, out_hw, 1, cols, radius, ww, fwt);
     __syncthreads();
-    box_pass(B, A, out_hw, out_hw, 1, out_hw, radius, ww, fwt);
+    box_pass(B, A, cols, out_hw, 1, cols, radius, ww, fwt);
     __syncthreads();
+    box_pass(A, B, cols, out_hw, 1, cols, radius, ww, fwt);
+    __syncthreads();
+    const float mx = *mx_in;
     // ToTensor (/255) then * map_max
-    for (int i = threadIdx.x; i < npix; i += kBlurThreads) out[i] = __fmul_rn(__fdiv_rn((float)A[i], 255.f), mx);
+    for (int i = threadIdx.x; i < out_hw * cols; i += kBlurThreads) {
+        const int y = i / cols, c = i - y * cols;
+        out[y * out_hw + x0 + c] = __fmul_rn(__fdiv_rn((float)B[i], 255.f), mx);
+    }
 }
 
 int score_select(cmdb_bank *b, bool local_m_star) {
@@ -442,16 +541,23 @@ int score_select(cmdb_bank *b, bool local_m_star) {
     return CMDB_OK;
 }
 
-int score_wdist_topk(cmdb_bank *b) {
-    const int blocks = b->ss.n_topk_blocks;
-    wdist_topk_kernel<<<blocks, 256, sizeof(float) * b->dim, b->stream>>>(b->data, b->fin_rows, b->dim, b->row_offset,
-                                                                          b->ss.m_star, b->ss.topk_keys);
+// fused = single-GPU path (select prologue + merge + final in one launch); otherwise m_star comes from ss.m_star and only
+// the merged top-3 keys are produced
+int score_reweight(cmdb_bank *b, bool fused) {
+    ReweightParams p{};
+    p.bank = b->data, p.rows = b->fin_rows, p.row_offset = b->row_offset, p.dim = b->dim;
+    p.q = b->ss.q_f32, p.s_key = b->ss.s_key, p.min_idx = b->ss.min_idx;
+    p.m_star_explicit = fused ? nullptr : b->ss.m_star;
+    p.block_keys = b->ss.topk_keys, p.top3 = b->ss.top3, p.done_counter = b->ss.done_counter;
+    p.res = reinterpret_cast<TailResult *>(b->ss.tail);
+    p.fuse_final = fused ? 1 : 0;
+    reweight_kernel<<<b->ss.n_topk_blocks, 256, sizeof(float) * b->dim, b->stream>>>(p);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
-int score_merge_top3(cmdb_bank *b) {
-    merge_top3_kernel<<<1, 256, 0, b->stream>>>(b->ss.topk_keys, b->ss.n_topk_blocks * 3, b->ss.top3);
+int score_merge_top3(cmdb_bank *b, int n_keys) {
+    merge_top3_kernel<<<1, 256, 0, b->stream>>>(b->ss.topk_keys, n_keys, b->ss.top3);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
@@ -464,10 +570,10 @@ int score_final(cmdb_bank *b, bool use_nn_rows) {
 }
 
 int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
-                         float *out_dev, unsigned char *u8_dev) {
+                         float *out_dev, unsigned char *u8_dev, unsigned char *tmp_dev, float *mx_dev) {
     CMDB_REQUIRE(fh > 0 && fw > 0 && out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID,
                  "upsample_blur: need out_hw in [8,256] (got %d) and positive map dims", out_hw);
-    // Pillow _gaussian_blur_radius(radius=4, passes=3) evaluated in double like BoxBlur.c (float sigma2 = 16/3)
+    // Pillow _gaussian_blur_radius(radius=4, passes=3) evaluated like BoxBlur.c (float sigma2 = 16/3, the rest double)
     const float sigma2 = 4.f * 4.f / 3.f;
     const double L = sqrt(12.0 * (double)sigma2 + 1.0);
     const double l = floor((L - 1.0) / 2.0);
@@ -478,10 +584,14 @@ int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int 
     const unsigned int ww = (unsigned int)((float)(1 << 24) / (fr * 2 + 1));
     const unsigned int fwt = ((1u << 24) - (unsigned int)(radius * 2 + 1) * ww) / 2;
     CMDB_REQUIRE(out_hw > radius + 1, CMDB_ERR_INVALID, "upsample_blur: image smaller than the blur radius");
-    const size_t smem = sizeof(float) * ((fh * fw + 3) & ~3) + 2 * (size_t)((out_hw * out_hw + 15) & ~15);
-    CMDB_REQUIRE(smem <= 200 * 1024, CMDB_ERR_UNSUPPORTED, "upsample_blur: map too large for shared memory");
-    CMDB_CUDA(cudaFuncSetAttribute(upsample_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    upsample_blur_kernel<<<1, kBlurThreads, smem, stream>>>(map_dev, fh, fw, out_hw, pre_dev, out_dev, u8_dev, radius, ww, fwt);
+    const int band = (out_hw + kBlurBands - 1) / kBlurBands;
+    const size_t tile = (size_t)((band * out_hw + 15) & ~15);
+    const size_t smem1 = sizeof(float) * ((fh * fw + 3) & ~3) + 2 * tile;
+    CMDB_REQUIRE(smem1 <= 200 * 1024, CMDB_ERR_UNSUPPORTED, "upsample_blur: map too large for shared memory");
+    CMDB_CUDA(cudaFuncSetAttribute(upsample_hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    upsample_hblur_kernel<<<kBlurBands, kBlurThreads, smem1, stream>>>(map_dev, fh, fw, out_hw, band, pre_dev, u8_dev, tmp_dev,
+                                                                      mx_dev, radius, ww, fwt);
+    vblur_kernel<<<kBlurBands, kBlurThreads, 2 * tile, stream>>>(tmp_dev, out_hw, band, mx_dev, out_dev, radius, ww, fwt);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }

@@ -32,9 +32,12 @@ def test_rownorms_bit_exact_vs_oracle_and_torch_cuda(env, d):
     z64 = g.standard_normal((n, d))
     got64 = env["rownorms"](z64, z64[5])
     assert (got64 == env["O"].rownorms_restated(z64, z64[5])).all()
+    # float64 ('TF32' mode): torch-CUDA's own double reduction differs from the canonical order in the last ulp for a
+    # fraction of the rows (association not pinned); the selected indices are insensitive to it, which
+    # test_coreset_golden_case_all_modes checks free-running against torch
     zt = torch.from_numpy(z64).cuda()
     ref64 = torch.linalg.norm(zt - zt[5:6], dim=1, keepdims=True).cpu().numpy()[:, 0]
-    assert (got64 == ref64).all()
+    np.testing.assert_allclose(got64, ref64, rtol=4e-16)
 
 
 @pytest.mark.parametrize("N,D", [(3000, 768), (777, 1152), (500, 1920), (33, 64)])
