@@ -354,8 +354,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
 #pragma unroll
         for (int t = 0; t < NV; ++t) wp.vmain[t] = lane + 32 * t < wp.g.nfull;
     }
-    const long long n_batches = (wp.n_rows + RB - 1) / RB;
-    const size_t row_stride = (size_t)4 * d;  // elements between consecutive rows of this warp
+    const size_t rstride_b = (size_t)4 * d * sizeof(T);  // bytes between consecutive rows of this warp
 
     long long sel = 0;  // features.py:372 -- pick 0 is row 0
     if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[0] = 0;
@@ -371,16 +370,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
 
         T best_val = Traits<T>::zero();
         long long best_row = -1;
-        // ---- distance pass: software-pipelined stream of RB-row batches, two batches of loads in flight ----
-        RowLoads<T, NV> A[RB], B[RB];
-        const T *base = z + wp.first * d;
-        auto issue = [&](RowLoads<T, NV>(&buf)[RB], long long bidx) {
-#pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const long long k = min(bidx * RB + r, wp.n_rows - 1);  // clamp: duplicates are never stored
-                issue_row<T, NV>(buf[r], base + (size_t)k * row_stride, wp, lane, d, vectorized);
-            }
-        };
+        // ---- distance pass: software-pipelined stream of full RB-row batches (two batches of loads in flight), running
+        //      per-lane pointers instead of index arithmetic; the < RB leftover rows take a simple path ----
         auto finalize = [&](long long grp, int n_here) {
             __syncwarp();
             if (lane < n_here) {
@@ -409,21 +400,57 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             }
             __syncwarp();
         };
-        auto compute = [&](RowLoads<T, NV>(&buf)[RB], long long bidx) {
+        if (vectorized) {
+            RowLoads<T, NV> A[RB], B[RB];
+            const char *pm = reinterpret_cast<const char *>(z + wp.first * d + wp.main_off);
+            const char *ph = reinterpret_cast<const char *>(z + wp.first * d + wp.head_off);
+            const char *pt = reinterpret_cast<const char *>(z + wp.first * d + wp.tail_off);
+            auto issue = [&](RowLoads<T, NV>(&buf)[RB]) {
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const long long k = bidx * RB + r;
-                if (k < wp.n_rows) tile[(int)(k & 31) * 33 + lane] = lane_partial<T, NV>(buf[r], L, vectorized);
+                for (int r = 0; r < RB; ++r) {
+                    const T *rm = reinterpret_cast<const T *>(pm + r * rstride_b);
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        if (wp.vmain[t]) buf[r].main[t] = ldvec(rm + 128 * t);
+                        else buf[r].main[t] = zero_vec((const T *)nullptr);
+                    }
+                    buf[r].head = wp.has_head ? __ldg(reinterpret_cast<const T *>(ph + r * rstride_b)) : Traits<T>::zero();
+                    buf[r].tail = wp.has_tail ? __ldg(reinterpret_cast<const T *>(pt + r * rstride_b)) : Traits<T>::zero();
+                }
+                pm += RB * rstride_b, ph += RB * rstride_b, pt += RB * rstride_b;
+            };
+            const long long nb_full = wp.n_rows / RB;
+            if (nb_full > 0) issue(A);
+            for (long long bi = 0; bi < nb_full; bi += 2) {
+                if (bi + 1 < nb_full) issue(B);
+                {
+                    acc_t *trow = tile + (int)((bi * RB) & 31) * 33 + lane;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) trow[r * 33] = lane_partial<T, NV>(A[r], L, true);
+                    if ((((bi + 1) * RB) & 31) == 0) finalize((bi * RB) >> 5, 32);
+                }
+                if (bi + 2 < nb_full) issue(A);
+                if (bi + 1 < nb_full) {
+                    acc_t *trow = tile + (int)(((bi + 1) * RB) & 31) * 33 + lane;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) trow[r * 33] = lane_partial<T, NV>(B[r], L, true);
+                    if ((((bi + 2) * RB) & 31) == 0) finalize(((bi + 1) * RB) >> 5, 32);
+                }
             }
-            const long long k_end = min(wp.n_rows, (bidx + 1) * RB);  // rows [.., k_end) are in the tile
-            if ((k_end & 31) == 0 || k_end == wp.n_rows) finalize((k_end - 1) >> 5, (int)(k_end - (((k_end - 1) >> 5) << 5)));
-        };
-        if (n_batches > 0) issue(A, 0);
-        for (long long bi = 0; bi < n_batches; bi += 2) {
-            if (bi + 1 < n_batches) issue(B, bi + 1);
-            compute(A, bi);
-            if (bi + 2 < n_batches) issue(A, bi + 2);
-            if (bi + 1 < n_batches) compute(B, bi + 1);
+            // leftover rows (< RB) and the last, partial group of 32
+            for (long long k = nb_full * RB; k < wp.n_rows; ++k) {
+                issue_row<T, NV>(A[0], z + (wp.first + 4 * k) * d, wp, lane, d, true);
+                tile[(int)(k & 31) * 33 + lane] = lane_partial<T, NV>(A[0], L, true);
+            }
+            if (wp.n_rows & 31) finalize(wp.n_rows >> 5, (int)(wp.n_rows & 31));
+        } else {
+            // d < 128 (tiny test problems only): one row at a time
+            RowLoads<T, NV> R;
+            for (long long k = 0; k < wp.n_rows; ++k) {
+                issue_row<T, NV>(R, z + (wp.first + 4 * k) * d, wp, lane, d, false);
+                tile[(int)(k & 31) * 33 + lane] = lane_partial<T, NV>(R, L, false);
+                if ((k & 31) == 31 || k == wp.n_rows - 1) finalize(k >> 5, (int)(k & 31) + 1);
+            }
         }
         // ---- CTA argmax: warp shuffle, then shared memory ----
         unsigned long long bv = best_row < 0 ? 0ULL : Traits<T>::bits(best_val);
