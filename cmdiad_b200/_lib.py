@@ -69,11 +69,12 @@ SYMBOLS = {
     "cmdb_project": (_I, [_VP, _VP, _VP, _VP, _I, _I64, _I64, _VP]),
     "cmdb_coreset_rownorms": (_I, [_I, _VP, _VP, _I64, _I, _I, _VP]),
     "cmdb_score": (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
-    "cmdb_score_shard_min": (_I, [_VP, _VP, _I, _I, _VP]),
-    "cmdb_score_shard_select": (_I, [_VP, _VP, _I, _VP]),
-    "cmdb_score_shard_topk": (_I, [_VP, _VP, _VP]),
-    "cmdb_score_shard_nn": (_I, [_VP, _VP, _I, _VP]),
-    "cmdb_score_shard_finish": (_I, [_VP, _VP, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
+    "cmdb_score_batch": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
+    "cmdb_score_shard_min": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "cmdb_score_shard_select": (_I, [_VP, _VP, _I, _I, _VP]),
+    "cmdb_score_shard_topk": (_I, [_VP, _VP, _I, _I, _VP]),
+    "cmdb_score_shard_nn": (_I, [_VP, _VP, _I, _I, _VP]),
+    "cmdb_score_shard_finish": (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
     "cmdb_upsample_blur": (_I, [_I, _VP, _I, _I, _I, _VP, _VP, _VP]),
 }
 # test hook exported by the library but deliberately not part of the public header

@@ -144,67 +144,88 @@ class Bank:
 
     # ---- scoring ---------------------------------------------------------------------------------------------
     @staticmethod
-    def _alloc_out(P, out_hw, full):
-        r = ScoreResult()
-        r.s = np.zeros(1, np.float32)
-        r.s_star = np.zeros(1, np.float32)
-        r.s_idx = np.zeros(1, np.int64)
-        r.min_val = np.zeros(P, np.float32)
-        r.min_idx = np.zeros(P, np.int64)
-        r.nn_idx = np.zeros(3, np.int64)
-        r.m_star_knn = np.zeros(2, np.float32)
-        r.w = np.zeros(1, np.float32)
-        r.s_map = np.zeros((out_hw, out_hw), np.float32)
-        r.s_map_pre = np.zeros((out_hw, out_hw), np.float32) if full else None
-        r.s_map_u8 = np.zeros((out_hw, out_hw), np.uint8) if full else None
-        so = L.ScoreOut()
-        for name, ctype in (("s", L.c_f32_p), ("s_star", L.c_f32_p), ("s_idx", L.c_i64_p), ("min_val", L.c_f32_p),
-                            ("min_idx", L.c_i64_p), ("nn_idx", L.c_i64_p), ("m_star_knn", L.c_f32_p), ("w", L.c_f32_p),
-                            ("s_map", L.c_f32_p), ("s_map_pre", L.c_f32_p), ("s_map_u8", L.c_u8_p)):
-            a = getattr(r, name)
-            setattr(so, name, a.ctypes.data_as(ctype) if a is not None else ctype())
-        return r, so
+    def _alloc_out(B, P, out_hw, full):
+        """B ScoreResult objects viewing batch arrays + the matching array of struct cmdb_score_out"""
+        arr = dict(s=np.zeros((B, 1), np.float32), s_star=np.zeros((B, 1), np.float32), s_idx=np.zeros((B, 1), np.int64),
+                   min_val=np.zeros((B, P), np.float32), min_idx=np.zeros((B, P), np.int64), nn_idx=np.zeros((B, 3), np.int64),
+                   m_star_knn=np.zeros((B, 2), np.float32), w=np.zeros((B, 1), np.float32),
+                   s_map=np.zeros((B, out_hw, out_hw), np.float32),
+                   s_map_pre=np.zeros((B, out_hw, out_hw), np.float32) if full else None,
+                   s_map_u8=np.zeros((B, out_hw, out_hw), np.uint8) if full else None)
+        ctype = dict(s=L.c_f32_p, s_star=L.c_f32_p, s_idx=L.c_i64_p, min_val=L.c_f32_p, min_idx=L.c_i64_p, nn_idx=L.c_i64_p,
+                     m_star_knn=L.c_f32_p, w=L.c_f32_p, s_map=L.c_f32_p, s_map_pre=L.c_f32_p, s_map_u8=L.c_u8_p)
+        outs = (L.ScoreOut * B)()
+        results = []
+        for i in range(B):
+            r = ScoreResult()
+            for name, a in arr.items():
+                v = a[i] if a is not None else None
+                setattr(r, name, v)
+                setattr(outs[i], name, v.ctypes.data_as(ctype[name]) if v is not None else ctype[name]())
+            results.append(r)
+        return results, outs, arr
 
     def score(self, patch, feature_map_dims, out_hw=224, full=False):
         """calculate_dist + compute_single_s_s_map for one image; patch [P,dim] float32, already normalised."""
         patch = _as_f32(patch)
-        P = patch.shape[0]
+        return self.score_batch(patch.unsqueeze(0), feature_map_dims, out_hw, full)[0]
+
+    def score_batch(self, patches, feature_map_dims, out_hw=224, full=False):
+        """B images at once: patches [B,P,dim] float32 (host or device).  Returns a list of B ScoreResult."""
+        patches = _as_f32(patches)
+        assert patches.dim() == 3 and patches.shape[2] == self.dim, f"expected [B,P,{self.dim}], got {tuple(patches.shape)}"
+        B, P = patches.shape[0], patches.shape[1]
         fh, fw = feature_map_dims
-        r, so = self._alloc_out(P, out_hw, full)
-        L.check(self._lib.cmdb_score(self._h, _ptr(patch), P, int(fh), int(fw), int(out_hw), int(patch.is_cuda),
-                                     ctypes.byref(so)))
-        return r
+        results, outs, _ = self._alloc_out(B, P, out_hw, full)
+        L.check(self._lib.cmdb_score_batch(self._h, _ptr(patches), B, P, int(fh), int(fw), int(out_hw), int(patches.is_cuda),
+                                           outs))
+        return results
+
+    def max_shard_batch(self):
+        """images per round of the sharded protocol (shared-memory bound of the re-weighting kernel)"""
+        return max(1, min(32, (160 * 1024) // (4 * self.dim + 8 * 3 * 8)))
 
     def score_sharded(self, patch, feature_map_dims, out_hw=224, full=False, group=None):
-        """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; the five phases
-        of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between."""
-        import torch.distributed as dist
         patch = _as_f32(patch)
-        P = patch.shape[0]
+        return self.score_sharded_batch(patch.unsqueeze(0), feature_map_dims, out_hw, full, group)[0]
+
+    def score_sharded_batch(self, patches, feature_map_dims, out_hw=224, full=False, group=None):
+        """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; the five phases
+        of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between.  The collectives are
+        per batch, not per image, so their latency is amortised over B images."""
+        import torch.distributed as dist
+        patches = _as_f32(patches)
+        Btot, P = patches.shape[0], patches.shape[1]
         fh, fw = feature_map_dims
         dev = torch.device("cuda", self.device)
         world = dist.get_world_size(group)
-        keys = torch.empty(P, dtype=torch.int64, device=dev)
-        L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(patch), P, int(patch.is_cuda), _ptr(keys)))
-        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
-        m_star = torch.empty(self.dim, dtype=torch.float32, device=dev)
-        torch.cuda.current_stream(dev).synchronize()
-        L.check(self._lib.cmdb_score_shard_select(self._h, _ptr(keys), P, _ptr(m_star)))
-        dist.all_reduce(m_star, op=dist.ReduceOp.SUM, group=group)
-        top = torch.empty(3, dtype=torch.int64, device=dev)
-        torch.cuda.current_stream(dev).synchronize()
-        L.check(self._lib.cmdb_score_shard_topk(self._h, _ptr(m_star), _ptr(top)))
-        gathered = torch.empty(3 * world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, top, group=group)
-        nn_rows = torch.empty(3 * self.dim, dtype=torch.float32, device=dev)
-        torch.cuda.current_stream(dev).synchronize()
-        L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), 3 * world, _ptr(nn_rows)))
-        dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.current_stream(dev).synchronize()
-        r, so = self._alloc_out(P, out_hw, full)
-        L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), P, int(fh), int(fw), int(out_hw),
-                                                  ctypes.byref(so)))
-        return r
+        results = []
+        step = self.max_shard_batch()
+        cur = torch.cuda.current_stream(dev)
+        for b0 in range(0, Btot, step):
+            chunk = patches[b0:b0 + step]
+            B = chunk.shape[0]
+            keys = torch.empty(B * P, dtype=torch.int64, device=dev)
+            L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+            m_star = torch.empty(B * self.dim, dtype=torch.float32, device=dev)
+            cur.synchronize()
+            L.check(self._lib.cmdb_score_shard_select(self._h, _ptr(keys), B, P, _ptr(m_star)))
+            dist.all_reduce(m_star, op=dist.ReduceOp.SUM, group=group)
+            top = torch.empty(B * 3, dtype=torch.int64, device=dev)
+            cur.synchronize()
+            L.check(self._lib.cmdb_score_shard_topk(self._h, _ptr(m_star), B, P, _ptr(top)))
+            gathered = torch.empty(world * B * 3, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, top, group=group)
+            nn_rows = torch.empty(B * 3 * self.dim, dtype=torch.float32, device=dev)
+            cur.synchronize()
+            L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), world, B, _ptr(nn_rows)))
+            dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
+            cur.synchronize()
+            res, outs, _ = self._alloc_out(B, P, out_hw, full)
+            L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), B, P, int(fh), int(fw), int(out_hw), outs))
+            results.extend(res)
+        return results
 
 
 def upsample_blur(s_map, out_hw=224, device=0):

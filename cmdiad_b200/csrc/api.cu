@@ -24,7 +24,7 @@ __global__ void pack_keys_kernel(const float *__restrict__ min_val, const long l
                         : (long long)(((unsigned long long)__float_as_uint(min_val[i]) << 32) | (unsigned long long)g);
     }
 }
-__global__ void unpack_keys_kernel(const long long *__restrict__ keys, int P, float *__restrict__ min_val,
+__global__ void unpack_keys_kernel(const long long *__restrict__ keys, int P, int P_img, float *__restrict__ min_val,
                                    long long *__restrict__ min_idx, unsigned long long *s_key) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P) {
@@ -32,7 +32,7 @@ __global__ void unpack_keys_kernel(const long long *__restrict__ keys, int P, fl
         const float v = __uint_as_float((unsigned int)(k >> 32));
         min_val[i] = v;
         min_idx[i] = (long long)(k & 0xffffffffULL);
-        atomicMax(s_key, ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - (unsigned int)i));
+        atomicMax(s_key + i / P_img, ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - (unsigned int)(i % P_img)));
     }
 }
 // out[c] = bank[global_row - offset][c] if this shard owns the row, else 0
@@ -46,60 +46,74 @@ __global__ void contrib_rows_kernel(const float *__restrict__ bank, long long ro
         out[i] = (g >= 0 && l >= 0 && l < rows) ? bank[(size_t)l * dim + c] : 0.f;
     }
 }
-__global__ void m_star_row_kernel(const void *tail, long long *out) { *out = reinterpret_cast<const TailResult *>(tail)->m_star_row; }
 
-static int check_score_args(cmdb_bank *b, const void *patch, int P, const char *fn) {
+static int check_score_args(cmdb_bank *b, const void *patch, int B, int P, const char *fn) {
     CMDB_REQUIRE(b && patch, CMDB_ERR_INVALID, "%s: NULL argument", fn);
     CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "%s: call cmdb_bank_finalize first", fn);
     CMDB_REQUIRE(P >= 1 && P <= (1 << 20), CMDB_ERR_INVALID, "%s: P=%d out of range", fn, P);
+    CMDB_REQUIRE(B >= 1 && B <= 4096, CMDB_ERR_INVALID, "%s: batch=%d out of range", fn, B);
     return CMDB_OK;
 }
 
-static int stage_patch(cmdb_bank *b, const float *patch, int P, int is_device, int out_hw) {
+static int stage_patch(cmdb_bank *b, const float *patch, int B, int P, int is_device, int out_hw) {
     CMDB_CUDA(cudaSetDevice(b->device));
-    CMDB_CHECK(score_scratch_alloc(b, P, out_hw));
-    CMDB_CUDA(cudaMemcpyAsync(b->ss.q_f32, patch, sizeof(float) * (size_t)P * b->dim,
+    CMDB_CHECK(score_scratch_alloc(b, B, P, out_hw));
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.q_f32, patch, sizeof(float) * (size_t)B * P * b->dim,
                               is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
     return CMDB_OK;
 }
 
-static int local_min(cmdb_bank *b, int P) {
+static int local_min(cmdb_bank *b, int B, int P) {
     int n_cand = 0;
     if (b->score_impl == CMDB_SCORE_TCGEN05) {
-        CMDB_CHECK(score_query_prep(b, P));
-        CMDB_CHECK(score_gemm_candidates(b, P, &n_cand));
+        CMDB_CHECK(score_query_prep(b, B * P));
+        CMDB_CHECK(score_gemm_candidates(b, B * P, &n_cand));
     } else {
-        CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
+        CMDB_CHECK(score_simt_candidates(b, B * P, &n_cand));
     }
-    return score_refine(b, P, n_cand);
+    return score_refine(b, B, P, n_cand);
 }
 
-static int copy_outputs(cmdb_bank *b, int P, int out_hw, cmdb_score_out *out) {
+// one device->host copy of the result block of a sub-batch, then scatter into the caller's buffers
+static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     const size_t npix = (size_t)out_hw * out_hw;
-    // one device->host copy of the result block (through the optional debug maps only when they are wanted)
-    size_t bytes = s.off_map_out + sizeof(float) * npix;
-    if (out->s_map_pre) bytes = s.off_map_pre + sizeof(float) * npix;
-    if (out->s_map_u8) bytes = s.off_map_u8 + npix;
+    bool want_pre = false, want_u8 = false;
+    for (int i = 0; i < B; ++i) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
+    size_t bytes = s.off_map_out + sizeof(float) * s.map_stride * B;
+    if (want_pre) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
+    if (want_u8) bytes = s.off_map_u8 + s.map_stride * B;
     CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, bytes, cudaMemcpyDeviceToHost, st));
     CMDB_CUDA(cudaStreamSynchronize(st));
     const unsigned char *h = s.out_block_host;
-    TailResult tr;
-    memcpy(&tr, h, sizeof(tr));
-    if (out->min_val) memcpy(out->min_val, h + s.off_min_val, sizeof(float) * P);
-    if (out->min_idx) memcpy(out->min_idx, h + s.off_min_idx, sizeof(long long) * P);
-    if (out->s_map) memcpy(out->s_map, h + s.off_map_out, sizeof(float) * npix);
-    if (out->s_map_pre) memcpy(out->s_map_pre, h + s.off_map_pre, sizeof(float) * npix);
-    if (out->s_map_u8) memcpy(out->s_map_u8, h + s.off_map_u8, npix);
-    if (out->s) *out->s = tr.s;
-    if (out->s_star) *out->s_star = tr.s_star;
-    if (out->s_idx) *out->s_idx = tr.s_idx;
-    if (out->w) *out->w = tr.w;
-    if (out->m_star_knn) out->m_star_knn[0] = tr.knn0, out->m_star_knn[1] = tr.knn1;
-    if (out->nn_idx)
-        for (int k = 0; k < 3; ++k) out->nn_idx[k] = tr.nn_idx[k];
+    for (int i = 0; i < B; ++i) {
+        cmdb_score_out *out = outs + i;
+        TailResult tr;
+        memcpy(&tr, h + sizeof(TailResult) * i, sizeof(tr));
+        if (out->min_val) memcpy(out->min_val, h + s.off_min_val + sizeof(float) * (size_t)i * P, sizeof(float) * P);
+        if (out->min_idx) memcpy(out->min_idx, h + s.off_min_idx + sizeof(long long) * (size_t)i * P, sizeof(long long) * P);
+        if (out->s_map) memcpy(out->s_map, h + s.off_map_out + sizeof(float) * s.map_stride * i, sizeof(float) * npix);
+        if (out->s_map_pre) memcpy(out->s_map_pre, h + s.off_map_pre + sizeof(float) * s.map_stride * i, sizeof(float) * npix);
+        if (out->s_map_u8) memcpy(out->s_map_u8, h + s.off_map_u8 + s.map_stride * i, npix);
+        if (out->s) *out->s = tr.s;
+        if (out->s_star) *out->s_star = tr.s_star;
+        if (out->s_idx) *out->s_idx = tr.s_idx;
+        if (out->w) *out->w = tr.w;
+        if (out->m_star_knn) out->m_star_knn[0] = tr.knn0, out->m_star_knn[1] = tr.knn1;
+        if (out->nn_idx)
+            for (int k = 0; k < 3; ++k) out->nn_idx[k] = tr.nn_idx[k];
+    }
     return CMDB_OK;
+}
+
+static int blur_batch(cmdb_bank *b, int B, int P, int fh, int fw, int out_hw) {
+    ScoreScratch &s = b->ss;
+    // the map sections of the result block are laid out with a fixed per-image stride
+    CMDB_REQUIRE((size_t)out_hw * out_hw == s.map_stride || B == 1, CMDB_ERR_INVALID,
+                 "scoring: out_hw changed within a batch-capable scratch (got %d)", out_hw);
+    (void)P;
+    return upsample_blur_launch(b->stream, B, s.min_val, fh, fw, out_hw, s.map_pre, s.map_out, s.map_u8, s.map_tmp, s.map_max);
 }
 
 }  // namespace cmdb
@@ -169,111 +183,135 @@ int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host,
     return coreset_rownorms(device, z_host, last_host, n_rows, d, dtype_mode, out_host);
 }
 
-int cmdb_score(cmdb_bank *b, const float *patch, int P, int fh, int fw, int out_hw, int patch_is_device,
-               cmdb_score_out *out) {
-    CMDB_CHECK(check_score_args(b, patch, P, "cmdb_score"));
-    CMDB_REQUIRE(out, CMDB_ERR_INVALID, "cmdb_score: out is NULL");
-    CMDB_REQUIRE(fh > 0 && fw > 0 && fh * fw == P, CMDB_ERR_INVALID, "cmdb_score: feature_map_dims %dx%d != P=%d", fh, fw, P);
+int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, int fw, int out_hw, int patch_is_device,
+                     cmdb_score_out *outs) {
+    CMDB_CHECK(check_score_args(b, patches, B, P, "cmdb_score_batch"));
+    CMDB_REQUIRE(outs, CMDB_ERR_INVALID, "cmdb_score_batch: outs is NULL");
+    CMDB_REQUIRE(fh > 0 && fw > 0 && fh * fw == P, CMDB_ERR_INVALID, "cmdb_score_batch: feature_map_dims %dx%d != P=%d", fh,
+                 fw, P);
+    CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_batch: out_hw=%d not in [8,256]", out_hw);
 #define CMDB_MARK(i)                                                   \
     do {                                                               \
         if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[i], b->stream)); \
     } while (0)
     CMDB_CUDA(cudaSetDevice(b->device));
-    CMDB_MARK(CMDB_T_STAGE_IN);
-    CMDB_CHECK(stage_patch(b, patch, P, patch_is_device, out_hw));
-    int n_cand = 0;
-    if (b->score_impl == CMDB_SCORE_TCGEN05) {
-        CMDB_CHECK(score_query_prep(b, P));
-        CMDB_MARK(CMDB_T_GEMM);
-        CMDB_CHECK(score_gemm_candidates(b, P, &n_cand));
-    } else {
-        CMDB_MARK(CMDB_T_GEMM);
-        CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
-    }
-    CMDB_MARK(CMDB_T_REFINE);
-    CMDB_CHECK(score_refine(b, P, n_cand));
-    CMDB_MARK(CMDB_T_REWEIGHT);
-    CMDB_CHECK(score_reweight(b, true));
-    CMDB_MARK(CMDB_T_MAP);
-    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8, b->ss.map_tmp, b->ss.map_max));
-    CMDB_MARK(CMDB_T_OUT);
-    const int rc = copy_outputs(b, P, out_hw, out);
-    if (b->timing && rc == CMDB_OK) {
-        CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->stream));
-        CMDB_CUDA(cudaEventSynchronize(b->ev[CMDB_T_COUNT]));
-        b->ev_valid = true;
+    const int bc_max = score_max_batch(b);
+    if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);  // map stride is fixed per scratch
+    for (int b0 = 0; b0 < B; b0 += bc_max) {
+        const int bc = std::min(bc_max, B - b0);
+        const float *src = patches + (size_t)b0 * P * b->dim;
+        CMDB_MARK(CMDB_T_STAGE_IN);
+        CMDB_CHECK(stage_patch(b, src, bc, P, patch_is_device, out_hw));
+        int n_cand = 0;
+        if (b->score_impl == CMDB_SCORE_TCGEN05) {
+            CMDB_CHECK(score_query_prep(b, bc * P));
+            CMDB_MARK(CMDB_T_GEMM);
+            CMDB_CHECK(score_gemm_candidates(b, bc * P, &n_cand));
+        } else {
+            CMDB_MARK(CMDB_T_GEMM);
+            CMDB_CHECK(score_simt_candidates(b, bc * P, &n_cand));
+        }
+        CMDB_MARK(CMDB_T_REFINE);
+        CMDB_CHECK(score_refine(b, bc, P, n_cand));
+        CMDB_MARK(CMDB_T_REWEIGHT);
+        CMDB_CHECK(score_reweight(b, bc, P, true));
+        CMDB_MARK(CMDB_T_MAP);
+        CMDB_CHECK(blur_batch(b, bc, P, fh, fw, out_hw));
+        CMDB_MARK(CMDB_T_OUT);
+        CMDB_CHECK(copy_outputs(b, bc, P, out_hw, outs + b0));
+        if (b->timing) {  // timings describe the last sub-batch
+            CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->stream));
+            CMDB_CUDA(cudaEventSynchronize(b->ev[CMDB_T_COUNT]));
+            b->ev_valid = true;
+        }
     }
 #undef CMDB_MARK
-    return rc;
+    return CMDB_OK;
 }
 
-int cmdb_score_shard_min(cmdb_bank *b, const float *patch, int P, int patch_is_device, int64_t *keys_device) {
-    CMDB_CHECK(check_score_args(b, patch, P, "cmdb_score_shard_min"));
+int cmdb_score(cmdb_bank *b, const float *patch, int P, int fh, int fw, int out_hw, int patch_is_device,
+               cmdb_score_out *out) {
+    return cmdb_score_batch(b, patch, 1, P, fh, fw, out_hw, patch_is_device, out);
+}
+
+static int check_shard_batch(cmdb_bank *b, int B, const char *fn) {
+    CMDB_REQUIRE(B >= 1 && B <= score_max_batch(b), CMDB_ERR_INVALID, "%s: batch=%d exceeds the per-call limit %d", fn, B,
+                 score_max_batch(b));
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int patch_is_device, int out_hw,
+                         int64_t *keys_device) {
+    CMDB_CHECK(check_score_args(b, patches, B, P, "cmdb_score_shard_min"));
+    CMDB_CHECK(check_shard_batch(b, B, "cmdb_score_shard_min"));
     CMDB_REQUIRE(keys_device, CMDB_ERR_INVALID, "cmdb_score_shard_min: keys_device is NULL");
-    CMDB_CHECK(stage_patch(b, patch, P, patch_is_device, 224));
-    CMDB_CHECK(local_min(b, P));
-    pack_keys_kernel<<<(P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, P, (long long *)keys_device);
+    CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_shard_min: out_hw=%d not in [8,256]", out_hw);
+    CMDB_CUDA(cudaSetDevice(b->device));
+    if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
+    CMDB_CHECK(stage_patch(b, patches, B, P, patch_is_device, out_hw));
+    CMDB_CHECK(local_min(b, B, P));
+    pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
     CMDB_CUDA(cudaStreamSynchronize(b->stream));  // the caller's collective runs on another stream
     return CMDB_OK;
 }
 
-int cmdb_score_shard_select(cmdb_bank *b, const int64_t *reduced_keys_device, int P, float *m_star_contrib_device) {
-    CMDB_CHECK(check_score_args(b, reduced_keys_device, P, "cmdb_score_shard_select"));
-    CMDB_REQUIRE(m_star_contrib_device && P <= b->ss.cap_p, CMDB_ERR_INVALID, "cmdb_score_shard_select: bad arguments");
+int cmdb_score_shard_select(cmdb_bank *b, const int64_t *reduced_keys_device, int B, int P, float *m_star_contrib_device) {
+    CMDB_CHECK(check_score_args(b, reduced_keys_device, B, P, "cmdb_score_shard_select"));
+    CMDB_REQUIRE(m_star_contrib_device && B * P <= b->ss.cap_p && B <= b->ss.cap_b, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_select: bad arguments (call cmdb_score_shard_min first)");
     CMDB_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = b->stream;
-    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long), st));
-    unpack_keys_kernel<<<(P + 255) / 256, 256, 0, st>>>((const long long *)reduced_keys_device, P, b->ss.min_val,
-                                                        b->ss.min_idx, b->ss.s_key);
-    CMDB_CHECK(score_select(b, false));
-    long long *row_dev = reinterpret_cast<long long *>(b->ss.top3);  // scratch, overwritten later by the merge
-    m_star_row_kernel<<<1, 1, 0, st>>>(b->ss.tail, row_dev);
-    contrib_rows_kernel<<<4, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, row_dev, nullptr, 1,
-                                           m_star_contrib_device);
-    CMDB_CUDA(cudaGetLastError());
+    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long) * B, st));
+    unpack_keys_kernel<<<(B * P + 255) / 256, 256, 0, st>>>((const long long *)reduced_keys_device, B * P, P, b->ss.min_val,
+                                                            b->ss.min_idx, b->ss.s_key);
+    CMDB_CHECK(score_select(b, B, P, true));  // m_star rows this rank owns, zeros elsewhere
+    CMDB_CUDA(cudaMemcpyAsync(m_star_contrib_device, b->ss.m_star, sizeof(float) * (size_t)B * b->dim, cudaMemcpyDeviceToDevice, st));
     CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
 }
 
-int cmdb_score_shard_topk(cmdb_bank *b, const float *m_star_device, int64_t *topk_keys_device) {
-    CMDB_CHECK(check_score_args(b, m_star_device, 1, "cmdb_score_shard_topk"));
-    CMDB_REQUIRE(topk_keys_device && b->ss.cap_p > 0, CMDB_ERR_INVALID, "cmdb_score_shard_topk: bad arguments");
+int cmdb_score_shard_topk(cmdb_bank *b, const float *m_star_device, int B, int P, int64_t *topk_keys_device) {
+    CMDB_CHECK(check_score_args(b, m_star_device, B, P, "cmdb_score_shard_topk"));
+    CMDB_REQUIRE(topk_keys_device && B <= b->ss.cap_b, CMDB_ERR_INVALID, "cmdb_score_shard_topk: bad arguments");
     CMDB_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = b->stream;
-    CMDB_CUDA(cudaMemcpyAsync(b->ss.m_star, m_star_device, sizeof(float) * b->dim, cudaMemcpyDeviceToDevice, st));
-    CMDB_CHECK(score_reweight(b, false));
-    CMDB_CUDA(cudaMemcpyAsync(topk_keys_device, b->ss.top3, sizeof(long long) * 3, cudaMemcpyDeviceToDevice, st));
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.m_star, m_star_device, sizeof(float) * (size_t)B * b->dim, cudaMemcpyDeviceToDevice, st));
+    CMDB_CHECK(score_reweight(b, B, P, false));
+    CMDB_CUDA(cudaMemcpyAsync(topk_keys_device, b->ss.top3, sizeof(long long) * 3 * B, cudaMemcpyDeviceToDevice, st));
     CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
 }
 
-int cmdb_score_shard_nn(cmdb_bank *b, const int64_t *gathered_keys_device, int n_keys, float *nn_rows_contrib_device) {
-    CMDB_CHECK(check_score_args(b, gathered_keys_device, 1, "cmdb_score_shard_nn"));
-    CMDB_REQUIRE(nn_rows_contrib_device && n_keys >= 3 && n_keys <= 3 * b->ss.n_topk_blocks, CMDB_ERR_INVALID,
+int cmdb_score_shard_nn(cmdb_bank *b, const int64_t *gathered_keys_device, int n_ranks, int B, float *nn_rows_contrib_device) {
+    CMDB_CHECK(check_score_args(b, gathered_keys_device, B, 1, "cmdb_score_shard_nn"));
+    CMDB_REQUIRE(nn_rows_contrib_device && n_ranks >= 1 && n_ranks <= b->ss.n_topk_blocks && B <= b->ss.cap_b, CMDB_ERR_INVALID,
                  "cmdb_score_shard_nn: bad arguments");
     CMDB_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = b->stream;
-    CMDB_CUDA(cudaMemcpyAsync(b->ss.topk_keys, gathered_keys_device, sizeof(long long) * n_keys, cudaMemcpyDeviceToDevice, st));
-    CMDB_CHECK(score_merge_top3(b, n_keys));
-    contrib_rows_kernel<<<8, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, nullptr, b->ss.top3, 3,
-                                           nn_rows_contrib_device);
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.topk_keys, gathered_keys_device, sizeof(long long) * 3 * (size_t)n_ranks * B,
+                              cudaMemcpyDeviceToDevice, st));
+    CMDB_CHECK(score_merge_top3(b, n_ranks, B));
+    contrib_rows_kernel<<<8 * B, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, nullptr, b->ss.top3, 3 * B,
+                                               nn_rows_contrib_device);
     CMDB_CUDA(cudaGetLastError());
     CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
 }
 
-int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int P, int fh, int fw, int out_hw,
-                            cmdb_score_out *out) {
-    CMDB_CHECK(check_score_args(b, nn_rows_device, P, "cmdb_score_shard_finish"));
-    CMDB_REQUIRE(out && fh > 0 && fw > 0 && fh * fw == P && P <= b->ss.cap_p, CMDB_ERR_INVALID,
+int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int B, int P, int fh, int fw, int out_hw,
+                            cmdb_score_out *outs) {
+    CMDB_CHECK(check_score_args(b, nn_rows_device, B, P, "cmdb_score_shard_finish"));
+    CMDB_REQUIRE(outs && fh > 0 && fw > 0 && fh * fw == P && B * P <= b->ss.cap_p && B <= b->ss.cap_b, CMDB_ERR_INVALID,
                  "cmdb_score_shard_finish: bad arguments");
-    CMDB_REQUIRE(out_hw * out_hw <= b->ss.map_cap, CMDB_ERR_INVALID, "cmdb_score_shard_finish: out_hw larger than in phase 1");
+    CMDB_REQUIRE((size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_finish: out_hw differs from cmdb_score_shard_min");
     CMDB_CUDA(cudaSetDevice(b->device));
-    CMDB_CUDA(cudaMemcpyAsync(b->ss.nn_rows, nn_rows_device, sizeof(float) * 3 * b->dim, cudaMemcpyDeviceToDevice, b->stream));
-    CMDB_CHECK(score_final(b, true));
-    CMDB_CHECK(upsample_blur_launch(b->stream, b->ss.min_val, fh, fw, out_hw, b->ss.map_pre, b->ss.map_out, b->ss.map_u8, b->ss.map_tmp, b->ss.map_max));
-    return copy_outputs(b, P, out_hw, out);
+    CMDB_CUDA(cudaMemcpyAsync(b->ss.nn_rows, nn_rows_device, sizeof(float) * 3 * (size_t)B * b->dim, cudaMemcpyDeviceToDevice,
+                              b->stream));
+    CMDB_CHECK(score_final(b, B));
+    CMDB_CHECK(blur_batch(b, B, P, fh, fw, out_hw));
+    return copy_outputs(b, B, P, out_hw, outs);
 }
 
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host, float *out_pre_host,
@@ -298,7 +336,7 @@ int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int ou
     if (e == cudaSuccess) e = cudaMalloc(&u8, npix);
     if (e == cudaSuccess) e = cudaMemcpy(in, map_host, sizeof(float) * fh * fw, cudaMemcpyHostToDevice);
     int rc = CMDB_OK;
-    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, in, fh, fw, out_hw, pre, o, u8, tmp, mx);
+    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, 1, in, fh, fw, out_hw, pre, o, u8, tmp, mx);
     if (e == cudaSuccess && rc == CMDB_OK) e = cudaMemcpy(out_host, o, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_pre_host) e = cudaMemcpy(out_pre_host, pre, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_u8_host) e = cudaMemcpy(out_u8_host, u8, npix, cudaMemcpyDeviceToHost);

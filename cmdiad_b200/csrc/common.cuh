@@ -46,12 +46,11 @@ constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 
 
 // device scratch of one scoring call, sized at finalize time
 struct ScoreScratch {
-    int cap_p = 0;                  // padded query capacity (multiple of 128)
+    int cap_p = 0;                  // padded query-row capacity of a sub-batch (multiple of 128)
+    int cap_b = 0;                  // image capacity of a sub-batch
     float *q_f32 = nullptr;         // [cap_p, D]  normalised query patches
     __half *q_hi = nullptr;         // [cap_p, D]  split-fp16 query operand
     __half *q_lo = nullptr;
-    float *q_norm = nullptr;        // [cap_p]     ||q||^2
-    unsigned int *q_absmax = nullptr;  // float bits of max|q|
     int *q_scale_exp = nullptr;     // device [cap_p]: per-row exponent e_q with q_hi + q_lo = q * 2^e_q
     void *tmap_qhi = nullptr;       // host CUtensorMap objects for q_hi / q_lo
     void *tmap_qlo = nullptr;
@@ -72,6 +71,7 @@ struct ScoreScratch {
     unsigned char *out_block = nullptr;
     unsigned char *out_block_host = nullptr;  // cudaMallocHost
     size_t off_min_val = 0, off_min_idx = 0, off_map_out = 0, off_map_pre = 0, off_map_u8 = 0, out_block_bytes = 0;
+    size_t map_stride = 0;  // pixels reserved per image in the map sections
     float *map_pre = nullptr;       // [out_hw^2]
     float *map_out = nullptr;
     unsigned char *map_u8 = nullptr;
@@ -129,7 +129,8 @@ int coreset_rownorms(int device, const void *z_host, const void *last_host, int6
                      void *out_host);
 
 // score_gemm.cu
-int score_scratch_alloc(cmdb_bank *b, int P, int out_hw);
+int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw);
+int score_max_batch(const cmdb_bank *b);  // images per internal sub-batch (shared-memory bound of reweight_kernel)
 void score_scratch_free(cmdb_bank *b);
 int score_make_tensor_maps(cmdb_bank *b);
 int score_query_prep(cmdb_bank *b, int P);  // q_f32 -> q_hi / q_lo (device-side scale selection)
@@ -143,12 +144,12 @@ struct TailResult {  // device-side result block (ScoreScratch::tail)
     long long m_star_row;  // global row of m_star
 };
 int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out);
-int score_refine(cmdb_bank *b, int P, int n_cand);
-int score_select(cmdb_bank *b, bool local_m_star);
-int score_reweight(cmdb_bank *b, bool fused);
-int score_merge_top3(cmdb_bank *b, int n_keys);
-int score_final(cmdb_bank *b, bool use_nn_rows);
-int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
+int score_refine(cmdb_bank *b, int B, int P_img, int n_cand);
+int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star);
+int score_reweight(cmdb_bank *b, int B, int P_img, bool fused);
+int score_merge_top3(cmdb_bank *b, int n_ranks, int B);
+int score_final(cmdb_bank *b, int B);
+int upsample_blur_launch(cudaStream_t stream, int B, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
                          float *out_dev, unsigned char *u8_dev, unsigned char *tmp_dev, float *mx_dev);
 
 }  // namespace cmdb

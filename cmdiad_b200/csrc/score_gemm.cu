@@ -358,7 +358,7 @@ int score_make_tensor_maps(cmdb_bank *b) {
 
 void score_scratch_free(cmdb_bank *b) {
     ScoreScratch &s = b->ss;
-    cudaFree(s.q_f32), cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_norm), cudaFree(s.q_absmax), cudaFree(s.q_scale_exp);
+    cudaFree(s.q_f32), cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_scale_exp);
     cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys), cudaFree(s.out_block);
     cudaFree(s.map_tmp), cudaFree(s.map_max), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
     cudaFree(s.top3), cudaFree(s.done_counter);
@@ -367,31 +367,36 @@ void score_scratch_free(cmdb_bank *b) {
     s = ScoreScratch();
 }
 
-int score_scratch_alloc(cmdb_bank *b, int P, int out_hw) {
+int score_max_batch(const cmdb_bank *b) {
+    // reweight_kernel keeps B m_star rows (B*dim floats) + 8*B*3 keys in shared memory
+    const int by_smem = (int)((160 * 1024) / (sizeof(float) * b->dim + 8 * 3 * sizeof(unsigned long long)));
+    return std::max(1, std::min(32, by_smem));
+}
+
+int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     ScoreScratch &s = b->ss;
-    const int p_pad = (P + BM - 1) / BM * BM;
+    const int p_pad = (B * P_img + BM - 1) / BM * BM;
     const int map_n = out_hw * out_hw;
-    if (s.cap_p >= p_pad && s.map_cap >= map_n) return CMDB_OK;
-    const int cap_p = std::max(p_pad, s.cap_p), map_cap = std::max(map_n, s.map_cap);
+    if (s.cap_p >= p_pad && s.cap_b >= B && (int)s.map_stride >= map_n) return CMDB_OK;
+    const int cap_p = std::max(p_pad, s.cap_p), cap_b = std::max(B, s.cap_b), map_cap = std::max(map_n, (int)s.map_stride);
     score_scratch_free(b);
     const size_t D = b->dim;
     s.n_topk_blocks = b->num_sms * 4;
     CMDB_CUDA(cudaMalloc(&s.q_f32, sizeof(float) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_hi, sizeof(__half) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
-    CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
-    CMDB_CUDA(cudaMalloc(&s.q_absmax, sizeof(unsigned int)));
     CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int) * cap_p));
     CMDB_CUDA(cudaMalloc(&s.done_counter, sizeof(unsigned int)));
     CMDB_CUDA(cudaMemset(s.done_counter, 0, sizeof(unsigned int)));
     CMDB_CUDA(cudaMalloc(&s.cand, sizeof(float4) * (size_t)cap_p * b->num_sms));
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
-    s.off_min_val = up(sizeof(TailResult));
+    s.map_stride = map_cap;
+    s.off_min_val = up(sizeof(TailResult) * cap_b);
     s.off_min_idx = s.off_min_val + up(sizeof(float) * cap_p);
     s.off_map_out = s.off_min_idx + up(sizeof(long long) * cap_p);
-    s.off_map_pre = s.off_map_out + up(sizeof(float) * map_cap);
-    s.off_map_u8 = s.off_map_pre + up(sizeof(float) * map_cap);
-    s.out_block_bytes = s.off_map_u8 + up(map_cap);
+    s.off_map_pre = s.off_map_out + up(sizeof(float) * map_cap * cap_b);
+    s.off_map_u8 = s.off_map_pre + up(sizeof(float) * map_cap * cap_b);
+    s.out_block_bytes = s.off_map_u8 + up((size_t)map_cap * cap_b);
     CMDB_CUDA(cudaMalloc(&s.out_block, s.out_block_bytes));
     CMDB_CUDA(cudaMallocHost(&s.out_block_host, s.out_block_bytes));
     s.tail = s.out_block;
@@ -400,15 +405,15 @@ int score_scratch_alloc(cmdb_bank *b, int P, int out_hw) {
     s.map_out = reinterpret_cast<float *>(s.out_block + s.off_map_out);
     s.map_pre = reinterpret_cast<float *>(s.out_block + s.off_map_pre);
     s.map_u8 = s.out_block + s.off_map_u8;
-    CMDB_CUDA(cudaMalloc(&s.map_tmp, map_cap));
-    CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float)));
-    CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long)));
-    CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks));
-    CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3));
-    CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D));
-    CMDB_CUDA(cudaMalloc(&s.m_star, sizeof(float) * D));
-    CMDB_CUDA(cudaMalloc(&s.nn_rows, sizeof(float) * 3 * D));
-    s.cap_p = cap_p, s.map_cap = map_cap;
+    CMDB_CUDA(cudaMalloc(&s.map_tmp, (size_t)map_cap * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long) * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3 * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.m_star, sizeof(float) * D * cap_b));
+    CMDB_CUDA(cudaMalloc(&s.nn_rows, sizeof(float) * 3 * D * cap_b));
+    s.cap_p = cap_p, s.cap_b = cap_b, s.map_cap = map_cap;
     CMDB_CHECK(make_map(&s.tmap_qhi, s.q_hi, cap_p, b->dim, BM));
     CMDB_CHECK(make_map(&s.tmap_qlo, s.q_lo, cap_p, b->dim, BM));
     return CMDB_OK;

@@ -41,8 +41,9 @@ constexpr int kRefineTop = 4;
 
 __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
-                                                     int P, long long row_offset, float *__restrict__ min_val,
+                                                     int P, int P_img, long long row_offset, float *__restrict__ min_val,
                                                      long long *__restrict__ min_idx, unsigned long long *s_key) {
+    // P = total query rows of the batch (B images of P_img patches each); s_key[b] is image b's packed argmax
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= P) return;
@@ -103,8 +104,9 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
         const float dv = sqrtf(best);
         min_val[qi] = dv;
         min_idx[qi] = best_i < 0 ? -1 : (long long)best_i + row_offset;
-        // argmax over queries, ties -> lowest query: max of (value bits, ~query)
-        atomicMax(s_key, ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)qi));
+        // argmax over the image's queries, ties -> lowest query: max of (value bits, ~query)
+        atomicMax(s_key + qi / P_img,
+                  ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
     }
 }
 
@@ -197,38 +199,40 @@ int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     return CMDB_OK;
 }
 
-int score_refine(cmdb_bank *b, int P, int n_cand) {
-    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long), b->stream));
-    refine_kernel<<<(P + 7) / 8, 256, 0, b->stream>>>(b->ss.cand, n_cand, b->num_sms, b->ss.q_f32, b->data, b->dim, P,
+int score_refine(cmdb_bank *b, int B, int P_img, int n_cand) {
+    const int P = B * P_img;
+    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long) * B, b->stream));
+    refine_kernel<<<(P + 7) / 8, 256, 0, b->stream>>>(b->ss.cand, n_cand, b->num_sms, b->ss.q_f32, b->data, b->dim, P, P_img,
                                                       b->row_offset, b->ss.min_val, b->ss.min_idx, b->ss.s_key);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// select: decode the argmax key, stage m_test and (single-GPU) m_star rows
+// select (sharded mode): image b = blockIdx.x: decode the argmax key, stage m_test and (if owned locally) m_star
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) select_kernel(const unsigned long long *s_key, const long long *min_idx,
+__global__ void __launch_bounds__(256) select_kernel(const unsigned long long *s_key, const long long *min_idx, int P_img,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                      long long row_offset, long long rows, float *m_test, float *m_star,
                                                      TailResult *res) {
-    const unsigned long long key = *s_key;
+    const int b = blockIdx.x;
+    const unsigned long long key = s_key[b];
     const int s_idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffu));
-    const long long g = min_idx[s_idx];
+    const long long g = min_idx[(size_t)b * P_img + s_idx];
     for (int c = threadIdx.x; c < dim; c += blockDim.x) {
-        m_test[c] = q[(size_t)s_idx * dim + c];
+        m_test[(size_t)b * dim + c] = q[((size_t)b * P_img + s_idx) * dim + c];
         const long long l = g - row_offset;
-        if (m_star && l >= 0 && l < rows) m_star[c] = bank[(size_t)l * dim + c];
+        if (m_star) m_star[(size_t)b * dim + c] = (l >= 0 && l < rows) ? bank[(size_t)l * dim + c] : 0.f;
     }
     if (threadIdx.x == 0) {
-        res->s_idx = s_idx;
-        res->s_star = __uint_as_float((unsigned int)(key >> 32));
-        res->m_star_row = g;
+        res[b].s_idx = s_idx;
+        res[b].s_star = __uint_as_float((unsigned int)(key >> 32));
+        res[b].m_star_row = g;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// reweight: exact ||m_star - bank_r||^2 for every local bank row, 3 smallest as packed keys
+// reweight: exact ||m_star_b - bank_r||^2 for every local bank row and every image b of the batch, 3 smallest per image
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void top3_insert(unsigned long long (&t)[3], unsigned long long k) {
     if (k < t[2]) {
@@ -241,11 +245,13 @@ __device__ __forceinline__ void top3_insert(unsigned long long (&t)[3], unsigned
         }
     }
 }
-
-// block-wide 3 smallest of the per-thread sorted triples t[]: three rounds of "everyone offers its head, winner pops"
-__device__ __forceinline__ void block_top3(unsigned long long (&t)[3], unsigned long long *sh /* [8] */,
-                                           unsigned long long (&out)[3]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void top3_insert_sh(unsigned long long *t, unsigned long long k) {  // t[3] in shared memory
+    unsigned long long r[3] = {t[0], t[1], t[2]};
+    top3_insert(r, k);
+    t[0] = r[0], t[1] = r[1], t[2] = r[2];
+}
+// warp-wide 3 smallest of per-lane sorted triples (keys unique): "everyone offers its head, the winner pops" x3
+__device__ __forceinline__ void warp_top3(unsigned long long (&t)[3], unsigned long long (&out)[3]) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         unsigned long long v = t[0];
@@ -254,155 +260,175 @@ __device__ __forceinline__ void block_top3(unsigned long long (&t)[3], unsigned 
             const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
             v = ov < v ? ov : v;
         }
-        __syncthreads();
-        if (lane == 0) sh[warp] = v;
-        __syncthreads();
-        v = sh[0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) v = sh[w] < v ? sh[w] : v;
         out[r] = v;
-        if (v != ~0ULL && t[0] == v) t[0] = t[1], t[1] = t[2], t[2] = ~0ULL;  // keys are unique (row in the low bits)
+        if (v != ~0ULL && t[0] == v) t[0] = t[1], t[1] = t[2], t[2] = ~0ULL;
     }
 }
 
 struct ReweightParams {
     const float *bank;               // [rows, dim] float32 (local shard)
     long long rows, row_offset;
-    int dim;
-    const float *q;                  // [P, dim] normalised patches
-    const unsigned long long *s_key; // packed argmax of min_val
-    const long long *min_idx;        // [P] global rows
-    const float *m_star_explicit;    // sharded mode: replicated m_star row; NULL = take it from the local bank
-    unsigned long long *block_keys;  // [gridDim.x * 3]
-    unsigned long long *top3;        // [3] merged result
+    int dim, B, P_img;
+    const float *q;                  // [B*P_img, dim] normalised patches
+    const unsigned long long *s_key; // [B] packed argmax of min_val
+    const long long *min_idx;        // [B*P_img] global rows
+    const float *m_star_explicit;    // sharded mode: replicated m_star rows [B, dim]; NULL = take them from the local bank
+    unsigned long long *block_keys;  // [B][gridDim.x * 3]
+    unsigned long long *top3;        // [B][3] merged result
     unsigned int *done_counter;      // last-block-done counter (self resetting)
-    TailResult *res;
+    TailResult *res;                 // [B]
     int fuse_final;                  // 1: the last block also computes m_star_knn, w, s (single-GPU path)
 };
 
-// w_dist pass (features.py:239-254): exact ||m_star - bank_r||^2 for every local bank row, 3 smallest.
-// Prologue = "select" (decode s*, s_idx, locate m_star); epilogue = last-block-done merge (+ final re-weighting), so the
-// whole re-weighting stage is one launch.  HBM bound: rows*dim*4 bytes.
+// w_dist pass (features.py:239-254) for a batch of B images in ONE sweep over the bank: every warp keeps a bank row in
+// registers and evaluates its exact squared distance to all B m_star rows (shared memory), so the bank is read once
+// per batch (rows*dim*4 bytes).  Prologue = "select" (decode s*, s_idx, locate m_star); epilogue = last-block-done
+// merge (+ final re-weighting), so the whole re-weighting stage is one launch.
+template <int DV>  // float4 vectors per lane: ceil(dim / 128)
 __global__ void __launch_bounds__(256) reweight_kernel(ReweightParams p) {
-    extern __shared__ __align__(16) float ms[];
-    __shared__ unsigned long long wk[8];
+    extern __shared__ __align__(16) float ms[];  // [B][dim] m_star rows, then wtop [8][B][3]
+    const int dim = p.dim, B = p.B;
+    unsigned long long *wtop = reinterpret_cast<unsigned long long *>(ms + (size_t)B * dim);
+    __shared__ int s_idx_sh[32];
+    __shared__ long long g_sh[32];
     __shared__ bool is_last;
-    __shared__ float knn[2];
-    const unsigned long long skey = *p.s_key;
-    const int s_idx = (int)(0xffffffffu - (unsigned int)(skey & 0xffffffffu));
-    const long long g_star = p.min_idx[s_idx];
-    const float *m_star = p.m_star_explicit ? p.m_star_explicit : p.bank + (size_t)(g_star - p.row_offset) * p.dim;
-    for (int c = threadIdx.x; c < p.dim; c += blockDim.x) ms[c] = m_star[c];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int dim = p.dim, dim4 = dim >> 2;
-    unsigned long long t[3] = {~0ULL, ~0ULL, ~0ULL};
+    if (threadIdx.x < B) {
+        const unsigned long long skey = p.s_key[threadIdx.x];
+        const int s_idx = (int)(0xffffffffu - (unsigned int)(skey & 0xffffffffu));
+        s_idx_sh[threadIdx.x] = s_idx;
+        g_sh[threadIdx.x] = p.min_idx[(size_t)threadIdx.x * p.P_img + s_idx];
+    }
+    for (int i = threadIdx.x; i < 8 * B * 3; i += blockDim.x) wtop[i] = ~0ULL;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * dim; i += blockDim.x) {
+        const int b = i / dim, c = i - b * dim;
+        ms[i] = p.m_star_explicit ? p.m_star_explicit[i] : p.bank[(size_t)(g_sh[b] - p.row_offset) * dim + c];
+    }
+    __syncthreads();
+    const float4 *ms4 = reinterpret_cast<const float4 *>(ms);
+    const int dim4 = dim >> 2;
+    unsigned long long *my_top = wtop + (size_t)warp * B * 3;
     const long long warps = (long long)gridDim.x * 8;
-    // two rows in flight per warp
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < p.rows; r += 2 * warps) {
-        const long long r2 = r + warps;
-        const bool has2 = r2 < p.rows;
-        const float4 *a = reinterpret_cast<const float4 *>(p.bank + (size_t)r * dim);
-        const float4 *a2 = reinterpret_cast<const float4 *>(p.bank + (size_t)(has2 ? r2 : r) * dim);
-        float acc = 0.f, acc2 = 0.f;
-        for (int c = lane; c < dim4; c += 32) {
-            const float4 x = __ldg(a + c), x2 = __ldg(a2 + c);
-            const float4 y = reinterpret_cast<const float4 *>(ms)[c];
-            float d;
-            d = x.x - y.x, acc = fmaf(d, d, acc);
-            d = x.y - y.y, acc = fmaf(d, d, acc);
-            d = x.z - y.z, acc = fmaf(d, d, acc);
-            d = x.w - y.w, acc = fmaf(d, d, acc);
-            d = x2.x - y.x, acc2 = fmaf(d, d, acc2);
-            d = x2.y - y.y, acc2 = fmaf(d, d, acc2);
-            d = x2.z - y.z, acc2 = fmaf(d, d, acc2);
-            d = x2.w - y.w, acc2 = fmaf(d, d, acc2);
+    long long r = (long long)blockIdx.x * 8 + warp;
+    float4 x[DV], xn[DV];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool valid[DV];  // dim is a multiple of 64: the last vector may cover only lanes 0..15
+#pragma unroll
+    for (int j = 0; j < DV; ++j) valid[j] = lane + 32 * j < dim4, x[j] = zero4, xn[j] = zero4;
+    if (r < p.rows) {
+#pragma unroll
+        for (int j = 0; j < DV; ++j)
+            if (valid[j]) x[j] = __ldg(reinterpret_cast<const float4 *>(p.bank + (size_t)r * dim) + lane + 32 * j);
+    }
+    for (; r < p.rows; r += warps) {
+        const long long rn = r + warps;
+        if (rn < p.rows) {  // prefetch the next row while this one is compared with the B targets
+#pragma unroll
+            for (int j = 0; j < DV; ++j)
+                if (valid[j]) xn[j] = __ldg(reinterpret_cast<const float4 *>(p.bank + (size_t)rn * dim) + lane + 32 * j);
+        }
+        const unsigned int grow = (unsigned int)(r + p.row_offset);
+        for (int b = 0; b < B; ++b) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < DV; ++j) {
+                const float4 y = valid[j] ? ms4[b * dim4 + lane + 32 * j] : zero4;
+                float d;
+                d = x[j].x - y.x, acc = fmaf(d, d, acc);
+                d = x[j].y - y.y, acc = fmaf(d, d, acc);
+                d = x[j].z - y.z, acc = fmaf(d, d, acc);
+                d = x[j].w - y.w, acc = fmaf(d, d, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const unsigned long long key = pack_min_key(acc, grow);
+                if (key < my_top[b * 3 + 2]) top3_insert_sh(my_top + b * 3, key);
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-        }
-        if (lane == 0) {  // one copy per warp keeps the keys unique for block_top3
-            top3_insert(t, pack_min_key(acc, (unsigned int)(r + p.row_offset)));
-            if (has2) top3_insert(t, pack_min_key(acc2, (unsigned int)(r2 + p.row_offset)));
-        }
+        for (int j = 0; j < DV; ++j) x[j] = xn[j];
     }
-    unsigned long long f[3];
-    block_top3(t, wk, f);
-    if (threadIdx.x == 0) {
-        p.block_keys[blockIdx.x * 3 + 0] = f[0];
-        p.block_keys[blockIdx.x * 3 + 1] = f[1];
-        p.block_keys[blockIdx.x * 3 + 2] = f[2];
-        __threadfence();
-        is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    // block result per image: merge the 8 warps' triples
+    if (threadIdx.x < B) {
+        unsigned long long f[3] = {~0ULL, ~0ULL, ~0ULL};
+        for (int w = 0; w < 8; ++w)
+            for (int k = 0; k < 3; ++k) top3_insert(f, wtop[((size_t)w * B + threadIdx.x) * 3 + k]);
+        unsigned long long *dst = p.block_keys + ((size_t)threadIdx.x * gridDim.x + blockIdx.x) * 3;
+        dst[0] = f[0], dst[1] = f[1], dst[2] = f[2];
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!is_last) return;
-    // ---- last block: merge every block's keys, then (single-GPU path) finish the re-weighting ----
+    // ---- last block: one warp per image merges every block's keys, then (single-GPU path) finishes the re-weighting ----
     __threadfence();
-    t[0] = t[1] = t[2] = ~0ULL;
-    for (int i = threadIdx.x; i < (int)gridDim.x * 3; i += blockDim.x) top3_insert(t, __ldcg(p.block_keys + i));
-    block_top3(t, wk, f);
-    if (threadIdx.x == 0) {
-        p.top3[0] = f[0], p.top3[1] = f[1], p.top3[2] = f[2];
-        *p.done_counter = 0;
-        p.res->s_idx = s_idx;
-        p.res->s_star = __uint_as_float((unsigned int)(skey >> 32));
-        p.res->m_star_row = g_star;
-        for (int k = 0; k < 3; ++k) p.res->nn_idx[k] = f[k] == ~0ULL ? -1 : (long long)(f[k] & 0xffffffffULL);
-    }
-    if (!p.fuse_final) return;
-    // features.py:275-283: m_star_knn = ||m_test - bank[nn_idx[1:]]||, m_test = patch[s_idx]
-    if (warp < 2) {
-        const unsigned long long key = f[1 + warp];
-        float d2 = 0.f;
-        if (key != ~0ULL)
-            d2 = warp_sqdist(p.q + (size_t)s_idx * dim, p.bank + (size_t)((long long)(key & 0xffffffffULL) - p.row_offset) * dim,
-                             dim4, lane);
-        if (lane == 0) knn[warp] = key != ~0ULL ? sqrtf(d2) : NAN;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))  (features.py:285)
+    if (threadIdx.x == 0) *p.done_counter = 0;
+    for (int b = warp; b < B; b += 8) {
+        unsigned long long t[3] = {~0ULL, ~0ULL, ~0ULL}, f[3];
+        const unsigned long long *src = p.block_keys + (size_t)b * gridDim.x * 3;
+        for (int i = lane; i < (int)gridDim.x * 3; i += 32) top3_insert(t, __ldcg(src + i));
+        warp_top3(t, f);
+        const unsigned long long skey = p.s_key[b];
         const float s_star = __uint_as_float((unsigned int)(skey >> 32));
-        const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
-        const float w = 1.f - expf(s_star / Dn) / den;  // features.py:287
-        p.res->w = w;
-        p.res->s = w * s_star;                          // features.py:290
-        p.res->knn0 = knn[0], p.res->knn1 = knn[1];
+        const int s_idx = s_idx_sh[b];
+        float knn[2] = {NAN, NAN};
+        if (p.fuse_final) {  // features.py:275-283: m_star_knn = ||m_test - bank[nn_idx[1:]]||, m_test = patch[s_idx]
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (f[1 + k] != ~0ULL)
+                    knn[k] = sqrtf(warp_sqdist(p.q + ((size_t)b * p.P_img + s_idx) * dim,
+                                               p.bank + (size_t)((long long)(f[1 + k] & 0xffffffffULL) - p.row_offset) * dim,
+                                               dim4, lane));
+        }
+        if (lane == 0) {
+            TailResult *res = p.res + b;
+            p.top3[b * 3 + 0] = f[0], p.top3[b * 3 + 1] = f[1], p.top3[b * 3 + 2] = f[2];
+            res->s_idx = s_idx;
+            res->s_star = s_star;
+            res->m_star_row = g_sh[b];
+            for (int k = 0; k < 3; ++k) res->nn_idx[k] = f[k] == ~0ULL ? -1 : (long long)(f[k] & 0xffffffffULL);
+            if (p.fuse_final) {
+                const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))  (features.py:285)
+                const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
+                const float w = 1.f - expf(s_star / Dn) / den;  // features.py:287
+                res->w = w;
+                res->s = w * s_star;  // features.py:290
+                res->knn0 = knn[0], res->knn1 = knn[1];
+            }
+        }
     }
 }
 
-// merge gathered keys -> 3 smallest (one block; sharded mode, after the all-gather)
-__global__ void __launch_bounds__(256) merge_top3_kernel(const unsigned long long *__restrict__ keys, int n_keys,
-                                                         unsigned long long *__restrict__ out3) {
-    __shared__ unsigned long long wk[8];
+// sharded mode, after the all-gather: image b = blockIdx.x merges the keys of all ranks ([rank][B][3] layout)
+__global__ void __launch_bounds__(32) merge_top3_kernel(const unsigned long long *__restrict__ gathered, int n_ranks, int B,
+                                                        unsigned long long *__restrict__ out3) {
+    const int b = blockIdx.x, lane = threadIdx.x;
     unsigned long long t[3] = {~0ULL, ~0ULL, ~0ULL}, f[3];
-    for (int i = threadIdx.x; i < n_keys; i += blockDim.x) top3_insert(t, keys[i]);
-    block_top3(t, wk, f);
-    if (threadIdx.x == 0) out3[0] = f[0], out3[1] = f[1], out3[2] = f[2];
+    for (int i = lane; i < n_ranks * 3; i += 32) top3_insert(t, gathered[((size_t)(i / 3) * B + b) * 3 + i % 3]);
+    warp_top3(t, f);
+    if (lane == 0) out3[b * 3 + 0] = f[0], out3[b * 3 + 1] = f[1], out3[b * 3 + 2] = f[2];
 }
 
-// final: m_star_knn = ||m_test - bank[nn[1:]]|| (features.py:275-283), w and s (:285-290).  nn_rows: optional
-// [3][dim] rows supplied by the caller (sharded mode); otherwise rows are read from the local bank.
-__global__ void __launch_bounds__(64) final_kernel(const unsigned long long *__restrict__ keys3, const float *__restrict__ m_test,
-                                                   const float *__restrict__ bank, const float *__restrict__ nn_rows, int dim,
-                                                   long long row_offset, TailResult *res) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 2 warps: one per neighbour
+// final (sharded mode): image b = blockIdx.x.  m_star_knn = ||m_test - nn_rows[1:]|| (features.py:275-283), w and s
+// (:285-290); nn_rows [B][3][dim] are the replicated neighbour rows.
+__global__ void __launch_bounds__(64) final_kernel(const unsigned long long *__restrict__ top3, const float *__restrict__ m_test,
+                                                   const float *__restrict__ nn_rows, int dim, TailResult *res_all) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 2 warps: one per neighbour
     __shared__ float knn[2];
+    const unsigned long long *keys3 = top3 + b * 3;
+    TailResult *res = res_all + b;
     const unsigned long long key = keys3[1 + warp];
-    const long long g = (long long)(key & 0xffffffffULL);
     const bool valid = key != ~0ULL;
     float d2 = 0.f;
-    if (valid) {
-        const float *row = nn_rows ? nn_rows + (size_t)(1 + warp) * dim : bank + (size_t)(g - row_offset) * dim;
-        d2 = warp_sqdist(m_test, row, dim >> 2, lane);
-    }
+    if (valid) d2 = warp_sqdist(m_test + (size_t)b * dim, nn_rows + ((size_t)b * 3 + 1 + warp) * dim, dim >> 2, lane);
     if (lane == 0) knn[warp] = valid ? sqrtf(d2) : NAN;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))
+        const float Dn = sqrtf((float)dim);
         const float s_star = res->s_star;
         const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
         const float w = 1.f - expf(s_star / Dn) / den;
@@ -467,6 +493,12 @@ __global__ void __launch_bounds__(kBlurThreads) upsample_hblur_kernel(const floa
                                                                       unsigned char *__restrict__ tmp, float *__restrict__ mx_out,
                                                                       int radius, unsigned int ww, unsigned int fwt) {
     extern __shared__ __align__(16) unsigned char sm[];
+    {  // image of the batch = blockIdx.y
+        const size_t img = blockIdx.y, npix_ = (size_t)out_hw * out_hw;
+        map_in += img * fh * fw_, tmp += img * npix_, mx_out += img;
+        if (pre) pre += img * npix_;
+        if (u8_out) u8_out += img * npix_;
+    }
     float *in_s = reinterpret_cast<float *>(sm);                    // [fh*fw]
     unsigned char *A = sm + sizeof(float) * ((fh * fw_ + 3) & ~3);  // [band][out_hw]
     unsigned char *B = A + ((band * out_hw + 15) & ~15);
@@ -510,6 +542,7 @@ __global__ void __launch_bounds__(kBlurThreads) vblur_kernel(const unsigned char
                                                              const float *__restrict__ mx_in, float *__restrict__ out,
                                                              int radius, unsigned int ww, unsigned int fwt) {
     extern __shared__ __align__(16) unsigned char sm[];
+    tmp += (size_t)blockIdx.y * out_hw * out_hw, out += (size_t)blockIdx.y * out_hw * out_hw, mx_in += blockIdx.y;
     const int x0 = blockIdx.x * band, cols = min(band, out_hw - x0);
     if (cols <= 0) return;
     unsigned char *A = sm;  // [out_hw][cols]: column band, lines = columns (stride 1), pass axis = rows (stride cols)
@@ -533,43 +566,57 @@ __global__ void __launch_bounds__(kBlurThreads) vblur_kernel(const unsigned char
     }
 }
 
-int score_select(cmdb_bank *b, bool local_m_star) {
-    select_kernel<<<1, 256, 0, b->stream>>>(b->ss.s_key, b->ss.min_idx, b->ss.q_f32, b->data, b->dim, b->row_offset,
+int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star) {
+    select_kernel<<<B, 256, 0, b->stream>>>(b->ss.s_key, b->ss.min_idx, P_img, b->ss.q_f32, b->data, b->dim, b->row_offset,
                                             b->fin_rows, b->ss.m_test, local_m_star ? b->ss.m_star : nullptr,
                                             reinterpret_cast<TailResult *>(b->ss.tail));
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
-// fused = single-GPU path (select prologue + merge + final in one launch); otherwise m_star comes from ss.m_star and only
-// the merged top-3 keys are produced
-int score_reweight(cmdb_bank *b, bool fused) {
+// fused = single-GPU path (select prologue + merge + final in one launch); otherwise the m_star rows come from
+// ss.m_star and only the merged top-3 keys (+ s*, s_idx) are produced
+int score_reweight(cmdb_bank *b, int B, int P_img, bool fused) {
     ReweightParams p{};
-    p.bank = b->data, p.rows = b->fin_rows, p.row_offset = b->row_offset, p.dim = b->dim;
+    p.bank = b->data, p.rows = b->fin_rows, p.row_offset = b->row_offset, p.dim = b->dim, p.B = B, p.P_img = P_img;
     p.q = b->ss.q_f32, p.s_key = b->ss.s_key, p.min_idx = b->ss.min_idx;
     p.m_star_explicit = fused ? nullptr : b->ss.m_star;
     p.block_keys = b->ss.topk_keys, p.top3 = b->ss.top3, p.done_counter = b->ss.done_counter;
     p.res = reinterpret_cast<TailResult *>(b->ss.tail);
     p.fuse_final = fused ? 1 : 0;
-    reweight_kernel<<<b->ss.n_topk_blocks, 256, sizeof(float) * b->dim, b->stream>>>(p);
+    const size_t smem = sizeof(float) * (size_t)B * b->dim + sizeof(unsigned long long) * 8 * B * 3;
+    const int blocks = b->ss.n_topk_blocks;
+#define CMDB_RW(DVV)                                                                                              \
+    case DVV:                                                                                                     \
+        CMDB_CUDA(cudaFuncSetAttribute(reweight_kernel<DVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        reweight_kernel<DVV><<<blocks, 256, smem, b->stream>>>(p);                                                \
+        break;
+    switch ((b->dim / 4 + 31) / 32) {
+        CMDB_RW(1) CMDB_RW(2) CMDB_RW(3) CMDB_RW(4) CMDB_RW(5) CMDB_RW(6) CMDB_RW(7) CMDB_RW(8) CMDB_RW(9) CMDB_RW(10)
+        CMDB_RW(11) CMDB_RW(12) CMDB_RW(13) CMDB_RW(14) CMDB_RW(15) CMDB_RW(16)
+        default:
+            set_error("scoring: dim=%d exceeds the supported 2048", b->dim);
+            return CMDB_ERR_UNSUPPORTED;
+    }
+#undef CMDB_RW
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
-int score_merge_top3(cmdb_bank *b, int n_keys) {
-    merge_top3_kernel<<<1, 256, 0, b->stream>>>(b->ss.topk_keys, n_keys, b->ss.top3);
+int score_merge_top3(cmdb_bank *b, int n_ranks, int B) {
+    merge_top3_kernel<<<B, 32, 0, b->stream>>>(b->ss.topk_keys, n_ranks, B, b->ss.top3);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
-int score_final(cmdb_bank *b, bool use_nn_rows) {
-    final_kernel<<<1, 64, 0, b->stream>>>(b->ss.top3, b->ss.m_test, b->data, use_nn_rows ? b->ss.nn_rows : nullptr, b->dim,
-                                          b->row_offset, reinterpret_cast<TailResult *>(b->ss.tail));
+int score_final(cmdb_bank *b, int B) {
+    final_kernel<<<B, 64, 0, b->stream>>>(b->ss.top3, b->ss.m_test, b->ss.nn_rows, b->dim,
+                                          reinterpret_cast<TailResult *>(b->ss.tail));
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
-int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
+int upsample_blur_launch(cudaStream_t stream, int B, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
                          float *out_dev, unsigned char *u8_dev, unsigned char *tmp_dev, float *mx_dev) {
     CMDB_REQUIRE(fh > 0 && fw > 0 && out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID,
                  "upsample_blur: need out_hw in [8,256] (got %d) and positive map dims", out_hw);
@@ -589,9 +636,9 @@ int upsample_blur_launch(cudaStream_t stream, const float *map_dev, int fh, int 
     const size_t smem1 = sizeof(float) * ((fh * fw + 3) & ~3) + 2 * tile;
     CMDB_REQUIRE(smem1 <= 200 * 1024, CMDB_ERR_UNSUPPORTED, "upsample_blur: map too large for shared memory");
     CMDB_CUDA(cudaFuncSetAttribute(upsample_hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    upsample_hblur_kernel<<<kBlurBands, kBlurThreads, smem1, stream>>>(map_dev, fh, fw, out_hw, band, pre_dev, u8_dev, tmp_dev,
-                                                                      mx_dev, radius, ww, fwt);
-    vblur_kernel<<<kBlurBands, kBlurThreads, 2 * tile, stream>>>(tmp_dev, out_hw, band, mx_dev, out_dev, radius, ww, fwt);
+    upsample_hblur_kernel<<<dim3(kBlurBands, B), kBlurThreads, smem1, stream>>>(map_dev, fh, fw, out_hw, band, pre_dev, u8_dev,
+                                                                               tmp_dev, mx_dev, radius, ww, fwt);
+    vblur_kernel<<<dim3(kBlurBands, B), kBlurThreads, 2 * tile, stream>>>(tmp_dev, out_hw, band, mx_dev, out_dev, radius, ww, fwt);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }

@@ -140,24 +140,36 @@ int cmdb_score(cmdb_bank *bank, const float *patch, int P, int fh, int fw, int o
                cmdb_score_out *out);
 
 /*
- * Row-sharded scoring (one process per GPU, SURVEY 8e).  Every rank holds a contiguous block of bank rows
- * (cmdb_bank_set_row_offset) and the full, replicated patch.  All buffers named *_device are device memory on the
- * bank's GPU, owned by the caller (torch tensors), so the collectives between the phases run on them directly:
- *   1. cmdb_score_shard_min     keys[p] = (float_bits(local min distance) << 32) | global_row   -> all-reduce MIN (int64)
- *      (non-negative, so integer MIN == argmin with lowest-global-row tie-break)
- *   2. cmdb_score_shard_select  decodes the reduced keys (min_val, min_idx, s_star, s_idx); writes m_star = the winning
- *      bank row if this rank owns it, zeros otherwise                                           -> all-reduce SUM (float[dim])
- *   3. cmdb_score_shard_topk    3 smallest local w_dist keys for the (now replicated) m_star     -> all-gather (int64[3])
- *   4. cmdb_score_shard_nn      merges the gathered keys; writes the rows of the 3 neighbours this rank owns, zeros
- *      otherwise                                                                                -> all-reduce SUM (float[3*dim])
- *   5. cmdb_score_shard_finish  m_star_knn, w, s, upsample + blur; identical result on every rank.
+ * Batch form: B images of P patches each, patches float32 [B, P, dim], outs[B].  One sweep of the distance GEMM and ONE
+ * sweep of the bank for the re-weighting serve the whole batch (the reference scores train and test images one by one,
+ * cmdiad_runner.py:58-65, 80-85; per-image results are identical to B calls of cmdb_score).  Large batches are
+ * processed in internal sub-batches.
  */
-int cmdb_score_shard_min(cmdb_bank *bank, const float *patch, int P, int patch_is_device, int64_t *keys_device);
-int cmdb_score_shard_select(cmdb_bank *bank, const int64_t *reduced_keys_device, int P, float *m_star_contrib_device);
-int cmdb_score_shard_topk(cmdb_bank *bank, const float *m_star_device, int64_t *topk_keys_device);
-int cmdb_score_shard_nn(cmdb_bank *bank, const int64_t *gathered_keys_device, int n_keys, float *nn_rows_contrib_device);
-int cmdb_score_shard_finish(cmdb_bank *bank, const float *nn_rows_device, int P, int fh, int fw, int out_hw,
-                            cmdb_score_out *out);
+int cmdb_score_batch(cmdb_bank *bank, const float *patches, int B, int P, int fh, int fw, int out_hw, int patch_is_device,
+                     cmdb_score_out *outs);
+
+/*
+ * Row-sharded scoring (one process per GPU, SURVEY 8e).  Every rank holds a contiguous block of bank rows
+ * (cmdb_bank_set_row_offset) and the full, replicated batch of patches.  All buffers named *_device are device memory on
+ * the bank's GPU, owned by the caller (torch tensors), so the collectives between the phases run on them directly.
+ * B images per round (B <= 32 and B*dim*4 <= 160 KB); all five phases of one round use the same B, P, out_hw:
+ *   1. cmdb_score_shard_min     keys[b*P+p] = (float_bits(local min distance) << 32) | global_row  -> all-reduce MIN (int64)
+ *      (non-negative, so integer MIN == argmin with lowest-global-row tie-break)
+ *   2. cmdb_score_shard_select  decodes the reduced keys (min_val, min_idx, s_star, s_idx per image); writes m_star[b] =
+ *      the winning bank row if this rank owns it, zeros otherwise                                  -> all-reduce SUM (float[B*dim])
+ *   3. cmdb_score_shard_topk    3 smallest local w_dist keys per image for the replicated m_star   -> all-gather (int64[B*3])
+ *   4. cmdb_score_shard_nn      merges the gathered keys ([rank][B][3]); writes the neighbour rows this rank owns, zeros
+ *      otherwise                                                                                   -> all-reduce SUM (float[B*3*dim])
+ *   5. cmdb_score_shard_finish  m_star_knn, w, s, upsample + blur; identical results on every rank.
+ */
+int cmdb_score_shard_min(cmdb_bank *bank, const float *patches, int B, int P, int patch_is_device, int out_hw,
+                         int64_t *keys_device);
+int cmdb_score_shard_select(cmdb_bank *bank, const int64_t *reduced_keys_device, int B, int P, float *m_star_contrib_device);
+int cmdb_score_shard_topk(cmdb_bank *bank, const float *m_star_device, int B, int P, int64_t *topk_keys_device);
+int cmdb_score_shard_nn(cmdb_bank *bank, const int64_t *gathered_keys_device, int n_ranks, int B,
+                        float *nn_rows_contrib_device);
+int cmdb_score_shard_finish(cmdb_bank *bank, const float *nn_rows_device, int B, int P, int fh, int fw, int out_hw,
+                            cmdb_score_out *outs);
 
 /* Stand-alone score-map post-processing (features.py:293-295, utils/utils.py:71-83): map [fh*fw] -> [out_hw^2]. */
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host,

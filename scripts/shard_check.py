@@ -23,6 +23,15 @@ full = Bank(D, R, device=local)
 full.append(lib)
 full.finalize()
 bad = 0
+# batch form: 5 images per round of collectives
+pb = np.stack([synth.patches(P, D, seed=80 + t, anomalous_frac=0.01, cent=cent) for t in range(5)])
+ab = shard.score_sharded_batch(pb, (28, 28), 224, full=True)
+bb = full.score_batch(pb, (28, 28), 224, full=True)
+for t in range(5):
+    same = all((getattr(ab[t], n) == getattr(bb[t], n)).all() for n in ("min_idx", "min_val", "s", "s_idx", "nn_idx", "s_map", "w"))
+    bad += int(not same)
+    if rank == 0:
+        print(f"batch image {t}: sharded == single-GPU: {same}", flush=True)
 for t in range(3):
     patch = synth.patches(P, D, seed=50 + t, anomalous_frac=0.01, cent=cent)
     a = shard.score_sharded(patch, (28, 28), 224, full=True)

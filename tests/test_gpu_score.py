@@ -103,6 +103,27 @@ def test_score_tcgen05_equals_simt(env):
     b.close()
 
 
+@pytest.mark.parametrize("B,P,fm,D", [(5, 784, 28, 768), (3, 3136, 56, 768), (40, 100, 10, 128), (18, 784, 28, 1920)])
+def test_score_batch_equals_single_calls(env, B, P, fm, D):
+    """cmdb_score_batch (one GEMM sweep + one re-weighting sweep for B images, internal sub-batches) must give exactly
+    the per-image results of B separate cmdb_score calls"""
+    from cmdiad_b200 import synth
+    cent = synth.centroids(D, 128)
+    lib = synth.patches(3000, D, seed=21, cent=cent)
+    patches = np.stack([synth.patches(P, D, seed=300 + i, anomalous_frac=0.01, cent=cent) for i in range(B)])
+    b = _bank(env, lib)
+    batch = b.score_batch(patches, (fm, fm), 224, full=True)
+    assert len(batch) == B
+    for i in (0, 1, B // 2, B - 1):
+        one = b.score(patches[i], (fm, fm), 224, full=True)
+        for name in ("s", "s_star", "s_idx", "min_val", "min_idx", "nn_idx", "m_star_knn", "w", "s_map", "s_map_pre", "s_map_u8"):
+            assert (getattr(batch[i], name) == getattr(one, name)).all(), (i, name)
+    # device-resident input gives the same result
+    dev = b.score_batch(torch.from_numpy(patches).cuda(), (fm, fm), 224)
+    assert all((dev[i].s_map == batch[i].s_map).all() and dev[i].s[0] == batch[i].s[0] for i in range(B))
+    b.close()
+
+
 def test_score_duplicate_rows_lowest_index(env):
     """exact ties in the bank: argmin must be the lowest row (torch.min semantics, features.py:227)"""
     from cmdiad_b200 import synth
