@@ -175,7 +175,7 @@ def run_ours(args):
     def step(patches):
         if world == 1:
             return bank.score_batch(patches, dims, OUT_HW)
-        return bank.score_sharded_batch(patches, dims, OUT_HW)
+        return bank.score_sharded_batch(patches, dims, OUT_HW, distribute=True)
 
     def timed(patches, steps, collect_stage=False):
         """K steps between barriers; device time from CUDA events on the bank's stream, max over ranks"""
@@ -225,7 +225,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "bank_rows": BANK_ROWS, "dim": DIM, "patches_per_image": P,
                        "images_per_step": B,
-                       "sharding": "single GPU" if world == 1 else f"bank row-sharded over {world} GPUs, NCCL MIN/SUM/all-gather",
+                       "sharding": "single GPU" if world == 1 else f"bank row-sharded over {world} GPUs, 4 NCCL collectives (MIN/SUM/all-gather) "
+                                                                    f"per step, map + device->host of image i on rank i % {world}",
                        "l2": "inputs larger than L2: the bank streams 1.2 GB (fp16 hi+lo, fp32 rows) per step vs 126 MB of L2"},
             "e2e": {"value": e2e, "unit": "patch-NN scores/s", "h2d_bytes_per_step": B * P * DIM * 4,
                     "d2h_bytes_per_step": B * (OUT_HW * OUT_HW * 4 + P * 12 + 64)},

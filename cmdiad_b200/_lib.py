@@ -74,7 +74,7 @@ SYMBOLS = {
     "cmdb_score_shard_select": (_I, [_VP, _VP, _I, _I, _VP]),
     "cmdb_score_shard_topk": (_I, [_VP, _VP, _I, _I, _VP]),
     "cmdb_score_shard_nn": (_I, [_VP, _VP, _I, _I, _VP]),
-    "cmdb_score_shard_finish": (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
+    "cmdb_score_shard_finish": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
     "cmdb_upsample_blur": (_I, [_I, _VP, _I, _I, _I, _VP, _VP, _VP]),
 }
 # test hook exported by the library but deliberately not part of the public header

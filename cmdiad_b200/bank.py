@@ -189,42 +189,46 @@ class Bank:
         patch = _as_f32(patch)
         return self.score_sharded_batch(patch.unsqueeze(0), feature_map_dims, out_hw, full, group)[0]
 
-    def score_sharded_batch(self, patches, feature_map_dims, out_hw=224, full=False, group=None):
+    def score_sharded_batch(self, patches, feature_map_dims, out_hw=224, full=False, group=None, distribute=False):
         """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; the five phases
-        of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between.  The collectives are
-        per batch, not per image, so their latency is amortised over B images."""
+        of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between.  Kernels and
+        collectives are all enqueued on the handle's stream, so there is no host synchronisation between the phases,
+        and the collectives are per round of up to 32 images, not per image.
+        distribute=False: every rank returns all results.  distribute=True: rank r finishes (blur, device->host) only
+        images r, r+world, ... and returns None for the others."""
         import torch.distributed as dist
         patches = _as_f32(patches)
         Btot, P = patches.shape[0], patches.shape[1]
         fh, fw = feature_map_dims
         dev = torch.device("cuda", self.device)
-        world = dist.get_world_size(group)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
         results = []
         step = self.max_shard_batch()
-        cur = torch.cuda.current_stream(dev)
-        for b0 in range(0, Btot, step):
-            chunk = patches[b0:b0 + step]
-            B = chunk.shape[0]
-            keys = torch.empty(B * P, dtype=torch.int64, device=dev)
-            L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
-            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
-            m_star = torch.empty(B * self.dim, dtype=torch.float32, device=dev)
-            cur.synchronize()
-            L.check(self._lib.cmdb_score_shard_select(self._h, _ptr(keys), B, P, _ptr(m_star)))
-            dist.all_reduce(m_star, op=dist.ReduceOp.SUM, group=group)
-            top = torch.empty(B * 3, dtype=torch.int64, device=dev)
-            cur.synchronize()
-            L.check(self._lib.cmdb_score_shard_topk(self._h, _ptr(m_star), B, P, _ptr(top)))
-            gathered = torch.empty(world * B * 3, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gathered, top, group=group)
-            nn_rows = torch.empty(B * 3 * self.dim, dtype=torch.float32, device=dev)
-            cur.synchronize()
-            L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), world, B, _ptr(nn_rows)))
-            dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
-            cur.synchronize()
-            res, outs, _ = self._alloc_out(B, P, out_hw, full)
-            L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), B, P, int(fh), int(fw), int(out_hw), outs))
-            results.extend(res)
+        with torch.cuda.stream(self.stream()):
+            for b0 in range(0, Btot, step):
+                chunk = patches[b0:b0 + step]
+                B = chunk.shape[0]
+                keys = torch.empty(B * P, dtype=torch.int64, device=dev)
+                L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
+                dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+                m_star = torch.empty(B * self.dim, dtype=torch.float32, device=dev)
+                L.check(self._lib.cmdb_score_shard_select(self._h, _ptr(keys), B, P, _ptr(m_star)))
+                dist.all_reduce(m_star, op=dist.ReduceOp.SUM, group=group)
+                top = torch.empty(B * 3, dtype=torch.int64, device=dev)
+                L.check(self._lib.cmdb_score_shard_topk(self._h, _ptr(m_star), B, P, _ptr(top)))
+                gathered = torch.empty(world * B * 3, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(gathered, top, group=group)
+                nn_rows = torch.empty(B * 3 * self.dim, dtype=torch.float32, device=dev)
+                L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), world, B, _ptr(nn_rows)))
+                dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
+                res, outs, _ = self._alloc_out(B, P, out_hw, full)
+                # image i of this round has global index b0 + i and belongs to rank (b0 + i) % world
+                first, stride = ((rank - b0) % world, world) if distribute else (0, 1)
+                L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), B, P, int(fh), int(fw), int(out_hw),
+                                                          int(first), int(stride), outs))
+                if distribute:
+                    res = [r if (i - first) % stride == 0 and i >= first else None for i, r in enumerate(res)]
+                results.extend(res)
         return results
 
 

@@ -74,20 +74,33 @@ static int local_min(cmdb_bank *b, int B, int P) {
     return score_refine(b, B, P, n_cand);
 }
 
-// one device->host copy of the result block of a sub-batch, then scatter into the caller's buffers
-static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs) {
+// device->host copy of the result block of a sub-batch, then scatter into the caller's buffers.  All images: ONE copy.
+// A strided subset (sharded finish: this rank owns images img_first, img_first + img_step, ...): the scalar / per-patch
+// prefix in one copy plus one map copy per owned image.
+static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs, int img_first = 0, int img_step = 1) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     const size_t npix = (size_t)out_hw * out_hw;
     bool want_pre = false, want_u8 = false;
-    for (int i = 0; i < B; ++i) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
-    size_t bytes = s.off_map_out + sizeof(float) * s.map_stride * B;
-    if (want_pre) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
-    if (want_u8) bytes = s.off_map_u8 + s.map_stride * B;
-    CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, bytes, cudaMemcpyDeviceToHost, st));
+    for (int i = img_first; i < B; i += img_step) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
+    if (img_step == 1 && img_first == 0) {
+        size_t bytes = s.off_map_out + sizeof(float) * s.map_stride * B;
+        if (want_pre) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
+        if (want_u8) bytes = s.off_map_u8 + s.map_stride * B;
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_map_out, cudaMemcpyDeviceToHost, st));
+        for (int i = img_first; i < B; i += img_step) {
+            const size_t o1 = s.off_map_out + sizeof(float) * s.map_stride * i, o2 = s.off_map_pre + sizeof(float) * s.map_stride * i;
+            const size_t o3 = s.off_map_u8 + s.map_stride * i;
+            CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o1, s.out_block + o1, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
+            if (want_pre) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o2, s.out_block + o2, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
+            if (want_u8) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o3, s.out_block + o3, npix, cudaMemcpyDeviceToHost, st));
+        }
+    }
     CMDB_CUDA(cudaStreamSynchronize(st));
     const unsigned char *h = s.out_block_host;
-    for (int i = 0; i < B; ++i) {
+    for (int i = img_first; i < B; i += img_step) {
         cmdb_score_out *out = outs + i;
         TailResult tr;
         memcpy(&tr, h + sizeof(TailResult) * i, sizeof(tr));
@@ -107,13 +120,12 @@ static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *
     return CMDB_OK;
 }
 
-static int blur_batch(cmdb_bank *b, int B, int P, int fh, int fw, int out_hw) {
+static int blur_batch(cmdb_bank *b, int B, int fh, int fw, int out_hw, int img_first = 0, int img_step = 1) {
     ScoreScratch &s = b->ss;
-    // the map sections of the result block are laid out with a fixed per-image stride
-    CMDB_REQUIRE((size_t)out_hw * out_hw == s.map_stride || B == 1, CMDB_ERR_INVALID,
-                 "scoring: out_hw changed within a batch-capable scratch (got %d)", out_hw);
-    (void)P;
-    return upsample_blur_launch(b->stream, B, s.min_val, fh, fw, out_hw, s.map_pre, s.map_out, s.map_u8, s.map_tmp, s.map_max);
+    CMDB_REQUIRE((size_t)out_hw * out_hw <= s.map_stride, CMDB_ERR_INVALID, "scoring: out_hw=%d larger than the scratch maps", out_hw);
+    const int n_img = img_first < B ? (B - img_first + img_step - 1) / img_step : 0;
+    return upsample_blur_launch(b->stream, n_img, img_first, img_step, s.map_stride, s.min_val, fh, fw, out_hw, s.map_pre,
+                                s.map_out, s.map_u8, s.map_tmp, s.map_max);
 }
 
 }  // namespace cmdb
@@ -216,7 +228,7 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
         CMDB_MARK(CMDB_T_REWEIGHT);
         CMDB_CHECK(score_reweight(b, bc, P, true));
         CMDB_MARK(CMDB_T_MAP);
-        CMDB_CHECK(blur_batch(b, bc, P, fh, fw, out_hw));
+        CMDB_CHECK(blur_batch(b, bc, fh, fw, out_hw));
         CMDB_MARK(CMDB_T_OUT);
         CMDB_CHECK(copy_outputs(b, bc, P, out_hw, outs + b0));
         if (b->timing) {  // timings describe the last sub-batch
@@ -252,8 +264,7 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_CHECK(local_min(b, B, P));
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
-    CMDB_CUDA(cudaStreamSynchronize(b->stream));  // the caller's collective runs on another stream
-    return CMDB_OK;
+    return CMDB_OK;  // stream-ordered on the handle's stream (cmdb_bank_stream): run the collective there
 }
 
 int cmdb_score_shard_select(cmdb_bank *b, const int64_t *reduced_keys_device, int B, int P, float *m_star_contrib_device) {
@@ -267,7 +278,6 @@ int cmdb_score_shard_select(cmdb_bank *b, const int64_t *reduced_keys_device, in
                                                             b->ss.min_idx, b->ss.s_key);
     CMDB_CHECK(score_select(b, B, P, true));  // m_star rows this rank owns, zeros elsewhere
     CMDB_CUDA(cudaMemcpyAsync(m_star_contrib_device, b->ss.m_star, sizeof(float) * (size_t)B * b->dim, cudaMemcpyDeviceToDevice, st));
-    CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
 }
 
@@ -279,7 +289,6 @@ int cmdb_score_shard_topk(cmdb_bank *b, const float *m_star_device, int B, int P
     CMDB_CUDA(cudaMemcpyAsync(b->ss.m_star, m_star_device, sizeof(float) * (size_t)B * b->dim, cudaMemcpyDeviceToDevice, st));
     CMDB_CHECK(score_reweight(b, B, P, false));
     CMDB_CUDA(cudaMemcpyAsync(topk_keys_device, b->ss.top3, sizeof(long long) * 3 * B, cudaMemcpyDeviceToDevice, st));
-    CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
 }
 
@@ -295,23 +304,23 @@ int cmdb_score_shard_nn(cmdb_bank *b, const int64_t *gathered_keys_device, int n
     contrib_rows_kernel<<<8 * B, 256, 0, st>>>(b->data, b->fin_rows, b->row_offset, b->dim, nullptr, b->ss.top3, 3 * B,
                                                nn_rows_contrib_device);
     CMDB_CUDA(cudaGetLastError());
-    CMDB_CUDA(cudaStreamSynchronize(st));
     return CMDB_OK;
 }
 
 int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int B, int P, int fh, int fw, int out_hw,
-                            cmdb_score_out *outs) {
+                            int img_first, int img_step, cmdb_score_out *outs) {
     CMDB_CHECK(check_score_args(b, nn_rows_device, B, P, "cmdb_score_shard_finish"));
     CMDB_REQUIRE(outs && fh > 0 && fw > 0 && fh * fw == P && B * P <= b->ss.cap_p && B <= b->ss.cap_b, CMDB_ERR_INVALID,
                  "cmdb_score_shard_finish: bad arguments");
     CMDB_REQUIRE((size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_INVALID,
                  "cmdb_score_shard_finish: out_hw differs from cmdb_score_shard_min");
+    CMDB_REQUIRE(img_first >= 0 && img_step >= 1, CMDB_ERR_INVALID, "cmdb_score_shard_finish: bad image subset");
     CMDB_CUDA(cudaSetDevice(b->device));
     CMDB_CUDA(cudaMemcpyAsync(b->ss.nn_rows, nn_rows_device, sizeof(float) * 3 * (size_t)B * b->dim, cudaMemcpyDeviceToDevice,
                               b->stream));
     CMDB_CHECK(score_final(b, B));
-    CMDB_CHECK(blur_batch(b, B, P, fh, fw, out_hw));
-    return copy_outputs(b, B, P, out_hw, outs);
+    CMDB_CHECK(blur_batch(b, B, fh, fw, out_hw, img_first, img_step));
+    return copy_outputs(b, B, P, out_hw, outs, img_first, img_step);
 }
 
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host, float *out_pre_host,
@@ -336,7 +345,7 @@ int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int ou
     if (e == cudaSuccess) e = cudaMalloc(&u8, npix);
     if (e == cudaSuccess) e = cudaMemcpy(in, map_host, sizeof(float) * fh * fw, cudaMemcpyHostToDevice);
     int rc = CMDB_OK;
-    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, 1, in, fh, fw, out_hw, pre, o, u8, tmp, mx);
+    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, 1, 0, 1, npix, in, fh, fw, out_hw, pre, o, u8, tmp, mx);
     if (e == cudaSuccess && rc == CMDB_OK) e = cudaMemcpy(out_host, o, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_pre_host) e = cudaMemcpy(out_pre_host, pre, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_u8_host) e = cudaMemcpy(out_u8_host, u8, npix, cudaMemcpyDeviceToHost);

@@ -39,7 +39,6 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 constexpr int kNumSMsDefault = 148;
-constexpr int kMaxQueryRows = 1024;  // query rows per GEMM launch (8 M-tiles of 128)
 constexpr int kScoreBN = 256;        // bank rows per GEMM tile
 constexpr int kScoreBM = 128;        // query rows per GEMM tile
 constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 128-byte swizzle row)
@@ -60,7 +59,7 @@ struct ScoreScratch {
     unsigned long long *top3 = nullptr;  // merged 3 smallest w_dist keys
     int n_topk_blocks = 0;
     unsigned int *done_counter = nullptr;  // last-block-done counter of reweight_kernel
-    float4 *cand = nullptr;         // [cap_p, n_ctas] per-CTA top-2 (val1, idx1, val2, idx2) of the GEMM epilogue
+    float4 *cand = nullptr;         // [n_ctas, cap_p] per-CTA running top-2 (val1, idx1, val2, idx2) of the GEMM epilogue
     float *min_val = nullptr;       // [cap_p]
     long long *min_idx = nullptr;   // [cap_p]
     unsigned long long *s_key = nullptr;    // packed argmax key of min_val
@@ -149,7 +148,8 @@ int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star);
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused);
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B);
 int score_final(cmdb_bank *b, int B);
-int upsample_blur_launch(cudaStream_t stream, int B, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
-                         float *out_dev, unsigned char *u8_dev, unsigned char *tmp_dev, float *mx_dev);
+int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,
+                         int fh, int fw, int out_hw, float *pre_dev, float *out_dev, unsigned char *u8_dev,
+                         unsigned char *tmp_dev, float *mx_dev);
 
 }  // namespace cmdb

@@ -10,9 +10,11 @@
 //     into a 2-stage ring), warp 1 = single-thread tcgen05.mma issuer (M=128 queries x N=256 bank rows, accumulators
 //     double-buffered in all 512 TMEM columns), warps 4-7 = epilogue;
 //   * epilogue: tcgen05.ld 32 columns at a time, val = ||b||^2 - 2 a.b (the per-query ||a||^2 is constant under argmin),
-//     branch-free per-thread top-2 (value, bank row) kept across all tiles of the CTA; one thread == one query row, so
-//     no cross-lane reduction is needed.  Per-CTA top-2 lists go to HBM (P x 148 x 16 B) and refine_kernel
-//     (score_tail.cu) re-checks the best candidates with exact float32 differences.
+//     branch-free per-thread top-2 (value, bank row) carried across all tiles of the CTA in a per-CTA list in L2
+//     (148 x P x 16 B, 2 KB read + written per tile); one thread == one query row, so no cross-lane reduction is
+//     needed.  refine_kernel (score_tail.cu) re-checks the best candidates with exact float32 differences.
+//   * one launch sweeps all M tiles of a batch in n-major order: the bank streams from HBM exactly once per launch and
+//     the (small) query operand is re-read from L2.
 // Algorithmic work: 2*P*R*D FLOP per image; tensor work is 3x that.
 #include <cuda.h>
 
@@ -25,7 +27,6 @@ constexpr int BN = kScoreBN;      // 256 bank rows   (UMMA N)
 constexpr int BK = kScoreBK;      // 64 fp16 = 128 B swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 2;
-constexpr int kMaxMT = kMaxQueryRows / BM;  // 8
 constexpr int kGemmThreads = 256;
 constexpr uint32_t kTileABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kTileBBytes = BN * BK * 2;  // 32 KB
@@ -39,8 +40,7 @@ struct GemmSmem {  // offsets inside dynamic shared memory (1024-byte aligned ba
     static constexpr uint32_t b_hi(int s) { return stage(s) + 2 * kTileABytes; }
     static constexpr uint32_t b_lo(int s) { return stage(s) + 2 * kTileABytes + kTileBBytes; }
     static constexpr uint32_t bnorm = kStages * kStageBytes;              // [2][BN] float
-    static constexpr uint32_t state = bnorm + 2 * BN * 4;                 // [kMaxMT][BM] float4
-    static constexpr uint32_t bars = state + kMaxMT * BM * 16;            // mbarriers
+    static constexpr uint32_t bars = bnorm + 2 * BN * 4;                  // mbarriers
     static constexpr uint32_t total = bars + 128;
 };
 
@@ -126,15 +126,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct GemmParams {
-    int mt;             // M tiles of this launch (<= kMaxMT)
-    int m_tile_base;    // first M tile (row m_tile_base*128 of q_hi/q_lo)
+    int mt;             // M tiles (padded query rows / 128), all handled by one launch
     int nt;             // N tiles (bank rows / 256)
     int kb;             // K blocks (D / 64)
     const float *bnorm; // [nt*256] ||b||^2, +inf on padding rows
     const int *q_scale_exp;
     int b_scale_exp;
-    float4 *cand;       // [P_pad][cand_stride]
-    int cand_stride;
+    float4 *cand;       // [gridDim.x][cand_stride]: CTA c keeps its running top-2 of query row q at cand[c*cand_stride + q]
+    int cand_stride;    // >= mt * 128
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -150,7 +149,9 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + GemmSmem::bars + 8 * (2 * kStages + 4));
     float *bnorm_s = reinterpret_cast<float *>(smem + GemmSmem::bnorm);
-    float4 *state = reinterpret_cast<float4 *>(smem + GemmSmem::state);
+    // running per-query top-2 of this CTA: lives in global memory (L2), 2 KB read + written per tile, so one launch can
+    // sweep any number of M tiles in n-major order (the bank is then read from HBM exactly once per launch)
+    float4 *state = p.cand + (size_t)blockIdx.x * p.cand_stride;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -166,6 +167,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     for (int i = threadIdx.x; i < p.mt * BM; i += kGemmThreads)
         state[i] = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+    __threadfence_block();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -178,7 +180,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n = t / p.mt, m = t - n * p.mt + p.m_tile_base;
+                const int n = t / p.mt, m = t - n * p.mt;
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
@@ -236,7 +238,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             bn[et] = __ldg(p.bnorm + (size_t)n * BN + et);
             bn[et + 128] = __ldg(p.bnorm + (size_t)n * BN + et + 128);
             // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
-            const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + (p.m_tile_base + m_local) * BM + row)));
+            const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + m_local * BM + row)));
             float4 st = state[m_local * BM + row];
             float b1 = st.x, b2 = st.z;
             int i1 = __float_as_int(st.y), i2 = __float_as_int(st.w);
@@ -269,9 +271,6 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    // per-CTA candidate lists -> HBM
-    for (int i = threadIdx.x; i < p.mt * BM; i += kGemmThreads)
-        p.cand[(size_t)(p.m_tile_base * BM + i) * p.cand_stride + blockIdx.x] = state[i];
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -441,16 +440,12 @@ int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     p.q_scale_exp = s.q_scale_exp;
     p.b_scale_exp = b->scale_exp;
     p.cand = s.cand;
-    p.cand_stride = b->num_sms;
-    const int mt_total = p_pad / BM;
-    for (int m0 = 0; m0 < mt_total; m0 += kMaxMT) {
-        p.m_tile_base = m0;
-        p.mt = std::min(kMaxMT, mt_total - m0);
-        score_gemm_kernel<<<b->num_sms, kGemmThreads, GemmSmem::total + 1024, st>>>(
-            *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
-            *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
-        CMDB_CUDA(cudaGetLastError());
-    }
+    p.cand_stride = s.cap_p;
+    p.mt = p_pad / BM;
+    score_gemm_kernel<<<b->num_sms, kGemmThreads, GemmSmem::total + 1024, st>>>(
+        *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
+        *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
+    CMDB_CUDA(cudaGetLastError());
     *n_cand_out = b->num_sms;
     return CMDB_OK;
 }

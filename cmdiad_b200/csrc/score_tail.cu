@@ -33,7 +33,7 @@ __device__ __forceinline__ float warp_sqdist(const float *__restrict__ a, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// refine: one warp per query.  cand[q][c] = (val1, idx1, val2, idx2) from n_cand producers (approximate d^2 up to a
+// refine: one warp per query.  cand[c][q] = (val1, idx1, val2, idx2) from n_cand producers (approximate d^2 up to a
 // per-query constant; idx < 0 = empty).  Takes the 4 best approximate candidates, recomputes their distance exactly
 // and keeps the smallest (ties -> lowest row).
 // ---------------------------------------------------------------------------------------------------------------
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
         }
     };
     for (int c = lane; c < n_cand; c += 32) {
-        const float4 t = cand[(size_t)qi * cand_stride + c];
+        const float4 t = cand[(size_t)c * cand_stride + qi];
         insert(t.x, __float_as_int(t.y));
         insert(t.z, __float_as_int(t.w));
     }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) simt_min_kernel(const float *__restrict__
                 if (j1 < 0 || v < c1 || (v == c1 && i < j1)) c2 = c1, j2 = j1, c1 = v, j1 = i;
                 else if (j2 < 0 || v < c2 || (v == c2 && i < j2)) c2 = v, j2 = i;
             }
-        cand[(size_t)(q0 + threadIdx.x) * cand_stride + blockIdx.y] = make_float4(c1, __int_as_float(j1), c2, __int_as_float(j2));
+        cand[(size_t)blockIdx.y * cand_stride + q0 + threadIdx.x] = make_float4(c1, __int_as_float(j1), c2, __int_as_float(j2));
     }
 }
 
@@ -193,7 +193,7 @@ int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     int slices = std::max(1, std::min(b->num_sms, (2 * b->num_sms + q_tiles - 1) / q_tiles));
     slices = (int)std::min<long long>(slices, (b->fin_rows + 63) / 64);
     simt_min_kernel<<<dim3(q_tiles, slices), 256, 0, b->stream>>>(b->ss.q_f32, P, b->data, b->fin_rows, b->dim, b->ss.cand,
-                                                                 b->num_sms);
+                                                                 b->ss.cap_p);
     CMDB_CUDA(cudaGetLastError());
     *n_cand_out = slices;
     return CMDB_OK;
@@ -202,7 +202,7 @@ int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out) {
 int score_refine(cmdb_bank *b, int B, int P_img, int n_cand) {
     const int P = B * P_img;
     CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long) * B, b->stream));
-    refine_kernel<<<(P + 7) / 8, 256, 0, b->stream>>>(b->ss.cand, n_cand, b->num_sms, b->ss.q_f32, b->data, b->dim, P, P_img,
+    refine_kernel<<<(P + 7) / 8, 256, 0, b->stream>>>(b->ss.cand, n_cand, b->ss.cap_p, b->ss.q_f32, b->data, b->dim, P, P_img,
                                                       b->row_offset, b->ss.min_val, b->ss.min_idx, b->ss.s_key);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
@@ -491,13 +491,14 @@ __global__ void __launch_bounds__(kBlurThreads) upsample_hblur_kernel(const floa
                                                                       int out_hw, int band, float *__restrict__ pre,
                                                                       unsigned char *__restrict__ u8_out,
                                                                       unsigned char *__restrict__ tmp, float *__restrict__ mx_out,
-                                                                      int radius, unsigned int ww, unsigned int fwt) {
+                                                                      int radius, unsigned int ww, unsigned int fwt, int img_first,
+                                                                      int img_step, size_t map_stride) {
     extern __shared__ __align__(16) unsigned char sm[];
-    {  // image of the batch = blockIdx.y
-        const size_t img = blockIdx.y, npix_ = (size_t)out_hw * out_hw;
-        map_in += img * fh * fw_, tmp += img * npix_, mx_out += img;
-        if (pre) pre += img * npix_;
-        if (u8_out) u8_out += img * npix_;
+    {  // image of the batch handled by this CTA
+        const size_t img = img_first + (size_t)blockIdx.y * img_step;
+        map_in += img * fh * fw_, tmp += img * map_stride, mx_out += img;
+        if (pre) pre += img * map_stride;
+        if (u8_out) u8_out += img * map_stride;
     }
     float *in_s = reinterpret_cast<float *>(sm);                    // [fh*fw]
     unsigned char *A = sm + sizeof(float) * ((fh * fw_ + 3) & ~3);  // [band][out_hw]
@@ -540,9 +541,13 @@ __global__ void __launch_bounds__(kBlurThreads) upsample_hblur_kernel(const floa
 
 __global__ void __launch_bounds__(kBlurThreads) vblur_kernel(const unsigned char *__restrict__ tmp, int out_hw, int band,
                                                              const float *__restrict__ mx_in, float *__restrict__ out,
-                                                             int radius, unsigned int ww, unsigned int fwt) {
+                                                             int radius, unsigned int ww, unsigned int fwt, int img_first,
+                                                             int img_step, size_t map_stride) {
     extern __shared__ __align__(16) unsigned char sm[];
-    tmp += (size_t)blockIdx.y * out_hw * out_hw, out += (size_t)blockIdx.y * out_hw * out_hw, mx_in += blockIdx.y;
+    {
+        const size_t img = img_first + (size_t)blockIdx.y * img_step;
+        tmp += img * map_stride, out += img * map_stride, mx_in += img;
+    }
     const int x0 = blockIdx.x * band, cols = min(band, out_hw - x0);
     if (cols <= 0) return;
     unsigned char *A = sm;  // [out_hw][cols]: column band, lines = columns (stride 1), pass axis = rows (stride cols)
@@ -616,8 +621,11 @@ int score_final(cmdb_bank *b, int B) {
     return CMDB_OK;
 }
 
-int upsample_blur_launch(cudaStream_t stream, int B, const float *map_dev, int fh, int fw, int out_hw, float *pre_dev,
-                         float *out_dev, unsigned char *u8_dev, unsigned char *tmp_dev, float *mx_dev) {
+// images img_first, img_first + img_step, ... (n_img of them); per-image stride of the map buffers = map_stride pixels
+int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,
+                         int fh, int fw, int out_hw, float *pre_dev, float *out_dev, unsigned char *u8_dev,
+                         unsigned char *tmp_dev, float *mx_dev) {
+    if (n_img <= 0) return CMDB_OK;
     CMDB_REQUIRE(fh > 0 && fw > 0 && out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID,
                  "upsample_blur: need out_hw in [8,256] (got %d) and positive map dims", out_hw);
     // Pillow _gaussian_blur_radius(radius=4, passes=3) evaluated like BoxBlur.c (float sigma2 = 16/3, the rest double)
@@ -636,9 +644,10 @@ int upsample_blur_launch(cudaStream_t stream, int B, const float *map_dev, int f
     const size_t smem1 = sizeof(float) * ((fh * fw + 3) & ~3) + 2 * tile;
     CMDB_REQUIRE(smem1 <= 200 * 1024, CMDB_ERR_UNSUPPORTED, "upsample_blur: map too large for shared memory");
     CMDB_CUDA(cudaFuncSetAttribute(upsample_hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    upsample_hblur_kernel<<<dim3(kBlurBands, B), kBlurThreads, smem1, stream>>>(map_dev, fh, fw, out_hw, band, pre_dev, u8_dev,
-                                                                               tmp_dev, mx_dev, radius, ww, fwt);
-    vblur_kernel<<<dim3(kBlurBands, B), kBlurThreads, 2 * tile, stream>>>(tmp_dev, out_hw, band, mx_dev, out_dev, radius, ww, fwt);
+    upsample_hblur_kernel<<<dim3(kBlurBands, n_img), kBlurThreads, smem1, stream>>>(
+        map_dev, fh, fw, out_hw, band, pre_dev, u8_dev, tmp_dev, mx_dev, radius, ww, fwt, img_first, img_step, map_stride);
+    vblur_kernel<<<dim3(kBlurBands, n_img), kBlurThreads, 2 * tile, stream>>>(tmp_dev, out_hw, band, mx_dev, out_dev, radius, ww,
+                                                                             fwt, img_first, img_step, map_stride);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }

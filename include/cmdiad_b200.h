@@ -160,7 +160,11 @@ int cmdb_score_batch(cmdb_bank *bank, const float *patches, int B, int P, int fh
  *   3. cmdb_score_shard_topk    3 smallest local w_dist keys per image for the replicated m_star   -> all-gather (int64[B*3])
  *   4. cmdb_score_shard_nn      merges the gathered keys ([rank][B][3]); writes the neighbour rows this rank owns, zeros
  *      otherwise                                                                                   -> all-reduce SUM (float[B*3*dim])
- *   5. cmdb_score_shard_finish  m_star_knn, w, s, upsample + blur; identical results on every rank.
+ *   5. cmdb_score_shard_finish  m_star_knn, w, s, upsample + blur for images img_first, img_first + img_step, ... of the
+ *      round (0, 1 = all images, identical results on every rank; rank, world = each rank finishes and returns only its
+ *      share, the other outs[] entries are left untouched).
+ * Phases 1-4 only enqueue work on the handle's stream (cmdb_bank_stream) and return; run the collectives on that same
+ * stream (or synchronise it first).  Phase 5 returns when its host outputs are complete.
  */
 int cmdb_score_shard_min(cmdb_bank *bank, const float *patches, int B, int P, int patch_is_device, int out_hw,
                          int64_t *keys_device);
@@ -169,7 +173,7 @@ int cmdb_score_shard_topk(cmdb_bank *bank, const float *m_star_device, int B, in
 int cmdb_score_shard_nn(cmdb_bank *bank, const int64_t *gathered_keys_device, int n_ranks, int B,
                         float *nn_rows_contrib_device);
 int cmdb_score_shard_finish(cmdb_bank *bank, const float *nn_rows_device, int B, int P, int fh, int fw, int out_hw,
-                            cmdb_score_out *outs);
+                            int img_first, int img_step, cmdb_score_out *outs);
 
 /* Stand-alone score-map post-processing (features.py:293-295, utils/utils.py:71-83): map [fh*fw] -> [out_hw^2]. */
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host,

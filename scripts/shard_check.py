@@ -32,6 +32,12 @@ for t in range(5):
     bad += int(not same)
     if rank == 0:
         print(f"batch image {t}: sharded == single-GPU: {same}", flush=True)
+# distributed finish: rank r returns only images r, r + world, ...
+dd = shard.score_sharded_batch(pb, (28, 28), 224, full=True, distribute=True)
+for t in range(5):
+    mine = t % world == rank
+    ok = (dd[t] is not None) == mine and (not mine or all((getattr(dd[t], n) == getattr(bb[t], n)).all() for n in ("min_idx", "s", "s_map", "nn_idx")))
+    bad += int(not ok)
 for t in range(3):
     patch = synth.patches(P, D, seed=50 + t, anomalous_frac=0.01, cent=cent)
     a = shard.score_sharded(patch, (28, 28), 224, full=True)
