@@ -31,6 +31,30 @@ class ScoreResult:
                  "s_map_u8")
 
 
+class BatchResult:
+    """Results of a batch: r[i] is a ScoreResult viewing image i of the batch arrays (created on demand)."""
+
+    def __init__(self, arrays, owned=None):
+        self.arrays = arrays
+        self.owned = owned  # None = all images; otherwise a set of image indices that were finished on this rank
+
+    def __len__(self):
+        return self.arrays["s"].shape[0]
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        if self.owned is not None and i not in self.owned:
+            return None
+        r = ScoreResult()
+        for name, a in self.arrays.items():
+            setattr(r, name, a[i] if a is not None else None)
+        return r
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class Bank:
     """One memory bank (patch_rgb_lib / patch_xyz_lib / patch_fusion_lib) resident in HBM on one GPU."""
 
@@ -145,25 +169,26 @@ class Bank:
     # ---- scoring ---------------------------------------------------------------------------------------------
     @staticmethod
     def _alloc_out(B, P, out_hw, full):
-        """B ScoreResult objects viewing batch arrays + the matching array of struct cmdb_score_out"""
-        arr = dict(s=np.zeros((B, 1), np.float32), s_star=np.zeros((B, 1), np.float32), s_idx=np.zeros((B, 1), np.int64),
-                   min_val=np.zeros((B, P), np.float32), min_idx=np.zeros((B, P), np.int64), nn_idx=np.zeros((B, 3), np.int64),
-                   m_star_knn=np.zeros((B, 2), np.float32), w=np.zeros((B, 1), np.float32),
-                   s_map=np.zeros((B, out_hw, out_hw), np.float32),
-                   s_map_pre=np.zeros((B, out_hw, out_hw), np.float32) if full else None,
-                   s_map_u8=np.zeros((B, out_hw, out_hw), np.uint8) if full else None)
-        ctype = dict(s=L.c_f32_p, s_star=L.c_f32_p, s_idx=L.c_i64_p, min_val=L.c_f32_p, min_idx=L.c_i64_p, nn_idx=L.c_i64_p,
-                     m_star_knn=L.c_f32_p, w=L.c_f32_p, s_map=L.c_f32_p, s_map_pre=L.c_f32_p, s_map_u8=L.c_u8_p)
+        """batch arrays + the matching array of struct cmdb_score_out (filled by pointer arithmetic, no per-image views)"""
+        arr = dict(s=np.empty((B, 1), np.float32), s_star=np.empty((B, 1), np.float32), s_idx=np.empty((B, 1), np.int64),
+                   min_val=np.empty((B, P), np.float32), min_idx=np.empty((B, P), np.int64), nn_idx=np.empty((B, 3), np.int64),
+                   m_star_knn=np.empty((B, 2), np.float32), w=np.empty((B, 1), np.float32),
+                   s_map=np.empty((B, out_hw, out_hw), np.float32),
+                   s_map_pre=np.empty((B, out_hw, out_hw), np.float32) if full else None,
+                   s_map_u8=np.empty((B, out_hw, out_hw), np.uint8) if full else None)
         outs = (L.ScoreOut * B)()
-        results = []
-        for i in range(B):
-            r = ScoreResult()
-            for name, a in arr.items():
-                v = a[i] if a is not None else None
-                setattr(r, name, v)
-                setattr(outs[i], name, v.ctypes.data_as(ctype[name]) if v is not None else ctype[name]())
-            results.append(r)
-        return results, outs, arr
+        base = ctypes.addressof(outs)
+        size = ctypes.sizeof(L.ScoreOut)
+        ptrs = (ctypes.c_void_p * (11 * B)).from_address(base)  # struct cmdb_score_out is 11 pointers
+        assert size == 11 * ctypes.sizeof(ctypes.c_void_p)
+        for f, (name, _) in enumerate(L.ScoreOut._fields_):
+            a = arr[name]
+            if a is None:
+                continue
+            p0, st = a.ctypes.data, a.strides[0]
+            for i in range(B):
+                ptrs[i * 11 + f] = p0 + i * st
+        return BatchResult(arr), outs, arr
 
     def score(self, patch, feature_map_dims, out_hw=224, full=False):
         """calculate_dist + compute_single_s_s_map for one image; patch [P,dim] float32, already normalised."""
@@ -227,7 +252,7 @@ class Bank:
                 L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), B, P, int(fh), int(fw), int(out_hw),
                                                           int(first), int(stride), outs))
                 if distribute:
-                    res = [r if (i - first) % stride == 0 and i >= first else None for i, r in enumerate(res)]
+                    res.owned = set(range(first, B, stride))
                 results.extend(res)
         return results
 

@@ -310,45 +310,58 @@ __global__ void __launch_bounds__(256) reweight_kernel(ReweightParams p) {
     const int dim4 = dim >> 2;
     unsigned long long *my_top = wtop + (size_t)warp * B * 3;
     const long long warps = (long long)gridDim.x * 8;
-    long long r = (long long)blockIdx.x * 8 + warp;
-    float4 x[DV], xn[DV];
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     bool valid[DV];  // dim is a multiple of 64: the last vector may cover only lanes 0..15
 #pragma unroll
-    for (int j = 0; j < DV; ++j) valid[j] = lane + 32 * j < dim4, x[j] = zero4, xn[j] = zero4;
-    if (r < p.rows) {
+    for (int j = 0; j < DV; ++j) valid[j] = lane + 32 * j < dim4;
+    // two bank rows per iteration share every shared-memory read of the B targets; the next pair is prefetched while
+    // the current one is compared
+    float4 x0[DV], x1[DV], n0[DV], n1[DV];
+    auto load_pair = [&](long long r, float4(&a)[DV], float4(&c)[DV]) {
+        const long long r2 = r + warps;
 #pragma unroll
-        for (int j = 0; j < DV; ++j)
-            if (valid[j]) x[j] = __ldg(reinterpret_cast<const float4 *>(p.bank + (size_t)r * dim) + lane + 32 * j);
-    }
-    for (; r < p.rows; r += warps) {
-        const long long rn = r + warps;
-        if (rn < p.rows) {  // prefetch the next row while this one is compared with the B targets
-#pragma unroll
-            for (int j = 0; j < DV; ++j)
-                if (valid[j]) xn[j] = __ldg(reinterpret_cast<const float4 *>(p.bank + (size_t)rn * dim) + lane + 32 * j);
+        for (int j = 0; j < DV; ++j) {
+            a[j] = (valid[j] && r < p.rows) ? __ldg(reinterpret_cast<const float4 *>(p.bank + (size_t)r * dim) + lane + 32 * j) : zero4;
+            c[j] = (valid[j] && r2 < p.rows) ? __ldg(reinterpret_cast<const float4 *>(p.bank + (size_t)r2 * dim) + lane + 32 * j) : zero4;
         }
-        const unsigned int grow = (unsigned int)(r + p.row_offset);
+    };
+    long long r = (long long)blockIdx.x * 8 + warp;
+    load_pair(r, x0, x1);
+    for (; r < p.rows; r += 2 * warps) {
+        load_pair(r + 2 * warps, n0, n1);
+        const long long r2 = r + warps;
+        const unsigned int grow0 = (unsigned int)(r + p.row_offset), grow1 = (unsigned int)(r2 + p.row_offset);
         for (int b = 0; b < B; ++b) {
-            float acc = 0.f;
+            float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
             for (int j = 0; j < DV; ++j) {
                 const float4 y = valid[j] ? ms4[b * dim4 + lane + 32 * j] : zero4;
                 float d;
-                d = x[j].x - y.x, acc = fmaf(d, d, acc);
-                d = x[j].y - y.y, acc = fmaf(d, d, acc);
-                d = x[j].z - y.z, acc = fmaf(d, d, acc);
-                d = x[j].w - y.w, acc = fmaf(d, d, acc);
+                d = x0[j].x - y.x, acc0 = fmaf(d, d, acc0);
+                d = x0[j].y - y.y, acc0 = fmaf(d, d, acc0);
+                d = x0[j].z - y.z, acc0 = fmaf(d, d, acc0);
+                d = x0[j].w - y.w, acc0 = fmaf(d, d, acc0);
+                d = x1[j].x - y.x, acc1 = fmaf(d, d, acc1);
+                d = x1[j].y - y.y, acc1 = fmaf(d, d, acc1);
+                d = x1[j].z - y.z, acc1 = fmaf(d, d, acc1);
+                d = x1[j].w - y.w, acc1 = fmaf(d, d, acc1);
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+            }
             if (lane == 0) {
-                const unsigned long long key = pack_min_key(acc, grow);
-                if (key < my_top[b * 3 + 2]) top3_insert_sh(my_top + b * 3, key);
+                const unsigned long long k0 = pack_min_key(acc0, grow0);
+                if (k0 < my_top[b * 3 + 2]) top3_insert_sh(my_top + b * 3, k0);
+                if (r2 < p.rows) {
+                    const unsigned long long k1 = pack_min_key(acc1, grow1);
+                    if (k1 < my_top[b * 3 + 2]) top3_insert_sh(my_top + b * 3, k1);
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < DV; ++j) x[j] = xn[j];
+        for (int j = 0; j < DV; ++j) x0[j] = n0[j], x1[j] = n1[j];
     }
     __syncthreads();
     // block result per image: merge the 8 warps' triples
