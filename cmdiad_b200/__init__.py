@@ -9,7 +9,7 @@ from . import synth  # noqa: F401  (pure numpy, importable without the library)
 
 def __getattr__(name):
     # lazy so that `import cmdiad_b200` works before the library is built; any use of the product path loads it
-    if name in ("Bank", "ScoreResult", "upsample_blur", "coreset_rownorms"):
+    if name in ("Bank", "Comm", "ScoreResult", "BatchResult", "upsample_blur", "coreset_rownorms"):
         from . import bank
         return getattr(bank, name)
     if name in ("Features", "RGBFeatures", "DepthFeatures", "PointFeatures", "DoubleRGBPointFeatures",

@@ -66,6 +66,14 @@ SYMBOLS = {
     "cmdb_bank_stream": (_I, [_VP, ctypes.POINTER(_VP)]),
     "cmdb_bank_get_timings": (_I, [_VP, c_f32_p]),
     "cmdb_coreset_select": (_I, [_VP, _I64, _VP, _VP, _VP, _I, _I, _VP]),
+    "cmdb_comm_create": (_I, [_I, _I, _I, ctypes.c_size_t, ctypes.POINTER(_VP)]),
+    "cmdb_comm_handle_bytes": (_I, []),
+    "cmdb_comm_export": (_I, [_VP, _VP]),
+    "cmdb_comm_import": (_I, [_VP, _VP]),
+    "cmdb_comm_reset": (_I, [_VP]),
+    "cmdb_comm_destroy": (None, [_VP]),
+    "cmdb_coreset_mailbox_bytes": (ctypes.c_size_t, [_I, _I]),
+    "cmdb_coreset_select_sharded": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _VP, _I, _I, _VP, _VP]),
     "cmdb_project": (_I, [_VP, _VP, _VP, _VP, _I, _I64, _I64, _VP]),
     "cmdb_coreset_rownorms": (_I, [_I, _VP, _VP, _I64, _I, _I, _VP]),
     "cmdb_score": (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),

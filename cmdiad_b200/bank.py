@@ -31,6 +31,46 @@ class ScoreResult:
                  "s_map_u8")
 
 
+class Comm:
+    """Peer mailboxes of this rank for the row-sharded coreset loop (CUDA IPC over NVLink, one process per GPU).
+    Collective constructor: every rank of `group` must create it together."""
+
+    def __init__(self, device, d_proj_max=512, group=None):
+        import torch.distributed as dist
+        self._lib = L.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._h = ctypes.c_void_p()
+        nbytes = self._lib.cmdb_coreset_mailbox_bytes(self.world, int(d_proj_max))
+        L.check(self._lib.cmdb_comm_create(int(device), self.rank, self.world, nbytes, ctypes.byref(self._h)))
+        hb = self._lib.cmdb_comm_handle_bytes()
+        mine = np.zeros(hb, np.uint8)
+        L.check(self._lib.cmdb_comm_export(self._h, _ptr(mine)))
+        dev = torch.device("cuda", int(device))
+        gathered = torch.empty(self.world * hb, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, torch.from_numpy(mine).to(dev), group=group)
+        handles = np.ascontiguousarray(gathered.cpu().numpy())
+        L.check(self._lib.cmdb_comm_import(self._h, _ptr(handles)))
+        self.device = int(device)
+        self.d_proj_max = int(d_proj_max)
+
+    def reset_and_barrier(self):
+        import torch.distributed as dist
+        L.check(self._lib.cmdb_comm_reset(self._h))
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cmdb_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class BatchResult:
     """Results of a batch: r[i] is a ScoreResult viewing image i of the batch arrays (created on demand)."""
 
@@ -157,6 +197,25 @@ class Bank:
         L.check(self._lib.cmdb_coreset_select_debug(self._h, int(n_select), _ptr(indptr), _ptr(indices), _ptr(data),
                                                     d_proj, int(dtype_mode), _ptr(out), _ptr(fi), _ptr(mn)))
         return (out, mn) if return_min else out
+
+    def coreset_select_sharded(self, comm, n_total_rows, n_select, csr, dtype_mode=L.CORESET_FP16):
+        """Row-sharded greedy selection: this bank holds global rows [row_offset, row_offset + rows) of an n_total_rows
+        bank; every rank calls this together and gets the same GLOBAL indices as the single-GPU coreset_select."""
+        import torch.distributed as dist
+        indptr, indices, data, d_proj = self._csr(csr)
+        assert d_proj <= comm.d_proj_max
+        dev = torch.device("cuda", self.device)
+        z0 = torch.zeros(d_proj, dtype=torch.float64, device=dev)
+        if comm.rank == 0:  # rank 0 owns global row 0 (contiguous shards in rank order)
+            z0.copy_(torch.from_numpy(self.project(csr, 0, 1)[0]))
+        dist.broadcast(z0, src=dist.get_global_rank(comm.group, 0) if comm.group is not None else 0, group=comm.group)
+        z0_host = np.ascontiguousarray(z0.cpu().numpy())
+        comm.reset_and_barrier()
+        out = np.zeros(int(n_select), dtype=np.int64)
+        L.check(self._lib.cmdb_coreset_select_sharded(self._h, comm._h, int(n_total_rows), int(n_select), _ptr(indptr),
+                                                      _ptr(indices), _ptr(data), d_proj, int(dtype_mode), _ptr(z0_host),
+                                                      _ptr(out)))
+        return out
 
     def project(self, csr, row0=0, n_rows=None):
         indptr, indices, data, d_proj = self._csr(csr)

@@ -6,9 +6,6 @@
 
 namespace cmdb {
 
-int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
-                       int64_t *out_idx_host, const int64_t *force_idx_host, void *out_min_last_host);
-
 __global__ void __launch_bounds__(512) f32_to_f64_kernel(const float *__restrict__ x, long long n, double *__restrict__ z) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         z[i] = (double)x[i];
@@ -151,19 +148,26 @@ int cmdb_project(cmdb_bank *b, const int32_t *indptr, const int32_t *indices, co
     return CMDB_OK;
 }
 
+static unsigned int mailbox_slot_stride(int d) { return 16u + (unsigned int)(((size_t)d * sizeof(double) + 15) & ~size_t(15)); }
+
 static int coreset_impl(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices, const double *data,
-                        int d_proj, int dtype_mode, int64_t *out_idx_host, const int64_t *force_idx, void *out_min_last) {
+                        int d_proj, int dtype_mode, int64_t *out_idx_host, const int64_t *force_idx, void *out_min_last,
+                        ShardCtx *sh = nullptr) {
     CMDB_REQUIRE(b && out_idx_host, CMDB_ERR_INVALID, "cmdb_coreset_select: NULL argument");
     CMDB_REQUIRE(b->rows > 0, CMDB_ERR_STATE, "cmdb_coreset_select: bank is empty");
-    CMDB_REQUIRE(n_select >= 1 && n_select <= b->rows, CMDB_ERR_INVALID, "cmdb_coreset_select: n_select=%lld not in [1,%lld]",
-                 (long long)n_select, (long long)b->rows);
+    const int64_t n_total = sh ? sh->n_total : b->rows;
+    CMDB_REQUIRE(n_select >= 1 && n_select <= n_total, CMDB_ERR_INVALID, "cmdb_coreset_select: n_select=%lld not in [1,%lld]",
+                 (long long)n_select, (long long)n_total);
     CMDB_REQUIRE(d_proj >= 0 && d_proj <= b->dim, CMDB_ERR_INVALID,
                  "cmdb_coreset_select: d_proj=%d exceeds dim=%d (sklearn raises ValueError here; pass 0 to skip the projection)",
                  d_proj, b->dim);
     CMDB_CUDA(cudaSetDevice(b->device));
     const int d = d_proj > 0 ? d_proj : b->dim;
-    double *z = nullptr;
-    CMDB_CUDA(cudaMalloc(&z, sizeof(double) * (size_t)b->rows * d));
+    // the shard's projected rows start (row_offset*d) & 3 elements past a 32-byte boundary (see coreset_greedy_dev)
+    const int pad = (int)((b->row_offset * d) & 3);
+    double *z_alloc = nullptr;
+    CMDB_CUDA(cudaMalloc(&z_alloc, sizeof(double) * ((size_t)b->rows * d + 4)));
+    double *z = z_alloc + pad;
     int rc;
     if (d_proj > 0) {
         rc = project_rows(b, b->data, b->rows, b->dim, indptr, indices, data, d_proj, z);
@@ -172,8 +176,8 @@ static int coreset_impl(cmdb_bank *b, int64_t n_select, const int32_t *indptr, c
         f32_to_f64_kernel<<<b->num_sms * 4, 512, 0, b->stream>>>(b->data, (long long)b->rows * d, z);
         rc = cudaGetLastError() == cudaSuccess ? CMDB_OK : CMDB_ERR_CUDA;
     }
-    if (rc == CMDB_OK) rc = coreset_greedy_dev(b, z, b->rows, d, n_select, dtype_mode, out_idx_host, force_idx, out_min_last);
-    cudaFree(z);
+    if (rc == CMDB_OK) rc = coreset_greedy_dev(b, z, b->rows, d, n_select, dtype_mode, out_idx_host, force_idx, out_min_last, sh);
+    cudaFree(z_alloc);
     return rc;
 }
 
@@ -188,6 +192,29 @@ int cmdb_coreset_select_debug(cmdb_bank *b, int64_t n_select, const int32_t *ind
                               const int64_t *force_idx_host, void *out_min_last_host) {
     return coreset_impl(b, n_select, indptr, indices, data, d_proj, dtype_mode, out_idx_host, force_idx_host,
                         out_min_last_host);
+}
+
+size_t cmdb_coreset_mailbox_bytes(int world, int d_proj_max) {
+    return (size_t)2 * (size_t)(world > 0 ? world : 1) * mailbox_slot_stride(d_proj_max > 0 ? d_proj_max : 1);
+}
+
+int cmdb_coreset_select_sharded(cmdb_bank *b, cmdb_comm *comm, int64_t n_total_rows, int64_t n_select, const int32_t *indptr,
+                                const int32_t *indices, const double *data, int d_proj, int dtype_mode, const double *z0_host,
+                                int64_t *out_idx_host) {
+    CMDB_REQUIRE(b && comm && z0_host && out_idx_host, CMDB_ERR_INVALID, "cmdb_coreset_select_sharded: NULL argument");
+    CMDB_REQUIRE(d_proj > 0, CMDB_ERR_UNSUPPORTED, "cmdb_coreset_select_sharded: needs a projection (d_proj > 0)");
+    ShardCtx sh{};
+    size_t mb_bytes = 0;
+    unsigned char *local = nullptr;
+    CMDB_CHECK(comm_info(comm, &sh.rank, &sh.world, &local, sh.peers, &mb_bytes));
+    sh.row_offset = b->row_offset, sh.n_total = n_total_rows, sh.z0_host = z0_host;
+    sh.slot_stride = mailbox_slot_stride(d_proj);
+    CMDB_REQUIRE(mb_bytes >= cmdb_coreset_mailbox_bytes(sh.world, d_proj), CMDB_ERR_INVALID,
+                 "cmdb_coreset_select_sharded: mailbox has %zu bytes, need %zu", mb_bytes,
+                 cmdb_coreset_mailbox_bytes(sh.world, d_proj));
+    CMDB_REQUIRE(b->row_offset + b->rows <= n_total_rows, CMDB_ERR_INVALID, "cmdb_coreset_select_sharded: shard exceeds n_total_rows");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    return coreset_impl(b, n_select, indptr, indices, data, d_proj, dtype_mode, out_idx_host, nullptr, nullptr, &sh);
 }
 
 int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,

@@ -39,6 +39,7 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 constexpr int kNumSMsDefault = 148;
+constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch box
 constexpr int kScoreBN = 256;        // bank rows per GEMM tile
 constexpr int kScoreBM = 128;        // query rows per GEMM tile
 constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 128-byte swizzle row)
@@ -121,7 +122,19 @@ void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t
 int project_rows(cmdb_bank *b, const float *x_dev, int64_t n_rows, int D, const int32_t *indptr_h,
                  const int32_t *indices_h, const double *data_h, int d_proj, double *z_dev);
 
+// comm.cu
+int comm_info(cmdb_comm *c, int *rank, int *world, unsigned char **local, unsigned char **peers, size_t *bytes);
+
 // coreset.cu
+struct ShardCtx {  // row-sharded coreset loop
+    int world, rank;
+    long long row_offset, n_total;
+    unsigned char *peers[kMaxRanks];
+    unsigned int slot_stride;
+    const double *z0_host;  // float64 projection of global row 0
+};
+int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
+                       int64_t *out_idx_host, const int64_t *force_idx_host, void *out_min_last_host, const ShardCtx *sh);
 int coreset_greedy(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
                    int64_t *out_idx_host);
 int coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,

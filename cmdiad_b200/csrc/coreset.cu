@@ -46,6 +46,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ __half ld_volatile(const __half *p) {
+    return __ushort_as_half(*reinterpret_cast<const volatile unsigned short *>(p));
+}
+__device__ __forceinline__ double ld_volatile(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
+__device__ __forceinline__ unsigned int ld_volatile(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+
 template <typename T>
 struct Traits;
 template <>
@@ -264,6 +270,15 @@ struct CoresetParams {
     PickSlot *slots;             // [2][gridDim.x]
     long long rows_per_cta;
     int mind_in_smem;
+    // row-sharded mode (world > 1): rows are local, row_offset maps them to global rows; per pick the GPUs exchange
+    // their candidate + its row through peer-mapped mailboxes
+    long long row_offset;
+    int world, rank;
+    unsigned char *mb_peer[kMaxRanks];  // mailbox of every rank (mb_peer[rank] is local memory)
+    unsigned int mb_slot_stride;        // bytes per (parity, source-rank) slot: 16-byte key header + row data
+    const void *last0;                  // [d] global row 0 in storage type (pick 1 measures distances to it)
+    unsigned int *abort_flag;           // set when a peer did not answer in time
+    long long spin_limit;               // clock64() ticks to wait for a peer
 };
 
 // per-warp constants of the streaming loop: every warp handles ONE alignment class (rows with row % 4 == warp % 4 of
@@ -341,8 +356,10 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
         const long long rows_per_group = (cta_rows + kGroups - 1) / kGroups;
         const long long g_row0 = cta_row0 + (warp >> 2) * rows_per_group;
         const long long g_row1 = min(cta_row1, g_row0 + rows_per_group);
-        const int c = warp & 3;
-        wp.first = g_row0 + ((c - (int)(g_row0 & 3)) & 3);
+        // alignment classes follow the GLOBAL row number (the reference's tensor is one contiguous [N,d] block); the
+        // shard's buffer starts (row_offset*d) & 3 elements past a vector boundary so addresses agree with it
+        const int c = warp & 3;  // this warp takes the local rows whose global row % 4 == c
+        wp.first = g_row0 + ((c - (int)((g_row0 + p.row_offset) & 3)) & 3);
         wp.n_rows = wp.first < g_row1 ? (g_row1 - wp.first + 3) >> 2 : 0;
         const int s = vectorized ? (int)(((long long)c * d) & 3) : 0;
         wp.g = class_geom(s, d);
@@ -356,14 +373,28 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     }
     const size_t rstride_b = (size_t)4 * d * sizeof(T);  // bytes between consecutive rows of this warp
 
-    long long sel = 0;  // features.py:372 -- pick 0 is row 0
+    long long sel = 0;  // features.py:372 -- pick 0 is (global) row 0
+    int win_rank = 0;   // sharded mode: rank whose candidate won the previous pick
+    __shared__ unsigned long long xkey_sh;
+    __shared__ int abort_sh;
     if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[0] = 0;
 
     for (long long pick = 1; pick < p.n_select; ++pick) {
         // ---- stage `last` = z[sel] in shared memory; owner CTA zeroes min_d[sel] (features.py:418-419) ----
         __syncthreads();
-        for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
-        if (threadIdx.x == 0 && pick > 1 && sel >= cta_row0 && sel < cta_row1) mind[sel - cta_row0] = Traits<T>::zero();
+        if (p.world > 1) {
+            // sel is a GLOBAL row: pick 1 uses the broadcast row 0, later picks the winner's row in the local mailbox
+            const T *src = pick == 1 ? reinterpret_cast<const T *>(p.last0)
+                                     : reinterpret_cast<const T *>(p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) *
+                                                                                           p.mb_slot_stride + 16);
+            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = ld_volatile(src + e);
+        } else {
+            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
+        }
+        {
+            const long long sl = sel - p.row_offset;  // local row of the previous pick, if this shard owns it
+            if (threadIdx.x == 0 && pick > 1 && sl >= cta_row0 && sl < cta_row1) mind[sl - cta_row0] = Traits<T>::zero();
+        }
         __syncthreads();
         LastRegs<T, NV> L;
         load_last<T, NV>(L, last_sh, wp.g, lane, d, vectorized);
@@ -502,13 +533,74 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             const unsigned long long ov = red_val[w], orow = red_row[w];
             if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
         }
-        const long long argmax = (long long)br;
+        long long argmax = (long long)br;  // local row (or ~0 when this GPU has no rows)
+        if (p.world > 1) {
+            // ---- cross-GPU exchange: CTA 0 pushes this GPU's candidate key + row into every rank's mailbox (NVLink
+            //      stores), then every CTA polls its LOCAL mailbox for the keys of all ranks ----
+            const unsigned int slot = (unsigned int)((pick & 1) * p.world + p.rank) * p.mb_slot_stride;
+            const bool have = br != ~0ULL;
+            if (blockIdx.x == 0) {
+                if (have)
+                    for (int e = threadIdx.x; e < d; e += kCsThreads) {
+                        const T v = __ldg(z + (long long)br * d + e);
+                        for (int r = 0; r < p.world; ++r) reinterpret_cast<T *>(p.mb_peer[r] + slot + 16)[e] = v;
+                    }
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < p.world) {
+                    const unsigned long long grow = have ? (unsigned long long)(br + p.row_offset) : 0xffffffffULL;
+                    const unsigned long long key = ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) |
+                                                   (0xffffffffULL - (grow & 0xffffffffULL));
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[threadIdx.x] + slot), "l"(key) : "memory");
+                }
+            }
+            if (warp == 0) {
+                unsigned long long key = 0ULL;
+                int ok = 1;
+                if (lane < p.world) {
+                    const unsigned long long *kp = reinterpret_cast<const unsigned long long *>(
+                        p.mb_peer[p.rank] + (size_t)((pick & 1) * p.world + lane) * p.mb_slot_stride);
+                    const long long t0 = clock64();
+                    for (;;) {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(key) : "l"(kp) : "memory");
+                        if ((key >> 48) == (unsigned long long)(pick & 0xffff)) break;
+                        if (clock64() - t0 > p.spin_limit || ld_volatile(p.abort_flag)) {
+                            ok = 0;
+                            break;
+                        }
+                        __nanosleep(64);
+                    }
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                }
+                ok = __all_sync(0xffffffffu, ok);
+                unsigned long long best = lane < p.world ? key : 0ULL;
+                int brank = lane;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {  // kMaxRanks == 8 lanes
+                    const unsigned long long ok2 = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int or2 = __shfl_xor_sync(0xffffffffu, brank, o);
+                    if (ok2 > best) best = ok2, brank = or2;
+                }
+                if (lane == 0) {
+                    xkey_sh = (best & 0xffffffffULL) | ((unsigned long long)brank << 32);
+                    abort_sh = !ok;
+                    if (!ok) *p.abort_flag = 1u;
+                }
+            }
+            __syncthreads();
+            if (abort_sh) return;  // every CTA of every rank reaches the same verdict within the timeout
+            win_rank = (int)(xkey_sh >> 32);
+            argmax = (long long)(0xffffffffULL - (xkey_sh & 0xffffffffULL));  // global row
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[pick] = argmax;
         sel = p.force_idx ? p.force_idx[pick] : argmax;
     }
     // final state of the min-distance vector (tests / diagnostics)
     __syncthreads();
-    if (threadIdx.x == 0 && p.n_select > 1 && sel >= cta_row0 && sel < cta_row1) mind[sel - cta_row0] = Traits<T>::zero();
+    {
+        const long long sl = sel - p.row_offset;
+        if (threadIdx.x == 0 && p.n_select > 1 && sl >= cta_row0 && sl < cta_row1) mind[sl - cta_row0] = Traits<T>::zero();
+    }
     __syncthreads();
     if (p.mind_in_smem)
         for (long long i = threadIdx.x; i < cta_rows; i += kCsThreads) reinterpret_cast<T *>(p.mind)[cta_row0 + i] = mind_sh[i];
@@ -519,7 +611,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) rownorm_kernel(const T *__restrict__ z, const T *__restrict__ last, long long N,
-                                                      int d, T *__restrict__ out_same, __half *__restrict__ out_half) {
+                                                      int d, T *__restrict__ out_same, __half *__restrict__ out_half,
+                                                      long long row_offset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *last_sh = reinterpret_cast<T *>(smem_raw);
     for (int e = threadIdx.x; e < d; e += blockDim.x) last_sh[e] = last[e];
@@ -528,7 +621,7 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const T *__restrict__ z, c
     const bool vectorized = d >= 128;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < N; row += warps) {
-        const int s = vectorized ? (int)((row * d) & 3) : 0;
+        const int s = vectorized ? (int)(((row + row_offset) * d) & 3) : 0;  // alignment class of the GLOBAL row
         const ClassGeom g = class_geom(s, d);
         LastRegs<T, NV> L;
         load_last<T, NV>(L, last_sh, g, lane, d, vectorized);
@@ -554,13 +647,13 @@ __global__ void __launch_bounds__(512) to_half_kernel(const double *__restrict__
 
 template <typename T>
 static int launch_rownorm(cudaStream_t st, int num_sms, const T *z, const T *last, long long N, int d, T *out_same,
-                          __half *out_half) {
+                          __half *out_half, long long row_offset = 0) {
     const int nv = (d / 4 + 31) / 32;
     const int grid = (int)std::min<long long>((N + 7) / 8, (long long)num_sms * 8);
     const size_t smem = sizeof(T) * (size_t)d;
 #define CMDB_RN(NVV)                                                                                   \
     case NVV:                                                                                          \
-        rownorm_kernel<T, NVV><<<grid, 256, smem, st>>>(z, last, N, d, out_same, out_half);            \
+        rownorm_kernel<T, NVV><<<grid, 256, smem, st>>>(z, last, N, d, out_same, out_half, row_offset); \
         break;
     switch (d >= 128 ? nv : 1) {
         CMDB_RN(1) CMDB_RN(2) CMDB_RN(3) CMDB_RN(4) CMDB_RN(5) CMDB_RN(6) CMDB_RN(7) CMDB_RN(8)
@@ -639,25 +732,30 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
 #undef CMDB_CS
 }
 
+// z_dev: float64 [N,d] projected rows of THIS shard; for a shard with row_offset != 0 the caller places row 0 of the
+// buffer (row_offset*d) & 3 elements past a 32-byte boundary so that address alignment == global alignment class.
 int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
-                       int64_t *out_idx_host, const int64_t *force_idx_host, void *out_min_last_host) {
-    CMDB_REQUIRE(N > 0 && d >= 32 && n_select >= 1 && n_select <= N, CMDB_ERR_INVALID,
-                 "coreset: need N>0, d>=32, 1<=n_select<=N (N=%lld d=%d n=%lld)", (long long)N, d, (long long)n_select);
-    CMDB_REQUIRE(N < (1LL << 32) - 1, CMDB_ERR_UNSUPPORTED, "coreset: N must fit 32 bits");
+                       int64_t *out_idx_host, const int64_t *force_idx_host, void *out_min_last_host, const ShardCtx *sh) {
+    const bool sharded = sh && sh->world > 1;
+    const long long n_total = sharded ? sh->n_total : N;
+    CMDB_REQUIRE(N >= 0 && n_total > 0 && d >= 32 && n_select >= 1 && n_select <= n_total, CMDB_ERR_INVALID,
+                 "coreset: need N>0, d>=32, 1<=n_select<=N (N=%lld d=%d n=%lld)", (long long)n_total, d, (long long)n_select);
+    CMDB_REQUIRE(n_total < (1LL << 32) - 1, CMDB_ERR_UNSUPPORTED, "coreset: N must fit 32 bits");
     CMDB_REQUIRE(dtype_mode == CMDB_CORESET_FP16 || dtype_mode == CMDB_CORESET_FP64, CMDB_ERR_INVALID,
                  "coreset: unknown dtype_mode %d", dtype_mode);
+    CMDB_REQUIRE(!sharded || (dtype_mode == CMDB_CORESET_FP16 && !force_idx_host && N > 0), CMDB_ERR_UNSUPPORTED,
+                 "coreset: the row-sharded loop supports FP16 mode on non-empty shards only");
     cudaStream_t st = b->stream;
     long long *idx_dev = nullptr, *force_dev = nullptr;
     PickSlot *slots = nullptr;
-    __half *zh = nullptr;
+    __half *zh_alloc = nullptr, *last0_h = nullptr;
+    double *z0_dev = nullptr;
+    unsigned int *abort_dev = nullptr;
     void *mind = nullptr;
     int rc = CMDB_OK;
     auto cleanup = [&]() {
-        cudaFree(idx_dev);
-        cudaFree(force_dev);
-        cudaFree(slots);
-        cudaFree(zh);
-        cudaFree(mind);
+        cudaFree(idx_dev), cudaFree(force_dev), cudaFree(slots), cudaFree(zh_alloc), cudaFree(mind);
+        cudaFree(last0_h), cudaFree(z0_dev), cudaFree(abort_dev);
     };
 #define CS_TRY(expr)                                                                                         \
     do {                                                                                                     \
@@ -671,17 +769,34 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     } while (0)
     CS_TRY(cudaMalloc(&idx_dev, sizeof(long long) * (size_t)n_select));
     CS_TRY(cudaMalloc(&slots, sizeof(PickSlot) * 2 * (size_t)b->num_sms));
+    CS_TRY(cudaMalloc(&abort_dev, sizeof(unsigned int)));
+    CS_TRY(cudaMemsetAsync(abort_dev, 0, sizeof(unsigned int), st));
     if (force_idx_host) {
         CS_TRY(cudaMalloc(&force_dev, sizeof(long long) * (size_t)n_select));
         CS_TRY(cudaMemcpyAsync(force_dev, force_idx_host, sizeof(long long) * (size_t)n_select, cudaMemcpyHostToDevice, st));
     }
     CoresetParams p{};
     p.N = N, p.d = d, p.n_select = n_select, p.out_idx = idx_dev, p.force_idx = force_dev, p.slots = slots;
+    p.world = 1, p.rank = 0, p.row_offset = 0, p.abort_flag = abort_dev, p.spin_limit = 20LL * 1000 * 1000 * 1000;  // ~10 s
+    const double *first_row = z_dev;  // pick 0 = global row 0
+    if (sharded) {
+        p.world = sh->world, p.rank = sh->rank, p.row_offset = sh->row_offset, p.mb_slot_stride = sh->slot_stride;
+        for (int r = 0; r < kMaxRanks; ++r) p.mb_peer[r] = sh->peers[r];
+        CS_TRY(cudaMalloc(&z0_dev, sizeof(double) * d));
+        CS_TRY(cudaMemcpyAsync(z0_dev, sh->z0_host, sizeof(double) * d, cudaMemcpyHostToDevice, st));
+        CS_TRY(cudaMalloc(&last0_h, sizeof(__half) * d));
+        to_half_kernel<<<1, 512, 0, st>>>(z0_dev, d, last0_h);
+        CS_TRY(cudaGetLastError());
+        p.last0 = last0_h;
+        first_row = z0_dev;
+    }
     if (dtype_mode == CMDB_CORESET_FP16) {
-        CS_TRY(cudaMalloc(&zh, sizeof(__half) * (size_t)N * d));
-        CS_TRY(cudaMalloc(&mind, sizeof(__half) * (size_t)N));
+        const int pad = (int)((p.row_offset * d) & 3);  // keep address alignment == global alignment class
+        CS_TRY(cudaMalloc(&zh_alloc, sizeof(__half) * ((size_t)N * d + 4)));
+        __half *zh = zh_alloc + pad;
+        CS_TRY(cudaMalloc(&mind, sizeof(__half) * (size_t)std::max<int64_t>(N, 1)));
         // features.py:378 initial distances in float64, then .half() (:389-391)
-        rc = launch_rownorm<double>(st, b->num_sms, z_dev, z_dev, N, d, nullptr, reinterpret_cast<__half *>(mind));
+        rc = launch_rownorm<double>(st, b->num_sms, z_dev, first_row, N, d, nullptr, reinterpret_cast<__half *>(mind), p.row_offset);
         if (rc == CMDB_OK) {
             to_half_kernel<<<b->num_sms * 4, 512, 0, st>>>(z_dev, (long long)N * d, zh);
             CS_TRY(cudaGetLastError());
@@ -700,7 +815,9 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
         cleanup();
         return rc;
     }
+    unsigned int aborted = 0;
     CS_TRY(cudaMemcpyAsync(out_idx_host, idx_dev, sizeof(long long) * (size_t)n_select, cudaMemcpyDeviceToHost, st));
+    CS_TRY(cudaMemcpyAsync(&aborted, abort_dev, sizeof(aborted), cudaMemcpyDeviceToHost, st));
     if (out_min_last_host)
         CS_TRY(cudaMemcpyAsync(out_min_last_host, mind,
                                (dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double)) * (size_t)N,
@@ -711,12 +828,17 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     (void)cudaGetLastError();
 #undef CS_TRY
     cleanup();
+    if (aborted) {
+        set_error("coreset: a peer rank did not answer within the exchange timeout (all ranks must call "
+                  "cmdb_coreset_select_sharded together)");
+        return CMDB_ERR_CUDA;
+    }
     return CMDB_OK;
 }
 
 int coreset_greedy(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,
                    int64_t *out_idx_host) {
-    return coreset_greedy_dev(b, z_dev, N, d, n_select, dtype_mode, out_idx_host, nullptr, nullptr);
+    return coreset_greedy_dev(b, z_dev, N, d, n_select, dtype_mode, out_idx_host, nullptr, nullptr, nullptr);
 }
 
 int coreset_rownorms(int device, const void *z_host, const void *last_host, int64_t n_rows, int d, int dtype_mode,

@@ -27,6 +27,7 @@
 extern "C" {
 #endif
 
+typedef struct cmdb_comm cmdb_comm; /* peer mailboxes of one rank for the row-sharded coreset loop (one process per GPU) */
 typedef struct cmdb_bank cmdb_bank; /* one memory bank (patch_rgb_lib / patch_xyz_lib / patch_fusion_lib) on one GPU */
 
 typedef enum cmdb_status {
@@ -103,6 +104,30 @@ int cmdb_bank_get_timings(cmdb_bank *bank, float *out_ms);
  */
 int cmdb_coreset_select(cmdb_bank *bank, int64_t n_select, const int32_t *csr_indptr, const int32_t *csr_indices,
                         const double *csr_data, int d_proj, int dtype_mode, int64_t *out_idx_host);
+
+/*
+ * Row-sharded coreset selection over the GPUs of one NVSwitch box (one process per GPU).  Every rank holds a
+ * contiguous block of bank rows (cmdb_bank_set_row_offset) and runs the same persistent kernel on its shard; per pick
+ * the ranks exchange their local (value,row) candidate AND the candidate row through peer-mapped mailboxes (CUDA IPC
+ * over NVLink) from inside the kernel -- there is no host round trip and no NCCL call per pick.  Setup, once:
+ *   cmdb_comm_create on every rank -> cmdb_comm_export -> all-gather the handles (any host transport) -> cmdb_comm_import.
+ * mailbox_bytes >= cmdb_coreset_mailbox_bytes(world, d_proj_max).
+ * cmdb_coreset_select_sharded: z0_host = the float64 projection of GLOBAL row 0 (cmdb_project on the owning rank,
+ * broadcast by the caller); n_total_rows = rows of all shards; out_idx_host gets the same n_select GLOBAL rows on every
+ * rank, bit-identical to the single-GPU cmdb_coreset_select on the un-sharded bank.  FP16 mode only in this version.
+ * All ranks must call it together (it waits for its peers inside the kernel, with a timeout).
+ */
+int cmdb_comm_create(int device, int rank, int world, size_t mailbox_bytes, cmdb_comm **out);
+int cmdb_comm_handle_bytes(void);
+int cmdb_comm_export(cmdb_comm *comm, void *handle_out);
+int cmdb_comm_import(cmdb_comm *comm, const void *handles /* [world][cmdb_comm_handle_bytes()] */);
+/* clears the local mailbox; every rank calls it, then the ranks barrier, before each cmdb_coreset_select_sharded */
+int cmdb_comm_reset(cmdb_comm *comm);
+void cmdb_comm_destroy(cmdb_comm *comm);
+size_t cmdb_coreset_mailbox_bytes(int world, int d_proj_max);
+int cmdb_coreset_select_sharded(cmdb_bank *bank, cmdb_comm *comm, int64_t n_total_rows, int64_t n_select,
+                                const int32_t *csr_indptr, const int32_t *csr_indices, const double *csr_data, int d_proj,
+                                int dtype_mode, const double *z0_host, int64_t *out_idx_host);
 
 /* Projection only: out_host float64 [n_rows, d_proj] for rows [row0, row0+n_rows) (bit-exact with sklearn). */
 int cmdb_project(cmdb_bank *bank, const int32_t *csr_indptr, const int32_t *csr_indices, const double *csr_data,
