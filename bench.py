@@ -254,32 +254,45 @@ def run_ours(args):
         line["reweight_roofline"] = {"bound": "hbm", "achieved": BANK_ROWS * DIM * 4 / (rw * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                                      "unit": "GB/s", "frac": BANK_ROWS * DIM * 4 / (rw * 1e-3) / 1e9 / pk["hbm_gbs"],
                                      "note": "one sweep of the fp32 bank (R*D*4 B) serves the whole batch"}
-        # coreset selection of 10 % of the same bank (BASELINE.json: "coreset-select seconds")
-        if not args.skip_coreset:
-            from sklearn import random_projection
-            tr = random_projection.SparseRandomProjection(eps=0.9, random_state=0)
-            tr.fit(np.broadcast_to(np.zeros((1, 1)), (BANK_ROWS, DIM)))
-            c = tr.components_
-            csr = (c.indptr, c.indices, c.data, c.shape[0])
-            n_sel = BANK_ROWS // 10
-            bank.coreset_select(64, csr, L.CORESET_FP16)  # warm-up (module load, allocations)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            idx = bank.coreset_select(n_sel, csr, L.CORESET_FP16)
-            cs = time.perf_counter() - t0
-            d_proj = c.shape[0]
-            byts = (n_sel - 1) * BANK_ROWS * d_proj * 2.0
-            line["coreset_select_s"] = cs
-            line["coreset_roofline"] = {"bound": "hbm", "achieved": byts / cs / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                        "frac": byts / cs / 1e9 / pk["hbm_gbs"], "kernel": "coreset_kernel<__half,3>",
-                                        "note": f"(n-1)*N*d'*2 B with N={BANK_ROWS}, d'={d_proj}, n={n_sel}; wall time of the "
-                                                f"whole call incl. projection; the bank ({BANK_ROWS * d_proj * 2 / 1e6:.0f} MB) "
-                                                f"fits L2, so achieved/HBM-peak may exceed 1", "unique": int(len(set(idx.tolist())))}
         if rank == 0 and not args.skip_cpu:
             v, ms = cpu_reference_leg(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "patch-NN scores/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"3 images x {P} patches against the full {BANK_ROWS}x{DIM} bank (oracle/restate.py "
                                               f"score_restated: torch.cdist + min + topk + bilinear + blur), {ms:.0f} ms/image"}
+    # coreset selection of 10 % of the same bank (BASELINE.json: "coreset-select seconds"); N > 1: row-sharded loop with
+    # the in-kernel NVLink mailbox exchange
+    if not args.skip_coreset:
+        from sklearn import random_projection
+        tr = random_projection.SparseRandomProjection(eps=0.9, random_state=0)
+        tr.fit(np.broadcast_to(np.zeros((1, 1)), (BANK_ROWS, DIM)))
+        c = tr.components_
+        csr = (c.indptr, c.indices, c.data, c.shape[0])
+        n_sel = BANK_ROWS // 10
+        if world == 1:
+            run = lambda n: bank.coreset_select(n, csr, L.CORESET_FP16)
+        else:
+            from cmdiad_b200 import Comm
+            comm = Comm(local, d_proj_max=512)
+            run = lambda n: bank.coreset_select_sharded(comm, BANK_ROWS, n, csr, L.CORESET_FP16)
+        run(64)  # warm-up (module load, allocations)
+        barrier()
+        t0 = time.perf_counter()
+        idx = run(n_sel)
+        torch.cuda.synchronize()
+        cs = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(cs, op=dist.ReduceOp.MAX)
+            comm.close()
+        cs = float(cs)
+        d_proj = c.shape[0]
+        byts = (n_sel - 1) * BANK_ROWS * d_proj * 2.0
+        line["coreset_select_s"] = cs
+        line["coreset_roofline"] = {"bound": "hbm", "achieved": byts / cs / 1e9, "peak": pk["hbm_gbs"] * world, "unit": "GB/s",
+                                    "frac": byts / cs / 1e9 / (pk["hbm_gbs"] * world), "kernel": "coreset_kernel<__half,3>",
+                                    "note": f"(n-1)*N*d'*2 B with N={BANK_ROWS}, d'={d_proj}, n={n_sel}; wall time of the whole "
+                                            f"call incl. projection (max over ranks); peak = {world} x HBM; the projected bank "
+                                            f"({BANK_ROWS * d_proj * 2 / 1e6:.0f} MB) is pinned in L2 as far as it fits, so "
+                                            f"achieved/HBM-peak may exceed 1", "unique": int(len(set(idx.tolist())))}
     if rank == 0:
         print(json.dumps(line), flush=True)
     bank.close()
