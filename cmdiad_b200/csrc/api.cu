@@ -148,7 +148,8 @@ int cmdb_project(cmdb_bank *b, const int32_t *indptr, const int32_t *indices, co
     return CMDB_OK;
 }
 
-static unsigned int mailbox_slot_stride(int d) { return 16u + (unsigned int)(((size_t)d * sizeof(double) + 15) & ~size_t(15)); }
+// 16-byte key header + one 8-byte flagged word per two halves of the row
+static unsigned int mailbox_slot_stride(int d) { return 16u + 8u * (unsigned int)((d + 1) / 2 + 1); }
 
 static int coreset_impl(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices, const double *data,
                         int d_proj, int dtype_mode, int64_t *out_idx_host, const int64_t *force_idx, void *out_min_last,

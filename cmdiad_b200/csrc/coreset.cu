@@ -60,6 +60,7 @@ struct Traits<__half> {
     static __device__ __forceinline__ unsigned long long bits(__half v) { return (unsigned long long)__half_as_ushort(v); }
     static __device__ __forceinline__ __half from_acc(float a) { return __float2half_rn(sqrtf(a)); }
     static __device__ __forceinline__ __half zero() { return __ushort_as_half((unsigned short)0); }
+    static __device__ __forceinline__ __half from_bits(unsigned short b) { return __ushort_as_half(b); }
     static __device__ __forceinline__ bool lt(__half a, __half b) { return __half2float(a) < __half2float(b); }
     static __device__ __forceinline__ bool gt(__half a, __half b) { return __half2float(a) > __half2float(b); }
 };
@@ -69,6 +70,7 @@ struct Traits<double> {
     static __device__ __forceinline__ unsigned long long bits(double v) { return (unsigned long long)__double_as_longlong(v); }
     static __device__ __forceinline__ double from_acc(double a) { return sqrt(a); }
     static __device__ __forceinline__ double zero() { return 0.0; }
+    static __device__ __forceinline__ double from_bits(unsigned short) { return 0.0; }  // sharded loop is half-only
     static __device__ __forceinline__ bool lt(double a, double b) { return a < b; }
     static __device__ __forceinline__ bool gt(double a, double b) { return a > b; }
 };
@@ -382,12 +384,25 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     for (long long pick = 1; pick < p.n_select; ++pick) {
         // ---- stage `last` = z[sel] in shared memory; owner CTA zeroes min_d[sel] (features.py:418-419) ----
         __syncthreads();
-        if (p.world > 1) {
-            // sel is a GLOBAL row: pick 1 uses the broadcast row 0, later picks the winner's row in the local mailbox
-            const T *src = pick == 1 ? reinterpret_cast<const T *>(p.last0)
-                                     : reinterpret_cast<const T *>(p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) *
-                                                                                           p.mb_slot_stride + 16);
-            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = ld_volatile(src + e);
+        if (p.world > 1 && pick == 1) {
+            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = reinterpret_cast<const T *>(p.last0)[e];
+        } else if (p.world > 1) {
+            // sel is a GLOBAL row: its values are the winner's row words in the local mailbox (flagged with pick - 1)
+            const unsigned char *src = p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) * p.mb_slot_stride + 16;
+            const long long t0 = clock64();
+            for (int w2 = threadIdx.x; w2 < ((d + 1) >> 1); w2 += kCsThreads) {
+                unsigned long long word;
+                for (;;) {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src + 8 * w2) : "memory");
+                    if ((word >> 32) == (unsigned long long)(unsigned int)(pick - 1)) break;
+                    if (clock64() - t0 > p.spin_limit) {  // reported through the key exchange of this pick
+                        *p.abort_flag = 1u;
+                        break;
+                    }
+                }
+                last_sh[2 * w2] = Traits<T>::from_bits((unsigned short)(word & 0xffffu));
+                if (2 * w2 + 1 < d) last_sh[2 * w2 + 1] = Traits<T>::from_bits((unsigned short)((word >> 16) & 0xffffu));
+            }
         } else {
             for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
         }
@@ -537,21 +552,29 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
         if (p.world > 1) {
             // ---- cross-GPU exchange: CTA 0 pushes this GPU's candidate key + row into every rank's mailbox (NVLink
             //      stores), then every CTA polls its LOCAL mailbox for the keys of all ranks ----
+            // LL-style protocol: every 8-byte word carries its own flag (the pick number), so neither side needs a
+            // system-scope fence -- stores are fire-and-forget over NVLink and the receiver spins on the words it needs.
+            //   key word : [63:48] pick & 0xffff | [47:32] value (half bits) | [31:0] ~global_row
+            //   row words: [63:32] pick          | [31:0] two consecutive halves of the candidate row
             const unsigned int slot = (unsigned int)((pick & 1) * p.world + p.rank) * p.mb_slot_stride;
             const bool have = br != ~0ULL;
             if (blockIdx.x == 0) {
-                if (have)
-                    for (int e = threadIdx.x; e < d; e += kCsThreads) {
-                        const T v = __ldg(z + (long long)br * d + e);
-                        for (int r = 0; r < p.world; ++r) reinterpret_cast<T *>(p.mb_peer[r] + slot + 16)[e] = v;
+                const int n_words = (d + 1) >> 1;
+                for (int w2 = threadIdx.x; w2 < n_words; w2 += kCsThreads) {
+                    unsigned int lo16 = 0, hi16 = 0;
+                    if (have) {
+                        lo16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2)) & 0xffffu;
+                        if (2 * w2 + 1 < d) hi16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2 + 1)) & 0xffffu;
                     }
-                __threadfence_system();
-                __syncthreads();
+                    const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | (hi16 << 16) | lo16;
+                    for (int r = 0; r < p.world; ++r)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + 16 + 8 * w2), "l"(word) : "memory");
+                }
                 if (threadIdx.x < p.world) {
                     const unsigned long long grow = have ? (unsigned long long)(br + p.row_offset) : 0xffffffffULL;
                     const unsigned long long key = ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) |
                                                    (0xffffffffULL - (grow & 0xffffffffULL));
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[threadIdx.x] + slot), "l"(key) : "memory");
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[threadIdx.x] + slot), "l"(key) : "memory");
                 }
             }
             if (warp == 0) {
@@ -568,10 +591,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                             ok = 0;
                             break;
                         }
-                        __nanosleep(64);
                     }
-                    asm volatile("fence.acq_rel.sys;" ::: "memory");
                 }
+                if (lane == 0 && ld_volatile(p.abort_flag)) ok = 0;
                 ok = __all_sync(0xffffffffu, ok);
                 unsigned long long best = lane < p.world ? key : 0ULL;
                 int brank = lane;
