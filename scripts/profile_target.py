@@ -14,9 +14,10 @@ torch.cuda.set_device(0)
 bank = bench.build_bank(0, 1)
 if what == "score":
     bank.finalize()
-    patches = [p.cuda() for p in bench.test_patches(2)]
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    patches = torch.stack(bench.test_patches(B)).cuda()
     for i in range(3):
-        bank.score(patches[i % 2], (28, 28), 224)
+        bank.score_batch(patches, (28, 28), 224)
 else:
     from sklearn import random_projection
     tr = random_projection.SparseRandomProjection(eps=0.9, random_state=0)

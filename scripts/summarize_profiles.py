@@ -1,0 +1,63 @@
+"""Turns gpurun_out/{launches.csv,*.ncu-rep} into the text summaries committed under profiles/ (run in the build
+container; ncu reads the reports without a GPU)."""
+import collections
+import csv
+import subprocess
+import sys
+
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed.sum.per_cycle_active", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+
+
+def launches(path, out, cmd):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    hdr = rows[hi]
+    k, v = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= v:
+            continue
+        name = r[k].split("(")[0][:64]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[v].replace(",", ""))
+    tot = sum(a[1] for a in agg.values())
+    with open(out, "w") as f:
+        f.write(f"# {cmd}\n# per-launch device times are cold-cache and serialised by ncu: compare SHARES, not absolutes\n")
+        for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"{n:66s} n={c:4d} avg={t / c / 1e3:12.2f} us total={t / 1e6:10.3f} ms share={t / tot * 100:5.1f}%\n")
+
+
+def full(rep, out, title):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    with open(out, "w") as f:
+        f.write(f"# {title}\n# kernel: {vals[hdr.index('Kernel Name')]}\n")
+        for i, h in enumerate(hdr):
+            if h in KEYS:
+                f.write(f"{h:92s} {units[i]:16s} {vals[i]}\n")
+
+
+if __name__ == "__main__":
+    import os
+    g = "gpurun_out"
+    if os.path.exists(f"{g}/launches.csv"):
+        launches(f"{g}/launches.csv", f"profiles/{TAG}_launches_bench.txt",
+                 "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 2 --warmup 3 --skip-cpu")
+    for rep, title in (("prof_gemm", "ncu --set full --clock-control none, score_gemm_kernel, batch of 16 images x 784 patches vs 200k x 768 bank"),
+                       ("prof_coreset", "ncu --set full --clock-control none, coreset_kernel<__half,3>, 200k x 301, 300 picks"),
+                       ("prof_reweight", "ncu --set full --clock-control none, reweight_kernel<6>, batch of 16, 200k x 768 bank")):
+        if os.path.exists(f"{g}/{rep}.ncu-rep"):
+            full(f"{g}/{rep}.ncu-rep", f"profiles/{TAG}_{rep}.txt", title)
