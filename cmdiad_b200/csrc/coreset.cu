@@ -797,6 +797,11 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
         CS_TRY(cudaMalloc(&force_dev, sizeof(long long) * (size_t)n_select));
         CS_TRY(cudaMemcpyAsync(force_dev, force_idx_host, sizeof(long long) * (size_t)n_select, cudaMemcpyHostToDevice, st));
     }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (getenv("CMDB_TRACE")) {
+        cudaEventCreate(&ev0), cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, st);
+    }
     CoresetParams p{};
     p.N = N, p.d = d, p.n_select = n_select, p.out_idx = idx_dev, p.force_idx = force_dev, p.slots = slots;
     p.world = 1, p.rank = 0, p.row_offset = 0, p.abort_flag = abort_dev, p.spin_limit = 20LL * 1000 * 1000 * 1000;  // ~10 s
@@ -838,6 +843,14 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
         return rc;
     }
     unsigned int aborted = 0;
+    if (getenv("CMDB_TRACE")) {
+        cudaEventRecord(ev1, st);
+        cudaEventSynchronize(ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        fprintf(stderr, "[cmdb] coreset: init + greedy kernel %.3f ms for %lld picks (%.2f us/pick)\n", ms, (long long)n_select,
+                ms * 1e3 / (double)std::max<int64_t>(1, n_select - 1));
+    }
     CS_TRY(cudaMemcpyAsync(out_idx_host, idx_dev, sizeof(long long) * (size_t)n_select, cudaMemcpyDeviceToHost, st));
     CS_TRY(cudaMemcpyAsync(&aborted, abort_dev, sizeof(aborted), cudaMemcpyDeviceToHost, st));
     if (out_min_last_host)
