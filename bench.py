@@ -239,9 +239,13 @@ def run_ours(args):
         flop = 2.0 * B * P * BANK_ROWS * DIM
         tf32_peak = pk["bf16_tflops"] / 2.0
         achieved = flop / (gemm_ms * 1e-3) / 1e12
+        # DRAM bytes of one launch from the ncu --set full capture of this workload (profiles/r01_prof_gemm.txt:
+        # dram__bytes_read.sum + dram__bytes_write.sum at batch 16); algorithmic bytes = bank hi+lo once = 614 MB
+        traffic = (836.76e6 + 183.79e6) if B == 16 else None
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                            "frac": achieved / tf32_peak, "traffic": None, "kernel": "score_gemm_kernel",
+                            "frac": achieved / tf32_peak, "traffic": traffic, "kernel": "score_gemm_kernel",
                             "kernel_ms": gemm_ms,
+                            "frac_of_sustained": achieved / (pk["bf16_sustained"] / 2.0) if pk.get("bf16_sustained") else None,
                             "note": f"algorithmic 2*P*R*D FLOP per launch / CUDA-event time of the kernel on its stream; peak = "
                                     f"TF32-equivalent = bf16_tflops/2 of {pk['source']} (burst, kernel timed alone); the kernel "
                                     f"issues 3x these FLOPs as fp16 MMAs (hi.hi + hi.lo + lo.hi): tensor-issue rate "

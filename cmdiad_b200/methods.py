@@ -267,8 +267,40 @@ class Features(torch.nn.Module):
     def predict(self, sample, mask, label, rgb_path):
         self.compute_s_s_map(self._patches(sample), mask, label, rgb_path)
 
+    # ---- batch forms (SURVEY 8f): same per-image results, one cmdb_score_batch call per modality ------------------
+    def _score_samples(self, patch_dicts):
+        """[(s [1,m], s_map [gt*gt,m])] for a list of samples: the reference's per-image loop (cmdiad_runner.py:58-65,
+        80-85) collapsed into one batched device call per modality"""
+        cols = []
+        for m in self._score_modals():
+            mean, std = getattr(self, f"{m}_mean"), getattr(self, f"{m}_std")
+            batch = torch.stack([(pd[m] - mean) / std for pd in patch_dicts])
+            side = int(math.sqrt(batch.shape[1]))
+            res = self._lib(m).bank.score_batch(batch, (side, side), out_hw=self.gt_size)
+            cols.append((getattr(self.args, f"{m}_s_lambda"), getattr(self.args, f"{m}_smap_lambda"), res))
+        out = []
+        for i in range(len(patch_dicts)):
+            s = torch.tensor([[lam_s * torch.tensor(res[i].s[0]) for lam_s, _, res in cols]])
+            maps = [lam_m * torch.from_numpy(res[i].s_map).view(1, self.gt_size, self.gt_size) for _, lam_m, res in cols]
+            out.append((s, torch.cat(maps, dim=0).squeeze().reshape(len(maps), -1).permute(1, 0)))
+        return out
+
+    def add_samples_to_late_fusion_mem_bank(self, samples):
+        for s, s_map in self._score_samples([self._patches(x) for x in samples]):
+            self.s_lib.append(s)
+            self.s_map_lib.append(s_map)
+
+    def predict_batch(self, samples, masks, labels, rgb_paths):
+        scored = self._score_samples([self._patches(x) for x in samples])
+        for (s, s_map), mask, label, path in zip(scored, masks, labels, rgb_paths):
+            self._record(s, s_map, mask, label, path)
+
     def compute_s_s_map(self, patches, mask, label, rgb_path=None):
         s, s_map = self._score_sample(patches)
+        self._record(s, s_map, mask, label, rgb_path)
+
+    def _record(self, s, s_map, mask, label, rgb_path):
+        """late-fusion head + result bookkeeping (multiple_features.py:986-1003)"""
         s = torch.tensor(self.detect_fuser.score_samples(s))
         s_map = torch.tensor(self.seg_fuser.score_samples(s_map))
         s_map = s_map.view(1, self.gt_size, self.gt_size)

@@ -84,6 +84,13 @@ def test_hallucination_class_wiring(env, main):
     m.run_late_fusion()
     m.predict({"rgb": rgb[0], "xyz": xyz[0], "fusion": fus[0]}, torch.zeros(1, 224, 224), 0, ["y.png"])
     m.predict({"rgb": rgb[1] + 3, "xyz": xyz[1], "fusion": fus[1] + 3}, torch.ones(1, 224, 224), 1, ["z.png"])
+    # batch forms give the per-image results of the one-by-one calls
+    n_before = len(m.image_preds)
+    samples = [{"rgb": rgb[0], "xyz": xyz[0], "fusion": fus[0]}, {"rgb": rgb[1] + 3, "xyz": xyz[1], "fusion": fus[1] + 3}]
+    m.predict_batch(samples, [torch.zeros(1, 224, 224), torch.ones(1, 224, 224)], [0, 1], [["y.png"], ["z.png"]])
+    for i in range(2):
+        assert (m.image_preds[n_before + i] == m.image_preds[i]).all()
+        assert (m.predictions[n_before + i] == m.predictions[i]).all()
     m.calculate_metrics()
     assert 0.0 <= m.image_rocauc <= 1.0 and 0.0 <= m.pixel_rocauc <= 1.0
     with pytest.raises(NotImplementedError):
