@@ -22,7 +22,7 @@ namespace cmdb {
 
 constexpr int kCsThreads = 512;
 constexpr int kCsWarps = kCsThreads / 32;
-constexpr int kRowBatch = 4;  // rows in flight per warp
+constexpr int kCoresetDynamicDefault = 1;  // grid-wide chunk queue (1) or static CTA->warp row split (0)
 
 struct __align__(16) PickSlot {
     unsigned long long val;  // value bits (non-negative half/double order like unsigned integers)
@@ -51,6 +51,11 @@ __device__ __forceinline__ __half ld_volatile(const __half *p) {
 }
 __device__ __forceinline__ double ld_volatile(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
 __device__ __forceinline__ unsigned int ld_volatile(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+
+__device__ __forceinline__ __half ld_cg(const __half *p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(__half *p, __half v) { __stcg(p, v); }
+__device__ __forceinline__ void st_cg(double *p, double v) { __stcg(p, v); }
 
 template <typename T>
 struct Traits;
@@ -278,6 +283,8 @@ struct CoresetParams {
     int world, rank;
     unsigned char *mb_peer[kMaxRanks];  // mailbox of every rank (mb_peer[rank] is local memory)
     unsigned int mb_slot_stride;        // bytes per (parity, source-rank) slot: 16-byte key header + row data
+    unsigned int *chunk_ctr;            // [3] dynamic scheduling: per-pick work counters (rotating, reset by CTA 0)
+    int dynamic;                        // 1: warps pull 32-row chunks from a grid-wide queue instead of a static split
     const void *last0;                  // [d] global row 0 in storage type (pick 1 measures distances to it)
     unsigned int *abort_flag;           // set when a peer did not answer in time
     long long spin_limit;               // clock64() ticks to wait for a peer
@@ -325,7 +332,7 @@ struct Batch<double> {
     static constexpr int rows = 2;  // 32-byte vectors: keep the register footprint of two batches in flight below 128
 };
 
-template <typename T, int NV>
+template <typename T, int NV, bool DYN>
 __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p) {
     using acc_t = typename Traits<T>::acc_t;
     constexpr int RB = Batch<T>::rows;
@@ -344,25 +351,19 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     const bool vectorized = d >= 128;
     acc_t *tile = tile_all + warp * 32 * 33;
 
-    const long long cta_row0 = (long long)blockIdx.x * p.rows_per_cta;
-    const long long cta_row1 = min(p.N, cta_row0 + p.rows_per_cta);
+    // static mode: this CTA owns rows [cta_row0, cta_row1) and keeps their min-distances in shared memory;
+    // dynamic mode: rows are pulled from a grid-wide queue, min-distances live in global memory (L2, .cg accesses)
+    const long long cta_row0 = DYN ? 0 : (long long)blockIdx.x * p.rows_per_cta;
+    const long long cta_row1 = DYN ? p.N : min(p.N, cta_row0 + p.rows_per_cta);
     const long long cta_rows = max(0LL, cta_row1 - cta_row0);
     T *mind = p.mind_in_smem ? mind_sh : reinterpret_cast<T *>(p.mind) + cta_row0;
+    const bool mind_global = !p.mind_in_smem;
     if (p.mind_in_smem)
         for (long long i = threadIdx.x; i < cta_rows; i += kCsThreads) mind_sh[i] = reinterpret_cast<T *>(p.mind)[cta_row0 + i];
 
     // ---- static work split: 4-warp groups share a contiguous chunk; warp (w & 3) takes its rows with row % 4 == w & 3 ----
     WarpPlan<T, NV> wp;
-    {
-        constexpr int kGroups = kCsWarps / 4;
-        const long long rows_per_group = (cta_rows + kGroups - 1) / kGroups;
-        const long long g_row0 = cta_row0 + (warp >> 2) * rows_per_group;
-        const long long g_row1 = min(cta_row1, g_row0 + rows_per_group);
-        // alignment classes follow the GLOBAL row number (the reference's tensor is one contiguous [N,d] block); the
-        // shard's buffer starts (row_offset*d) & 3 elements past a vector boundary so addresses agree with it
-        const int c = warp & 3;  // this warp takes the local rows whose global row % 4 == c
-        wp.first = g_row0 + ((c - (int)((g_row0 + p.row_offset) & 3)) & 3);
-        wp.n_rows = wp.first < g_row1 ? (g_row1 - wp.first + 3) >> 2 : 0;
+    auto plan_class = [&](int c) {  // geometry of the alignment class of global rows with row % 4 == c
         const int s = vectorized ? (int)(((long long)c * d) & 3) : 0;
         wp.g = class_geom(s, d);
         wp.main_off = wp.g.voff - s + 4 * lane;
@@ -372,7 +373,20 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
         wp.tail_off = wp.g.base + 4 * wp.g.nfull + lane;
 #pragma unroll
         for (int t = 0; t < NV; ++t) wp.vmain[t] = lane + 32 * t < wp.g.nfull;
+    };
+    if (!DYN) {
+        constexpr int kGroups = kCsWarps / 4;
+        const long long rows_per_group = (cta_rows + kGroups - 1) / kGroups;
+        const long long g_row0 = cta_row0 + (warp >> 2) * rows_per_group;
+        const long long g_row1 = min(cta_row1, g_row0 + rows_per_group);
+        // alignment classes follow the GLOBAL row number (the reference's tensor is one contiguous [N,d] block); the
+        // shard's buffer starts (row_offset*d) & 3 elements past a vector boundary so addresses agree with it
+        const int c = warp & 3;  // this warp takes the local rows whose global row % 4 == c
+        wp.first = g_row0 + ((c - (int)((g_row0 + p.row_offset) & 3)) & 3);
+        wp.n_rows = wp.first < g_row1 ? (g_row1 - wp.first + 3) >> 2 : 0;
+        plan_class(c);
     }
+    const long long n_chunks = ((p.N + 127) >> 7) * 4;  // dynamic mode: (128-row block, class) pairs
     const size_t rstride_b = (size_t)4 * d * sizeof(T);  // bytes between consecutive rows of this warp
 
     long long sel = 0;  // features.py:372 -- pick 0 is (global) row 0
@@ -408,11 +422,17 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
         }
         {
             const long long sl = sel - p.row_offset;  // local row of the previous pick, if this shard owns it
-            if (threadIdx.x == 0 && pick > 1 && sl >= cta_row0 && sl < cta_row1) mind[sl - cta_row0] = Traits<T>::zero();
+            if (threadIdx.x == 0 && pick > 1 && sl >= cta_row0 && sl < cta_row1 && (!DYN || blockIdx.x == 0)) {
+                if (mind_global) st_cg(mind + (sl - cta_row0), Traits<T>::zero());
+                else mind[sl - cta_row0] = Traits<T>::zero();
+            }
+            // the counter of the NEXT pick was last used two picks ago and nobody can touch it before this CTA
+            // publishes its slot for the current pick
+            if (DYN && blockIdx.x == 0 && threadIdx.x == 0) p.chunk_ctr[(pick + 1) % 3] = 0u;
         }
         __syncthreads();
         LastRegs<T, NV> L;
-        load_last<T, NV>(L, last_sh, wp.g, lane, d, vectorized);
+        if (!DYN) load_last<T, NV>(L, last_sh, wp.g, lane, d, vectorized);
 
         T best_val = Traits<T>::zero();
         long long best_row = -1;
@@ -433,19 +453,21 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                 }
                 const T dist = Traits<T>::from_acc((q4[0] + q4[1]) + (q4[2] + q4[3]));
                 const long long row = wp.first + 4 * (grp * 32 + lane);
-                T m = mind[row - cta_row0];
+                T m = mind_global ? ld_cg(mind + (row - cta_row0)) : mind[row - cta_row0];
                 if (Traits<T>::lt(dist, m)) {  // torch.minimum (features.py:413)
                     m = dist;
-                    mind[row - cta_row0] = m;
+                    if (mind_global) st_cg(mind + (row - cta_row0), m);
+                    else mind[row - cta_row0] = m;
                 }
-                // argmax, ties -> lowest index (features.py:415); rows of one lane increase, so strict > suffices
-                if (best_row < 0 || Traits<T>::gt(m, best_val)) {
+                // argmax, ties -> lowest index (features.py:415)
+                if (best_row < 0 || Traits<T>::gt(m, best_val) || (!Traits<T>::lt(m, best_val) && row < best_row)) {
                     best_val = m;
                     best_row = row;
                 }
             }
             __syncwarp();
         };
+        auto run_rows = [&]() {  // distance pass over rows wp.first, wp.first + 4, ... (wp.n_rows of them)
         if (vectorized) {
             RowLoads<T, NV> A[RB], B[RB];
             const char *pm = reinterpret_cast<const char *>(z + wp.first * d + wp.main_off);
@@ -496,6 +518,30 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                 issue_row<T, NV>(R, z + (wp.first + 4 * k) * d, wp, lane, d, false);
                 tile[(int)(k & 31) * 33 + lane] = lane_partial<T, NV>(R, L, false);
                 if ((k & 31) == 31 || k == wp.n_rows - 1) finalize(k >> 5, (int)(k & 31) + 1);
+            }
+        }
+        };
+        if constexpr (!DYN) {
+            run_rows();
+        } else {
+            // grid-wide work queue: chunk id -> (128-row block, alignment class); the next id is fetched while the
+            // current chunk is processed
+            unsigned int *ctr = p.chunk_ctr + pick % 3;
+            unsigned int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(ctr, 1u);
+            for (;;) {
+                const unsigned int cur = __shfl_sync(0xffffffffu, nxt, 0);
+                if (cur >= n_chunks) break;
+                if (lane == 0) nxt = atomicAdd(ctr, 1u);
+                const long long blk0 = (long long)(cur >> 2) << 7;
+                const int c = (int)(cur & 3);  // global row % 4 of this chunk's rows
+                wp.first = blk0 + ((c - (int)((blk0 + p.row_offset) & 3)) & 3);
+                const long long blk1 = min(p.N, blk0 + 128);
+                wp.n_rows = wp.first < blk1 ? (blk1 - wp.first + 3) >> 2 : 0;
+                if (wp.n_rows == 0) continue;
+                plan_class(c);
+                load_last<T, NV>(L, last_sh, wp.g, lane, d, vectorized);
+                run_rows();
             }
         }
         // ---- CTA argmax: warp shuffle, then shared memory ----
@@ -694,10 +740,13 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
     const int nv = d >= 128 ? (d / 4 + 31) / 32 : 1;
     int grid = b->num_sms;
     const size_t fixed = sizeof(typename Traits<T>::acc_t) * kCsWarps * 32 * 33 + sizeof(T) * (size_t)d + 16 + 64 * 8;
+    const char *dyn = getenv("CMDB_CORESET_DYNAMIC");
+    const bool dynamic = dyn ? (dyn[0] != '0') : (kCoresetDynamicDefault != 0);
     auto run = [&](auto kern) -> int {
         p.rows_per_cta = (p.N + grid - 1) / grid;
         size_t smem = fixed + sizeof(T) * (size_t)p.rows_per_cta;
-        p.mind_in_smem = smem <= 200 * 1024;
+        p.dynamic = dynamic;
+        p.mind_in_smem = !p.dynamic && smem <= 200 * 1024;
         if (!p.mind_in_smem) smem = fixed;
         CMDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -729,8 +778,8 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
             (void)cudaGetLastError();
         }
         if (getenv("CMDB_TRACE"))
-            fprintf(stderr, "[cmdb] coreset: N=%lld d=%d grid=%d smem=%zu mind_in_smem=%d z=%.1f MB L2 persist=%d (max %d MB, window %d MB, hitRatio %.2f)\n",
-                    p.N, p.d, grid, smem, p.mind_in_smem, z_bytes / 1e6, (int)persisting, max_persist >> 20, max_window >> 20,
+            fprintf(stderr, "[cmdb] coreset: N=%lld d=%d grid=%d smem=%zu dynamic=%d mind_in_smem=%d z=%.1f MB L2 persist=%d (max %d MB, window %d MB, hitRatio %.2f)\n",
+                    p.N, p.d, grid, smem, p.dynamic, p.mind_in_smem, z_bytes / 1e6, (int)persisting, max_persist >> 20, max_window >> 20,
                     persisting ? attr.accessPolicyWindow.hitRatio : 0.f);
         void *args[] = {&p};
         cudaError_t le = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kCsThreads), args, smem, b->stream);
@@ -742,9 +791,9 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
         CMDB_CUDA(le);
         return CMDB_OK;
     };
-#define CMDB_CS(NVV) \
-    case NVV:        \
-        return run(coreset_kernel<T, NVV>);
+#define CMDB_CS(NVV)                                            \
+    case NVV:                                                   \
+        return dynamic ? run(coreset_kernel<T, NVV, true>) : run(coreset_kernel<T, NVV, false>);
     switch (nv) {
         CMDB_CS(1) CMDB_CS(2) CMDB_CS(3) CMDB_CS(4) CMDB_CS(5) CMDB_CS(6) CMDB_CS(7) CMDB_CS(8)
         default:
@@ -791,8 +840,8 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     } while (0)
     CS_TRY(cudaMalloc(&idx_dev, sizeof(long long) * (size_t)n_select));
     CS_TRY(cudaMalloc(&slots, sizeof(PickSlot) * 2 * (size_t)b->num_sms));
-    CS_TRY(cudaMalloc(&abort_dev, sizeof(unsigned int)));
-    CS_TRY(cudaMemsetAsync(abort_dev, 0, sizeof(unsigned int), st));
+    CS_TRY(cudaMalloc(&abort_dev, 4 * sizeof(unsigned int)));  // abort flag + 3 rotating chunk counters
+    CS_TRY(cudaMemsetAsync(abort_dev, 0, 4 * sizeof(unsigned int), st));
     if (force_idx_host) {
         CS_TRY(cudaMalloc(&force_dev, sizeof(long long) * (size_t)n_select));
         CS_TRY(cudaMemcpyAsync(force_dev, force_idx_host, sizeof(long long) * (size_t)n_select, cudaMemcpyHostToDevice, st));
@@ -804,6 +853,7 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     }
     CoresetParams p{};
     p.N = N, p.d = d, p.n_select = n_select, p.out_idx = idx_dev, p.force_idx = force_dev, p.slots = slots;
+    p.chunk_ctr = abort_dev + 1;
     p.world = 1, p.rank = 0, p.row_offset = 0, p.abort_flag = abort_dev, p.spin_limit = 20LL * 1000 * 1000 * 1000;  // ~10 s
     const double *first_row = z_dev;  // pick 0 = global row 0
     if (sharded) {
