@@ -22,7 +22,7 @@ namespace cmdb {
 
 constexpr int kCsThreads = 512;
 constexpr int kCsWarps = kCsThreads / 32;
-constexpr int kCoresetDynamicDefault = 1;  // grid-wide chunk queue (1) or static CTA->warp row split (0)
+constexpr int kCoresetDynamicDefault = 0;  // grid-wide chunk queue (1) or static CTA->warp row split (0)
 
 struct __align__(16) PickSlot {
     unsigned long long val;  // value bits (non-negative half/double order like unsigned integers)
@@ -564,19 +564,32 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                 if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
             }
             if (lane == 0) {
-                st_relaxed_u64(&slots[blockIdx.x].val, bv);
-                st_release_u64(&slots[blockIdx.x].tag, ((unsigned long long)pick << 32) | (br & 0xffffffffULL));
+                if constexpr (sizeof(T) == 2) {
+                    // half: value, row and pick number fit ONE self-flagged 64-bit word -> no fence on either side
+                    st_relaxed_u64(&slots[blockIdx.x].tag,
+                                   ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) | (br & 0xffffffffULL));
+                } else {
+                    st_relaxed_u64(&slots[blockIdx.x].val, bv);
+                    st_release_u64(&slots[blockIdx.x].tag, ((unsigned long long)pick << 32) | (br & 0xffffffffULL));
+                }
             }
         }
-        // ---- grid all-gather of the per-CTA winners through L2 (relaxed polling, one acquire fence at the end) ----
+        // ---- grid all-gather of the per-CTA winners through L2 (relaxed polling) ----
         bv = 0ULL, br = ~0ULL;
         for (int c = threadIdx.x; c < (int)gridDim.x; c += kCsThreads) {
-            unsigned long long tag;
-            do {
-                tag = ld_relaxed_u64(&slots[c].tag);
-            } while ((tag >> 32) != (unsigned long long)pick);
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            const unsigned long long ov = ld_relaxed_u64(&slots[c].val);
+            unsigned long long tag, ov;
+            if constexpr (sizeof(T) == 2) {
+                do {
+                    tag = ld_relaxed_u64(&slots[c].tag);
+                } while ((tag >> 48) != (unsigned long long)(pick & 0xffff));
+                ov = (tag >> 32) & 0xffffULL;
+            } else {
+                do {
+                    tag = ld_relaxed_u64(&slots[c].tag);
+                } while ((tag >> 32) != (unsigned long long)pick);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                ov = ld_relaxed_u64(&slots[c].val);
+            }
             const unsigned long long orow = (tag & 0xffffffffULL) == 0xffffffffULL ? ~0ULL : (tag & 0xffffffffULL);
             if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
         }
