@@ -337,13 +337,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     using acc_t = typename Traits<T>::acc_t;
     constexpr int RB = Batch<T>::rows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: tile [kCsWarps][32][33] acc_t | last [kCsWarps][d_al] T (one copy per warp: no CTA barrier around the
-    //         staging) | red (val,row) [32] | mind [rows_per_cta] T
+    // layout: tile [kCsWarps][32][33] acc_t | last_sh [d] T | red (val,row) [32] | mind [rows_per_cta] T
     acc_t *tile_all = reinterpret_cast<acc_t *>(smem_raw);
-    const int d_al = (p.d + 7) & ~7;
-    T *last_sh = reinterpret_cast<T *>(tile_all + kCsWarps * 32 * 33) + (threadIdx.x >> 5) * d_al;  // this warp's copy of `last`
+    T *last_sh = reinterpret_cast<T *>(tile_all + kCsWarps * 32 * 33);
     unsigned long long *red_val = reinterpret_cast<unsigned long long *>(
-        (reinterpret_cast<uintptr_t>(reinterpret_cast<T *>(tile_all + kCsWarps * 32 * 33) + kCsWarps * d_al) + 15) & ~uintptr_t(15));
+        (reinterpret_cast<uintptr_t>(last_sh + p.d) + 15) & ~uintptr_t(15));
     unsigned long long *red_row = red_val + 32;
     T *mind_sh = reinterpret_cast<T *>(red_row + 32);
 
@@ -398,15 +396,15 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[0] = 0;
 
     for (long long pick = 1; pick < p.n_select; ++pick) {
-        // ---- every warp stages its own copy of `last` = z[sel]; the owner CTA zeroes min_d[sel] (features.py:418-419).
-        //      No CTA barrier: the only cross-warp dependency of a pick is the argmax hand-over below ----
+        // ---- stage `last` = z[sel] in shared memory; owner CTA zeroes min_d[sel] (features.py:418-419) ----
+        __syncthreads();
         if (p.world > 1 && pick == 1) {
-            for (int e = lane; e < d; e += 32) last_sh[e] = reinterpret_cast<const T *>(p.last0)[e];
+            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = reinterpret_cast<const T *>(p.last0)[e];
         } else if (p.world > 1) {
             // sel is a GLOBAL row: its values are the winner's row words in the local mailbox (flagged with pick - 1)
             const unsigned char *src = p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) * p.mb_slot_stride + 16;
             const long long t0 = clock64();
-            for (int w2 = lane; w2 < ((d + 1) >> 1); w2 += 32) {
+            for (int w2 = threadIdx.x; w2 < ((d + 1) >> 1); w2 += kCsThreads) {
                 unsigned long long word;
                 for (;;) {
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src + 8 * w2) : "memory");
@@ -420,10 +418,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                 if (2 * w2 + 1 < d) last_sh[2 * w2 + 1] = Traits<T>::from_bits((unsigned short)((word >> 16) & 0xffffu));
             }
         } else {
-            for (int e = lane; e < d; e += 32) last_sh[e] = __ldg(z + sel * d + e);
+            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
         }
         {
-            // benign race with the owning warp's update of the same entry: ||z_sel - z_sel|| = 0 wins the min anyway
             const long long sl = sel - p.row_offset;  // local row of the previous pick, if this shard owns it
             if (threadIdx.x == 0 && pick > 1 && sl >= cta_row0 && sl < cta_row1 && (!DYN || blockIdx.x == 0)) {
                 if (mind_global) st_cg(mind + (sl - cta_row0), Traits<T>::zero());
@@ -431,12 +428,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             }
             // the counter of the NEXT pick was last used two picks ago and nobody can touch it before this CTA
             // publishes its slot for the current pick
-            if (DYN && blockIdx.x == 0 && threadIdx.x == 0) {
-                p.chunk_ctr[(pick + 1) % 3] = 0u;
-                __threadfence();
-            }
+            if (DYN && blockIdx.x == 0 && threadIdx.x == 0) p.chunk_ctr[(pick + 1) % 3] = 0u;
         }
-        __syncwarp();
+        __syncthreads();
         LastRegs<T, NV> L;
         if (!DYN) load_last<T, NV>(L, last_sh, wp.g, lane, d, vectorized);
 
@@ -580,10 +574,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                 }
             }
         }
-        // ---- grid all-gather of the per-CTA winners through L2: EVERY warp polls all slots itself (relaxed loads), so
-        //      no CTA barrier / shared-memory broadcast follows ----
+        // ---- grid all-gather of the per-CTA winners through L2 (relaxed polling) ----
         bv = 0ULL, br = ~0ULL;
-        for (int c = lane; c < (int)gridDim.x; c += 32) {
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += kCsThreads) {
             unsigned long long tag, ov;
             if constexpr (sizeof(T) == 2) {
                 do {
@@ -603,6 +596,15 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             unsigned long long ov = __shfl_xor_sync(0xffffffffu, bv, o), orow = __shfl_xor_sync(0xffffffffu, br, o);
+            if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+        }
+        __syncthreads();  // red_* reads of the CTA stage are done
+        if (lane == 0) red_val[warp] = bv, red_row[warp] = br;
+        __syncthreads();
+        bv = red_val[0], br = red_row[0];
+#pragma unroll
+        for (int w = 1; w < kCsWarps; ++w) {
+            const unsigned long long ov = red_val[w], orow = red_row[w];
             if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
         }
         long long argmax = (long long)br;  // local row (or ~0 when this GPU has no rows)
@@ -750,7 +752,7 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
     const int d = p.d;
     const int nv = d >= 128 ? (d / 4 + 31) / 32 : 1;
     int grid = b->num_sms;
-    const size_t fixed = sizeof(typename Traits<T>::acc_t) * kCsWarps * 32 * 33 + sizeof(T) * (size_t)((d + 7) & ~7) * kCsWarps + 16 + 64 * 8;
+    const size_t fixed = sizeof(typename Traits<T>::acc_t) * kCsWarps * 32 * 33 + sizeof(T) * (size_t)d + 16 + 64 * 8;
     const char *dyn = getenv("CMDB_CORESET_DYNAMIC");
     const bool dynamic = dyn ? (dyn[0] != '0') : (kCoresetDynamicDefault != 0);
     auto run = [&](auto kern) -> int {
