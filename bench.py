@@ -292,6 +292,34 @@ def run_ours(args):
                                             f"call incl. projection (max over ranks); peak = {world} x HBM; the projected bank "
                                             f"({BANK_ROWS * d_proj * 2 / 1e6:.0f} MB) is pinned in L2 as far as it fits, so "
                                             f"achieved/HBM-peak may exceed 1", "unique": int(len(set(idx.tolist())))}
+    if world == 1 and rank == 0 and not args.skip_cpu and not args.skip_coreset:
+        # the reference's own coreset path on the same projected bank: its torch loop on this GPU ("reference
+        # GPU" line, features.py:401-420 as shipped) and on the host cores, both timed on a bounded number of picks and
+        # extrapolated linearly (per-pick cost is constant); sklearn's projection timed on a row sample
+        from oracle import restate as O
+        z = torch.from_numpy(bank.project(csr))
+        picks_gpu, picks_cpu = 200, 12
+        O.coreset_torch_literal(z[:4096], 8, "FP16", device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref_idx = O.coreset_torch_literal(z, picks_gpu + 1, "FP16", device="cuda")
+        torch.cuda.synchronize()
+        t_gpu = (time.perf_counter() - t0) / picks_gpu
+        t0 = time.perf_counter()
+        O.coreset_torch_literal(z, picks_cpu + 1, "FP16", device="cpu")
+        t_cpu = (time.perf_counter() - t0) / picks_cpu
+        sample = bank.read(0, 20_000)
+        from sklearn import random_projection as _rp
+        t0 = time.perf_counter()
+        _rp.SparseRandomProjection(n_components=csr[3], random_state=0).fit_transform(sample)
+        t_proj = (time.perf_counter() - t0) * (BANK_ROWS / 20_000)
+        line["coreset_baselines"] = {
+            "reference_torch_cuda_loop_s": t_gpu * (n_sel - 1), "reference_torch_cpu_loop_s": t_cpu * (n_sel - 1),
+            "sklearn_projection_s": t_proj, "cores": torch.get_num_threads(),
+            "first_picks_equal_ours": bool((ref_idx.numpy() == idx[:picks_gpu + 1]).all()),
+            "sample": f"torch loop: {picks_gpu} picks on cuda / {picks_cpu} picks on cpu of the same {BANK_ROWS}x{csr[3]} projected bank, "
+                      f"extrapolated to {n_sel - 1}; projection: 20000 rows extrapolated to {BANK_ROWS}"}
+        del z
     if world == 1 and rank == 0 and not args.skip_cpu:  # after every GPU measurement: it keeps all host cores busy
         v, ms = cpu_reference_leg(3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "patch-NN scores/s", "cores": torch.get_num_threads(), "kind": "port",

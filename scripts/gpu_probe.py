@@ -185,10 +185,58 @@ def s_score_big():
     b.close()
 
 
+@section("big banks: 1M x 768 (coreset + scoring) and 627k x 1152 (cfg2 XYZ scoring)")
+def s_big():
+    for (R, D, P, fm) in ((1_000_000, 768, 784, 28), (627_200, 1152, 3136, 56)):
+        cent = synth.centroids(D)
+        b = Bank(D, R)
+        t = time.time()
+        for i in range(R // 50_000 + 1):
+            n = min(50_000, R - i * 50_000)
+            if n > 0:
+                b.append(synth.patches(n, D, seed=800 + i, cent=cent))
+        print(f"R={R} D={D}: filled in {time.time() - t:.1f}s")
+        mean, std, _, _ = b.stats()
+        b.normalize(mean, std)
+        if D == 768:
+            csr = O.sparse_components(R, D, 0.9, 0)
+            b.coreset_select(64, csr, L.CORESET_FP16)
+            t = time.time()
+            idx = b.coreset_select(2000, csr, L.CORESET_FP16)
+            dt = time.time() - t
+            print(f"  coreset d'={csr[3]} 2000 picks: {dt:.3f} s ({dt / 1999 * 1e6:.1f} us/pick, {1999 * R * csr[3] * 2 / dt / 1e9:.0f} GB/s algorithmic), unique {len(set(idx.tolist()))}")
+        t = time.time()
+        b.finalize()
+        print(f"  finalize {time.time() - t:.3f}s")
+        nb = 4
+        patches = torch.from_numpy(np.stack([synth.patches(P, D, seed=900 + i, anomalous_frac=0.01, cent=cent) for i in range(nb)])).cuda()
+        patches = (patches - mean) / std
+        r = b.score_batch(patches, (fm, fm), 224)
+        st = b.stream()
+        best, med = ev_time(st, lambda: b.score_batch(patches, (fm, fm), 224), iters=3, warm=1)
+        print(f"  score batch of {nb}x{P}: {med:.2f} ms -> {nb * P / med * 1e3:.0f} patches/s, {2.0 * nb * P * R * D / med / 1e9:.0f} algorithmic TFLOP/s")
+        # brute-force check of image 0 on the GPU (chunks of bank rows to bound memory)
+        q = patches[0]
+        bank_dev = None
+        best_v = torch.full((P,), float("inf"), device="cuda")
+        best_i = torch.zeros(P, dtype=torch.long, device="cuda")
+        for c0 in range(0, R, 100_000):
+            rows = b.read(c0, min(100_000, R - c0)).cuda()
+            dd = torch.cdist(q, rows, compute_mode="donot_use_mm_for_euclid_dist")
+            v, i = dd.min(1)
+            upd = v < best_v
+            best_v = torch.where(upd, v, best_v)
+            best_i = torch.where(upd, i + c0, best_i)
+        mism = (torch.from_numpy(r[0].min_idx).cuda() != best_i).sum().item()
+        rel = (torch.from_numpy(r[0].min_val).cuda() - best_v).abs().max().item() / best_v.max().item()
+        print(f"  vs GPU brute force: argmin mismatches {mism}/{P}, max rel err {rel:.2e}")
+        b.close()
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), torch.__version__)
     which = sys.argv[1:] or ["rownorms", "proj", "blur", "score_small", "coreset_small", "score_big", "coreset_big"]
-    table = dict(rownorms=s_rownorms, proj=s_proj, coreset_small=s_coreset_small, coreset_big=s_coreset_big,
+    table = dict(big=s_big, rownorms=s_rownorms, proj=s_proj, coreset_small=s_coreset_small, coreset_big=s_coreset_big,
                  score_small=s_score_small, blur=s_blur, score_big=s_score_big)
     for w in which:
         table[w]()
