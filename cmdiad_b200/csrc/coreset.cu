@@ -2,18 +2,25 @@
 //
 // Per pick the reference launches >= 8 ATen kernels, materialises z - last as an [N,d'] temporary and syncs the host
 // twice.  Here the whole loop of n-1 dependent picks runs inside one kernel:
-//   * the projected bank z ([N,d'] half or double, natural row-major layout) is streamed once per pick (HBM/L2 bound:
-//     N*d'*sizeof(T) algorithmic bytes per pick); rows are statically partitioned CTA -> warp, so every warp keeps
-//     re-reading the same rows and the running min-distance vector never leaves shared memory;
+//   * the projected bank z ([N,d'] half or double, natural row-major layout) is streamed once per pick
+//     (N*d'*sizeof(T) algorithmic bytes per pick) and pinned in L2 as far as the persisting carve-out allows; rows are
+//     statically split CTA -> 4-warp group -> warp (a warp owns one alignment class of its group's chunk), so the
+//     running min-distance vector never leaves shared memory (a grid-wide chunk queue exists as a template variant,
+//     CMDB_CORESET_DYNAMIC=1; it measured slower);
 //   * the distance ||z_i - last|| is evaluated in the CANONICAL reduction order documented in
 //     oracle/coreset_oracle.c (the order of ATen's CUDA reduction for torch.linalg.norm on a contiguous [N,d'] tensor:
 //     32 lanes per row, aligned 4-element vectors round-robin over lanes, 4 accumulators per lane, fma accumulate,
 //     ((a0+a1)+a2)+a3, shfl_down-shaped tree, IEEE sqrt, one rounding to the storage type), so the selected indices
 //     are bit-identical to the torch-CUDA reference, including its lowest-index tie-break;
-//   * the 32 per-lane partials of 32 rows are transposed through shared memory so that the tree, sqrt, min and
-//     argmax bookkeeping run lane-parallel (one row per lane) instead of as 5 shuffles per row;
-//   * the per-pick grid-wide argmax is an all-gather of one (value,row) slot per CTA through L2 (release store +
-//     acquire polling, double-buffered by pick parity) -- no atomics, no host round trip, ~1 us per pick.
+//   * hot loop: two 4-row batches of loads in flight per warp (running per-lane pointers), HSUB2 + fma.rn.f32.f16
+//     (SASS FHFMA), per-lane partials of 32 rows transposed through shared memory so the tree, sqrt, min and argmax
+//     bookkeeping run lane-parallel (one row per lane) instead of as 5 shuffles per row;
+//   * the per-pick grid-wide argmax is an all-gather of one self-flagged 64-bit word per CTA through L2 (relaxed
+//     stores / relaxed polling, double-buffered by pick parity) -- no atomics, no fences, no host round trip;
+//   * row-sharded mode (one process per GPU): CTA 0 of every GPU pushes its candidate key + row into all ranks'
+//     mailboxes with plain NVLink stores of self-flagged 8-byte words (CUDA-IPC mapped peer memory, csrc/comm.cu); all
+//     CTAs spin on their LOCAL mailbox -- no NCCL call, no system fence per pick; bounded spins turn a missing peer
+//     into an error instead of a hang.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -34,11 +41,6 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -255,17 +257,6 @@ __device__ __forceinline__ typename Traits<T>::acc_t lane_partial(const RowLoads
     return ((acc[0] + acc[1]) + acc[2]) + acc[3];
 }
 
-// shfl_down-shaped tree over 32 partials held by one thread: offsets 1,2,4,8,16, value of "lane 0"
-template <typename A>
-__device__ __forceinline__ A tree32(A (&v)[32]) {
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-#pragma unroll
-        for (int l = 0; l + off < 32; l += 2 * off) v[l] = v[l] + v[l + off];
-    }
-    return v[0];
-}
-
 struct CoresetParams {
     const void *z;               // [N,d] half or double
     void *mind;                  // [N] running min distances (global copy; shared memory is used when it fits)
@@ -442,7 +433,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             __syncwarp();
             if (lane < n_here) {
                 // shfl_down-shaped tree over the row's 32 lane partials, evaluated as 4 sub-trees of 8 to keep the
-                // register footprint small while two batches of loads are in flight (same association as tree32)
+                // register footprint small while two batches of loads are in flight (same association as the shfl_down tree with offsets 1,2,4,8,16)
                 acc_t q4[4];
 #pragma unroll 1
                 for (int blk = 0; blk < 4; ++blk) {
