@@ -21,6 +21,7 @@ SCORE_TCGEN05 = 0
 SCORE_SIMT = 1
 OPT_SCORE_IMPL = 1
 OPT_TIMING = 2
+OPT_PREFILTER_TERMS = 3
 T_STAGES = ("stage_in", "gemm", "refine", "reweight", "map", "out")
 
 c_i64_p = ctypes.POINTER(ctypes.c_int64)

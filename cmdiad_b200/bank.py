@@ -132,6 +132,10 @@ class Bank:
     def set_score_impl(self, impl):
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_SCORE_IMPL, int(impl)))
 
+    def set_prefilter_terms(self, terms):
+        """3 (default): FP32-equivalent distance GEMM; 1: hi.hi pre-filter + exact re-check (opt-in speed mode)"""
+        L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_PREFILTER_TERMS, int(terms)))
+
     def set_timing(self, on=True):
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_TIMING, int(bool(on))))
 

@@ -308,6 +308,11 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
         b->score_impl = value;
         return CMDB_OK;
     }
+    if (option == CMDB_OPT_PREFILTER_TERMS) {
+        CMDB_REQUIRE(value == 1 || value == 3, CMDB_ERR_INVALID, "cmdb_bank_set_option: prefilter terms must be 1 or 3");
+        b->prefilter_terms = value;
+        return CMDB_OK;
+    }
     if (option == CMDB_OPT_TIMING) {
         b->timing = value != 0;
         if (b->timing && !b->ev[0]) {

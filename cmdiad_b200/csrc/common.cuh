@@ -90,6 +90,7 @@ struct cmdb_bank {
     int64_t rows = 0;
     int64_t row_offset = 0;
     int score_impl = CMDB_SCORE_TCGEN05;
+    int prefilter_terms = 3;  // MMAs per K step of the distance GEMM: 3 = FP32-equivalent split, 1 = hi.hi pre-filter
     cudaStream_t stream = nullptr;
     float *data = nullptr;  // [capacity, dim] float32 row-major
     // scoring layout (cmdb_bank_finalize)

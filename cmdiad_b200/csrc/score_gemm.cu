@@ -26,18 +26,21 @@ constexpr int BM = kScoreBM;      // 128 query rows  (UMMA M)
 constexpr int BN = kScoreBN;      // 256 bank rows   (UMMA N)
 constexpr int BK = kScoreBK;      // 64 fp16 = 128 B swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 2;
 constexpr int kGemmThreads = 256;
 constexpr uint32_t kTileABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kTileBBytes = BN * BK * 2;  // 32 KB
-constexpr uint32_t kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // 96 KB
 constexpr uint32_t kTmemCols = 512;
 
+// TERMS = 3: FP32-equivalent split (hi.hi + hi.lo + lo.hi), 96 KB per stage, 2 stages      -- the default product path
+// TERMS = 1: hi.hi only (11-bit operands) as a pre-filter for the exact re-check, 48 KB per stage, 4 stages -- opt-in
+template <int TERMS>
 struct GemmSmem {  // offsets inside dynamic shared memory (1024-byte aligned base)
+    static constexpr int kStages = TERMS == 3 ? 2 : 4;
+    static constexpr uint32_t kStageBytes = (TERMS == 3 ? 2u : 1u) * (kTileABytes + kTileBBytes);
     static constexpr uint32_t stage(int s) { return s * kStageBytes; }
     static constexpr uint32_t a_hi(int s) { return stage(s); }
-    static constexpr uint32_t a_lo(int s) { return stage(s) + kTileABytes; }
-    static constexpr uint32_t b_hi(int s) { return stage(s) + 2 * kTileABytes; }
+    static constexpr uint32_t b_hi(int s) { return stage(s) + kTileABytes; }
+    static constexpr uint32_t a_lo(int s) { return stage(s) + kTileABytes + kTileBBytes; }
     static constexpr uint32_t b_lo(int s) { return stage(s) + 2 * kTileABytes + kTileBBytes; }
     static constexpr uint32_t bnorm = kStages * kStageBytes;              // [2][BN] float
     static constexpr uint32_t bars = bnorm + 2 * BN * 4;                  // mbarriers
@@ -136,25 +139,27 @@ struct GemmParams {
     int cand_stride;    // >= mt * 128
 };
 
+template <int TERMS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, GemmParams p) {
+    using S = GemmSmem<TERMS>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this round-up
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
-    const uint32_t bar_full = sbase + GemmSmem::bars, bar_empty = bar_full + 8 * kStages;
-    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + GemmSmem::bars + 8 * (2 * kStages + 4));
-    float *bnorm_s = reinterpret_cast<float *>(smem + GemmSmem::bnorm);
+    // barriers: full[S::kStages], empty[S::kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+    const uint32_t bar_full = sbase + S::bars, bar_empty = bar_full + 8 * S::kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * S::kStages, bar_tempty = bar_tfull + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bars + 8 * (2 * S::kStages + 4));
+    float *bnorm_s = reinterpret_cast<float *>(smem + S::bnorm);
     // running per-query top-2 of this CTA: lives in global memory (L2), 2 KB read + written per tile, so one launch can
     // sweep any number of M tiles in n-major order (the bank is then read from HBM exactly once per launch)
     float4 *state = p.cand + (size_t)blockIdx.x * p.cand_stride;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < S::kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
@@ -184,12 +189,14 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, kStageBytes);
-                    tma_load_2d(sbase + GemmSmem::a_hi(stage), &tm_qhi, full, kb * BK, m * BM);
-                    tma_load_2d(sbase + GemmSmem::a_lo(stage), &tm_qlo, full, kb * BK, m * BM);
-                    tma_load_2d(sbase + GemmSmem::b_hi(stage), &tm_bhi, full, kb * BK, n * BN);
-                    tma_load_2d(sbase + GemmSmem::b_lo(stage), &tm_blo, full, kb * BK, n * BN);
-                    if (++stage == kStages) stage = 0, phase ^= 1;
+                    mbar_expect_tx(full, S::kStageBytes);
+                    tma_load_2d(sbase + S::a_hi(stage), &tm_qhi, full, kb * BK, m * BM);
+                    tma_load_2d(sbase + S::b_hi(stage), &tm_bhi, full, kb * BK, n * BN);
+                    if constexpr (TERMS == 3) {
+                        tma_load_2d(sbase + S::a_lo(stage), &tm_qlo, full, kb * BK, m * BM);
+                        tma_load_2d(sbase + S::b_lo(stage), &tm_blo, full, kb * BK, n * BN);
+                    }
+                    if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
             }
         }
@@ -207,19 +214,21 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint64_t a_hi = make_sw128_desc(sbase + GemmSmem::a_hi(stage));
-                    const uint64_t a_lo = make_sw128_desc(sbase + GemmSmem::a_lo(stage));
-                    const uint64_t b_hi = make_sw128_desc(sbase + GemmSmem::b_hi(stage));
-                    const uint64_t b_lo = make_sw128_desc(sbase + GemmSmem::b_lo(stage));
+                    const uint64_t a_hi = make_sw128_desc(sbase + S::a_hi(stage));
+                    const uint64_t a_lo = make_sw128_desc(sbase + S::a_lo(stage));
+                    const uint64_t b_hi = make_sw128_desc(sbase + S::b_hi(stage));
+                    const uint64_t b_lo = make_sw128_desc(sbase + S::b_lo(stage));
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                         const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
                         umma_f16(tmem_d, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) != 0);
-                        umma_f16(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1);
-                        umma_f16(tmem_d, a_lo + adv, b_hi + adv, kIdesc, 1);
+                        if constexpr (TERMS == 3) {
+                            umma_f16(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1);
+                            umma_f16(tmem_d, a_lo + adv, b_hi + adv, kIdesc, 1);
+                        }
                     }
                     umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
-                    if (++stage == kStages) stage = 0, phase ^= 1;
+                    if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
                 umma_commit(bar_tfull + 8 * buf);  // accumulator complete
             }
@@ -432,7 +441,7 @@ int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
     cudaStream_t st = b->stream;
-    CMDB_CUDA(cudaFuncSetAttribute(score_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem::total + 1024));
+
     GemmParams p{};
     p.nt = (int)(b->fin_rows_pad / BN);
     p.kb = b->dim / BK;
@@ -442,10 +451,16 @@ int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     p.cand = s.cand;
     p.cand_stride = s.cap_p;
     p.mt = p_pad / BM;
-    score_gemm_kernel<<<b->num_sms, kGemmThreads, GemmSmem::total + 1024, st>>>(
-        *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
-        *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
-    CMDB_CUDA(cudaGetLastError());
+    auto launch = [&](auto kern, size_t smem) -> int {
+        CMDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<b->num_sms, kGemmThreads, smem, st>>>(
+            *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
+            *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
+        CMDB_CUDA(cudaGetLastError());
+        return CMDB_OK;
+    };
+    if (b->prefilter_terms == 1) CMDB_CHECK(launch(score_gemm_kernel<1>, GemmSmem<1>::total + 1024));
+    else CMDB_CHECK(launch(score_gemm_kernel<3>, GemmSmem<3>::total + 1024));
     *n_cand_out = b->num_sms;
     return CMDB_OK;
 }

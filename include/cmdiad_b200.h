@@ -48,6 +48,11 @@ typedef enum cmdb_status {
 #define CMDB_SCORE_SIMT 1    /* plain fp32 CUDA-core kernel, diagnostics only (same outputs, ~10x slower) */
 
 #define CMDB_OPT_SCORE_IMPL 1
+/* MMAs per K step of the distance GEMM.  3 (default): FP32-equivalent split hi.hi + hi.lo + lo.hi.  1: hi.hi only --
+ * the GEMM then only PRE-FILTERS candidates with 11-bit operands; final indices and distances still come from the exact
+ * float32 re-check of the best candidates, so results are unchanged unless more than 3 bank rows tie with the true
+ * nearest neighbour within ~1e-5 relative.  Opt-in speed mode, not used for the headline numbers. */
+#define CMDB_OPT_PREFILTER_TERMS 3
 #define CMDB_OPT_TIMING 2 /* 1 = record CUDA events between the stages of cmdb_score (see cmdb_bank_get_timings) */
 
 /* stage indices of cmdb_bank_get_timings */

@@ -124,6 +124,23 @@ def test_score_batch_equals_single_calls(env, B, P, fm, D):
     b.close()
 
 
+def test_prefilter_mode_gives_identical_results(env):
+    """CMDB_OPT_PREFILTER_TERMS = 1 (hi.hi GEMM as a pre-filter + exact re-check) must reproduce the default
+    FP32-equivalent path bit for bit on clustered and on iid data"""
+    from cmdiad_b200 import synth
+    for dist, R in (("C", 60000), ("G", 30000)):
+        lib = synth.patches(R, 768, seed=33, dist=dist)
+        patches = np.stack([synth.patches(784, 768, seed=400 + i, dist=dist, anomalous_frac=0.01) for i in range(4)])
+        b = _bank(env, lib)
+        ref = b.score_batch(patches, (28, 28), 224)
+        b.set_prefilter_terms(1)
+        fast = b.score_batch(patches, (28, 28), 224)
+        for i in range(4):
+            for name in ("min_idx", "min_val", "s", "s_idx", "nn_idx", "s_map"):
+                assert (getattr(ref[i], name) == getattr(fast[i], name)).all(), (dist, i, name)
+        b.close()
+
+
 def test_score_duplicate_rows_lowest_index(env):
     """exact ties in the bank: argmin must be the lowest row (torch.min semantics, features.py:227)"""
     from cmdiad_b200 import synth
