@@ -128,6 +128,7 @@ class Bank:
 
     def set_row_offset(self, off):
         L.check(self._lib.cmdb_bank_set_row_offset(self._h, int(off)))
+        self._row_off = int(off)
 
     def set_score_impl(self, impl):
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_SCORE_IMPL, int(impl)))
@@ -178,6 +179,28 @@ class Bank:
 
     def finalize(self):
         L.check(self._lib.cmdb_bank_finalize(self._h))
+
+    # ---- persistence (the reference rebuilds its banks on every run and never saves them) -------------------
+    def save(self, path, **meta):
+        """rows (float32, exactly as stored: normalised / subsampled) + row_offset + caller metadata -> one .npz"""
+        np.savez(path, rows=self.read().numpy(), dim=np.int64(self.dim), row_offset=np.int64(self._row_offset()),
+                 **{f"meta_{k}": np.asarray(v) for k, v in meta.items()})
+
+    @classmethod
+    def load(cls, path, device=0, finalize=True, capacity_rows=None):
+        """returns (bank, meta dict); the scoring layout is rebuilt on the device (finalize=True)"""
+        with np.load(path) as f:
+            rows = f["rows"]
+            bank = cls(int(f["dim"]), capacity_rows or max(1, rows.shape[0]), device=device, row_offset=int(f["row_offset"]))
+            meta = {k[5:]: f[k] for k in f.files if k.startswith("meta_")}
+        if rows.shape[0]:
+            bank.append(rows)
+            if finalize:
+                bank.finalize()
+        return bank, meta
+
+    def _row_offset(self):
+        return getattr(self, "_row_off", 0)
 
     # ---- coreset ---------------------------------------------------------------------------------------------
     @staticmethod

@@ -321,6 +321,33 @@ class Features(torch.nn.Module):
         self.image_rocauc = roc_auc_score(self.image_labels, self.image_preds)
         self.pixel_rocauc = roc_auc_score(self.pixel_labels, self.pixel_preds)
 
+    # ---- persistence of the fitted state (banks after run_coreset, statistics, late-fusion head) ----------------------
+    def save_state(self, directory):
+        """after run_coreset (and optionally run_late_fusion): one .npz per bank + the scalars; load_state restores a
+        ready-to-predict object without re-running the coreset selection"""
+        import os
+        import pickle
+        os.makedirs(directory, exist_ok=True)
+        for m in self.bank_modals:
+            self._banks[m].save(os.path.join(directory, f"bank_{m}.npz"), mean=np.float32(getattr(self, f"{m}_mean")),
+                                std=np.float32(getattr(self, f"{m}_std")))
+        with open(os.path.join(directory, "fusers.pkl"), "wb") as f:
+            pickle.dump({"detect": self.detect_fuser, "seg": self.seg_fuser, "coreset_idx": self.coreset_idx}, f)
+
+    def load_state(self, directory):
+        import os
+        import pickle
+        for m in self.bank_modals:
+            bank, meta = Bank.load(os.path.join(directory, f"bank_{m}.npz"), device=self.cuda_device,
+                                   finalize=m in self._score_modals())
+            self._banks[m] = bank
+            setattr(self, f"{m}_mean", torch.tensor(np.float32(meta["mean"])))
+            setattr(self, f"{m}_std", torch.tensor(np.float32(meta["std"])))
+            setattr(self, f"patch_{m}_lib", DeviceLib(bank))
+        with open(os.path.join(directory, "fusers.pkl"), "rb") as f:
+            d = pickle.load(f)
+        self.detect_fuser, self.seg_fuser, self.coreset_idx = d["detect"], d["seg"], d["coreset_idx"]
+
     def close(self):
         for b in self._banks.values():
             b.close()

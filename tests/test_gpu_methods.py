@@ -52,6 +52,16 @@ def test_rgb_features_fp16_pipeline_vs_oracle(env):
     assert m.predictions[0].shape == (224, 224) and len(m.pixel_preds) == 224 * 224
     s_ref = m.detect_fuser.score_samples(np.array([[m.args.rgb_s_lambda * ref["s"]]]))
     np.testing.assert_allclose(m.image_preds[0], s_ref, rtol=1e-4)
+    # persistence: a fresh object restored from disk predicts identically without re-running the coreset
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        m.save_state(tmp)
+        m2 = RGBFeatures(default_args(coreset_dtype="FP16", random_state=None))
+        m2.load_state(tmp)
+        m2.predict({"rgb": test}, torch.zeros(1, 224, 224), 1, ["x.png"])
+        assert (m2.image_preds[0] == m.image_preds[0]).all() and (m2.predictions[0] == m.predictions[0]).all()
+        assert (m2.patch_rgb_lib[:] == m.patch_rgb_lib[:]).all() and float(m2.rgb_std) == float(m.rgb_std)
+        m2.close()
     m.close()
 
 
