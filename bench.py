@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 BANK_ROWS, DIM, P, FMAP, OUT_HW = 200_000, 768, 784, 28, 224
 METRIC = "patch-NN scores/sec at 200k x 768 bank"
+# dram__bytes_read.sum + dram__bytes_write.sum of one score_gemm_kernel<1> launch at batch 16 (ncu --set full capture,
+# profiles/r01_prof_gemm.txt); None until captured
+GEMM1_DRAM_BYTES_B16 = None
 WORKLOAD = ("cfg5 headline: score 784-patch images (28x28x768) against an un-subsampled 200000x768 fp32 bank "
             "(min/argmin + s*/m*/top-3 reweight + bilinear 224^2 + blur); coreset 10% of the same bank reported beside")
 
@@ -221,47 +224,57 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": "patch-NN scores/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate, exact fp32 re-check)",
+            "vs_baseline": None,
+            "dtype": "f32 (fp16 tensor-core pre-filter with an error-bound certificate, exact fp32 re-check, FP32-equivalent "
+                     "fp16 hi/lo fallback)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "bank_rows": BANK_ROWS, "dim": DIM, "patches_per_image": P,
                        "images_per_step": B,
                        "sharding": "single GPU" if world == 1 else f"bank row-sharded over {world} GPUs, 4 NCCL collectives (MIN/SUM/all-gather) "
                                                                     f"per step, map + device->host of image i on rank i % {world}",
-                       "l2": "inputs larger than L2: the bank streams 1.2 GB (fp16 hi+lo, fp32 rows) per step vs 126 MB of L2"},
+                       "l2": "inputs larger than L2: the bank streams 0.9 GB (fp16 rows for the GEMM, fp32 rows for the re-weighting) per step vs 126 MB of L2"},
             "e2e": {"value": e2e, "unit": "patch-NN scores/s", "h2d_bytes_per_step": B * P * DIM * 4,
                     "d2h_bytes_per_step": B * (OUT_HW * OUT_HW * 4 + P * 12 + 64)},
-            # per step: q_split, ceil(B*P/1024) GEMM launches, refine, reweight, 2 blur kernels (+ pack/unpack/select/merge/
-            # final/contrib in the sharded protocol); two timed loops (device-resident and host inputs)
-            "gpu_launches": args.steps * 2 * ((B * P + 1023) // 1024 + (5 if world == 1 else 11)),
+            # per step: q_split, GEMM, certified refine, decide, rescan, rescan-finish, GEMM-fallback chain (q_split, GEMM,
+            # refine: sized on the device, empty unless many certificates fail), reweight, 2 blur kernels (+ pack/unpack/
+            # select/merge/final/contrib in the sharded protocol); two timed loops (device-resident and host inputs)
+            "gpu_launches": args.steps * 2 * (12 if world == 1 else 18),
             "clocks": clk.summary()}
     if world == 1:
         gemm_ms = float(np.mean([s["gemm"] for s in stages]))
         flop = 2.0 * B * P * BANK_ROWS * DIM
-        tf32_peak = pk["bf16_tflops"] / 2.0
         achieved = flop / (gemm_ms * 1e-3) / 1e12
+        stats = bank.score_stats()
         # DRAM bytes of one launch from the ncu --set full capture of this workload (profiles/r01_prof_gemm.txt:
-        # dram__bytes_read.sum + dram__bytes_write.sum at batch 16); algorithmic bytes = bank hi+lo once = 614 MB
-        traffic = (836.76e6 + 183.79e6) if B == 16 else None
-        line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                            "frac": achieved / tf32_peak, "traffic": traffic, "kernel": "score_gemm_kernel",
+        # dram__bytes_read.sum + dram__bytes_write.sum at batch 16); algorithmic bytes = fp16 bank once = 307 MB
+        traffic = GEMM1_DRAM_BYTES_B16 if B == 16 else None
+        line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "kernel": "score_gemm_kernel<1>",
                             "kernel_ms": gemm_ms,
-                            "frac_of_sustained": achieved / (pk["bf16_sustained"] / 2.0) if pk.get("bf16_sustained") else None,
-                            "note": f"algorithmic 2*P*R*D FLOP per launch / CUDA-event time of the kernel on its stream; peak = "
-                                    f"TF32-equivalent = bf16_tflops/2 of {pk['source']} (burst, kernel timed alone); the kernel "
-                                    f"issues 3x these FLOPs as fp16 MMAs (hi.hi + hi.lo + lo.hi): tensor-issue rate "
-                                    f"{3 * achieved:.0f} of {pk['bf16_tflops']:.0f} fp16 TFLOP/s"}
+                            "frac_of_sustained": achieved / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
+                            "note": f"algorithmic 2*P*R*D FLOP per launch / CUDA-event time of the kernel on its stream; the "
+                                    f"certified pre-filter issues exactly these FLOPs as fp16 tcgen05 MMAs, so peak = dense "
+                                    f"16-bit tensor throughput of {pk['source']} (burst, kernel timed alone)"}
+        line["prefilter"] = {"mode": stats["mode"], "queries_per_step": stats["queries"],
+                             "uncertified_queries_last_step": stats["fallback_queries"],
+                             "rescan_pairs_last_step": stats["rescan_pairs"], "gemm_fallback_last_step": stats["gemm_fallback"],
+                             "note": "mode 0 = certified hi.hi pre-filter; where the error-bound certificate fails the rows it could not "
+                                     "exclude are rescanned exactly (or, for many failures, the queries are redone with the "
+                                     "FP32-equivalent 3-term GEMM) inside the same call; results identical to mode 3"}
         line["stage_ms"] = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
-        # opt-in speed mode (NOT the headline): hi.hi GEMM as a pre-filter, final results from the same exact re-check
-        bank.set_prefilter_terms(1)
+        # the FP32-equivalent 3-term GEMM for every query (CMDB_OPT_PREFILTER_TERMS=3), same results, for comparison
+        bank.set_prefilter_terms(3)
         for i in range(3):
             step(dev[i % n_img])
-        ms_fast, wall_fast, st_fast = timed(dev, max(5, args.steps // 2), collect_stage=True)
-        bank.set_prefilter_terms(3)
-        n_fast = max(5, args.steps // 2)
-        line["prefilter_1term_mode"] = {"value": B * P * n_fast / (max(ms_fast, wall_fast) * 1e-3), "unit": "patch-NN scores/s",
-                                        "gemm_ms": float(np.mean([x["gemm"] for x in st_fast])),
-                                        "note": "CMDB_OPT_PREFILTER_TERMS=1: 11-bit operands in the GEMM, identical final "
-                                                "indices/distances via the exact float32 re-check; opt-in, not the headline"}
+        n_full = max(5, args.steps // 2)
+        ms_full, wall_full, st_full = timed(dev, n_full, collect_stage=True)
+        bank.set_prefilter_terms(0)
+        g3 = float(np.mean([x["gemm"] for x in st_full]))
+        line["fp32_equivalent_3term_mode"] = {"value": B * P * n_full / (max(ms_full, wall_full) * 1e-3), "unit": "patch-NN scores/s",
+                                              "gemm_ms": g3, "gemm_tflops_algorithmic": flop / (g3 * 1e-3) / 1e12,
+                                              "frac_of_tf32_equivalent_peak": flop / (g3 * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2.0),
+                                              "note": "CMDB_OPT_PREFILTER_TERMS=3: hi.hi + hi.lo + lo.hi for every query; 3x the "
+                                                      "tensor work; identical outputs"}
         line["single_image"] = {"ms_per_image": single_ms, "value": P / (single_ms * 1e-3), "unit": "patch-NN scores/s",
                                 "stage_ms": single_stage}
         # reweight pass (w_dist over the whole bank) is HBM bound: R*D*4 bytes

@@ -134,8 +134,18 @@ class Bank:
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_SCORE_IMPL, int(impl)))
 
     def set_prefilter_terms(self, terms):
-        """3 (default): FP32-equivalent distance GEMM; 1: hi.hi pre-filter + exact re-check (opt-in speed mode)"""
+        """Distance-GEMM mode.  0 (default): certified hi.hi pre-filter, uncertified queries redone with the
+        FP32-equivalent GEMM; 3: FP32-equivalent GEMM for every query; 1: uncertified pre-filter (diagnostics)."""
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_PREFILTER_TERMS, int(terms)))
+
+    def score_stats(self):
+        """Counters of the last scoring call on this handle: queries, GEMM mode that ran, and for the certified
+        pre-filter how many queries it could not certify, how many (query, producer) pairs were rescanned exactly,
+        whether the 3-term GEMM fallback ran instead, and how many calls the adaptive mode still runs in mode 3."""
+        arr = (ctypes.c_int64 * 6)()
+        L.check(self._lib.cmdb_bank_score_stats(self._h, arr))
+        return {"queries": int(arr[0]), "mode": int(arr[1]), "fallback_queries": int(arr[2]),
+                "rescan_pairs": int(arr[3]), "gemm_fallback": bool(arr[4]), "direct_calls_left": int(arr[5])}
 
     def set_timing(self, on=True):
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_TIMING, int(bool(on))))

@@ -60,17 +60,6 @@ static int stage_patch(cmdb_bank *b, const float *patch, int B, int P, int is_de
     return CMDB_OK;
 }
 
-static int local_min(cmdb_bank *b, int B, int P) {
-    int n_cand = 0;
-    if (b->score_impl == CMDB_SCORE_TCGEN05) {
-        CMDB_CHECK(score_query_prep(b, B * P));
-        CMDB_CHECK(score_gemm_candidates(b, B * P, &n_cand));
-    } else {
-        CMDB_CHECK(score_simt_candidates(b, B * P, &n_cand));
-    }
-    return score_refine(b, B, P, n_cand);
-}
-
 // device->host copy of the result block of a sub-batch, then scatter into the caller's buffers.  All images: ONE copy.
 // A strided subset (sharded finish: this rank owns images img_first, img_first + img_step, ...): the scalar / per-patch
 // prefix in one copy plus one map copy per owned image.
@@ -242,17 +231,7 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
         const float *src = patches + (size_t)b0 * P * b->dim;
         CMDB_MARK(CMDB_T_STAGE_IN);
         CMDB_CHECK(stage_patch(b, src, bc, P, patch_is_device, out_hw));
-        int n_cand = 0;
-        if (b->score_impl == CMDB_SCORE_TCGEN05) {
-            CMDB_CHECK(score_query_prep(b, bc * P));
-            CMDB_MARK(CMDB_T_GEMM);
-            CMDB_CHECK(score_gemm_candidates(b, bc * P, &n_cand));
-        } else {
-            CMDB_MARK(CMDB_T_GEMM);
-            CMDB_CHECK(score_simt_candidates(b, bc * P, &n_cand));
-        }
-        CMDB_MARK(CMDB_T_REFINE);
-        CMDB_CHECK(score_refine(b, bc, P, n_cand));
+        CMDB_CHECK(score_local_min(b, bc, P, CMDB_T_GEMM, CMDB_T_REFINE));
         CMDB_MARK(CMDB_T_REWEIGHT);
         CMDB_CHECK(score_reweight(b, bc, P, true));
         CMDB_MARK(CMDB_T_MAP);
@@ -289,7 +268,7 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_CUDA(cudaSetDevice(b->device));
     if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
     CMDB_CHECK(stage_patch(b, patches, B, P, patch_is_device, out_hw));
-    CMDB_CHECK(local_min(b, B, P));
+    CMDB_CHECK(score_local_min(b, B, P, -1, -1));
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;  // stream-ordered on the handle's stream (cmdb_bank_stream): run the collective there
@@ -349,6 +328,17 @@ int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int B, in
     CMDB_CHECK(score_final(b, B));
     CMDB_CHECK(blur_batch(b, B, fh, fw, out_hw, img_first, img_step));
     return copy_outputs(b, B, P, out_hw, outs, img_first, img_step);
+}
+
+// test hook (not in the public header): the GEMM epilogue's per-CTA top-2 lists of the last call, [n_cta][n_q][4] floats
+int cmdb_debug_read_candidates(cmdb_bank *b, float *out_host, int n_cta, int n_q) {
+    CMDB_REQUIRE(b && out_host && b->ss.cand && n_cta >= 1 && n_cta <= 2 * b->num_sms && n_q >= 1 && n_q <= b->ss.cap_p,
+                 CMDB_ERR_INVALID, "cmdb_debug_read_candidates: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    CMDB_CUDA(cudaMemcpy2D(out_host, sizeof(float4) * n_q, b->ss.cand, sizeof(float4) * b->ss.cap_p, sizeof(float4) * n_q, n_cta,
+                           cudaMemcpyDeviceToHost));
+    return CMDB_OK;
 }
 
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host, float *out_pre_host,

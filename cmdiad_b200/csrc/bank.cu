@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(512) absmax_kernel(const float *__restrict__ x
 __global__ void __launch_bounds__(256) split_rows_kernel_impl(const float *__restrict__ x, int64_t n_rows, int64_t n_pad,
                                                          int dim, float scale, __half *__restrict__ hi,
                                                          __half *__restrict__ lo, float *__restrict__ norm,
-                                                         float pad_norm) {
+                                                         float pad_norm, unsigned int *cert_buf) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const int dim4 = dim >> 2;
@@ -127,26 +127,38 @@ __global__ void __launch_bounds__(256) split_rows_kernel_impl(const float *__res
             continue;
         }
         const float4 *s = reinterpret_cast<const float4 *>(x + r * dim);
-        double acc = 0.0;
+        double acc = 0.0, err = 0.0;  // ||x||^2 (true units), ||x*scale - hi||^2 (scaled units; the residuals are exact)
         for (int c = lane; c < dim4; c += 32) {
             float4 v = __ldg(s + c);
             acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;  // true units
             v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;  // power of two: exact
             __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
             float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            const float r0 = v.x - f0.x, r1 = v.y - f0.y, r2 = v.z - f1.x, r3 = v.w - f1.y;
+            err += (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2 + (double)r3 * r3;
+            __half2 l0 = __floats2half2_rn(r0, r1), l1 = __floats2half2_rn(r2, r3);
             h[c] = make_uint2(*reinterpret_cast<unsigned int *>(&h0), *reinterpret_cast<unsigned int *>(&h1));
             l[c] = make_uint2(*reinterpret_cast<unsigned int *>(&l0), *reinterpret_cast<unsigned int *>(&l1));
         }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) norm[r] = (float)acc;
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            err += __shfl_xor_sync(0xffffffffu, err, o);
+        }
+        if (lane == 0) {
+            norm[r] = (float)acc;
+            if (cert_buf) {  // maxima of ||b|| and ||b - b_hi|| in true units, rounded up (non-negative floats order as uints)
+                atomicMax(cert_buf + 0, __float_as_uint(__double2float_ru(sqrt(acc) * (1.0 + 1e-6))));
+                atomicMax(cert_buf + 1, __float_as_uint(__double2float_ru(sqrt(err) / (double)scale * (1.0 + 1e-6))));
+            }
+        }
     }
 }
 
 void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t n_rows, int64_t n_pad, int dim,
-                       int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm) {
+                       int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm, unsigned int *cert_buf) {
     int grid = (int)std::min<int64_t>((n_pad + 7) / 8, (int64_t)num_sms * 8);
-    split_rows_kernel_impl<<<grid, 256, 0, stream>>>(x, n_rows, n_pad, dim, ldexpf(1.f, scale_exp), hi, lo, norm, pad_norm);
+    split_rows_kernel_impl<<<grid, 256, 0, stream>>>(x, n_rows, n_pad, dim, ldexpf(1.f, scale_exp), hi, lo, norm, pad_norm,
+                                                     cert_buf);
 }
 
 int bank_max_abs(cmdb_bank *b, const float *x, int64_t n, float *out_host) {
@@ -261,6 +273,7 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     cudaFree(b->data);
     cudaFree(b->stats_buf);
     cudaFree(b->absmax_buf);
+    cudaFree(b->cert_buf);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -309,8 +322,11 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
         return CMDB_OK;
     }
     if (option == CMDB_OPT_PREFILTER_TERMS) {
-        CMDB_REQUIRE(value == 1 || value == 3, CMDB_ERR_INVALID, "cmdb_bank_set_option: prefilter terms must be 1 or 3");
+        CMDB_REQUIRE(value == 0 || value == 1 || value == 3, CMDB_ERR_INVALID,
+                     "cmdb_bank_set_option: prefilter terms must be 0 (certified), 1 or 3");
         b->prefilter_terms = value;
+        b->direct_calls_left = 0;
+        b->fail_pending = false;
         return CMDB_OK;
     }
     if (option == CMDB_OPT_TIMING) {
@@ -336,6 +352,20 @@ int cmdb_bank_get_timings(cmdb_bank *b, float *out_ms) {
     CMDB_REQUIRE(b && out_ms, CMDB_ERR_INVALID, "cmdb_bank_get_timings: bad arguments");
     CMDB_REQUIRE(b->timing && b->ev_valid, CMDB_ERR_STATE, "cmdb_bank_get_timings: enable CMDB_OPT_TIMING and call cmdb_score first");
     for (int i = 0; i < CMDB_T_COUNT; ++i) CMDB_CUDA(cudaEventElapsedTime(out_ms + i, b->ev[i], b->ev[i + 1]));
+    return CMDB_OK;
+}
+
+int cmdb_bank_score_stats(cmdb_bank *b, int64_t *out6) {
+    CMDB_REQUIRE(b && out6, CMDB_ERR_INVALID, "cmdb_bank_score_stats: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    const bool cert = b->last_mode == 0 && b->ss.fail_count_host;
+    out6[0] = b->last_queries;
+    out6[1] = b->last_mode;
+    out6[2] = cert ? (int64_t)b->ss.fail_count_host[0] : 0;
+    out6[3] = cert ? (int64_t)b->ss.fail_count_host[1] : 0;
+    out6[4] = cert && b->ss.fail_count_host[1] > cmdb::kRescanMaxPairs;
+    out6[5] = b->direct_calls_left;
     return CMDB_OK;
 }
 
@@ -434,9 +464,16 @@ int cmdb_bank_finalize(cmdb_bank *b) {
     CMDB_CHECK(bank_max_abs(b, b->data, b->rows * b->dim, &absmax));
     CMDB_REQUIRE(isfinite(absmax), CMDB_ERR_INVALID, "cmdb_bank_finalize: bank contains non-finite values");
     b->scale_exp = pick_scale_exp(absmax);
-    launch_split_rows(b->stream, b->num_sms, b->data, b->rows, pad, b->dim, b->scale_exp, b->hi, b->lo, b->norm, INFINITY);
+    if (!b->cert_buf) CMDB_CUDA(cudaMalloc(&b->cert_buf, 2 * sizeof(unsigned int)));
+    CMDB_CUDA(cudaMemsetAsync(b->cert_buf, 0, 2 * sizeof(unsigned int), b->stream));
+    launch_split_rows(b->stream, b->num_sms, b->data, b->rows, pad, b->dim, b->scale_exp, b->hi, b->lo, b->norm, INFINITY,
+                      b->cert_buf);
     CMDB_CUDA(cudaGetLastError());
+    float cert[2] = {0.f, 0.f};
+    CMDB_CUDA(cudaMemcpyAsync(cert, b->cert_buf, sizeof(cert), cudaMemcpyDeviceToHost, b->stream));
     CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    b->cert_bmax = cert[0], b->cert_eb_max = cert[1];
+    b->direct_calls_left = 0, b->fail_pending = false;
     b->fin_rows = b->rows;
     b->fin_rows_pad = pad;
     CMDB_CHECK(score_make_tensor_maps(b));

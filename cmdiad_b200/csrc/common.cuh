@@ -42,6 +42,8 @@ constexpr int kNumSMsDefault = 148;
 constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch box
 constexpr int kScoreBN = 256;        // bank rows per GEMM tile
 constexpr int kScoreBM = 128;        // query rows per GEMM tile
+constexpr int kWorkCap = 8192;       // capacity of ScoreScratch::work_list
+constexpr int kRescanMaxPairs = 4096; // more uncertified (query, producer) pairs than this: 3-term GEMM fallback
 constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 128-byte swizzle row)
 
 // device scratch of one scoring call, sized at finalize time
@@ -52,6 +54,16 @@ struct ScoreScratch {
     __half *q_hi = nullptr;         // [cap_p, D]  split-fp16 query operand
     __half *q_lo = nullptr;
     int *q_scale_exp = nullptr;     // device [cap_p]: per-row exponent e_q with q_hi + q_lo = q * 2^e_q
+    float *q_norm = nullptr;        // [cap_p] ||q|| (rounded up)            -- certified pre-filter, score_tail.cu
+    float *q_eps = nullptr;         // [cap_p] ||q - q_hi * 2^-e_q|| (rounded up)
+    int *fail_list = nullptr;       // [cap_p] query rows whose pre-filter result could not be certified
+    // device control block of the fallback: [0] uncertified queries, [1] (query, producer) pairs to rescan,
+    // [2] rows of the 3-term GEMM fallback, [3] pairs of the exact rescan, [4] queries the rescan finishes
+    // ([2..4] are derived from [0..1] by fallback_decide_kernel: few pairs -> rescan, many -> GEMM)
+    int *fail_ctl = nullptr;
+    int *fail_count_host = nullptr; // pinned copy of [0..1] (statistics / adaptive mode)
+    int2 *work_list = nullptr;      // [kWorkCap] (query row, producer) pairs whose producer may hide rows inside the band
+    unsigned long long *best_key = nullptr;  // [cap_p] running exact (d^2 bits << 32 | row) of the uncertified queries
     void *tmap_qhi = nullptr;       // host CUtensorMap objects for q_hi / q_lo
     void *tmap_qlo = nullptr;
     float *m_test = nullptr;        // [D] patch[s_idx]
@@ -90,7 +102,18 @@ struct cmdb_bank {
     int64_t rows = 0;
     int64_t row_offset = 0;
     int score_impl = CMDB_SCORE_TCGEN05;
-    int prefilter_terms = 3;  // MMAs per K step of the distance GEMM: 3 = FP32-equivalent split, 1 = hi.hi pre-filter
+    // distance GEMM mode: 0 = certified hi.hi pre-filter with FP32-equivalent fallback for uncertified queries (default),
+    // 3 = FP32-equivalent split for every query, 1 = uncertified hi.hi pre-filter (diagnostics)
+    int prefilter_terms = 0;
+    // error-bound inputs of the certificate, true units, rounded up (cmdb_bank_finalize)
+    float cert_bmax = 0.f;    // max ||b||
+    float cert_eb_max = 0.f;  // max ||b - b_hi * 2^-scale_exp||
+    unsigned int *cert_buf = nullptr;  // device [2]: the two maxima as float bits
+    // statistics of the last scoring call / adaptive fallback to the direct 3-term GEMM
+    int64_t last_queries = 0;
+    int last_mode = 0;           // GEMM mode the last call actually ran
+    bool fail_pending = false;   // fail_count_host holds the count of a finished-or-in-flight call
+    int direct_calls_left = 0;   // certified mode: calls to run directly with 3 terms before probing the pre-filter again
     cudaStream_t stream = nullptr;
     float *data = nullptr;  // [capacity, dim] float32 row-major
     // scoring layout (cmdb_bank_finalize)
@@ -117,7 +140,7 @@ namespace cmdb {
 int bank_max_abs(cmdb_bank *b, const float *x, int64_t n, float *out_host);
 int pick_scale_exp(float absmax);
 void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t n_rows, int64_t n_pad, int dim,
-                       int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm);
+                       int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm, unsigned int *cert_buf);
 
 // project.cu
 int project_rows(cmdb_bank *b, const float *x_dev, int64_t n_rows, int D, const int32_t *indptr_h,
@@ -146,8 +169,15 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw);
 int score_max_batch(const cmdb_bank *b);  // images per internal sub-batch (shared-memory bound of reweight_kernel)
 void score_scratch_free(cmdb_bank *b);
 int score_make_tensor_maps(cmdb_bank *b);
-int score_query_prep(cmdb_bank *b, int P);  // q_f32 -> q_hi / q_lo (device-side scale selection)
-int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out);  // q_f32 -> cand via the tcgen05 distance GEMM
+// q_f32 -> q_hi / q_lo (device-side scale selection).  compact = true: only the rows of ss.fail_list (count on the
+// device), written to rows 0..count-1
+int score_query_prep(cmdb_bank *b, int P, bool compact);
+// q_hi / q_lo -> cand via the tcgen05 distance GEMM with `terms` MMAs per K step; compact = true: the M extent is the
+// device-side fail count
+int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out);
+int score_gemm_groups();              // epilogue warp groups per CTA: producers = groups * CTAs
+int score_tile_stride(int mt, int G); // host copy of the GEMM's tile schedule stride
+int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine);  // candidates + refine, all modes
 
 // score_tail.cu
 struct TailResult {  // device-side result block (ScoreScratch::tail)
@@ -157,7 +187,8 @@ struct TailResult {  // device-side result block (ScoreScratch::tail)
     long long m_star_row;  // global row of m_star
 };
 int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out);
-int score_refine(cmdb_bank *b, int B, int P_img, int n_cand);
+int score_refine(cmdb_bank *b, int B, int P_img, int n_cand, bool compact);
+int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand);
 int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star);
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused);
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B);

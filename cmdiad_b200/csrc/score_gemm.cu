@@ -18,6 +18,8 @@
 // Algorithmic work: 2*P*R*D FLOP per image; tensor work is 3x that.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cmdb {
@@ -26,7 +28,7 @@ constexpr int BM = kScoreBM;      // 128 query rows  (UMMA M)
 constexpr int BN = kScoreBN;      // 256 bank rows   (UMMA N)
 constexpr int BK = kScoreBK;      // 64 fp16 = 128 B swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmCtlThreads = 128;  // warps 0-3: TMA / MMA / TMEM alloc / idle; then EG groups of 4 epilogue warps
 constexpr uint32_t kTileABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kTileBBytes = BN * BK * 2;  // 32 KB
 constexpr uint32_t kTmemCols = 512;
@@ -128,8 +130,67 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // N >> 3 in [17,23), M >> 4 in [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Tile schedule shared by the three warp roles: N tiles in order (the bank streams from HBM once); the mt M tiles of
+// N tile n go to the consecutive CTAs (n*s + m) % G, where the stride s >= mt is the next integer coprime with G.
+// With s == mt this is plain round-robin dealing; making s coprime with G keeps the load balanced (every G N-tiles each
+// CTA receives exactly mt tiles) AND lets every CTA see ~R/G rows of every query whatever gcd(mt, G) is -- the
+// certificate of the pre-filter (score_tail.cu) needs the rows inside a query's error band to land in different CTAs'
+// top-2 lists.  Start with n = -1, m = mt.
+__device__ __forceinline__ int tile_stride(int mt) {
+    const int G = (int)gridDim.x;
+    for (int s = mt;; ++s) {
+        int a = s % G, b = G;
+        if (a == 0) a = G;
+        while (b) {
+            const int t = a % b;
+            a = b, b = t;
+        }
+        if (a == 1 || G == 1) return s;
+    }
+}
+__device__ __forceinline__ bool next_tile(int &n, int &m, int mt, int nt, int stride) {
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+    m += G;
+    while (m >= mt) {
+        if (++n >= nt) return false;
+        m = (int)((c + G - ((long long)n * stride) % G) % G);
+    }
+    return true;
+}
+
+// running two smallest (value, bank row) of a stream visited in ascending row order: ties keep the lower row
+struct Top2 {
+    float b1, b2;
+    int i1, i2;
+};
+__device__ __forceinline__ void top2_update(Top2 &t, float v, int col) {
+    const bool c1 = v < t.b1, c2 = v < t.b2;
+    t.i2 = c1 ? t.i1 : (c2 ? col : t.i2);
+    t.b2 = fminf(t.b2, fmaxf(t.b1, v));
+    t.i1 = c1 ? col : t.i1;
+    t.b1 = fminf(t.b1, v);
+}
+// general insert (rows in any order): lexicographic (value, row); row < 0 = empty
+__device__ __forceinline__ void top2_insert(Top2 &t, float v, int i) {
+    if (i < 0) return;
+    const bool c1 = t.i1 < 0 || v < t.b1 || (v == t.b1 && i < t.i1);
+    const bool c2 = t.i2 < 0 || v < t.b2 || (v == t.b2 && i < t.i2);
+    if (c1) t.b2 = t.b1, t.i2 = t.i1, t.b1 = v, t.i1 = i;
+    else if (c2) t.b2 = v, t.i2 = i;
+}
+// 32 accumulator columns of one query row: v = ||b||^2 - 2 a.b, even columns feed list A, odd columns list B
+__device__ __forceinline__ void top2_chunk(const uint32_t (&r)[32], float c, const float *bn, int col, Top2 &ta, Top2 &tb) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+        top2_update(ta, fmaf(__uint_as_float(r[k]), c, bn[k]), col + k);
+        top2_update(tb, fmaf(__uint_as_float(r[k + 1]), c, bn[k + 1]), col + k + 1);
+    }
+}
+
 struct GemmParams {
     int mt;             // M tiles (padded query rows / 128), all handled by one launch
+    const int *m_count; // optional device-side query-row count that overrides mt (fallback launch over the compacted
+                        // uncertified queries; 0 rows -> the kernel returns at once)
     int nt;             // N tiles (bank rows / 256)
     int kb;             // K blocks (D / 64)
     const float *bnorm; // [nt*256] ||b||^2, +inf on padding rows
@@ -139,16 +200,22 @@ struct GemmParams {
     int cand_stride;    // >= mt * 128
 };
 
-template <int TERMS>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int TERMS, int EG>
+__global__ void __launch_bounds__(kGemmCtlThreads + 128 * EG, 1)
 score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, GemmParams p) {
     using S = GemmSmem<TERMS>;
+    constexpr int kGemmThreads = kGemmCtlThreads + 128 * EG;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this round-up
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.m_count) {
+        p.mt = (__ldg(p.m_count) + BM - 1) / BM;
+        if (p.mt == 0) return;  // uniform over the grid, before any barrier / TMEM allocation
+    }
+    const int stride = tile_stride(p.mt);
     // barriers: full[S::kStages], empty[S::kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
     const uint32_t bar_full = sbase + S::bars, bar_empty = bar_full + 8 * S::kStages;
     const uint32_t bar_tfull = bar_empty + 8 * S::kStages, bar_tempty = bar_tfull + 16;
@@ -156,7 +223,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     float *bnorm_s = reinterpret_cast<float *>(smem + S::bnorm);
     // running per-query top-2 of this CTA: lives in global memory (L2), 2 KB read + written per tile, so one launch can
     // sweep any number of M tiles in n-major order (the bank is then read from HBM exactly once per launch)
-    float4 *state = p.cand + (size_t)blockIdx.x * p.cand_stride;
+    // (each epilogue warp group keeps its own list: producer id = EG * CTA + column group)
+    float4 *state = p.cand + (size_t)blockIdx.x * EG * p.cand_stride;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::kStages; ++s) {
@@ -165,27 +233,27 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4);
+            mbar_init(bar_tempty + 8 * b, 4 * EG);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     for (int i = threadIdx.x; i < p.mt * BM; i += kGemmThreads)
-        state[i] = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+#pragma unroll
+        for (int g = 0; g < EG; ++g)
+            state[(size_t)g * p.cand_stride + i] = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
     __threadfence_block();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.mt * p.nt;
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n = t / p.mt, m = t - n * p.mt;
+            for (int n = -1, m = p.mt; next_tile(n, m, p.mt, p.nt, stride);) {
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
@@ -206,7 +274,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int j = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+            for (int n = -1, m = p.mt; next_tile(n, m, p.mt, p.nt, stride); ++j) {
                 const int buf = j & 1;
                 mbar_wait(bar_tempty + 8 * buf, ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -234,48 +302,57 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue: 4 warps, thread == query row =================
+        // ================= epilogue: EG groups of 4 warps; thread == (query row, column group) =================
+        // A warp may only touch the TMEM lane quarter warp % 4, so group g (warps 4+4g .. 7+4g) takes columns
+        // [g, g+1) * 256/EG of every accumulator.  Each group owns a separate running list (no merge needed: the refine
+        // kernels treat every (CTA, group) as one producer).
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;        // column group of the accumulator
         const int row = quarter * 32 + lane;     // row inside the M tile
-        const int et = threadIdx.x - 128;        // 0..127
+        const int et = threadIdx.x - kGemmCtlThreads;  // 0 .. 128*EG-1
+        constexpr int kHalfCols = BN / EG;
+        float4 *my_state = state + (size_t)half * p.cand_stride;
         int j = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
-            const int n = t / p.mt, m_local = t - n * p.mt;
+        for (int n = -1, m_local = p.mt; next_tile(n, m_local, p.mt, p.nt, stride); ++j) {
             const int buf = j & 1;
             float *bn = bnorm_s + buf * BN;
             // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
-            bn[et] = __ldg(p.bnorm + (size_t)n * BN + et);
-            bn[et + 128] = __ldg(p.bnorm + (size_t)n * BN + et + 128);
+#pragma unroll
+            for (int g = 0; g < 2 / EG; ++g) bn[et + g * 128 * EG] = __ldg(p.bnorm + (size_t)n * BN + et + g * 128 * EG);
             // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
             const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + m_local * BM + row)));
-            float4 st = state[m_local * BM + row];
-            float b1 = st.x, b2 = st.z;
-            int i1 = __float_as_int(st.y), i2 = __float_as_int(st.w);
+            // two independent running top-2 lists (even / odd columns) halve the dependent min/select chain; list A
+            // continues this producer's state for the query, list B starts empty and is merged into A after the tile
+            const float4 st = my_state[m_local * BM + row];
+            Top2 ta{st.x, st.z, __float_as_int(st.y), __float_as_int(st.w)};
+            Top2 tb{INFINITY, INFINITY, -1, -1};
             mbar_wait(bar_tfull + 8 * buf, (j >> 1) & 1);
             tc_fence_after();
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // bn[] visible to the 4 epilogue warps
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
-            const int col0 = n * BN;
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");  // bn[] visible to all epilogue warps
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * kHalfCols;
+            const int col0 = n * BN + half * kHalfCols;
+            const float *bnh = bn + half * kHalfCols;
+            // tcgen05.ld of chunk ch + 1 is in flight while chunk ch is processed (ping-pong register sets)
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t r[32];
-                tmem_ld32(taddr + ch * 32, r);
+            for (int ch = 0; ch < kHalfCols / 32; ch += 2) {
                 tmem_ld_wait();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float v = fmaf(__uint_as_float(r[k]), c, bn[ch * 32 + k]);
-                    const int col = col0 + ch * 32 + k;
-                    const bool c1 = v < b1, c2 = v < b2;
-                    i2 = c1 ? i1 : (c2 ? col : i2);
-                    b2 = fminf(b2, fmaxf(b1, v));
-                    i1 = c1 ? col : i1;
-                    b1 = fminf(b1, v);
+                tmem_ld32(taddr + (ch + 1) * 32, rb);
+                top2_chunk(ra, c, bnh + ch * 32, col0 + ch * 32, ta, tb);
+                tmem_ld_wait();
+                if (ch + 2 < kHalfCols / 32) {
+                    tmem_ld32(taddr + (ch + 2) * 32, ra);
+                } else {  // this warp's part of the accumulator is in registers: hand the TMEM buffer back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
                 }
+                top2_chunk(rb, c, bnh + (ch + 1) * 32, col0 + (ch + 1) * 32, ta, tb);
             }
-            state[m_local * BM + row] = make_float4(b1, __int_as_float(i1), b2, __int_as_float(i2));
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            top2_insert(ta, tb.b1, tb.i1);
+            top2_insert(ta, tb.b2, tb.i2);
+            my_state[m_local * BM + row] = make_float4(ta.b1, __int_as_float(ta.i1), ta.b2, __int_as_float(ta.i2));
         }
     }
     tc_fence_before();
@@ -289,17 +366,25 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
 // ---------------------------------------------------------------- query preparation
 // One warp per query row: per-ROW power-of-two scale (max|q_row| -> [2^12, 2^13)), q * 2^e -> fp16 hi/lo; rows >= P are
 // zero.  A per-row scale needs no grid-wide reduction (one launch, no host sync) and is free in the GEMM epilogue,
-// where one thread owns one query row.
+// where one thread owns one query row.  Also emits ||q|| and ||q - q_hi|| (true units, rounded up) for the certificate
+// of the pre-filter.  Compact mode (list != nullptr): output row r is query list[r], r < *count (device-side count).
 __global__ void __launch_bounds__(256) q_split_kernel(const float *__restrict__ q, int P, int P_pad, int dim,
                                                       __half *__restrict__ hi, __half *__restrict__ lo,
-                                                      int *__restrict__ scale_exp_out) {
+                                                      int *__restrict__ scale_exp_out, float *__restrict__ q_norm,
+                                                      float *__restrict__ q_eps, const int *__restrict__ list,
+                                                      const int *__restrict__ count) {
     const int lane = threadIdx.x & 31, dim4 = dim >> 2;
+    if (count) {
+        P = __ldg(count);
+        P_pad = (P + BM - 1) / BM * BM;
+    }
     for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < P_pad; r += gridDim.x * 8) {
         uint2 *h = reinterpret_cast<uint2 *>(hi + (size_t)r * dim), *l = reinterpret_cast<uint2 *>(lo + (size_t)r * dim);
+        const float *src = q + (size_t)((list && r < P) ? __ldg(list + r) : r) * dim;
         float amax = 0.f;
         if (r < P)
             for (int cc = lane; cc < dim4; cc += 32) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(q + (size_t)r * dim) + cc);
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + cc);
                 amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
             }
 #pragma unroll
@@ -312,15 +397,31 @@ __global__ void __launch_bounds__(256) q_split_kernel(const float *__restrict__ 
         }
         if (lane == 0) scale_exp_out[r] = e;
         const float scale = ldexpf(1.f, e);
+        float n2 = 0.f, e2 = 0.f;  // ||q * scale||^2 and ||q * scale - hi||^2 (the residuals are exact in float32)
         for (int cc = lane; cc < dim4; cc += 32) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < P) v = __ldg(reinterpret_cast<const float4 *>(q + (size_t)r * dim) + cc);
+            if (r < P) v = __ldg(reinterpret_cast<const float4 *>(src) + cc);
             v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
             __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
             const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            const float r0 = v.x - f0.x, r1 = v.y - f0.y, r2 = v.z - f1.x, r3 = v.w - f1.y;
+            n2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, n2))));
+            e2 = fmaf(r0, r0, fmaf(r1, r1, fmaf(r2, r2, fmaf(r3, r3, e2))));
+            __half2 l0 = __floats2half2_rn(r0, r1), l1 = __floats2half2_rn(r2, r3);
             h[cc] = make_uint2(*reinterpret_cast<unsigned int *>(&h0), *reinterpret_cast<unsigned int *>(&h1));
             l[cc] = make_uint2(*reinterpret_cast<unsigned int *>(&l0), *reinterpret_cast<unsigned int *>(&l1));
+        }
+        if (q_norm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+            }
+            if (lane == 0) {  // float32 sums of <= 2^20 non-negative terms: 1e-3 relative slack covers their rounding
+                const float inv = ldexpf(1.f, -e);
+                q_norm[r] = __fmul_ru(__fsqrt_ru(n2), inv) * 1.001f;
+                q_eps[r] = __fmul_ru(__fsqrt_ru(e2), inv) * 1.001f;
+            }
         }
     }
 }
@@ -370,6 +471,9 @@ void score_scratch_free(cmdb_bank *b) {
     cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys), cudaFree(s.out_block);
     cudaFree(s.map_tmp), cudaFree(s.map_max), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
     cudaFree(s.top3), cudaFree(s.done_counter);
+    cudaFree(s.q_norm), cudaFree(s.q_eps), cudaFree(s.fail_list), cudaFree(s.fail_ctl);
+    cudaFree(s.work_list), cudaFree(s.best_key);
+    if (s.fail_count_host) cudaFreeHost(s.fail_count_host);
     if (s.out_block_host) cudaFreeHost(s.out_block_host);
     free(s.tmap_qhi), free(s.tmap_qlo);
     s = ScoreScratch();
@@ -394,9 +498,18 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     CMDB_CUDA(cudaMalloc(&s.q_hi, sizeof(__half) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.q_eps, sizeof(float) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.fail_list, sizeof(int) * cap_p));
+    CMDB_CUDA(cudaMalloc(&s.fail_ctl, 8 * sizeof(int)));
+    CMDB_CUDA(cudaMalloc(&s.work_list, sizeof(int2) * kWorkCap));
+    CMDB_CUDA(cudaMalloc(&s.best_key, sizeof(unsigned long long) * cap_p));
+    CMDB_CUDA(cudaMallocHost(&s.fail_count_host, 2 * sizeof(int)));
+    s.fail_count_host[0] = s.fail_count_host[1] = 0;
+    b->fail_pending = false;
     CMDB_CUDA(cudaMalloc(&s.done_counter, sizeof(unsigned int)));
     CMDB_CUDA(cudaMemset(s.done_counter, 0, sizeof(unsigned int)));
-    CMDB_CUDA(cudaMalloc(&s.cand, sizeof(float4) * (size_t)cap_p * b->num_sms));
+    CMDB_CUDA(cudaMalloc(&s.cand, sizeof(float4) * (size_t)cap_p * 2 * b->num_sms));
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
     s.map_stride = map_cap;
     s.off_min_val = up(sizeof(TailResult) * cap_b);
@@ -427,17 +540,38 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     return CMDB_OK;
 }
 
-int score_query_prep(cmdb_bank *b, int P) {
+int score_query_prep(cmdb_bank *b, int P, bool compact) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
     cudaStream_t st = b->stream;
-    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(s.q_f32, P, p_pad, b->dim, s.q_hi, s.q_lo,
-                                                                              s.q_scale_exp);
+    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(
+        s.q_f32, P, p_pad, b->dim, s.q_hi, s.q_lo, s.q_scale_exp, compact ? nullptr : s.q_norm, compact ? nullptr : s.q_eps,
+        compact ? s.fail_list : nullptr, compact ? s.fail_ctl + 2 : nullptr);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
 
-int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
+int score_gemm_groups() {
+    static const int eg = [] {
+        const char *e = getenv("CMDB_GEMM_EPI_GROUPS");
+        return (e && atoi(e) == 1) ? 1 : 2;
+    }();
+    return eg;
+}
+
+int score_tile_stride(int mt, int G) {  // == tile_stride() of the kernel
+    for (int s = mt;; ++s) {
+        int a = s % G, b = G;
+        if (a == 0) a = G;
+        while (b) {
+            const int t = a % b;
+            a = b, b = t;
+        }
+        if (a == 1 || G == 1) return s;
+    }
+}
+
+int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
     cudaStream_t st = b->stream;
@@ -451,17 +585,22 @@ int score_gemm_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     p.cand = s.cand;
     p.cand_stride = s.cap_p;
     p.mt = p_pad / BM;
-    auto launch = [&](auto kern, size_t smem) -> int {
+    p.m_count = compact ? s.fail_ctl + 2 : nullptr;
+    const int eg_env = score_gemm_groups();
+    auto launch = [&](auto kern, size_t smem, int threads) -> int {
         CMDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<b->num_sms, kGemmThreads, smem, st>>>(
+        kern<<<b->num_sms, threads, smem, st>>>(
             *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
             *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
         CMDB_CUDA(cudaGetLastError());
         return CMDB_OK;
     };
-    if (b->prefilter_terms == 1) CMDB_CHECK(launch(score_gemm_kernel<1>, GemmSmem<1>::total + 1024));
-    else CMDB_CHECK(launch(score_gemm_kernel<3>, GemmSmem<3>::total + 1024));
-    *n_cand_out = b->num_sms;
+    const int threads = kGemmCtlThreads + 128 * eg_env;
+    if (terms == 1 && eg_env == 2) CMDB_CHECK(launch(score_gemm_kernel<1, 2>, GemmSmem<1>::total + 1024, threads));
+    else if (terms == 1) CMDB_CHECK(launch(score_gemm_kernel<1, 1>, GemmSmem<1>::total + 1024, threads));
+    else if (eg_env == 2) CMDB_CHECK(launch(score_gemm_kernel<3, 2>, GemmSmem<3>::total + 1024, threads));
+    else CMDB_CHECK(launch(score_gemm_kernel<3, 1>, GemmSmem<3>::total + 1024, threads));
+    *n_cand_out = eg_env * b->num_sms;  // (CTA, column group) producers
     return CMDB_OK;
 }
 

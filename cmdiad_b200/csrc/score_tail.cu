@@ -42,11 +42,14 @@ constexpr int kRefineTop = 4;
 __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                      int P, int P_img, long long row_offset, float *__restrict__ min_val,
-                                                     long long *__restrict__ min_idx, unsigned long long *s_key) {
-    // P = total query rows of the batch (B images of P_img patches each); s_key[b] is image b's packed argmax
+                                                     long long *__restrict__ min_idx, unsigned long long *s_key,
+                                                     const int *__restrict__ list, const int *__restrict__ count) {
+    // P = total query rows of the batch (B images of P_img patches each); s_key[b] is image b's packed argmax.
+    // Compact mode (list != nullptr): candidate column c belongs to query list[c], c < *count.
     const int lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (qi >= P) return;
+    const int qc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // candidate column
+    if (qc >= (count ? __ldg(count) : P)) return;
+    const int qi = list ? __ldg(list + qc) : qc;
     // each lane keeps its own sorted top-4 (approx value, row) over the candidates it scans
     float tv[kRefineTop];
     int ti[kRefineTop];
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
         }
     };
     for (int c = lane; c < n_cand; c += 32) {
-        const float4 t = cand[(size_t)c * cand_stride + qi];
+        const float4 t = cand[(size_t)c * cand_stride + qc];
         insert(t.x, __float_as_int(t.y));
         insert(t.z, __float_as_int(t.w));
     }
@@ -105,6 +108,168 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
         min_val[qi] = dv;
         min_idx[qi] = best_i < 0 ? -1 : (long long)best_i + row_offset;
         // argmax over the image's queries, ties -> lowest query: max of (value bits, ~query)
+        atomicMax(s_key + qi / P_img,
+                  ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// certified refine (hi.hi pre-filter GEMM): one warp per query.  The epilogue's value of bank row r for query q is
+//     v(q,r) = fl(||b_r||^2) - 2 * acc(q_hi . b_hi)        and the exact re-check is  f(q,r) = warp_sqdist(q, b_r).
+// |v + ||q||^2 - f| <= E(q) for every bank row, with
+//     E = 2 (eps_q * Bh + ||q|| * eps_b + kAccModel * (||q|| + eps_q) * Bh) + gamma * (||q|| + B)^2
+//   eps_q = ||q - q_hi||, eps_b = max_r ||b_r - b_hi,r||, B = max ||b||, Bh = B + eps_b          (Cauchy-Schwarz on the
+//   operand rounding), acc_model bounds the accumulation of the exact fp16 products in the tensor core (D/16 MMAs of
+//   16 products each, every addend aligned to the largest exponent and truncated to >= 24 bits: <= (D/16 + 1) * 17 *
+//   2^-23 relative to ||q_hi|| ||b_hi||; tests/test_gpu_score.py measures the real error against this model), gamma =
+//   (D + 16) * 2^-24 covers the float32 rounding of ||b||^2, of the epilogue fma and of warp_sqdist itself.
+// Any row whose v exceeds v_min + 2E therefore cannot be the float32 nearest neighbour (not even through a tie).  Each
+// producer CTA kept its two smallest v; if every CTA's SECOND value is above the threshold, all rows inside the band
+// are first values -> they are ALL re-checked exactly and the result is certified identical to a full exact scan.
+// A producer whose second value is inside the band may hide further rows: the (query, producer) pair is queued and
+// the producer's ~R/producers rows are rescanned exactly (rescan_kernel) -- or, when a call queues more than
+// kRescanMaxPairs pairs (banks full of near-duplicates), the uncertified queries are redone with the FP32-equivalent
+// 3-term GEMM.  Either way min_val / min_idx equal those of an exact scan of the whole bank.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
+                                                          const float *__restrict__ q, const float *__restrict__ bank, int dim,
+                                                          int P, int P_img, long long row_offset,
+                                                          const float *__restrict__ q_norm, const float *__restrict__ q_eps,
+                                                          float bmax, float eb_max, float acc_model,
+                                                          float *__restrict__ min_val,
+                                                          long long *__restrict__ min_idx, unsigned long long *s_key,
+                                                          int *__restrict__ fail_list, int *__restrict__ ctl,
+                                                          int2 *__restrict__ work_list, unsigned long long *__restrict__ best_key) {
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= P) return;
+    float v1min = INFINITY;
+    for (int c = lane; c < n_cand; c += 32) {
+        const float4 t = cand[(size_t)c * cand_stride + qi];
+        if (__float_as_int(t.y) >= 0) v1min = fminf(v1min, t.x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v1min = fminf(v1min, __shfl_xor_sync(0xffffffffu, v1min, o));
+    const float qn = q_norm[qi], qe = q_eps[qi];
+    const float bh = __fadd_ru(bmax, eb_max);
+    float E = __fmul_ru(qe, bh);
+    E = __fmaf_ru(qn, eb_max, E);
+    E = __fmaf_ru(__fmul_ru(acc_model, __fadd_ru(qn, qe)), bh, E);
+    E = __fmul_ru(2.f, E);
+    const float span = __fadd_ru(qn, bmax);
+    E = __fmaf_ru(__fmul_ru((float)(dim + 16) * 5.9604645e-8f, span), span, E);
+    const float thr = __fadd_ru(v1min, __fmul_ru(2.0625f, E));  // 2E plus slack for the float32 evaluation of E itself
+    const bool orderable = v1min < INFINITY && thr < INFINITY;  // false for NaN / overflow: never certify those
+    // exact re-check of every kept value inside the band; producers whose SECOND value is inside the band may hide more
+    float best = INFINITY;
+    int best_i = -1, n_bad = 0;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        const int c = c0 + lane;
+        float4 t = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+        if (c < n_cand) t = cand[(size_t)c * cand_stride + qi];
+        const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
+        const bool in1 = i1 >= 0 && (t.x <= thr || !orderable), in2 = i2 >= 0 && (t.z <= thr || !orderable);
+        unsigned int m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
+        const unsigned int bad = m2;
+        n_bad += __popc(bad);
+        while (m1 | m2) {
+            const bool first = m1 != 0;
+            unsigned int &m = first ? m1 : m2;
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int row = __shfl_sync(0xffffffffu, first ? i1 : i2, src);
+            const float d2 = warp_sqdist(q + (size_t)qi * dim, bank + (size_t)row * dim, dim >> 2, lane);
+            if (best_i < 0 || d2 < best || (d2 == best && row < best_i)) best = d2, best_i = row;
+        }
+        if (bad) {  // queue (query, producer) pairs for the exact rescan of the producer's rows
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ctl + 1, __popc(bad));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (in2) {
+                const int slot = base + __popc(bad & ((1u << lane) - 1u));
+                if (slot < kWorkCap) work_list[slot] = make_int2(qi, c);
+            }
+        }
+    }
+    if (lane != 0) return;
+    if (n_bad == 0 && best_i >= 0) {
+        const float dv = sqrtf(best);
+        min_val[qi] = dv;
+        min_idx[qi] = (long long)best_i + row_offset;
+        atomicMax(s_key + qi / P_img,
+                  ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
+    } else {
+        fail_list[atomicAdd(ctl + 0, 1)] = qi;
+        best_key[qi] = best_i < 0 ? ~0ULL : (((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_i);
+    }
+}
+
+// [2] rows of the GEMM fallback, [3] pairs of the rescan, [4] queries the rescan path finishes
+__global__ void fallback_decide_kernel(int *ctl) {
+    const bool rescan = ctl[1] <= kRescanMaxPairs;
+    ctl[2] = rescan ? 0 : ctl[0];
+    ctl[3] = rescan ? ctl[1] : 0;
+    ctl[4] = rescan ? ctl[0] : 0;
+}
+
+// exact rescan: work item = (query, producer); the producer (CTA c, column group g) saw, for the query's M tile m, the
+// N tiles n with n * stride = c - m (mod G) and of each the columns [g, g+1) * 256 / EG (tile schedule of
+// score_gemm.cu).  Unit = (item, k-th such N tile): one block computes the exact distances of its <= 256/EG rows and
+// folds the smallest (d^2 bits, row) into best_key[query] (atomicMin; d^2 >= 0 so the bits order like the value).
+__global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ work, const int *__restrict__ n_items_ptr,
+                                                     const float *__restrict__ q, const float *__restrict__ bank, int dim,
+                                                     long long rows, int G, int EG, int stride, int nt,
+                                                     unsigned long long *best_key) {
+    __shared__ unsigned long long red[8];
+    const int n_items = min(*n_items_ptr, kWorkCap);
+    const int tiles_per = (nt + G - 1) / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cols = kScoreBN / EG;
+    constexpr int kUnitRows = 32;  // rows per block and step: 4 per warp, so a handful of pairs still fills the GPU
+    const int units_per_tile = cols / kUnitRows;
+    const long long n_units = (long long)n_items * tiles_per * units_per_tile;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int item = (int)(u / (tiles_per * units_per_tile));
+        const int rem = (int)(u % (tiles_per * units_per_tile));
+        const int k = rem / units_per_tile, sub = rem % units_per_tile;
+        const int2 w = work[item];
+        const int qi = w.x, c = w.y / EG, g = w.y % EG;
+        const int m = (qi / kScoreBM) % G;
+        int n0 = 0;  // smallest n with (n * stride) % G == (c - m) mod G (stride is coprime with G)
+        const int want = ((c - m) % G + G) % G;
+        while ((int)(((long long)n0 * stride) % G) != want) ++n0;
+        const int n = n0 + k * G;
+        unsigned long long key = ~0ULL;
+        if (n < nt) {
+            const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows;
+            for (int j = warp; j < kUnitRows; j += 8) {
+                const long long r = r0 + j;
+                if (r >= rows) break;
+                const float d2 = warp_sqdist(q + (size_t)qi * dim, bank + (size_t)r * dim, dim >> 2, lane);
+                const unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)r;
+                key = kk < key ? kk : key;
+            }
+        }
+        __syncthreads();
+        if (lane == 0) red[warp] = key;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < 8; ++i) key = red[i] < key ? red[i] : key;
+            if (key != ~0ULL) atomicMin(best_key + qi, key);
+        }
+    }
+}
+
+__global__ void rescan_finish_kernel(const int *__restrict__ fail_list, const int *__restrict__ count_ptr,
+                                     const unsigned long long *__restrict__ best_key, int P_img, long long row_offset,
+                                     float *__restrict__ min_val, long long *__restrict__ min_idx, unsigned long long *s_key) {
+    const int n = *count_ptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int qi = fail_list[i];
+        const unsigned long long key = best_key[qi];
+        const float dv = sqrtf(__uint_as_float((unsigned int)(key >> 32)));
+        min_val[qi] = dv;
+        min_idx[qi] = key == ~0ULL ? -1 : (long long)(key & 0xffffffffULL) + row_offset;
         atomicMax(s_key + qi / P_img,
                   ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
     }
@@ -199,13 +364,92 @@ int score_simt_candidates(cmdb_bank *b, int P, int *n_cand_out) {
     return CMDB_OK;
 }
 
-int score_refine(cmdb_bank *b, int B, int P_img, int n_cand) {
+int score_refine(cmdb_bank *b, int B, int P_img, int n_cand, bool compact) {
     const int P = B * P_img;
-    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long) * B, b->stream));
+    // compact mode follows score_refine_certified, which already reset s_key and published the certified queries
+    if (!compact) CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long) * B, b->stream));
     refine_kernel<<<(P + 7) / 8, 256, 0, b->stream>>>(b->ss.cand, n_cand, b->ss.cap_p, b->ss.q_f32, b->data, b->dim, P, P_img,
-                                                      b->row_offset, b->ss.min_val, b->ss.min_idx, b->ss.s_key);
+                                                      b->row_offset, b->ss.min_val, b->ss.min_idx, b->ss.s_key,
+                                                      compact ? b->ss.fail_list : nullptr, compact ? b->ss.fail_ctl + 2 : nullptr);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
+}
+
+int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
+    const int P = B * P_img;
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
+    CMDB_CUDA(cudaMemsetAsync(s.fail_ctl, 0, 8 * sizeof(int), st));
+    refine_cert_kernel<<<(P + 7) / 8, 256, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img, b->row_offset,
+                                                    s.q_norm, s.q_eps, b->cert_bmax, b->cert_eb_max,
+                                                    (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f, s.min_val, s.min_idx, s.s_key,
+                                                    s.fail_list, s.fail_ctl, s.work_list, s.best_key);
+    CMDB_CUDA(cudaGetLastError());
+    fallback_decide_kernel<<<1, 1, 0, st>>>(s.fail_ctl);
+    CMDB_CUDA(cudaGetLastError());
+    // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
+    const int p_pad = (P + kScoreBM - 1) / kScoreBM * kScoreBM;
+    const int G = b->num_sms, EG = score_gemm_groups();
+    rescan_kernel<<<b->num_sms * 8, 256, 0, st>>>(s.work_list, s.fail_ctl + 3, s.q_f32, b->data, b->dim, b->fin_rows, G, EG,
+                                                  score_tile_stride(p_pad / kScoreBM, G), (int)(b->fin_rows_pad / kScoreBN),
+                                                  s.best_key);
+    CMDB_CUDA(cudaGetLastError());
+    rescan_finish_kernel<<<8, 256, 0, st>>>(s.fail_list, s.fail_ctl + 4, s.best_key, P_img, b->row_offset, s.min_val, s.min_idx,
+                                            s.s_key);
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
+// min_val / min_idx / s_key of a staged sub-batch (ss.q_f32) in the bank's GEMM mode.  ev_gemm / ev_refine: timing event
+// slots recorded before the (first) GEMM and before the (first) refine, or -1.
+int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    const int P = B * P_img;
+    int n_cand = 0;
+    auto mark = [&](int i) -> int {
+        if (b->timing && i >= 0) CMDB_CUDA(cudaEventRecord(b->ev[i], st));
+        return CMDB_OK;
+    };
+    const int64_t prev_queries = b->last_queries;
+    b->last_queries = P;
+    if (b->score_impl != CMDB_SCORE_TCGEN05) {
+        b->last_mode = 3;
+        CMDB_CHECK(mark(ev_gemm));
+        CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
+        CMDB_CHECK(mark(ev_refine));
+        return score_refine(b, B, P_img, n_cand, false);
+    }
+    int mode = b->prefilter_terms;
+    if (mode == 0) {
+        // adaptive: when most queries of the previous certified call needed the fallback (dense near-duplicate banks),
+        // run the FP32-equivalent GEMM directly for a while, then probe the pre-filter again
+        if (b->fail_pending) {
+            CMDB_CUDA(cudaStreamSynchronize(st));  // the count was copied by the previous call; normally long complete
+            b->fail_pending = false;
+            if (prev_queries > 0 && s.fail_count_host[1] > kRescanMaxPairs && (double)s.fail_count_host[0] > 0.5 * (double)prev_queries)
+                b->direct_calls_left = 32;
+        }
+        if (b->direct_calls_left > 0) {
+            --b->direct_calls_left;
+            mode = 3;
+        }
+    }
+    b->last_mode = mode;
+    CMDB_CHECK(score_query_prep(b, P, false));
+    CMDB_CHECK(mark(ev_gemm));
+    CMDB_CHECK(score_gemm_candidates(b, P, mode == 3 ? 3 : 1, false, &n_cand));
+    CMDB_CHECK(mark(ev_refine));
+    if (mode != 0) return score_refine(b, B, P_img, n_cand, false);
+    CMDB_CHECK(score_refine_certified(b, B, P_img, n_cand));
+    CMDB_CUDA(cudaMemcpyAsync(s.fail_count_host, s.fail_ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    b->fail_pending = true;
+    // tier 2 (many uncertified pairs): FP32-equivalent GEMM over the compacted uncertified queries; every launch sizes
+    // itself from the device-side control block and returns at once in the common case
+    CMDB_CHECK(score_query_prep(b, P, true));
+    CMDB_CHECK(score_gemm_candidates(b, P, 3, true, &n_cand));
+    return score_refine(b, B, P_img, n_cand, true);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

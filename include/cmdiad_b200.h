@@ -48,10 +48,16 @@ typedef enum cmdb_status {
 #define CMDB_SCORE_SIMT 1    /* plain fp32 CUDA-core kernel, diagnostics only (same outputs, ~10x slower) */
 
 #define CMDB_OPT_SCORE_IMPL 1
-/* MMAs per K step of the distance GEMM.  3 (default): FP32-equivalent split hi.hi + hi.lo + lo.hi.  1: hi.hi only --
- * the GEMM then only PRE-FILTERS candidates with 11-bit operands; final indices and distances still come from the exact
- * float32 re-check of the best candidates, so results are unchanged unless more than 3 bank rows tie with the true
- * nearest neighbour within ~1e-5 relative.  Opt-in speed mode, not used for the headline numbers. */
+/* Mode of the distance GEMM behind calculate_dist (features.py:186-190):
+ *  0 (default) CERTIFIED PRE-FILTER: one hi.hi MMA per K step (11-bit operands) finds candidates; a per-query error bound
+ *              (Cauchy-Schwarz on the operand rounding + a model of the tensor-core accumulation) proves for each query
+ *              that every bank row outside the re-checked candidate set is strictly farther in float32 than the row
+ *              returned.  Where the certificate fails, the rows it could not exclude are rescanned exactly (few cases) or
+ *              the queries are redone with mode 3 (many cases) inside the same call.  min_val / min_idx are identical
+ *              to mode 3; cmdb_bank_score_stats reports the counts, and a bank where most queries fail (dense
+ *              near-duplicates) switches itself to mode 3 for the next 32 calls.
+ *  3           FP32-equivalent split for every query: hi.hi + hi.lo + lo.hi, three MMAs per K step.
+ *  1           uncertified hi.hi pre-filter + exact re-check of the 4 best candidates (diagnostics). */
 #define CMDB_OPT_PREFILTER_TERMS 3
 #define CMDB_OPT_TIMING 2 /* 1 = record CUDA events between the stages of cmdb_score (see cmdb_bank_get_timings) */
 
@@ -97,6 +103,12 @@ int cmdb_bank_stream(cmdb_bank *bank, void **out_stream);
 /* milliseconds of each stage (CMDB_T_*) of the last cmdb_score call on this handle; needs CMDB_OPT_TIMING = 1.
  * out_ms: float [CMDB_T_COUNT].  Measured with CUDA events on the handle's stream. */
 int cmdb_bank_get_timings(cmdb_bank *bank, float *out_ms);
+/* statistics of the last scoring call on this handle (waits for the handle's stream): out6[0] = query rows, out6[1] = GEMM
+ * mode that ran (0 / 1 / 3, see CMDB_OPT_PREFILTER_TERMS); mode 0 only: out6[2] = query rows the pre-filter could not
+ * certify, out6[3] = (query, producer) pairs queued for the exact rescan, out6[4] = 1 if there were too many pairs and
+ * the uncertified queries went through the 3-term GEMM instead; out6[5] = calls the adaptive mode will still run
+ * directly in mode 3. */
+int cmdb_bank_score_stats(cmdb_bank *bank, int64_t *out6);
 
 /* ---- coreset: replaces Features.get_coreset_idx_randomp (features.py:360-425) ---- */
 

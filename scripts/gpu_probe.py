@@ -185,6 +185,29 @@ def s_score_big():
     b.close()
 
 
+@section("GEMM mode / batch sweep on the 200k x 768 bank (stage times from the library's CUDA events)")
+def s_gemm_sweep():
+    import bench
+    b = bench.build_bank(0, 1)
+    b.finalize()
+    b.set_timing(True)
+    imgs = torch.stack(bench.test_patches(16)).cuda()
+    for mode in (0, 3):
+        b.set_prefilter_terms(mode)
+        for B in (1, 2, 4, 8, 16):
+            x = imgs[:B].contiguous()
+            for _ in range(3):
+                b.score_batch(x, (28, 28), 224)
+            ts = []
+            for _ in range(6):
+                b.score_batch(x, (28, 28), 224)
+                ts.append(b.timings())
+            med = {k: float(np.median([t[k] for t in ts])) for k in ts[0]}
+            print(f"mode {mode} B={B:2d} gemm {med['gemm']:.3f} refine {med['refine']:.3f} reweight {med['reweight']:.3f} "
+                  f"map {med['map']:.3f} out {med['out']:.3f} stage_in {med['stage_in']:.3f}  stats {b.score_stats()}", flush=True)
+    b.close()
+
+
 @section("big banks: 1M x 768 (coreset + scoring) and 627k x 1152 (cfg2 XYZ scoring)")
 def s_big():
     for (R, D, P, fm) in ((1_000_000, 768, 784, 28), (627_200, 1152, 3136, 56)):
@@ -237,6 +260,6 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), torch.__version__)
     which = sys.argv[1:] or ["rownorms", "proj", "blur", "score_small", "coreset_small", "score_big", "coreset_big"]
     table = dict(big=s_big, rownorms=s_rownorms, proj=s_proj, coreset_small=s_coreset_small, coreset_big=s_coreset_big,
-                 score_small=s_score_small, blur=s_blur, score_big=s_score_big)
+                 score_small=s_score_small, blur=s_blur, score_big=s_score_big, gemm_sweep=s_gemm_sweep)
     for w in which:
         table[w]()

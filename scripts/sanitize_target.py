@@ -23,7 +23,7 @@ print("coreset ok", idx[:5])
 b.gather(np.arange(0, 1200, 2))
 b.finalize()
 p = np.stack([synth.patches(196, D, seed=5 + i, k=32) for i in range(3)])
-for terms in (3, 1):
+for terms in (0, 3, 1):
     b.set_prefilter_terms(terms)
     r = b.score_batch(p, (14, 14), 64, full=True)
 b.set_score_impl(L.SCORE_SIMT)

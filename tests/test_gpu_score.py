@@ -124,21 +124,129 @@ def test_score_batch_equals_single_calls(env, B, P, fm, D):
     b.close()
 
 
-def test_prefilter_mode_gives_identical_results(env):
-    """CMDB_OPT_PREFILTER_TERMS = 1 (hi.hi GEMM as a pre-filter + exact re-check) must reproduce the default
-    FP32-equivalent path bit for bit on clustered and on iid data"""
+_RESULT_FIELDS = ("min_idx", "min_val", "s", "s_star", "s_idx", "nn_idx", "m_star_knn", "w", "s_map")
+
+
+def _assert_same_results(a, b, tag):
+    for i in range(len(a)):
+        for name in _RESULT_FIELDS:
+            assert (getattr(a[i], name) == getattr(b[i], name)).all(), (tag, i, name)
+
+
+@pytest.mark.parametrize("dist,R,D,P,fm", [("C", 60000, 768, 784, 28), ("G", 30000, 768, 784, 28),
+                                            ("C", 20000, 1920, 784, 28), ("C", 9000, 128, 100, 10),
+                                            ("C", 40000, 768, 3136, 56)])
+def test_gemm_modes_give_identical_results(env, dist, R, D, P, fm):
+    """The default certified pre-filter (hi.hi GEMM + error-bound certificate + 3-term fallback), the FP32-equivalent
+    3-term GEMM, the uncertified pre-filter and the exact CUDA-core scan must agree bit for bit."""
     from cmdiad_b200 import synth
-    for dist, R in (("C", 60000), ("G", 30000)):
-        lib = synth.patches(R, 768, seed=33, dist=dist)
-        patches = np.stack([synth.patches(784, 768, seed=400 + i, dist=dist, anomalous_frac=0.01) for i in range(4)])
-        b = _bank(env, lib)
-        ref = b.score_batch(patches, (28, 28), 224)
-        b.set_prefilter_terms(1)
-        fast = b.score_batch(patches, (28, 28), 224)
-        for i in range(4):
-            for name in ("min_idx", "min_val", "s", "s_idx", "nn_idx", "s_map"):
-                assert (getattr(ref[i], name) == getattr(fast[i], name)).all(), (dist, i, name)
-        b.close()
+    L = env["L"]
+    cent = synth.centroids(D, 256) if dist == "C" else None
+    lib = synth.patches(R, D, seed=33, dist=dist, cent=cent)
+    patches = np.stack([synth.patches(P, D, seed=400 + i, dist=dist, anomalous_frac=0.01, cent=cent) for i in range(3)])
+    b = _bank(env, lib)
+    cert = b.score_batch(patches, (fm, fm), 224, full=True)
+    st = b.score_stats()
+    assert st["mode"] == 0 and st["queries"] == 3 * P
+    print("certified pre-filter:", st)
+    assert st["fallback_queries"] <= 0.25 * st["queries"] and not st["gemm_fallback"], st   # certificate + rescan carry the load
+    b.set_prefilter_terms(3)
+    full = b.score_batch(patches, (fm, fm), 224, full=True)
+    assert b.score_stats()["mode"] == 3
+    _assert_same_results(cert, full, "certified vs 3-term")
+    b.set_prefilter_terms(1)
+    _assert_same_results(cert, b.score_batch(patches, (fm, fm), 224, full=True), "certified vs uncertified 1-term")
+    b.set_score_impl(L.SCORE_SIMT)
+    _assert_same_results(cert, b.score_batch(patches, (fm, fm), 224, full=True), "certified vs exact scan")
+    b.close()
+
+
+def test_certificate_fallback_on_near_duplicates(env):
+    """Groups of near-duplicate bank rows defeat an 11-bit pre-filter: the certificate must notice (fallback > 0), the
+    answers must still equal the 3-term path, and a bank where most queries fail switches itself to the direct mode."""
+    from cmdiad_b200 import synth
+    g = np.random.Generator(np.random.PCG64(5))
+    unique = synth.patches(8000, 768, seed=49, dist="G")
+    base = synth.patches(200, 768, seed=50, dist="G")
+    dup = np.concatenate([base + 2e-4 * g.standard_normal(base.shape, dtype=np.float32) for _ in range(40)], 0)
+    lib = np.concatenate([unique, dup], 0)
+    lib = lib[g.permutation(lib.shape[0])]
+    near_dup = np.stack([base[g.integers(0, 200, 784)] + 0.05 * synth.patches(784, 768, seed=60 + i, dist="G") for i in range(2)])
+    near_unique = unique[:784] + 0.05 * synth.patches(784, 768, seed=70, dist="G")
+    b = _bank(env, lib)
+    # mixed batch first: image 0 keeps its certificate, image 1 falls back
+    mixed = np.stack([near_unique, near_dup[0], near_unique[::-1].copy()])
+    r_mixed = b.score_batch(mixed, (28, 28), 224, full=True)
+    st = b.score_stats()
+    assert st["mode"] == 0 and 700 <= st["fallback_queries"] <= 784 + 80 and st["gemm_fallback"], st
+    assert st["direct_calls_left"] == 0
+    b.set_prefilter_terms(3)
+    _assert_same_results(r_mixed, b.score_batch(mixed, (28, 28), 224, full=True), "mixed batch")
+    # mostly-failed call -> the next calls run the 3-term GEMM directly
+    b.set_prefilter_terms(0)
+    cert = b.score_batch(near_dup, (28, 28), 224, full=True)
+    st = b.score_stats()
+    assert st["mode"] == 0 and st["fallback_queries"] > 0.5 * st["queries"], st
+    again = b.score_batch(near_dup, (28, 28), 224, full=True)
+    st2 = b.score_stats()
+    assert st2["mode"] == 3 and st2["direct_calls_left"] == 31, st2
+    b.set_prefilter_terms(3)
+    full = b.score_batch(near_dup, (28, 28), 224, full=True)
+    _assert_same_results(cert, full, "certified(fallback) vs 3-term")
+    _assert_same_results(again, full, "adaptive direct vs 3-term")
+    b.close()
+
+
+def test_prefilter_error_model(env):
+    """The certificate rests on (a) Cauchy-Schwarz bounds of the fp16 operand rounding -- mathematics -- and (b) a model
+    of the tensor-core accumulation error, (D/16 + 1) * 17 * 2^-23 * ||q_hi|| ||b_hi||.  (b) is measured here: the GEMM
+    epilogue's values are compared with a float64 evaluation of the same fp16 operands."""
+    import ctypes
+    from cmdiad_b200 import synth
+    D, R, P = 768, 20000, 784
+    lib = synth.patches(R, D, seed=91)
+    patch = synth.patches(P, D, seed=92, anomalous_frac=0.02)
+    b = _bank(env, lib)
+    b.set_prefilter_terms(1)
+    b.score(patch, (28, 28), 224)
+    n_cta = 296   # producers = (CTA, accumulator column half)
+    cand = np.zeros((n_cta, P, 4), np.float32)
+    rc = b._lib.cmdb_debug_read_candidates(b._h, cand.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_cta), ctypes.c_int(P))
+    assert rc == 0
+    val = cand[:, :, 0]
+    idx = cand[:, :, 1].copy().view(np.int32)
+    ok = idx >= 0
+    assert ok.any()
+    # the fp16 operands exactly as the library builds them (power-of-two scales, round to nearest even)
+    eb = 13 - int(np.frexp(np.abs(lib).max())[1])
+    bh = (lib * np.float32(2.0 ** eb)).astype(np.float16).astype(np.float64) * 2.0 ** -eb
+    eq = 13 - np.frexp(np.abs(patch).max(1))[1].astype(np.int64)
+    qh = (patch * (2.0 ** eq)[:, None].astype(np.float32)).astype(np.float16).astype(np.float64) * (2.0 ** -eq)[:, None]
+    bn = (lib.astype(np.float64) ** 2).sum(1).astype(np.float32).astype(np.float64)
+    qhn, bhn = np.linalg.norm(qh, axis=1), np.linalg.norm(bh, axis=1)
+    worst_acc, worst_total = 0.0, 0.0
+    acc_model = (D // 16 + 1) * 17 * 2.0 ** -23
+    qn = np.linalg.norm(patch.astype(np.float64), axis=1)
+    qe = np.linalg.norm(patch.astype(np.float64) - qh, axis=1)
+    bmax, ebmax = np.linalg.norm(lib.astype(np.float64), axis=1).max(), np.linalg.norm(lib.astype(np.float64) - bh, axis=1).max()
+    for c in range(0, n_cta, 7):
+        qs = np.nonzero(ok[c])[0]
+        if qs.size == 0:
+            continue
+        rows = idx[c, qs]
+        dot = np.einsum("ij,ij->i", qh[qs], bh[rows])
+        v64 = bn[rows] - 2.0 * dot
+        err = np.abs(val[c, qs].astype(np.float64) - v64)
+        # accumulation error alone (the final fma rounds once more: 2^-24 |v|)
+        worst_acc = max(worst_acc, float(((err - 2.0 ** -24 * np.abs(v64)) / (2 * acc_model * qhn[qs] * bhn[rows])).max()))
+        exact = ((patch[qs].astype(np.float64) - lib[rows].astype(np.float64)) ** 2).sum(1)
+        E = 2 * (qe[qs] * (bmax + ebmax) + qn[qs] * ebmax + acc_model * (qn[qs] + qe[qs]) * (bmax + ebmax)) \
+            + (D + 16) * 2.0 ** -24 * (qn[qs] + bmax) ** 2
+        worst_total = max(worst_total, float((np.abs(val[c, qs] + qn[qs] ** 2 - exact) / E).max()))
+    print(f"accumulation error / model = {worst_acc:.4f}, total error / certificate bound = {worst_total:.4f}")
+    assert worst_acc < 0.25, worst_acc      # the model keeps >= 4x margin over what the hardware does
+    assert worst_total < 0.5, worst_total
+    b.close()
 
 
 def test_score_duplicate_rows_lowest_index(env):
