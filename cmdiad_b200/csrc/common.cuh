@@ -175,6 +175,7 @@ int score_query_prep(cmdb_bank *b, int P, bool compact);
 // q_hi / q_lo -> cand via the tcgen05 distance GEMM with `terms` MMAs per K step; compact = true: the M extent is the
 // device-side fail count
 int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out);
+void q_split_rows(cmdb_bank *b, const float *rows_dev, int n);
 int score_gemm_groups();              // epilogue warp groups per CTA: producers = groups * CTAs
 int score_tile_stride(int mt, int G); // host copy of the GEMM's tile schedule stride
 int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine);  // candidates + refine, all modes

@@ -135,7 +135,7 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t
 // With s == mt this is plain round-robin dealing; making s coprime with G keeps the load balanced (every G N-tiles each
 // CTA receives exactly mt tiles) AND lets every CTA see ~R/G rows of every query whatever gcd(mt, G) is -- the
 // certificate of the pre-filter (score_tail.cu) needs the rows inside a query's error band to land in different CTAs'
-// top-2 lists.  Start with n = -1, m = mt.
+// top-2 lists.
 __device__ __forceinline__ int tile_stride(int mt) {
     const int G = (int)gridDim.x;
     for (int s = mt;; ++s) {
@@ -148,15 +148,27 @@ __device__ __forceinline__ int tile_stride(int mt) {
         if (a == 1 || G == 1) return s;
     }
 }
-__device__ __forceinline__ bool next_tile(int &n, int &m, int mt, int nt, int stride) {
-    const int G = (int)gridDim.x, c = (int)blockIdx.x;
-    m += G;
-    while (m >= mt) {
-        if (++n >= nt) return false;
-        m = (int)((c + G - ((long long)n * stride) % G) % G);
+struct TileIter {  // n, m: current tile; base: first M tile of this CTA inside N tile n
+    int n, m, base, smod;
+    __device__ __forceinline__ TileIter(int mt, int stride) {
+        const int G = (int)gridDim.x;
+        smod = stride % G;
+        n = -1, m = mt, base = ((int)blockIdx.x + smod) % G;
     }
-    return true;
-}
+    // incremental form of m = (c - n * stride) mod G: no division per step (a CTA walks over ALL N tiles, also the ones in
+    // which it owns no M tile, so the step has to be cheap when mt is small)
+    __device__ __forceinline__ bool next(int mt, int nt) {
+        const int G = (int)gridDim.x;
+        m += G;
+        while (m >= mt) {
+            if (++n >= nt) return false;
+            base -= smod;
+            if (base < 0) base += G;
+            m = base;
+        }
+        return true;
+    }
+};
 
 // running two smallest (value, bank row) of a stream visited in ascending row order: ties keep the lower row
 struct Top2 {
@@ -253,7 +265,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int n = -1, m = p.mt; next_tile(n, m, p.mt, p.nt, stride);) {
+            for (TileIter it(p.mt, stride); it.next(p.mt, p.nt);) {
+                const int n = it.n, m = it.m;
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
@@ -274,7 +287,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int j = 0;
-            for (int n = -1, m = p.mt; next_tile(n, m, p.mt, p.nt, stride); ++j) {
+            for (TileIter it(p.mt, stride); it.next(p.mt, p.nt); ++j) {
                 const int buf = j & 1;
                 mbar_wait(bar_tempty + 8 * buf, ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -313,7 +326,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         constexpr int kHalfCols = BN / EG;
         float4 *my_state = state + (size_t)half * p.cand_stride;
         int j = 0;
-        for (int n = -1, m_local = p.mt; next_tile(n, m_local, p.mt, p.nt, stride); ++j) {
+        for (TileIter it(p.mt, stride); it.next(p.mt, p.nt); ++j) {
+            const int n = it.n, m_local = it.m;
             const int buf = j & 1;
             float *bn = bnorm_s + buf * BN;
             // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
@@ -549,6 +563,13 @@ int score_query_prep(cmdb_bank *b, int P, bool compact) {
         compact ? s.fail_list : nullptr, compact ? s.fail_ctl + 2 : nullptr);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
+}
+
+// fp16 split (+ norms for the certificate) of n <= 128 explicit rows into rows 0..127 of the query operand
+void q_split_rows(cmdb_bank *b, const float *rows_dev, int n) {
+    ScoreScratch &s = b->ss;
+    q_split_kernel<<<BM / 8, 256, 0, b->stream>>>(rows_dev, n, BM, b->dim, s.q_hi, s.q_lo, s.q_scale_exp, s.q_norm, s.q_eps, nullptr,
+                                                  nullptr);
 }
 
 int score_gemm_groups() {

@@ -8,6 +8,8 @@
 //               truncation, Pillow's 3+3 pass integer box blur, /255, *max -- one CTA, whole image in shared memory
 #include <math.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cmdb {
@@ -143,8 +145,18 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= P) return;
+    // the producers' lists of this query stay in registers (kCertRegs * 32 producers; beyond that they are re-read)
+    constexpr int kCertRegs = 10;
+    const float4 empty = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+    float4 held[kCertRegs];
     float v1min = INFINITY;
-    for (int c = lane; c < n_cand; c += 32) {
+#pragma unroll
+    for (int k = 0; k < kCertRegs; ++k) {
+        const int c = lane + 32 * k;
+        held[k] = c < n_cand ? cand[(size_t)c * cand_stride + qi] : empty;
+        if (__float_as_int(held[k].y) >= 0) v1min = fminf(v1min, held[k].x);
+    }
+    for (int c = lane + 32 * kCertRegs; c < n_cand; c += 32) {
         const float4 t = cand[(size_t)c * cand_stride + qi];
         if (__float_as_int(t.y) >= 0) v1min = fminf(v1min, t.x);
     }
@@ -163,10 +175,7 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
     // exact re-check of every kept value inside the band; producers whose SECOND value is inside the band may hide more
     float best = INFINITY;
     int best_i = -1, n_bad = 0;
-    for (int c0 = 0; c0 < n_cand; c0 += 32) {
-        const int c = c0 + lane;
-        float4 t = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
-        if (c < n_cand) t = cand[(size_t)c * cand_stride + qi];
+    auto band_step = [&](const float4 t, int c) {
         const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
         const bool in1 = i1 >= 0 && (t.x <= thr || !orderable), in2 = i2 >= 0 && (t.z <= thr || !orderable);
         unsigned int m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
@@ -190,6 +199,13 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
                 if (slot < kWorkCap) work_list[slot] = make_int2(qi, c);
             }
         }
+    };
+#pragma unroll
+    for (int k = 0; k < kCertRegs; ++k)
+        if (32 * k < n_cand) band_step(held[k], lane + 32 * k);
+    for (int c0 = 32 * kCertRegs; c0 < n_cand; c0 += 32) {
+        const int c = c0 + lane;
+        band_step(c < n_cand ? cand[(size_t)c * cand_stride + qi] : empty, c);
     }
     if (lane != 0) return;
     if (n_bad == 0 && best_i >= 0) {
@@ -216,6 +232,18 @@ __global__ void fallback_decide_kernel(int *ctl) {
 // N tiles n with n * stride = c - m (mod G) and of each the columns [g, g+1) * 256 / EG (tile schedule of
 // score_gemm.cu).  Unit = (item, k-th such N tile): one block computes the exact distances of its <= 256/EG rows and
 // folds the smallest (d^2 bits, row) into best_key[query] (atomicMin; d^2 >= 0 so the bits order like the value).
+// first N tile that CTA c processes for M tile m under the GEMM's schedule: smallest n with n * stride = c - m (mod G);
+// the others follow every G tiles (stride is coprime with G)
+__device__ __forceinline__ int producer_first_tile(int c, int m, int G, int stride) {
+    const int want = ((c - m % G) % G + G) % G, smod = stride % G;
+    int n0 = 0;
+    for (int x = 0; x != want; ++n0) {  // x = (n0 * stride) % G, stepped without a division
+        x += smod;
+        if (x >= G) x -= G;
+    }
+    return n0;
+}
+
 __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ work, const int *__restrict__ n_items_ptr,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                      long long rows, int G, int EG, int stride, int nt,
@@ -235,10 +263,7 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
         const int2 w = work[item];
         const int qi = w.x, c = w.y / EG, g = w.y % EG;
         const int m = (qi / kScoreBM) % G;
-        int n0 = 0;  // smallest n with (n * stride) % G == (c - m) mod G (stride is coprime with G)
-        const int want = ((c - m) % G + G) % G;
-        while ((int)(((long long)n0 * stride) % G) != want) ++n0;
-        const int n = n0 + k * G;
+        const int n = producer_first_tile(c, m, G, stride) + k * G;
         unsigned long long key = ~0ULL;
         if (n < nt) {
             const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows;
@@ -660,6 +685,146 @@ __global__ void __launch_bounds__(256) reweight_kernel(ReweightParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// re-weighting on the tensor cores: the B m_star rows go through the same hi.hi distance GEMM (one M tile), and this
+// kernel -- one block per image -- turns the producers' top-2 lists into the EXACT three nearest bank rows:
+//   thr = (third smallest kept value) + 2E, E as in refine_cert_kernel.  Three kept rows lie at or below v3, so any
+//   row above thr is strictly farther (in float32) than three other rows and cannot be in the top-3.  Every kept value
+//   <= thr is re-checked exactly; a producer whose SECOND value is <= thr may hide more rows, so its ~R/producers rows
+//   are scanned exactly by the block.  Keys are (d^2 bits << 32 | global row) with d^2 from warp_sqdist -- the same
+//   arithmetic as reweight_kernel, hence identical keys, order and ties.
+// ---------------------------------------------------------------------------------------------------------------
+struct ReweightCertParams {
+    const float4 *cand;
+    int n_cand, cand_stride;
+    const float *m_star;             // [B, dim]
+    const float *m_test;             // [B, dim] (fused final only)
+    const float *bank;
+    long long rows, row_offset;
+    int dim;
+    const float *q_norm, *q_eps;     // of the m_star rows (q_split_kernel)
+    float bmax, eb_max, acc_model;
+    int G, EG, stride, nt;           // tile schedule of the GEMM launch (mt = 1)
+    const unsigned long long *s_key;
+    unsigned long long *top3;
+    TailResult *res;
+    int fuse_final;
+};
+
+__device__ __forceinline__ unsigned int float_order_bits(float v) {  // monotone float -> uint (handles negatives)
+    const unsigned int b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_bits(unsigned int u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+__global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p) {
+    constexpr int kMaxProd = 2 * 160;            // producers (CTAs x epilogue groups) this kernel supports
+    __shared__ unsigned long long wkeys[8][3];
+    __shared__ int cand_rows[kMaxProd];
+    __shared__ int bad_prod[kMaxProd];
+    __shared__ int n_rows_sh, n_bad_sh;
+    __shared__ float thr_sh;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dim = p.dim, dim4 = dim >> 2;
+    const float *ms = p.m_star + (size_t)b * dim;
+    if (threadIdx.x == 0) n_rows_sh = 0, n_bad_sh = 0;
+    // ---- third smallest kept approximate value ----
+    unsigned long long t3[3] = {~0ULL, ~0ULL, ~0ULL}, f3[3];
+    for (int c = threadIdx.x; c < p.n_cand; c += blockDim.x) {
+        const float4 t = p.cand[(size_t)c * p.cand_stride + b];
+        const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
+        if (i1 >= 0) top3_insert(t3, ((unsigned long long)float_order_bits(t.x) << 32) | (unsigned int)i1);
+        if (i2 >= 0) top3_insert(t3, ((unsigned long long)float_order_bits(t.z) << 32) | (unsigned int)i2);
+    }
+    warp_top3(t3, f3);
+    if (lane == 0) wkeys[warp][0] = f3[0], wkeys[warp][1] = f3[1], wkeys[warp][2] = f3[2];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long g3[3] = {~0ULL, ~0ULL, ~0ULL};
+        for (int w = 0; w < 8; ++w)
+            for (int k = 0; k < 3; ++k) top3_insert(g3, wkeys[w][k]);
+        float thr = INFINITY;  // fewer than three real rows: everything is a candidate
+        if (g3[2] != ~0ULL) {
+            const float v3 = float_from_order_bits((unsigned int)(g3[2] >> 32));
+            const float qn = p.q_norm[b], qe = p.q_eps[b];
+            const float bh = __fadd_ru(p.bmax, p.eb_max);
+            float E = __fmul_ru(qe, bh);
+            E = __fmaf_ru(qn, p.eb_max, E);
+            E = __fmaf_ru(__fmul_ru(p.acc_model, __fadd_ru(qn, qe)), bh, E);
+            E = __fmul_ru(2.f, E);
+            const float span = __fadd_ru(qn, p.bmax);
+            E = __fmaf_ru(__fmul_ru((float)(dim + 16) * 5.9604645e-8f, span), span, E);
+            thr = __fadd_ru(v3, __fmul_ru(2.0625f, E));
+            if (!(thr == thr)) thr = INFINITY;  // NaN: certify nothing, scan everything
+        }
+        thr_sh = thr;
+    }
+    __syncthreads();
+    const float thr = thr_sh;
+    // ---- candidate rows (kept values inside the band) and producers that may hide more ----
+    for (int c = threadIdx.x; c < p.n_cand; c += blockDim.x) {
+        const float4 t = p.cand[(size_t)c * p.cand_stride + b];
+        const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
+        // second value inside the band: the whole producer is rescanned (that covers its two kept rows as well)
+        if (i2 >= 0 && !(t.z > thr)) bad_prod[atomicAdd(&n_bad_sh, 1)] = c;
+        else if (i1 >= 0 && !(t.x > thr)) cand_rows[atomicAdd(&n_rows_sh, 1)] = i1;
+    }
+    __syncthreads();
+    // ---- exact keys: candidates, then every row of the producers that could not be certified ----
+    unsigned long long w3[3] = {~0ULL, ~0ULL, ~0ULL};  // identical in all lanes of the warp
+    auto visit = [&](long long r) {
+        const float d2 = warp_sqdist(ms, p.bank + (size_t)r * dim, dim4, lane);
+        const unsigned long long key = pack_min_key(d2, (unsigned int)(r + p.row_offset));
+        if (key != w3[0] && key != w3[1] && key != w3[2]) top3_insert(w3, key);
+    };
+    const int n_rows = n_rows_sh, n_bad = n_bad_sh;
+    for (int i = warp; i < n_rows; i += 8) visit(cand_rows[i]);
+    const int cols = kScoreBN / p.EG, tiles_per = (p.nt + p.G - 1) / p.G;
+    for (int i = 0; i < n_bad; ++i) {
+        const int c = bad_prod[i] / p.EG, g = bad_prod[i] % p.EG;
+        const int n0 = producer_first_tile(c, 0, p.G, p.stride);
+        for (int j = warp; j < tiles_per * cols; j += 8) {
+            const int n = n0 + (j / cols) * p.G;
+            const long long r = (long long)n * kScoreBN + g * cols + j % cols;
+            if (n < p.nt && r < p.rows) visit(r);
+        }
+    }
+    if (lane == 0) wkeys[warp][0] = w3[0], wkeys[warp][1] = w3[1], wkeys[warp][2] = w3[2];
+    __syncthreads();
+    if (warp != 0) return;
+    unsigned long long f[3] = {~0ULL, ~0ULL, ~0ULL};
+    for (int w = 0; w < 8; ++w)
+        for (int k = 0; k < 3; ++k) {
+            const unsigned long long key = wkeys[w][k];
+            if (key != f[0] && key != f[1] && key != f[2]) top3_insert(f, key);
+        }
+    const unsigned long long skey = p.s_key[b];
+    const float s_star = __uint_as_float((unsigned int)(skey >> 32));
+    float knn[2] = {NAN, NAN};
+    if (p.fuse_final) {  // features.py:275-283: m_star_knn = ||m_test - bank[nn_idx[1:]]||, m_test = patch[s_idx]
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (f[1 + k] != ~0ULL)
+                knn[k] = sqrtf(warp_sqdist(p.m_test + (size_t)b * dim,
+                                           p.bank + (size_t)((long long)(f[1 + k] & 0xffffffffULL) - p.row_offset) * dim, dim4, lane));
+    }
+    if (lane == 0) {
+        TailResult *res = p.res + b;
+        p.top3[b * 3 + 0] = f[0], p.top3[b * 3 + 1] = f[1], p.top3[b * 3 + 2] = f[2];
+        for (int k = 0; k < 3; ++k) res->nn_idx[k] = f[k] == ~0ULL ? -1 : (long long)(f[k] & 0xffffffffULL);
+        if (p.fuse_final) {
+            const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))  (features.py:285)
+            const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
+            const float w = 1.f - expf(s_star / Dn) / den;  // features.py:287
+            res->w = w;
+            res->s = w * s_star;  // features.py:290
+            res->knn0 = knn[0], res->knn1 = knn[1];
+        }
+    }
+}
+
 // sharded mode, after the all-gather: image b = blockIdx.x merges the keys of all ranks ([rank][B][3] layout)
 __global__ void __launch_bounds__(32) merge_top3_kernel(const unsigned long long *__restrict__ gathered, int n_ranks, int B,
                                                         unsigned long long *__restrict__ out3) {
@@ -838,7 +1003,39 @@ int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star) {
 
 // fused = single-GPU path (select prologue + merge + final in one launch); otherwise the m_star rows come from
 // ss.m_star and only the merged top-3 keys (+ s*, s_idx) are produced
+// tensor-core variant: (select ->) fp16 split of the m_star rows -> hi.hi GEMM with one M tile -> reweight_cert_kernel
+static int score_reweight_tensor(cmdb_bank *b, int B, int P_img, bool fused) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    if (fused) CMDB_CHECK(score_select(b, B, P_img, true));  // m_test, m_star, s*, s_idx, m_star_row
+    // the min/argmin phase is complete: its query operand buffers and candidate lists are free again
+    q_split_rows(b, s.m_star, B);
+    CMDB_CUDA(cudaGetLastError());
+    int n_cand = 0;
+    CMDB_CHECK(score_gemm_candidates(b, B, 1, false, &n_cand));
+    ReweightCertParams p{};
+    p.cand = s.cand, p.n_cand = n_cand, p.cand_stride = s.cap_p;
+    p.m_star = s.m_star, p.m_test = s.m_test, p.bank = b->data, p.rows = b->fin_rows, p.row_offset = b->row_offset;
+    p.dim = b->dim, p.q_norm = s.q_norm, p.q_eps = s.q_eps;
+    p.bmax = b->cert_bmax, p.eb_max = b->cert_eb_max, p.acc_model = (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f;
+    p.G = b->num_sms, p.EG = score_gemm_groups(), p.stride = score_tile_stride(1, b->num_sms);
+    p.nt = (int)(b->fin_rows_pad / kScoreBN);
+    p.s_key = s.s_key, p.top3 = s.top3, p.res = reinterpret_cast<TailResult *>(s.tail), p.fuse_final = fused ? 1 : 0;
+    CMDB_REQUIRE(n_cand <= 320, CMDB_ERR_UNSUPPORTED, "scoring: %d GEMM producers exceed reweight_cert_kernel's limit", n_cand);
+    reweight_cert_kernel<<<B, 256, 0, st>>>(p);
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused) {
+    // a single image: the one-launch CUDA-core sweep is as fast as a one-tile GEMM over the whole bank; batches go to the
+    // tensor cores, whose cost does not grow with B (identical keys either way).  CMDB_REWEIGHT_TENSOR=0/1 forces one path (tests).
+    static const int force = [] {
+        const char *e = getenv("CMDB_REWEIGHT_TENSOR");
+        return e ? atoi(e) : -1;
+    }();
+    if (b->score_impl == CMDB_SCORE_TCGEN05 && b->prefilter_terms == 0 && B <= kScoreBM && (force == 1 || (force < 0 && B >= 2)))
+        return score_reweight_tensor(b, B, P_img, fused);
     ReweightParams p{};
     p.bank = b->data, p.rows = b->fin_rows, p.row_offset = b->row_offset, p.dim = b->dim, p.B = B, p.P_img = P_img;
     p.q = b->ss.q_f32, p.s_key = b->ss.s_key, p.min_idx = b->ss.min_idx;
