@@ -52,12 +52,9 @@ static int check_score_args(cmdb_bank *b, const void *patch, int B, int P, const
     return CMDB_OK;
 }
 
-static int stage_patch(cmdb_bank *b, const float *patch, int B, int P, int is_device, int out_hw) {
+static int stage_alloc(cmdb_bank *b, int B, int P, int out_hw) {
     CMDB_CUDA(cudaSetDevice(b->device));
-    CMDB_CHECK(score_scratch_alloc(b, B, P, out_hw));
-    CMDB_CUDA(cudaMemcpyAsync(b->ss.q_f32, patch, sizeof(float) * (size_t)B * P * b->dim,
-                              is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
-    return CMDB_OK;
+    return score_scratch_alloc(b, B, P, out_hw);
 }
 
 // device->host copy of the result block of a sub-batch, then scatter into the caller's buffers.  All images: ONE copy.
@@ -230,8 +227,8 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
         const int bc = std::min(bc_max, B - b0);
         const float *src = patches + (size_t)b0 * P * b->dim;
         CMDB_MARK(CMDB_T_STAGE_IN);
-        CMDB_CHECK(stage_patch(b, src, bc, P, patch_is_device, out_hw));
-        CMDB_CHECK(score_local_min(b, bc, P, CMDB_T_GEMM, CMDB_T_REFINE));
+        CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
+        CMDB_CHECK(score_local_min(b, src, patch_is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE));
         CMDB_MARK(CMDB_T_REWEIGHT);
         CMDB_CHECK(score_reweight(b, bc, P, true));
         CMDB_MARK(CMDB_T_MAP);
@@ -267,8 +264,8 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_shard_min: out_hw=%d not in [8,256]", out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
     if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
-    CMDB_CHECK(stage_patch(b, patches, B, P, patch_is_device, out_hw));
-    CMDB_CHECK(score_local_min(b, B, P, -1, -1));
+    CMDB_CHECK(stage_alloc(b, B, P, out_hw));
+    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1));
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;  // stream-ordered on the handle's stream (cmdb_bank_stream): run the collective there

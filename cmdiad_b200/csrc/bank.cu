@@ -238,6 +238,9 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
     b->capacity = capacity_rows;
     cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t err = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
+    for (auto &e : b->ev_chunk)
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaMalloc(&b->data, sizeof(float) * (size_t)capacity_rows * dim);
     if (err == cudaSuccess) err = cudaMalloc(&b->stats_buf, 2 * sizeof(double));
     if (err == cudaSuccess) err = cudaMalloc(&b->absmax_buf, sizeof(unsigned int));
@@ -277,6 +280,9 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    for (auto &e : b->ev_chunk)
+        if (e) cudaEventDestroy(e);
     delete b;
 }
 

@@ -42,6 +42,7 @@ constexpr int kNumSMsDefault = 148;
 constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch box
 constexpr int kScoreBN = 256;        // bank rows per GEMM tile
 constexpr int kScoreBM = 128;        // query rows per GEMM tile
+constexpr int kMaxStageChunks = 4;   // host query batches are staged and multiplied in up to this many chunks
 constexpr int kWorkCap = 8192;       // capacity of ScoreScratch::work_list
 constexpr int kRescanMaxPairs = 4096; // more uncertified (query, producer) pairs than this: 3-term GEMM fallback
 constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 128-byte swizzle row)
@@ -62,6 +63,7 @@ struct ScoreScratch {
     // ([2..4] are derived from [0..1] by fallback_decide_kernel: few pairs -> rescan, many -> GEMM)
     int *fail_ctl = nullptr;
     int *fail_count_host = nullptr; // pinned copy of [0..1] (statistics / adaptive mode)
+    int chunk_tiles = 0, mt_total = 0;  // M-tile layout of the last first-pass GEMM: chunks of chunk_tiles tiles (rescan needs it)
     int2 *work_list = nullptr;      // [kWorkCap] (query row, producer) pairs whose producer may hide rows inside the band
     unsigned long long *best_key = nullptr;  // [cap_p] running exact (d^2 bits << 32 | row) of the uncertified queries
     void *tmap_qhi = nullptr;       // host CUtensorMap objects for q_hi / q_lo
@@ -115,6 +117,8 @@ struct cmdb_bank {
     bool fail_pending = false;   // fail_count_host holds the count of a finished-or-in-flight call
     int direct_calls_left = 0;   // certified mode: calls to run directly with 3 terms before probing the pre-filter again
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device staging of query chunks, overlapped with the GEMM of earlier chunks
+    cudaEvent_t ev_chunk[cmdb::kMaxStageChunks] = {};
     float *data = nullptr;  // [capacity, dim] float32 row-major
     // scoring layout (cmdb_bank_finalize)
     bool finalized = false;
@@ -171,14 +175,15 @@ void score_scratch_free(cmdb_bank *b);
 int score_make_tensor_maps(cmdb_bank *b);
 // q_f32 -> q_hi / q_lo (device-side scale selection).  compact = true: only the rows of ss.fail_list (count on the
 // device), written to rows 0..count-1
-int score_query_prep(cmdb_bank *b, int P, bool compact);
+int score_query_prep(cmdb_bank *b, int P, bool compact, int row0 = 0);  // rows [row0, row0 + P) (row0 % 128 == 0)
 // q_hi / q_lo -> cand via the tcgen05 distance GEMM with `terms` MMAs per K step; compact = true: the M extent is the
 // device-side fail count
-int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out);
+int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out, int row0 = 0);
 void q_split_rows(cmdb_bank *b, const float *rows_dev, int n);
 int score_gemm_groups();              // epilogue warp groups per CTA: producers = groups * CTAs
 int score_tile_stride(int mt, int G); // host copy of the GEMM's tile schedule stride
-int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine);  // candidates + refine, all modes
+// stage the queries (src: host or device, [B*P_img, dim]) + candidates + refine, all modes
+int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine);
 
 // score_tail.cu
 struct TailResult {  // device-side result block (ScoreScratch::tail)

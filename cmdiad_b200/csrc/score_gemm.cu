@@ -200,7 +200,8 @@ __device__ __forceinline__ void top2_chunk(const uint32_t (&r)[32], float c, con
 }
 
 struct GemmParams {
-    int mt;             // M tiles (padded query rows / 128), all handled by one launch
+    int mt;             // M tiles (padded query rows / 128) handled by this launch
+    int m_base;         // first M tile of this launch inside the query operand / the candidate lists
     const int *m_count; // optional device-side query-row count that overrides mt (fallback launch over the compacted
                         // uncertified queries; 0 rows -> the kernel returns at once)
     int nt;             // N tiles (bank rows / 256)
@@ -250,7 +251,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    for (int i = threadIdx.x; i < p.mt * BM; i += kGemmThreads)
+    for (int i = p.m_base * BM + threadIdx.x; i < (p.m_base + p.mt) * BM; i += kGemmThreads)
 #pragma unroll
         for (int g = 0; g < EG; ++g)
             state[(size_t)g * p.cand_stride + i] = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
@@ -271,10 +272,10 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     mbar_expect_tx(full, S::kStageBytes);
-                    tma_load_2d(sbase + S::a_hi(stage), &tm_qhi, full, kb * BK, m * BM);
+                    tma_load_2d(sbase + S::a_hi(stage), &tm_qhi, full, kb * BK, (p.m_base + m) * BM);
                     tma_load_2d(sbase + S::b_hi(stage), &tm_bhi, full, kb * BK, n * BN);
                     if constexpr (TERMS == 3) {
-                        tma_load_2d(sbase + S::a_lo(stage), &tm_qlo, full, kb * BK, m * BM);
+                        tma_load_2d(sbase + S::a_lo(stage), &tm_qlo, full, kb * BK, (p.m_base + m) * BM);
                         tma_load_2d(sbase + S::b_lo(stage), &tm_blo, full, kb * BK, n * BN);
                     }
                     if (++stage == S::kStages) stage = 0, phase ^= 1;
@@ -327,7 +328,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         float4 *my_state = state + (size_t)half * p.cand_stride;
         int j = 0;
         for (TileIter it(p.mt, stride); it.next(p.mt, p.nt); ++j) {
-            const int n = it.n, m_local = it.m;
+            const int n = it.n, m_local = p.m_base + it.m;
             const int buf = j & 1;
             float *bn = bnorm_s + buf * BN;
             // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
@@ -554,13 +555,13 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     return CMDB_OK;
 }
 
-int score_query_prep(cmdb_bank *b, int P, bool compact) {
+int score_query_prep(cmdb_bank *b, int P, bool compact, int row0) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
-    cudaStream_t st = b->stream;
-    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, st>>>(
-        s.q_f32, P, p_pad, b->dim, s.q_hi, s.q_lo, s.q_scale_exp, compact ? nullptr : s.q_norm, compact ? nullptr : s.q_eps,
-        compact ? s.fail_list : nullptr, compact ? s.fail_ctl + 2 : nullptr);
+    const size_t o = (size_t)row0 * b->dim;
+    q_split_kernel<<<std::min(b->num_sms * 2, (p_pad + 7) / 8), 256, 0, b->stream>>>(
+        s.q_f32 + o, P, p_pad, b->dim, s.q_hi + o, s.q_lo + o, s.q_scale_exp + row0, compact ? nullptr : s.q_norm + row0,
+        compact ? nullptr : s.q_eps + row0, compact ? s.fail_list : nullptr, compact ? s.fail_ctl + 2 : nullptr);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
@@ -592,7 +593,7 @@ int score_tile_stride(int mt, int G) {  // == tile_stride() of the kernel
     }
 }
 
-int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out) {
+int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out, int row0) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
     cudaStream_t st = b->stream;
@@ -606,6 +607,7 @@ int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_c
     p.cand = s.cand;
     p.cand_stride = s.cap_p;
     p.mt = p_pad / BM;
+    p.m_base = row0 / BM;
     p.m_count = compact ? s.fail_ctl + 2 : nullptr;
     const int eg_env = score_gemm_groups();
     auto launch = [&](auto kern, size_t smem, int threads) -> int {

@@ -228,8 +228,8 @@ __global__ void fallback_decide_kernel(int *ctl) {
     ctl[4] = rescan ? ctl[0] : 0;
 }
 
-// exact rescan: work item = (query, producer); the producer (CTA c, column group g) saw, for the query's M tile m, the
-// N tiles n with n * stride = c - m (mod G) and of each the columns [g, g+1) * 256 / EG (tile schedule of
+// exact rescan: work item = (query, producer); the producer (CTA c, column group g) saw, for the query's M tile m (counted
+// inside its GEMM launch), the N tiles n with n * stride = c - m (mod G) and of each the columns [g, g+1) * 256 / EG (tile schedule of
 // score_gemm.cu).  Unit = (item, k-th such N tile): one block computes the exact distances of its <= 256/EG rows and
 // folds the smallest (d^2 bits, row) into best_key[query] (atomicMin; d^2 >= 0 so the bits order like the value).
 // first N tile that CTA c processes for M tile m under the GEMM's schedule: smallest n with n * stride = c - m (mod G);
@@ -246,8 +246,8 @@ __device__ __forceinline__ int producer_first_tile(int c, int m, int G, int stri
 
 __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ work, const int *__restrict__ n_items_ptr,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
-                                                     long long rows, int G, int EG, int stride, int nt,
-                                                     unsigned long long *best_key) {
+                                                     long long rows, int G, int EG, int nt, int chunk_tiles, int mt_total,
+                                                     int stride_full, int stride_last, unsigned long long *best_key) {
     __shared__ unsigned long long red[8];
     const int n_items = min(*n_items_ptr, kWorkCap);
     const int tiles_per = (nt + G - 1) / G;
@@ -262,8 +262,10 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
         const int k = rem / units_per_tile, sub = rem % units_per_tile;
         const int2 w = work[item];
         const int qi = w.x, c = w.y / EG, g = w.y % EG;
-        const int m = (qi / kScoreBM) % G;
-        const int n = producer_first_tile(c, m, G, stride) + k * G;
+        // the first-pass GEMM ran in chunks of chunk_tiles M tiles (the last one may be shorter), each with its own schedule
+        const int mtile = qi / kScoreBM, chunk = mtile / chunk_tiles;
+        const bool last = (chunk + 1) * chunk_tiles >= mt_total;
+        const int n = producer_first_tile(c, mtile - chunk * chunk_tiles, G, last ? stride_last : stride_full) + k * G;
         unsigned long long key = ~0ULL;
         if (n < nt) {
             const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows;
@@ -414,11 +416,11 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     fallback_decide_kernel<<<1, 1, 0, st>>>(s.fail_ctl);
     CMDB_CUDA(cudaGetLastError());
     // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
-    const int p_pad = (P + kScoreBM - 1) / kScoreBM * kScoreBM;
     const int G = b->num_sms, EG = score_gemm_groups();
+    const int last_tiles = s.mt_total - (s.mt_total - 1) / s.chunk_tiles * s.chunk_tiles;
     rescan_kernel<<<b->num_sms * 8, 256, 0, st>>>(s.work_list, s.fail_ctl + 3, s.q_f32, b->data, b->dim, b->fin_rows, G, EG,
-                                                  score_tile_stride(p_pad / kScoreBM, G), (int)(b->fin_rows_pad / kScoreBN),
-                                                  s.best_key);
+                                                  (int)(b->fin_rows_pad / kScoreBN), s.chunk_tiles, s.mt_total,
+                                                  score_tile_stride(s.chunk_tiles, G), score_tile_stride(last_tiles, G), s.best_key);
     CMDB_CUDA(cudaGetLastError());
     rescan_finish_kernel<<<8, 256, 0, st>>>(s.fail_list, s.fail_ctl + 4, s.best_key, P_img, b->row_offset, s.min_val, s.min_idx,
                                             s.s_key);
@@ -426,12 +428,17 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     return CMDB_OK;
 }
 
-// min_val / min_idx / s_key of a staged sub-batch (ss.q_f32) in the bank's GEMM mode.  ev_gemm / ev_refine: timing event
-// slots recorded before the (first) GEMM and before the (first) refine, or -1.
-int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine) {
+// min_val / min_idx / s_key of a sub-batch in the bank's GEMM mode: stages the queries into ss.q_f32, builds the
+// candidate lists, refines.  ev_gemm / ev_refine: timing event slots recorded before the (first) GEMM and before the
+// (first) refine, or -1.
+// Host queries are staged in up to kMaxStageChunks chunks on a copy stream; chunk c is split and multiplied while chunk
+// c + 1 is still crossing PCIe.  (One GEMM launch per chunk: each streams the fp16 bank once more, which is cheap next to
+// the host link.)  Device-resident queries use one chunk.
+int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     const int P = B * P_img;
+    const size_t D = b->dim;
     int n_cand = 0;
     auto mark = [&](int i) -> int {
         if (b->timing && i >= 0) CMDB_CUDA(cudaEventRecord(b->ev[i], st));
@@ -441,6 +448,7 @@ int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine) 
     b->last_queries = P;
     if (b->score_impl != CMDB_SCORE_TCGEN05) {
         b->last_mode = 3;
+        CMDB_CUDA(cudaMemcpyAsync(s.q_f32, src, sizeof(float) * P * D, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         CMDB_CHECK(mark(ev_gemm));
         CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
         CMDB_CHECK(mark(ev_refine));
@@ -448,8 +456,8 @@ int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine) 
     }
     int mode = b->prefilter_terms;
     if (mode == 0) {
-        // adaptive: when most queries of the previous certified call needed the fallback (dense near-duplicate banks),
-        // run the FP32-equivalent GEMM directly for a while, then probe the pre-filter again
+        // adaptive: when most queries of the previous certified call needed the GEMM fallback (dense near-duplicate
+        // banks), run the FP32-equivalent GEMM directly for a while, then probe the pre-filter again
         if (b->fail_pending) {
             CMDB_CUDA(cudaStreamSynchronize(st));  // the count was copied by the previous call; normally long complete
             b->fail_pending = false;
@@ -462,9 +470,40 @@ int score_local_min(cmdb_bank *b, int B, int P_img, int ev_gemm, int ev_refine) 
         }
     }
     b->last_mode = mode;
-    CMDB_CHECK(score_query_prep(b, P, false));
-    CMDB_CHECK(mark(ev_gemm));
-    CMDB_CHECK(score_gemm_candidates(b, P, mode == 3 ? 3 : 1, false, &n_cand));
+    const int mt_total = (P + kScoreBM - 1) / kScoreBM;
+    static const int env_chunks = [] {
+        const char *e = getenv("CMDB_STAGE_CHUNKS");
+        return e ? atoi(e) : 0;
+    }();
+    int n_chunks = 1;
+    if (!src_is_device) n_chunks = env_chunks > 0 ? env_chunks : (mt_total >= 64 ? 4 : (mt_total >= 16 ? 2 : 1));
+    n_chunks = std::max(1, std::min(std::min(n_chunks, kMaxStageChunks), mt_total));
+    const int chunk_tiles = (mt_total + n_chunks - 1) / n_chunks;
+    n_chunks = (mt_total + chunk_tiles - 1) / chunk_tiles;
+    s.chunk_tiles = chunk_tiles, s.mt_total = mt_total;
+    if (n_chunks > 1) {
+        // the copy stream may only start once everything queued on the compute stream (an earlier sub-batch still
+        // reading q_f32) is done
+        CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], st));
+        CMDB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_chunk[0], 0));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int row0 = c * chunk_tiles * kScoreBM, rows = std::min(P, (c + 1) * chunk_tiles * kScoreBM) - row0;
+        const size_t o = (size_t)row0 * D;
+        if (n_chunks == 1) {
+            CMDB_CUDA(cudaMemcpyAsync(s.q_f32, src, sizeof(float) * P * D, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        } else {
+            CMDB_CUDA(cudaMemcpyAsync(s.q_f32 + o, src + o, sizeof(float) * rows * D, cudaMemcpyHostToDevice, b->copy_stream));
+            CMDB_CUDA(cudaEventRecord(b->ev_chunk[c], b->copy_stream));
+        }
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int row0 = c * chunk_tiles * kScoreBM, rows = std::min(P, (c + 1) * chunk_tiles * kScoreBM) - row0;
+        if (n_chunks > 1) CMDB_CUDA(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
+        CMDB_CHECK(score_query_prep(b, rows, false, row0));
+        if (c == 0) CMDB_CHECK(mark(ev_gemm));
+        CMDB_CHECK(score_gemm_candidates(b, rows, mode == 3 ? 3 : 1, false, &n_cand, row0));
+    }
     CMDB_CHECK(mark(ev_refine));
     if (mode != 0) return score_refine(b, B, P_img, n_cand, false);
     CMDB_CHECK(score_refine_certified(b, B, P_img, n_cand));
