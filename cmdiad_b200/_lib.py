@@ -22,7 +22,7 @@ SCORE_SIMT = 1
 OPT_SCORE_IMPL = 1
 OPT_TIMING = 2
 OPT_PREFILTER_TERMS = 3
-T_STAGES = ("stage_in", "gemm", "refine", "reweight", "map", "out")
+T_STAGES = ("stage_in", "gemm", "refine", "map", "reweight", "out")
 
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)

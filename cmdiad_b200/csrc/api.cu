@@ -60,17 +60,41 @@ static int stage_alloc(cmdb_bank *b, int B, int P, int out_hw) {
 // device->host copy of the result block of a sub-batch, then scatter into the caller's buffers.  All images: ONE copy.
 // A strided subset (sharded finish: this rank owns images img_first, img_first + img_step, ...): the scalar / per-patch
 // prefix in one copy plus one map copy per owned image.
-static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs, int img_first = 0, int img_step = 1) {
+// bytes of the result block that a full-batch copy has to move
+static size_t out_block_extent(const cmdb_bank *b, int B, const cmdb_score_out *outs) {
+    const ScoreScratch &s = b->ss;
+    bool want_pre = false, want_u8 = false;
+    for (int i = 0; i < B; ++i) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
+    size_t bytes = s.off_map_out + sizeof(float) * s.map_stride * B;
+    if (want_pre) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
+    if (want_u8) bytes = s.off_map_u8 + s.map_stride * B;
+    return bytes;
+}
+
+// min_val / min_idx / maps do not depend on the re-weighting: their device->host copy starts on the copy stream as soon
+// as the blur is done and overlaps the re-weighting pass
+static int copy_maps_early(cmdb_bank *b, int B, const cmdb_score_out *outs) {
+    ScoreScratch &s = b->ss;
+    CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], b->stream));
+    CMDB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_chunk[0], 0));
+    const size_t bytes = out_block_extent(b, B, outs);
+    CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + s.off_min_val, s.out_block + s.off_min_val, bytes - s.off_min_val,
+                              cudaMemcpyDeviceToHost, b->copy_stream));
+    return CMDB_OK;
+}
+
+static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs, int img_first = 0, int img_step = 1,
+                        bool maps_early = false) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     const size_t npix = (size_t)out_hw * out_hw;
     bool want_pre = false, want_u8 = false;
     for (int i = img_first; i < B; i += img_step) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
-    if (img_step == 1 && img_first == 0) {
-        size_t bytes = s.off_map_out + sizeof(float) * s.map_stride * B;
-        if (want_pre) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
-        if (want_u8) bytes = s.off_map_u8 + s.map_stride * B;
-        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, bytes, cudaMemcpyDeviceToHost, st));
+    if (maps_early) {  // everything but the per-image scalars is already on its way (copy_maps_early)
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_min_val, cudaMemcpyDeviceToHost, st));
+        CMDB_CUDA(cudaStreamSynchronize(b->copy_stream));
+    } else if (img_step == 1 && img_first == 0) {
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, out_block_extent(b, B, outs), cudaMemcpyDeviceToHost, st));
     } else {
         CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_map_out, cudaMemcpyDeviceToHost, st));
         for (int i = img_first; i < B; i += img_step) {
@@ -229,12 +253,13 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
         CMDB_MARK(CMDB_T_STAGE_IN);
         CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
         CMDB_CHECK(score_local_min(b, src, patch_is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE));
-        CMDB_MARK(CMDB_T_REWEIGHT);
-        CMDB_CHECK(score_reweight(b, bc, P, true));
         CMDB_MARK(CMDB_T_MAP);
         CMDB_CHECK(blur_batch(b, bc, fh, fw, out_hw));
+        CMDB_CHECK(copy_maps_early(b, bc, outs + b0));
+        CMDB_MARK(CMDB_T_REWEIGHT);
+        CMDB_CHECK(score_reweight(b, bc, P, true));
         CMDB_MARK(CMDB_T_OUT);
-        CMDB_CHECK(copy_outputs(b, bc, P, out_hw, outs + b0));
+        CMDB_CHECK(copy_outputs(b, bc, P, out_hw, outs + b0, 0, 1, true));
         if (b->timing) {  // timings describe the last sub-batch
             CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->stream));
             CMDB_CUDA(cudaEventSynchronize(b->ev[CMDB_T_COUNT]));

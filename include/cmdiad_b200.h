@@ -65,9 +65,9 @@ typedef enum cmdb_status {
 #define CMDB_T_STAGE_IN 0   /* patch copy + fp16 split of the queries */
 #define CMDB_T_GEMM 1       /* tcgen05 distance GEMM + fused top-2 epilogue (or the SIMT diagnostics kernel) */
 #define CMDB_T_REFINE 2     /* exact re-check -> min_val / min_idx / s_star */
-#define CMDB_T_REWEIGHT 3   /* m_star selection, w_dist top-3 pass over the bank, w and s */
-#define CMDB_T_MAP 4        /* bilinear upsample + Gaussian blur */
-#define CMDB_T_OUT 5        /* device -> host copies of the results */
+#define CMDB_T_MAP 3        /* bilinear upsample + Gaussian blur (then the maps start their device -> host copy) */
+#define CMDB_T_REWEIGHT 4   /* m_star selection, w_dist top-3 over the bank, w and s (overlaps the copy of the maps) */
+#define CMDB_T_OUT 5        /* rest of the device -> host copies of the results */
 #define CMDB_T_COUNT 6
 
 int cmdb_version(void);
