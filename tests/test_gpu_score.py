@@ -162,6 +162,32 @@ def test_gemm_modes_give_identical_results(env, dist, R, D, P, fm):
     b.close()
 
 
+@pytest.mark.parametrize("R", [3, 5, 255, 256, 257, 700])
+def test_tiny_banks_all_paths_agree(env, R):
+    """Edge shapes: banks smaller than one GEMM tile / than the number of producers, D = 64, 7x7 feature maps, batches
+    (tensor-core re-weighting) and single images (CUDA-core sweep): certified mode == exact scan == oracle restatement."""
+    from cmdiad_b200 import synth
+    L, O = env["L"], env["O"]
+    D, P, fm = 64, 49, 7
+    lib = synth.patches(R, D, seed=900 + R, dist="G")
+    patches = np.stack([synth.patches(P, D, seed=950 + i, dist="G") for i in range(3)])
+    b = _bank(env, lib)
+    cert = b.score_batch(patches, (fm, fm), 64, full=True)
+    assert b.score_stats()["mode"] == 0
+    singles = [b.score(patches[i], (fm, fm), 64, full=True) for i in range(3)]
+    _assert_same_results(cert, singles, "batch vs single")
+    b.set_score_impl(L.SCORE_SIMT)
+    _assert_same_results(cert, b.score_batch(patches, (fm, fm), 64, full=True), "certified vs exact scan")
+    for i in range(3):
+        ref = O.score_restated(patches[i], lib, (fm, fm), 64)
+        ok, nbad = cases.tie_aware_idx_ok(cert[i].min_idx, ref["min_idx"], ref["dist"].numpy())
+        assert ok and nbad <= 1
+        np.testing.assert_allclose(cert[i].min_val, ref["min_val"], rtol=1e-4)
+        assert set(cert[i].nn_idx.tolist()) == set(ref["nn_idx"].tolist())
+        np.testing.assert_allclose(cert[i].s[0], ref["s"], rtol=1e-4)
+    b.close()
+
+
 def test_certificate_fallback_on_near_duplicates(env):
     """Groups of near-duplicate bank rows defeat an 11-bit pre-filter: the certificate must notice (fallback > 0), the
     answers must still equal the 3-term path, and a bank where most queries fail switches itself to the direct mode."""
