@@ -80,6 +80,8 @@ SYMBOLS = {
     "cmdb_coreset_rownorms": (_I, [_I, _VP, _VP, _I64, _I, _I, _VP]),
     "cmdb_score": (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
     "cmdb_score_batch": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
+    "cmdb_score_batch_submit": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, ctypes.c_uint, ctypes.POINTER(ctypes.c_int64)]),
+    "cmdb_score_batch_wait": (_I, [_VP, ctypes.c_int64, ctypes.POINTER(ScoreOut)]),
     "cmdb_score_shard_min": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "cmdb_score_shard_select": (_I, [_VP, _VP, _I, _I, _VP]),
     "cmdb_score_shard_topk": (_I, [_VP, _VP, _I, _I, _VP]),

@@ -302,6 +302,27 @@ class Bank:
                                            outs))
         return results
 
+    def score_batch_async(self, patches, feature_map_dims, out_hw=224, full=False):
+        """Pipelined score_batch: enqueues the batch (at most max_shard_batch() images) and returns a ticket at once;
+        ticket.wait() returns the list of ScoreResult.  Two batches may be outstanding per bank, so the result copy of
+        batch k and the staging of batch k+1 overlap the kernels of the other batch:
+
+            pending = None
+            for batch in batches:
+                t = bank.score_batch_async(batch, dims)
+                if pending is not None: consume(pending.wait())
+                pending = t
+            consume(pending.wait())
+        """
+        patches = _as_f32(patches)
+        assert patches.dim() == 3 and patches.shape[2] == self.dim, f"expected [B,P,{self.dim}], got {tuple(patches.shape)}"
+        B, P = patches.shape[0], patches.shape[1]
+        fh, fw = feature_map_dims
+        ticket = ctypes.c_int64()
+        L.check(self._lib.cmdb_score_batch_submit(self._h, _ptr(patches), B, P, int(fh), int(fw), int(out_hw),
+                                                  int(patches.is_cuda), 3 if full else 0, ctypes.byref(ticket)))
+        return _Ticket(self, ticket.value, patches, B, P, out_hw, full)
+
     def max_shard_batch(self):
         """images per round of the sharded protocol (shared-memory bound of the re-weighting kernel)"""
         return max(1, min(32, (160 * 1024) // (4 * self.dim + 8 * 3 * 8)))
@@ -351,6 +372,22 @@ class Bank:
                     res.owned = set(range(first, B, stride))
                 results.extend(res)
         return results
+
+
+class _Ticket:
+    """An outstanding score_batch_async call (keeps the input alive until the results are fetched)."""
+
+    def __init__(self, bank, ticket, patches, B, P, out_hw, full):
+        self._bank, self._ticket, self._patches = bank, ticket, patches
+        self._shape = (B, P, out_hw, full)
+        self._results = None
+
+    def wait(self):
+        if self._results is None:
+            results, outs, _ = Bank._alloc_out(*self._shape)
+            L.check(self._bank._lib.cmdb_score_batch_wait(self._bank._h, self._ticket, outs))
+            self._results, self._patches = results, None
+        return self._results
 
 
 def upsample_blur(s_map, out_hw=224, device=0):

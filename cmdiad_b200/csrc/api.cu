@@ -60,53 +60,25 @@ static int stage_alloc(cmdb_bank *b, int B, int P, int out_hw) {
 // device->host copy of the result block of a sub-batch, then scatter into the caller's buffers.  All images: ONE copy.
 // A strided subset (sharded finish: this rank owns images img_first, img_first + img_step, ...): the scalar / per-patch
 // prefix in one copy plus one map copy per owned image.
-// bytes of the result block that a full-batch copy has to move
-static size_t out_block_extent(const cmdb_bank *b, int B, const cmdb_score_out *outs) {
+// bytes of the result block that a full-batch copy has to move (want: bit 0 = pre-blur maps, bit 1 = 8-bit maps)
+static size_t out_block_extent(const cmdb_bank *b, int B, unsigned want) {
     const ScoreScratch &s = b->ss;
-    bool want_pre = false, want_u8 = false;
-    for (int i = 0; i < B; ++i) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
     size_t bytes = s.off_map_out + sizeof(float) * s.map_stride * B;
-    if (want_pre) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
-    if (want_u8) bytes = s.off_map_u8 + s.map_stride * B;
+    if (want & 1u) bytes = s.off_map_pre + sizeof(float) * s.map_stride * B;
+    if (want & 2u) bytes = s.off_map_u8 + s.map_stride * B;
     return bytes;
 }
-
-// min_val / min_idx / maps do not depend on the re-weighting: their device->host copy starts on the copy stream as soon
-// as the blur is done and overlaps the re-weighting pass
-static int copy_maps_early(cmdb_bank *b, int B, const cmdb_score_out *outs) {
-    ScoreScratch &s = b->ss;
-    CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], b->stream));
-    CMDB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_chunk[0], 0));
-    const size_t bytes = out_block_extent(b, B, outs);
-    CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + s.off_min_val, s.out_block + s.off_min_val, bytes - s.off_min_val,
-                              cudaMemcpyDeviceToHost, b->copy_stream));
-    return CMDB_OK;
+static unsigned want_mask_of(const cmdb_score_out *outs, int B, int first = 0, int step = 1) {
+    unsigned w = 0;
+    for (int i = first; i < B; i += step) w |= (outs[i].s_map_pre ? 1u : 0u) | (outs[i].s_map_u8 ? 2u : 0u);
+    return w;
 }
 
-static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs, int img_first = 0, int img_step = 1,
-                        bool maps_early = false) {
-    ScoreScratch &s = b->ss;
-    cudaStream_t st = b->stream;
+// host block of a slot -> the caller's buffers
+static void scatter_outputs(const cmdb_bank *b, const unsigned char *h, int B, int P, int out_hw, cmdb_score_out *outs,
+                            int img_first = 0, int img_step = 1) {
+    const ScoreScratch &s = b->ss;
     const size_t npix = (size_t)out_hw * out_hw;
-    bool want_pre = false, want_u8 = false;
-    for (int i = img_first; i < B; i += img_step) want_pre |= outs[i].s_map_pre != nullptr, want_u8 |= outs[i].s_map_u8 != nullptr;
-    if (maps_early) {  // everything but the per-image scalars is already on its way (copy_maps_early)
-        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_min_val, cudaMemcpyDeviceToHost, st));
-        CMDB_CUDA(cudaStreamSynchronize(b->copy_stream));
-    } else if (img_step == 1 && img_first == 0) {
-        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, out_block_extent(b, B, outs), cudaMemcpyDeviceToHost, st));
-    } else {
-        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_map_out, cudaMemcpyDeviceToHost, st));
-        for (int i = img_first; i < B; i += img_step) {
-            const size_t o1 = s.off_map_out + sizeof(float) * s.map_stride * i, o2 = s.off_map_pre + sizeof(float) * s.map_stride * i;
-            const size_t o3 = s.off_map_u8 + s.map_stride * i;
-            CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o1, s.out_block + o1, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
-            if (want_pre) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o2, s.out_block + o2, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
-            if (want_u8) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o3, s.out_block + o3, npix, cudaMemcpyDeviceToHost, st));
-        }
-    }
-    CMDB_CUDA(cudaStreamSynchronize(st));
-    const unsigned char *h = s.out_block_host;
     for (int i = img_first; i < B; i += img_step) {
         cmdb_score_out *out = outs + i;
         TailResult tr;
@@ -124,6 +96,30 @@ static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *
         if (out->nn_idx)
             for (int k = 0; k < 3; ++k) out->nn_idx[k] = tr.nn_idx[k];
     }
+}
+
+// sharded finish: device->host copy of the result block (all images: ONE copy; a strided subset -- this rank owns images
+// img_first, img_first + img_step, ... -- the scalar / per-patch prefix in one copy plus one map copy per owned image),
+// then scatter into the caller's buffers
+static int copy_outputs(cmdb_bank *b, int B, int P, int out_hw, cmdb_score_out *outs, int img_first, int img_step) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    const size_t npix = (size_t)out_hw * out_hw;
+    const unsigned want = want_mask_of(outs, B, img_first, img_step);
+    if (img_step == 1 && img_first == 0) {
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, out_block_extent(b, B, want), cudaMemcpyDeviceToHost, st));
+    } else {
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_map_out, cudaMemcpyDeviceToHost, st));
+        for (int i = img_first; i < B; i += img_step) {
+            const size_t o1 = s.off_map_out + sizeof(float) * s.map_stride * i, o2 = s.off_map_pre + sizeof(float) * s.map_stride * i;
+            const size_t o3 = s.off_map_u8 + s.map_stride * i;
+            CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o1, s.out_block + o1, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
+            if (want & 1u) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o2, s.out_block + o2, sizeof(float) * npix, cudaMemcpyDeviceToHost, st));
+            if (want & 2u) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o3, s.out_block + o3, npix, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CMDB_CUDA(cudaStreamSynchronize(st));
+    scatter_outputs(b, s.out_block_host, B, P, out_hw, outs, img_first, img_step);
     return CMDB_OK;
 }
 
@@ -233,41 +229,106 @@ int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host,
     return coreset_rownorms(device, z_host, last_host, n_rows, d, dtype_mode, out_host);
 }
 
-int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, int fw, int out_hw, int patch_is_device,
-                     cmdb_score_out *outs) {
-    CMDB_CHECK(check_score_args(b, patches, B, P, "cmdb_score_batch"));
-    CMDB_REQUIRE(outs, CMDB_ERR_INVALID, "cmdb_score_batch: outs is NULL");
-    CMDB_REQUIRE(fh > 0 && fw > 0 && fh * fw == P, CMDB_ERR_INVALID, "cmdb_score_batch: feature_map_dims %dx%d != P=%d", fh,
-                 fw, P);
-    CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_batch: out_hw=%d not in [8,256]", out_hw);
+// Enqueue one sub-batch (<= score_max_batch images) on buffer slot `slot`: staging, GEMM + certificate, maps, re-weighting
+// and the device->host copies of the results (on the d2h stream, the maps as soon as the blur is done).  No host sync.
+static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int bc, int P, int fh, int fw, int out_hw,
+                            unsigned want, int slot) {
 #define CMDB_MARK(i)                                                   \
     do {                                                               \
         if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[i], b->stream)); \
     } while (0)
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
+    score_select_slot(b, slot);
+    CMDB_MARK(CMDB_T_STAGE_IN);
+    // this slot's q_f32 was last read by the batch submitted two calls ago
+    CMDB_CHECK(score_local_min(b, src, is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE, b->ev_compute[slot]));
+    CMDB_MARK(CMDB_T_MAP);
+    CMDB_CHECK(blur_batch(b, bc, fh, fw, out_hw));
+    // min_val / min_idx / maps do not depend on the re-weighting: their copy overlaps it
+    CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_chunk[0], 0));
+    CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + s.off_min_val, s.out_block + s.off_min_val,
+                              out_block_extent(b, bc, want) - s.off_min_val, cudaMemcpyDeviceToHost, b->d2h_stream));
+    CMDB_MARK(CMDB_T_REWEIGHT);
+    CMDB_CHECK(score_reweight(b, bc, P, true));
+    CMDB_MARK(CMDB_T_OUT);
+    CMDB_CUDA(cudaEventRecord(b->ev_compute[slot], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
+    CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_min_val, cudaMemcpyDeviceToHost, b->d2h_stream));
+    CMDB_CUDA(cudaEventRecord(b->ev_done[slot], b->d2h_stream));
+    if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->d2h_stream));
+#undef CMDB_MARK
+    cmdb_bank::Pending &pd = b->pending[slot];
+    pd.active = true, pd.B = bc, pd.P = P, pd.out_hw = out_hw, pd.want = want;
+    return CMDB_OK;
+}
+
+static int wait_slot(cmdb_bank *b, int slot, cmdb_score_out *outs) {
+    cmdb_bank::Pending &pd = b->pending[slot];
+    CMDB_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+    pd.active = false;
+    scatter_outputs(b, b->ss.out_block_host_buf[slot], pd.B, pd.P, pd.out_hw, outs);
+    if (b->timing) b->ev_valid = true;
+    return CMDB_OK;
+}
+
+static int check_batch_args(cmdb_bank *b, const float *patches, int B, int P, int fh, int fw, int out_hw, const char *fn) {
+    CMDB_CHECK(check_score_args(b, patches, B, P, fn));
+    CMDB_REQUIRE(fh > 0 && fw > 0 && fh * fw == P, CMDB_ERR_INVALID, "%s: feature_map_dims %dx%d != P=%d", fn, fh, fw, P);
+    CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "%s: out_hw=%d not in [8,256]", fn, out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
+    if (b->ss.map_stride && (size_t)out_hw * out_hw != b->ss.map_stride) {  // map stride is fixed per scratch
+        CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
+                     "%s: out_hw changes while a submitted batch is outstanding; wait for it first", fn);
+        score_scratch_free(b);
+    }
+    return CMDB_OK;
+}
+
+int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, int fw, int out_hw, int patch_is_device,
+                     cmdb_score_out *outs) {
+    CMDB_REQUIRE(outs, CMDB_ERR_INVALID, "cmdb_score_batch: outs is NULL");
+    CMDB_CHECK(check_batch_args(b, patches, B, P, fh, fw, out_hw, "cmdb_score_batch"));
     const int bc_max = score_max_batch(b);
-    if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);  // map stride is fixed per scratch
     for (int b0 = 0; b0 < B; b0 += bc_max) {
         const int bc = std::min(bc_max, B - b0);
-        const float *src = patches + (size_t)b0 * P * b->dim;
-        CMDB_MARK(CMDB_T_STAGE_IN);
-        CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
-        CMDB_CHECK(score_local_min(b, src, patch_is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE));
-        CMDB_MARK(CMDB_T_MAP);
-        CMDB_CHECK(blur_batch(b, bc, fh, fw, out_hw));
-        CMDB_CHECK(copy_maps_early(b, bc, outs + b0));
-        CMDB_MARK(CMDB_T_REWEIGHT);
-        CMDB_CHECK(score_reweight(b, bc, P, true));
-        CMDB_MARK(CMDB_T_OUT);
-        CMDB_CHECK(copy_outputs(b, bc, P, out_hw, outs + b0, 0, 1, true));
-        if (b->timing) {  // timings describe the last sub-batch
-            CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->stream));
-            CMDB_CUDA(cudaEventSynchronize(b->ev[CMDB_T_COUNT]));
-            b->ev_valid = true;
-        }
+        const int slot = b->next_slot;
+        CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE, "cmdb_score_batch: two submitted batches are outstanding; wait for one first");
+        b->next_slot ^= 1;
+        CMDB_CHECK(submit_sub_batch(b, patches + (size_t)b0 * P * b->dim, patch_is_device, bc, P, fh, fw, out_hw,
+                                    want_mask_of(outs + b0, bc), slot));
+        CMDB_CHECK(wait_slot(b, slot, outs + b0));
     }
-#undef CMDB_MARK
     return CMDB_OK;
+}
+
+int cmdb_score_batch_submit(cmdb_bank *b, const float *patches, int B, int P, int fh, int fw, int out_hw, int patch_is_device,
+                            unsigned want_maps, int64_t *out_ticket) {
+    CMDB_REQUIRE(out_ticket, CMDB_ERR_INVALID, "cmdb_score_batch_submit: out_ticket is NULL");
+    CMDB_CHECK(check_batch_args(b, patches, B, P, fh, fw, out_hw, "cmdb_score_batch_submit"));
+    CMDB_REQUIRE(B <= score_max_batch(b), CMDB_ERR_INVALID, "cmdb_score_batch_submit: batch=%d exceeds the per-call limit %d", B,
+                 score_max_batch(b));
+    const int slot = b->next_slot;
+    CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
+                 "cmdb_score_batch_submit: two batches are already outstanding; call cmdb_score_batch_wait first");
+    CMDB_CHECK(submit_sub_batch(b, patches, patch_is_device, B, P, fh, fw, out_hw, want_maps & 3u, slot));
+    b->next_slot ^= 1;
+    b->pending[slot].ticket = ++b->ticket_counter;
+    *out_ticket = b->pending[slot].ticket;
+    return CMDB_OK;
+}
+
+int cmdb_score_batch_wait(cmdb_bank *b, int64_t ticket, cmdb_score_out *outs) {
+    CMDB_REQUIRE(b && outs, CMDB_ERR_INVALID, "cmdb_score_batch_wait: NULL argument");
+    for (int slot = 0; slot < 2; ++slot)
+        if (b->pending[slot].active && b->pending[slot].ticket == ticket) {
+            CMDB_CUDA(cudaSetDevice(b->device));
+            return wait_slot(b, slot, outs);
+        }
+    set_error("cmdb_score_batch_wait: ticket %lld is not outstanding", (long long)ticket);
+    return CMDB_ERR_STATE;
 }
 
 int cmdb_score(cmdb_bank *b, const float *patch, int P, int fh, int fw, int out_hw, int patch_is_device,
@@ -288,8 +349,11 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_REQUIRE(keys_device, CMDB_ERR_INVALID, "cmdb_score_shard_min: keys_device is NULL");
     CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_shard_min: out_hw=%d not in [8,256]", out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
+                 "cmdb_score_shard_min: a submitted batch is outstanding on this handle; wait for it first");
     if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
     CMDB_CHECK(stage_alloc(b, B, P, out_hw));
+    score_select_slot(b, 0);
     CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1));
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());

@@ -239,6 +239,12 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
     cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t err = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->d2h_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_compute[i], cudaEventDisableTiming);
+    }
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fail, cudaEventDisableTiming);
     for (auto &e : b->ev_chunk)
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaMalloc(&b->data, sizeof(float) * (size_t)capacity_rows * dim);
@@ -272,6 +278,8 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
     free_scoring_layout(b);
     cudaFree(b->data);
     cudaFree(b->stats_buf);
@@ -281,6 +289,12 @@ void cmdb_bank_destroy(cmdb_bank *b) {
         if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    if (b->d2h_stream) cudaStreamDestroy(b->d2h_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+        if (b->ev_compute[i]) cudaEventDestroy(b->ev_compute[i]);
+    }
+    if (b->ev_fail) cudaEventDestroy(b->ev_fail);
     for (auto &e : b->ev_chunk)
         if (e) cudaEventDestroy(e);
     delete b;

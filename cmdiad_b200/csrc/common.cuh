@@ -51,7 +51,8 @@ constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 
 struct ScoreScratch {
     int cap_p = 0;                  // padded query-row capacity of a sub-batch (multiple of 128)
     int cap_b = 0;                  // image capacity of a sub-batch
-    float *q_f32 = nullptr;         // [cap_p, D]  normalised query patches
+    float *q_f32 = nullptr;         // [cap_p, D]  normalised query patches (the slot selected by score_select_slot)
+    float *q_f32_buf[2] = {nullptr, nullptr};   // double-buffered: batch k+1 is staged while batch k is still scored
     __half *q_hi = nullptr;         // [cap_p, D]  split-fp16 query operand
     __half *q_lo = nullptr;
     int *q_scale_exp = nullptr;     // device [cap_p]: per-row exponent e_q with q_hi + q_lo = q * 2^e_q
@@ -82,8 +83,10 @@ struct ScoreScratch {
     void *tail = nullptr;           // TailResult
     // results live in ONE device block (tail | min_val | min_idx | map_out | map_pre | map_u8) mirrored by a pinned
     // host block, so a scoring call ends with a single device->host copy
-    unsigned char *out_block = nullptr;
+    unsigned char *out_block = nullptr;       // (current slot)
     unsigned char *out_block_host = nullptr;  // cudaMallocHost
+    unsigned char *out_block_buf[2] = {nullptr, nullptr};       // double-buffered: the results of batch k travel to the
+    unsigned char *out_block_host_buf[2] = {nullptr, nullptr};  // host while batch k+1 is scored
     size_t off_min_val = 0, off_min_idx = 0, off_map_out = 0, off_map_pre = 0, off_map_u8 = 0, out_block_bytes = 0;
     size_t map_stride = 0;  // pixels reserved per image in the map sections
     float *map_pre = nullptr;       // [out_hw^2]
@@ -119,6 +122,18 @@ struct cmdb_bank {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host -> device staging of query chunks, overlapped with the GEMM of earlier chunks
     cudaEvent_t ev_chunk[cmdb::kMaxStageChunks] = {};
+    cudaStream_t d2h_stream = nullptr;    // device -> host copies of the results
+    cudaEvent_t ev_done[2] = {};          // slot's results are in the pinned host block
+    cudaEvent_t ev_compute[2] = {};       // slot's kernels are done (its q_f32 may be overwritten)
+    cudaEvent_t ev_fail = nullptr;        // the certificate counters of the last certified call are on the host
+    struct Pending {
+        bool active = false;
+        int B = 0, P = 0, out_hw = 0;
+        unsigned want = 0;
+        long long ticket = 0;
+    } pending[2];
+    long long ticket_counter = 0;
+    int next_slot = 0;
     float *data = nullptr;  // [capacity, dim] float32 row-major
     // scoring layout (cmdb_bank_finalize)
     bool finalized = false;
@@ -170,6 +185,7 @@ int coreset_rownorms(int device, const void *z_host, const void *last_host, int6
 
 // score_gemm.cu
 int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw);
+void score_select_slot(cmdb_bank *b, int slot);  // point ss.q_f32 / ss.out_block / result pointers at buffer `slot`
 int score_max_batch(const cmdb_bank *b);  // images per internal sub-batch (shared-memory bound of reweight_kernel)
 void score_scratch_free(cmdb_bank *b);
 int score_make_tensor_maps(cmdb_bank *b);
@@ -183,7 +199,9 @@ void q_split_rows(cmdb_bank *b, const float *rows_dev, int n);
 int score_gemm_groups();              // epilogue warp groups per CTA: producers = groups * CTAs
 int score_tile_stride(int mt, int G); // host copy of the GEMM's tile schedule stride
 // stage the queries (src: host or device, [B*P_img, dim]) + candidates + refine, all modes
-int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine);
+// stage_after: event the copy stream waits for before it overwrites q_f32 (nullptr: everything queued so far)
+int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine,
+                    cudaEvent_t stage_after = nullptr);
 
 // score_tail.cu
 struct TailResult {  // device-side result block (ScoreScratch::tail)

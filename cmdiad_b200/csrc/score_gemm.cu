@@ -482,14 +482,22 @@ int score_make_tensor_maps(cmdb_bank *b) {
 
 void score_scratch_free(cmdb_bank *b) {
     ScoreScratch &s = b->ss;
-    cudaFree(s.q_f32), cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_scale_exp);
-    cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys), cudaFree(s.out_block);
+    // no copy may still be in flight into / out of the buffers
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s.q_f32_buf[i]), cudaFree(s.out_block_buf[i]);
+        if (s.out_block_host_buf[i]) cudaFreeHost(s.out_block_host_buf[i]);
+        b->pending[i].active = false;
+    }
+    cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_scale_exp);
+    cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys);
     cudaFree(s.map_tmp), cudaFree(s.map_max), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
     cudaFree(s.top3), cudaFree(s.done_counter);
     cudaFree(s.q_norm), cudaFree(s.q_eps), cudaFree(s.fail_list), cudaFree(s.fail_ctl);
     cudaFree(s.work_list), cudaFree(s.best_key);
     if (s.fail_count_host) cudaFreeHost(s.fail_count_host);
-    if (s.out_block_host) cudaFreeHost(s.out_block_host);
     free(s.tmap_qhi), free(s.tmap_qlo);
     s = ScoreScratch();
 }
@@ -500,16 +508,31 @@ int score_max_batch(const cmdb_bank *b) {
     return std::max(1, std::min(32, by_smem));
 }
 
+void score_select_slot(cmdb_bank *b, int slot) {
+    ScoreScratch &s = b->ss;
+    s.q_f32 = s.q_f32_buf[slot];
+    s.out_block = s.out_block_buf[slot];
+    s.out_block_host = s.out_block_host_buf[slot];
+    s.tail = s.out_block;
+    s.min_val = reinterpret_cast<float *>(s.out_block + s.off_min_val);
+    s.min_idx = reinterpret_cast<long long *>(s.out_block + s.off_min_idx);
+    s.map_out = reinterpret_cast<float *>(s.out_block + s.off_map_out);
+    s.map_pre = reinterpret_cast<float *>(s.out_block + s.off_map_pre);
+    s.map_u8 = s.out_block + s.off_map_u8;
+}
+
 int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     ScoreScratch &s = b->ss;
     const int p_pad = (B * P_img + BM - 1) / BM * BM;
     const int map_n = out_hw * out_hw;
     if (s.cap_p >= p_pad && s.cap_b >= B && (int)s.map_stride >= map_n) return CMDB_OK;
+    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
+                 "scoring: the scratch buffers have to grow while a submitted batch is outstanding; wait for it first");
     const int cap_p = std::max(p_pad, s.cap_p), cap_b = std::max(B, s.cap_b), map_cap = std::max(map_n, (int)s.map_stride);
     score_scratch_free(b);
     const size_t D = b->dim;
     s.n_topk_blocks = b->num_sms * 4;
-    CMDB_CUDA(cudaMalloc(&s.q_f32, sizeof(float) * cap_p * D));
+    for (int i = 0; i < 2; ++i) CMDB_CUDA(cudaMalloc(&s.q_f32_buf[i], sizeof(float) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_hi, sizeof(__half) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
     CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int) * cap_p));
@@ -533,14 +556,11 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     s.off_map_pre = s.off_map_out + up(sizeof(float) * map_cap * cap_b);
     s.off_map_u8 = s.off_map_pre + up(sizeof(float) * map_cap * cap_b);
     s.out_block_bytes = s.off_map_u8 + up((size_t)map_cap * cap_b);
-    CMDB_CUDA(cudaMalloc(&s.out_block, s.out_block_bytes));
-    CMDB_CUDA(cudaMallocHost(&s.out_block_host, s.out_block_bytes));
-    s.tail = s.out_block;
-    s.min_val = reinterpret_cast<float *>(s.out_block + s.off_min_val);
-    s.min_idx = reinterpret_cast<long long *>(s.out_block + s.off_min_idx);
-    s.map_out = reinterpret_cast<float *>(s.out_block + s.off_map_out);
-    s.map_pre = reinterpret_cast<float *>(s.out_block + s.off_map_pre);
-    s.map_u8 = s.out_block + s.off_map_u8;
+    for (int i = 0; i < 2; ++i) {
+        CMDB_CUDA(cudaMalloc(&s.out_block_buf[i], s.out_block_bytes));
+        CMDB_CUDA(cudaMallocHost(&s.out_block_host_buf[i], s.out_block_bytes));
+    }
+    score_select_slot(b, 0);
     CMDB_CUDA(cudaMalloc(&s.map_tmp, (size_t)map_cap * cap_b));
     CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b));
     CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long) * cap_b));

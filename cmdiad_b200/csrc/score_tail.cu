@@ -434,7 +434,8 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
 // Host queries are staged in up to kMaxStageChunks chunks on a copy stream; chunk c is split and multiplied while chunk
 // c + 1 is still crossing PCIe.  (One GEMM launch per chunk: each streams the fp16 bank once more, which is cheap next to
 // the host link.)  Device-resident queries use one chunk.
-int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine) {
+int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine,
+                    cudaEvent_t stage_after) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     const int P = B * P_img;
@@ -458,8 +459,9 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     if (mode == 0) {
         // adaptive: when most queries of the previous certified call needed the GEMM fallback (dense near-duplicate
         // banks), run the FP32-equivalent GEMM directly for a while, then probe the pre-filter again
-        if (b->fail_pending) {
-            CMDB_CUDA(cudaStreamSynchronize(st));  // the count was copied by the previous call; normally long complete
+        // (the counters of the previous certified call; if their copy has not landed yet -- pipelined submits -- look again
+        // next time instead of stalling the host)
+        if (b->fail_pending && cudaEventQuery(b->ev_fail) == cudaSuccess) {
             b->fail_pending = false;
             if (prev_queries > 0 && s.fail_count_host[1] > kRescanMaxPairs && (double)s.fail_count_host[0] > 0.5 * (double)prev_queries)
                 b->direct_calls_left = 32;
@@ -475,22 +477,29 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
         const char *e = getenv("CMDB_STAGE_CHUNKS");
         return e ? atoi(e) : 0;
     }();
+    // another batch in flight on this handle (submit / wait pipeline): the whole copy already overlaps that batch's
+    // kernels, so one chunk -- and one GEMM launch -- is best
+    const bool overlapped = b->pending[0].active || b->pending[1].active;
+    const bool via_copy_stream = !src_is_device && (overlapped || mt_total >= 16);
     int n_chunks = 1;
-    if (!src_is_device) n_chunks = env_chunks > 0 ? env_chunks : (mt_total >= 64 ? 4 : (mt_total >= 16 ? 2 : 1));
+    if (via_copy_stream && !overlapped) n_chunks = env_chunks > 0 ? env_chunks : (mt_total >= 64 ? 4 : 2);
     n_chunks = std::max(1, std::min(std::min(n_chunks, kMaxStageChunks), mt_total));
     const int chunk_tiles = (mt_total + n_chunks - 1) / n_chunks;
     n_chunks = (mt_total + chunk_tiles - 1) / chunk_tiles;
     s.chunk_tiles = chunk_tiles, s.mt_total = mt_total;
-    if (n_chunks > 1) {
-        // the copy stream may only start once everything queued on the compute stream (an earlier sub-batch still
-        // reading q_f32) is done
-        CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], st));
-        CMDB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_chunk[0], 0));
+    if (via_copy_stream) {
+        // the copy stream may only overwrite q_f32 once its previous readers are done: the event the caller names, or
+        // everything queued on the compute stream so far
+        if (!stage_after) {
+            CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], st));
+            stage_after = b->ev_chunk[0];
+        }
+        CMDB_CUDA(cudaStreamWaitEvent(b->copy_stream, stage_after, 0));
     }
     for (int c = 0; c < n_chunks; ++c) {
         const int row0 = c * chunk_tiles * kScoreBM, rows = std::min(P, (c + 1) * chunk_tiles * kScoreBM) - row0;
         const size_t o = (size_t)row0 * D;
-        if (n_chunks == 1) {
+        if (!via_copy_stream) {
             CMDB_CUDA(cudaMemcpyAsync(s.q_f32, src, sizeof(float) * P * D, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         } else {
             CMDB_CUDA(cudaMemcpyAsync(s.q_f32 + o, src + o, sizeof(float) * rows * D, cudaMemcpyHostToDevice, b->copy_stream));
@@ -499,7 +508,7 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     }
     for (int c = 0; c < n_chunks; ++c) {
         const int row0 = c * chunk_tiles * kScoreBM, rows = std::min(P, (c + 1) * chunk_tiles * kScoreBM) - row0;
-        if (n_chunks > 1) CMDB_CUDA(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
+        if (via_copy_stream) CMDB_CUDA(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
         CMDB_CHECK(score_query_prep(b, rows, false, row0));
         if (c == 0) CMDB_CHECK(mark(ev_gemm));
         CMDB_CHECK(score_gemm_candidates(b, rows, mode == 3 ? 3 : 1, false, &n_cand, row0));
@@ -508,6 +517,7 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     if (mode != 0) return score_refine(b, B, P_img, n_cand, false);
     CMDB_CHECK(score_refine_certified(b, B, P_img, n_cand));
     CMDB_CUDA(cudaMemcpyAsync(s.fail_count_host, s.fail_ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CMDB_CUDA(cudaEventRecord(b->ev_fail, st));
     b->fail_pending = true;
     // tier 2 (many uncertified pairs): FP32-equivalent GEMM over the compacted uncertified queries; every launch sizes
     // itself from the device-side control block and returns at once in the common case

@@ -181,6 +181,17 @@ typedef struct cmdb_score_out {
 int cmdb_score(cmdb_bank *bank, const float *patch, int P, int fh, int fw, int out_hw, int patch_is_device,
                cmdb_score_out *out);
 
+/* Pipelined form of cmdb_score_batch.  submit enqueues everything for one batch (B <= 32 images, <= 160 KB of m_star rows:
+ * the limit cmdb_score_batch splits larger batches by) -- host->device staging, scoring, device->host copies into an
+ * internal pinned block -- and returns without waiting; wait blocks until that batch is complete and fills outs[B].
+ * Up to two batches may be outstanding per handle (double-buffered query and result blocks), so the result copy of
+ * batch k and the staging of batch k+1 overlap the kernels of the other batch.  `patches` must stay valid until the
+ * matching wait returns.  want_maps: bit 0 = outs[].s_map_pre will be requested, bit 1 = outs[].s_map_u8.
+ * Results are identical to cmdb_score_batch.  Not combined with the sharded phases on the same handle. */
+int cmdb_score_batch_submit(cmdb_bank *bank, const float *patches, int batch, int P, int fh, int fw, int out_hw,
+                            int patch_is_device, unsigned want_maps, int64_t *out_ticket);
+int cmdb_score_batch_wait(cmdb_bank *bank, int64_t ticket, cmdb_score_out *outs);
+
 /*
  * Batch form: B images of P patches each, patches float32 [B, P, dim], outs[B].  One sweep of the distance GEMM and ONE
  * sweep of the bank for the re-weighting serve the whole batch (the reference scores train and test images one by one,

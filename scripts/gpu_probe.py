@@ -208,6 +208,59 @@ def s_gemm_sweep():
     b.close()
 
 
+@section("pipelined submit/wait: device vs pinned-host inputs, raw copy rates")
+def s_pipeline():
+    import bench
+    b = bench.build_bank(0, 1)
+    b.finalize()
+    imgs = bench.test_patches(16)
+    host = [torch.stack([imgs[(k * 5 + i) % 16] for i in range(16)]).pin_memory() for k in range(3)]
+    dev = [h.cuda() for h in host]
+    # raw copy rates of one batch
+    cs = torch.cuda.Stream()
+    tgt = torch.empty_like(dev[0])
+    back = torch.empty(16, 224, 224, dtype=torch.float32).pin_memory()
+    src_maps = torch.empty(16, 224, 224, dtype=torch.float32, device="cuda")
+    for name, fn in (("H2D 38.5 MB", lambda: tgt.copy_(host[0], non_blocking=True)),
+                     ("D2H 3.2 MB", lambda: back.copy_(src_maps, non_blocking=True))):
+        with torch.cuda.stream(cs):
+            best, med = ev_time(cs, fn, iters=8, warm=2)
+        print(f"{name}: best {best:.3f} ms median {med:.3f} ms")
+
+    def loop(xs, n, pipelined):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pending = None
+        for i in range(n):
+            if pipelined:
+                t = b.score_batch_async(xs[i % 3], (28, 28), 224)
+                if pending is not None:
+                    pending.wait()
+                pending = t
+            else:
+                b.score_batch(xs[i % 3], (28, 28), 224)
+        if pending is not None:
+            pending.wait()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    for name, xs in (("device", dev), ("host", host)):
+        for pipe in (False, True):
+            loop(xs, 5, pipe)
+            print(f"{name:6s} pipelined={pipe}: {loop(xs, 30, pipe):.3f} ms/step", flush=True)
+    # host-side cost of one submit and one wait while the GPU is idle
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    t = b.score_batch_async(dev[0], (28, 28), 224)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    t.wait()
+    t3 = time.perf_counter()
+    print(f"host time: submit {1e3 * (t1 - t0):.3f} ms, wait (results already on the host) {1e3 * (t3 - t2):.3f} ms")
+    b.close()
+
+
 @section("big banks: 1M x 768 (coreset + scoring) and 627k x 1152 (cfg2 XYZ scoring)")
 def s_big():
     for (R, D, P, fm) in ((1_000_000, 768, 784, 28), (627_200, 1152, 3136, 56)):
@@ -260,6 +313,6 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), torch.__version__)
     which = sys.argv[1:] or ["rownorms", "proj", "blur", "score_small", "coreset_small", "score_big", "coreset_big"]
     table = dict(big=s_big, rownorms=s_rownorms, proj=s_proj, coreset_small=s_coreset_small, coreset_big=s_coreset_big,
-                 score_small=s_score_small, blur=s_blur, score_big=s_score_big, gemm_sweep=s_gemm_sweep)
+                 score_small=s_score_small, blur=s_blur, score_big=s_score_big, gemm_sweep=s_gemm_sweep, pipeline=s_pipeline)
     for w in which:
         table[w]()
