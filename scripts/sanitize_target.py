@@ -26,6 +26,12 @@ p = np.stack([synth.patches(196, D, seed=5 + i, k=32) for i in range(3)])
 for terms in (0, 3, 1):
     b.set_prefilter_terms(terms)
     r = b.score_batch(p, (14, 14), 64, full=True)
+b.set_prefilter_terms(0)
+# near-duplicate rows: the certificate fails for many queries -> exact rescans (and the GEMM fallback chain runs empty)
+t0 = b.score_batch_async(p, (14, 14), 64)
+t1 = b.score_batch_async(torch.from_numpy(p).cuda(), (14, 14), 64, full=True)
+ra, rb = t0.wait(), t1.wait()
+print("async ok", ra[0].s, rb[0].s, b.score_stats())
 b.set_score_impl(L.SCORE_SIMT)
 r2 = b.score(p[0], (14, 14), 64)
 print("score ok", r[0].s, r2.s)
