@@ -256,7 +256,8 @@ def run_ours(args):
                        "call": ("cmdb_score_batch_submit / _wait, two batches in flight" if pipe else
                                 "cmdb_score_batch" if world == 1 else "cmdb_score_shard_* phases"),
                        "sharding": "single GPU" if world == 1 else f"bank row-sharded over {world} GPUs, 4 NCCL collectives (MIN/SUM/all-gather) "
-                                                                    f"per step, map + device->host of image i on rank i % {world}",
+                                                                    f"per step, map + device->host of image i on rank i % {world}; host queries: every rank "
+                                                                    f"stages 1/{world} of the rows over PCIe, NVLink all-gather",
                        "l2": "inputs larger than L2: the bank streams 0.9 GB (fp16 rows for the GEMM, fp32 rows for the re-weighting) per step vs 126 MB of L2"},
             "e2e": {"value": e2e, "unit": "patch-NN scores/s", "h2d_bytes_per_step": B * P * DIM * 4,
                     "d2h_bytes_per_step": B * (OUT_HW * OUT_HW * 4 + P * 12 + 64)},

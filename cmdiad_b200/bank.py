@@ -331,6 +331,24 @@ class Bank:
         patch = _as_f32(patch)
         return self.score_sharded_batch(patch.unsqueeze(0), feature_map_dims, out_hw, full, group)[0]
 
+    def _stage_sharded(self, chunk, dev, world, rank, group):
+        """Host queries of a sharded round: every rank copies only its 1/world slice of the rows over PCIe and the
+        slices are all-gathered over NVLink (every rank needs all queries, but NVLink is ~10x the host link)."""
+        import torch.distributed as dist
+        B, P, D = chunk.shape
+        rows = B * P
+        per = (rows + world - 1) // world
+        flat = chunk.reshape(rows, D)
+        lo, hi = min(rows, rank * per), min(rows, (rank + 1) * per)
+        part = torch.empty(per, D, dtype=torch.float32, device=dev)
+        if hi > lo:
+            part[:hi - lo].copy_(flat[lo:hi], non_blocking=True)
+        if hi - lo < per:
+            part[hi - lo:].zero_()
+        full = torch.empty(per * world, D, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, part, group=group)
+        return full[:rows].view(B, P, D)
+
     def score_sharded_batch(self, patches, feature_map_dims, out_hw=224, full=False, group=None, distribute=False):
         """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; the five phases
         of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between.  Kernels and
@@ -350,6 +368,8 @@ class Bank:
             for b0 in range(0, Btot, step):
                 chunk = patches[b0:b0 + step]
                 B = chunk.shape[0]
+                if not chunk.is_cuda and world > 1 and B * P >= 1024:
+                    chunk = self._stage_sharded(chunk, dev, world, rank, group)
                 keys = torch.empty(B * P, dtype=torch.int64, device=dev)
                 L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
                 dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
