@@ -384,7 +384,7 @@ int cmdb_bank_score_stats(cmdb_bank *b, int64_t *out6) {
     out6[1] = b->last_mode;
     out6[2] = cert ? (int64_t)b->ss.fail_count_host[0] : 0;
     out6[3] = cert ? (int64_t)b->ss.fail_count_host[1] : 0;
-    out6[4] = cert && b->ss.fail_count_host[1] > cmdb::kRescanMaxPairs;
+    out6[4] = cert && !cmdb::fallback_use_rescan(b->ss.fail_count_host[0], b->ss.fail_count_host[1]);
     out6[5] = b->direct_calls_left;
     return CMDB_OK;
 }

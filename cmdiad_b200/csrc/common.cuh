@@ -44,7 +44,14 @@ constexpr int kScoreBN = 256;        // bank rows per GEMM tile
 constexpr int kScoreBM = 128;        // query rows per GEMM tile
 constexpr int kMaxStageChunks = 4;   // host query batches are staged and multiplied in up to this many chunks
 constexpr int kWorkCap = 8192;       // capacity of ScoreScratch::work_list
-constexpr int kRescanMaxPairs = 4096; // more uncertified (query, producer) pairs than this: 3-term GEMM fallback
+// Fallback tier of the certified pre-filter.  Exact rescan: ~R/296 rows x D x 4 B per (query, producer) pair, HBM bound
+// (~0.32 us per pair at 200k x 768).  3-term GEMM over the compacted uncertified queries: at least one sweep of the
+// hi + lo bank (~0.25 ms), then ~0.55 us per query.  Pick the cheaper one; the work list bounds the rescan.
+__host__ __device__ inline bool fallback_use_rescan(int fails, int pairs) {
+    const float cost_rescan = 0.32f * (float)pairs;
+    const float cost_gemm = 0.55f * (float)fails > 250.f ? 0.55f * (float)fails : 250.f;
+    return pairs <= kWorkCap && cost_rescan <= cost_gemm;
+}
 constexpr int kScoreBK = 64;         // fp16 K elements per pipeline stage (one 128-byte swizzle row)
 
 // device scratch of one scoring call, sized at finalize time

@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
 // producer CTA kept its two smallest v; if every CTA's SECOND value is above the threshold, all rows inside the band
 // are first values -> they are ALL re-checked exactly and the result is certified identical to a full exact scan.
 // A producer whose second value is inside the band may hide further rows: the (query, producer) pair is queued and
-// the producer's ~R/producers rows are rescanned exactly (rescan_kernel) -- or, when a call queues more than
-// kRescanMaxPairs pairs (banks full of near-duplicates), the uncertified queries are redone with the FP32-equivalent
-// 3-term GEMM.  Either way min_val / min_idx equal those of an exact scan of the whole bank.
+// the producer's ~R/producers rows are rescanned exactly (rescan_kernel) -- or, when a call queues so many pairs that
+// this would cost more than a GEMM (fallback_use_rescan; banks full of near-duplicates), the uncertified queries are
+// redone with the FP32-equivalent 3-term GEMM.  Either way min_val / min_idx equal those of an exact scan of the whole bank.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
                                                           const float *__restrict__ q, const float *__restrict__ bank, int dim,
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
 
 // [2] rows of the GEMM fallback, [3] pairs of the rescan, [4] queries the rescan path finishes
 __global__ void fallback_decide_kernel(int *ctl) {
-    const bool rescan = ctl[1] <= kRescanMaxPairs;
+    const bool rescan = fallback_use_rescan(ctl[0], ctl[1]);
     ctl[2] = rescan ? 0 : ctl[0];
     ctl[3] = rescan ? ctl[1] : 0;
     ctl[4] = rescan ? ctl[0] : 0;
@@ -463,7 +463,8 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
         // next time instead of stalling the host)
         if (b->fail_pending && cudaEventQuery(b->ev_fail) == cudaSuccess) {
             b->fail_pending = false;
-            if (prev_queries > 0 && s.fail_count_host[1] > kRescanMaxPairs && (double)s.fail_count_host[0] > 0.5 * (double)prev_queries)
+            if (prev_queries > 0 && !fallback_use_rescan(s.fail_count_host[0], s.fail_count_host[1]) &&
+                (double)s.fail_count_host[0] > 0.5 * (double)prev_queries)
                 b->direct_calls_left = 32;
         }
         if (b->direct_calls_left > 0) {

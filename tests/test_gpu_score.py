@@ -259,6 +259,29 @@ def test_certificate_fallback_on_near_duplicates(env):
     b.close()
 
 
+def test_rescan_tier_under_load(env):
+    """Groups of 12 near-duplicates: a fifth of the queries has two band rows in one producer, few enough for the exact
+    rescan tier (no GEMM fallback).  Results must equal the exact CUDA-core scan."""
+    from cmdiad_b200 import synth
+    L = env["L"]
+    g = np.random.Generator(np.random.PCG64(9))
+    base = synth.patches(1500, 768, seed=52, dist="G")
+    lib = np.concatenate([base + 2e-4 * g.standard_normal(base.shape, dtype=np.float32) for _ in range(12)], 0)
+    lib = lib[g.permutation(lib.shape[0])]
+    patches = np.stack([base[g.integers(0, 1500, 784)] + 0.05 * synth.patches(784, 768, seed=65 + i, dist="G") for i in range(3)])
+    b = _bank(env, lib)
+    cert = b.score_batch(patches, (28, 28), 224, full=True)
+    st = b.score_stats()
+    print("rescan tier:", st)
+    assert st["mode"] == 0 and st["rescan_pairs"] >= 100 and not st["gemm_fallback"], st
+    b.set_score_impl(L.SCORE_SIMT)
+    exact = b.score_batch(patches, (28, 28), 224, full=True)
+    for i in range(3):   # min_val / min_idx are certified identical; the re-weighting keys too
+        for name in ("min_idx", "min_val", "s", "s_idx", "nn_idx", "s_map"):
+            assert (getattr(cert[i], name) == getattr(exact[i], name)).all(), (i, name)
+    b.close()
+
+
 def test_prefilter_error_model(env):
     """The certificate rests on (a) Cauchy-Schwarz bounds of the fp16 operand rounding -- mathematics -- and (b) a model
     of the tensor-core accumulation error, (D/16 + 1) * 17 * 2^-23 * ||q_hi|| ||b_hi||.  (b) is measured here: the GEMM
