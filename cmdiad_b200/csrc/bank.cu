@@ -269,7 +269,9 @@ static void free_scoring_layout(cmdb_bank *b) {
     b->norm = nullptr;
     free(b->tmap_hi);
     free(b->tmap_lo);
-    b->tmap_hi = b->tmap_lo = nullptr;
+    free(b->tmap_hi2);
+    free(b->tmap_lo2);
+    b->tmap_hi = b->tmap_lo = b->tmap_hi2 = b->tmap_lo2 = nullptr;
     score_scratch_free(b);
     b->finalized = false;
 }

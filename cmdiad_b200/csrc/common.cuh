@@ -71,6 +71,8 @@ struct ScoreScratch {
     // ([2..4] are derived from [0..1] by fallback_decide_kernel: few pairs -> rescan, many -> GEMM)
     int *fail_ctl = nullptr;
     int *fail_count_host = nullptr; // pinned copy of [0..1] (statistics / adaptive mode)
+    bool sched_pair = false;            // the last first-pass GEMM ran on CTA pairs (cta_group::2)
+    bool sched_pair_last = false;       // ... and the most recent GEMM launch of any kind
     int chunk_tiles = 0, mt_total = 0;  // M-tile layout of the last first-pass GEMM: chunks of chunk_tiles tiles (rescan needs it)
     int2 *work_list = nullptr;      // [kWorkCap] (query row, producer) pairs whose producer may hide rows inside the band
     unsigned long long *best_key = nullptr;  // [cap_p] running exact (d^2 bits << 32 | row) of the uncertified queries
@@ -152,6 +154,8 @@ struct cmdb_bank {
     int scale_exp = 0;
     void *tmap_hi = nullptr;  // host copies of the CUtensorMap objects (128 B each)
     void *tmap_lo = nullptr;
+    void *tmap_hi2 = nullptr;  // box of 128 bank rows (CTA-pair kernels)
+    void *tmap_lo2 = nullptr;
     cmdb::ScoreScratch ss;
     int timing = 0;
     cudaEvent_t ev[CMDB_T_COUNT + 1] = {};

@@ -33,17 +33,21 @@ constexpr uint32_t kTileABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kTileBBytes = BN * BK * 2;  // 32 KB
 constexpr uint32_t kTmemCols = 512;
 
-// TERMS = 3: FP32-equivalent split (hi.hi + hi.lo + lo.hi), 96 KB per stage, 2 stages      -- the default product path
-// TERMS = 1: hi.hi only (11-bit operands) as a pre-filter for the exact re-check, 48 KB per stage, 4 stages -- opt-in
-template <int TERMS>
+// TERMS = 3: FP32-equivalent split (hi.hi + hi.lo + lo.hi)     TERMS = 1: hi.hi only (certified pre-filter)
+// CG = 1: one CTA per tile (96 / 48 KB per stage, 2 / 4 stages)
+// CG = 2: CTA pair, tcgen05 cta_group::2: M = 256 (128 query rows per CTA), each CTA stages its own A tile and HALF of the
+//         bank tile (64 / 32 KB per stage, 3 / 6 stages) -- the tensor core reads every bank element from shared memory
+//         once per pair instead of once per CTA
+template <int TERMS, int CG>
 struct GemmSmem {  // offsets inside dynamic shared memory (1024-byte aligned base)
-    static constexpr int kStages = TERMS == 3 ? 2 : 4;
-    static constexpr uint32_t kStageBytes = (TERMS == 3 ? 2u : 1u) * (kTileABytes + kTileBBytes);
+    static constexpr uint32_t kTileB = kTileBBytes / CG;
+    static constexpr int kStages = (TERMS == 3 ? 2 : 4) * (CG == 2 ? 3 : 2) / 2;
+    static constexpr uint32_t kStageBytes = (TERMS == 3 ? 2u : 1u) * (kTileABytes + kTileB);
     static constexpr uint32_t stage(int s) { return s * kStageBytes; }
     static constexpr uint32_t a_hi(int s) { return stage(s); }
     static constexpr uint32_t b_hi(int s) { return stage(s) + kTileABytes; }
-    static constexpr uint32_t a_lo(int s) { return stage(s) + kTileABytes + kTileBBytes; }
-    static constexpr uint32_t b_lo(int s) { return stage(s) + 2 * kTileABytes + kTileBBytes; }
+    static constexpr uint32_t a_lo(int s) { return stage(s) + kTileABytes + kTileB; }
+    static constexpr uint32_t b_lo(int s) { return stage(s) + 2 * kTileABytes + kTileB; }
     static constexpr uint32_t bnorm = kStages * kStageBytes;              // [2][BN] float
     static constexpr uint32_t bars = bnorm + 2 * BN * 4;                  // mbarriers
     static constexpr uint32_t total = bars + 128;
@@ -99,6 +103,55 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {  // shared::cluster address of a peer's smem
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// both CTAs of the pair issue their loads; the transaction bytes are credited to the barrier `bar_cluster_addr`, which
+// lives in the LEADER's shared memory
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once all prior MMAs have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -129,6 +182,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B fp16 (0), both K-major,
 // N >> 3 in [17,23), M >> 4 in [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256 over 2 CTAs
 
 // Tile schedule shared by the three warp roles: N tiles in order (the bank streams from HBM once); the mt M tiles of
 // N tile n go to the consecutive CTAs (n*s + m) % G, where the stride s >= mt is the next integer coprime with G.
@@ -136,8 +190,7 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t
 // CTA receives exactly mt tiles) AND lets every CTA see ~R/G rows of every query whatever gcd(mt, G) is -- the
 // certificate of the pre-filter (score_tail.cu) needs the rows inside a query's error band to land in different CTAs'
 // top-2 lists.
-__device__ __forceinline__ int tile_stride(int mt) {
-    const int G = (int)gridDim.x;
+__device__ __forceinline__ int tile_stride(int mt, int G) {
     for (int s = mt;; ++s) {
         int a = s % G, b = G;
         if (a == 0) a = G;
@@ -148,17 +201,17 @@ __device__ __forceinline__ int tile_stride(int mt) {
         if (a == 1 || G == 1) return s;
     }
 }
+// c: this CTA (or CTA pair), G: number of CTAs (pairs), mt: M tiles (M tile pairs) per N tile
 struct TileIter {  // n, m: current tile; base: first M tile of this CTA inside N tile n
-    int n, m, base, smod;
-    __device__ __forceinline__ TileIter(int mt, int stride) {
-        const int G = (int)gridDim.x;
+    int n, m, base, smod, G;
+    __device__ __forceinline__ TileIter(int c, int G_, int mt, int stride) {
+        G = G_;
         smod = stride % G;
-        n = -1, m = mt, base = ((int)blockIdx.x + smod) % G;
+        n = -1, m = mt, base = (c + smod) % G;
     }
     // incremental form of m = (c - n * stride) mod G: no division per step (a CTA walks over ALL N tiles, also the ones in
     // which it owns no M tile, so the step has to be cheap when mt is small)
     __device__ __forceinline__ bool next(int mt, int nt) {
-        const int G = (int)gridDim.x;
         m += G;
         while (m >= mt) {
             if (++n >= nt) return false;
@@ -213,11 +266,11 @@ struct GemmParams {
     int cand_stride;    // >= mt * 128
 };
 
-template <int TERMS, int EG>
+template <int TERMS, int EG, int CG>
 __global__ void __launch_bounds__(kGemmCtlThreads + 128 * EG, 1)
 score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, GemmParams p) {
-    using S = GemmSmem<TERMS>;
+    using S = GemmSmem<TERMS, CG>;
     constexpr int kGemmThreads = kGemmCtlThreads + 128 * EG;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this round-up
@@ -228,8 +281,14 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         p.mt = (__ldg(p.m_count) + BM - 1) / BM;
         if (p.mt == 0) return;  // uniform over the grid, before any barrier / TMEM allocation
     }
-    const int stride = tile_stride(p.mt);
+    // CG == 2: the two CTAs of a cluster form a pair; the pair owns M tiles 2*mp and 2*mp + 1 (one per CTA) of its tiles
+    const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const int unit = (int)blockIdx.x / CG, n_units = (int)gridDim.x / CG;  // scheduling unit = CTA or CTA pair
+    const int mt_units = (p.mt + CG - 1) / CG;
+    const int stride = tile_stride(mt_units, n_units);
     // barriers: full[S::kStages], empty[S::kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+    // (pair: full[] and tmem_empty[] are only used in the leader, rank 0; empty[] and tmem_full[] exist in both CTAs and
+    // are signalled by the leader's multicast commits)
     const uint32_t bar_full = sbase + S::bars, bar_empty = bar_full + 8 * S::kStages;
     const uint32_t bar_tfull = bar_empty + 8 * S::kStages, bar_tempty = bar_tfull + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bars + 8 * (2 * S::kStages + 4));
@@ -246,11 +305,14 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4 * EG);  // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * b, 4 * EG * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == 2) {
+        if constexpr (CG == 2) tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
+        else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    }
     for (int i = p.m_base * BM + threadIdx.x; i < (p.m_base + p.mt) * BM; i += kGemmThreads)
 #pragma unroll
         for (int g = 0; g < EG; ++g)
@@ -258,37 +320,50 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     __threadfence_block();
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled there
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (every CTA loads its own query tile and its share of the bank tile) =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (TileIter it(p.mt, stride); it.next(p.mt, p.nt);) {
-                const int n = it.n, m = it.m;
+            for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, p.nt);) {
+                const int n = it.n, m = it.m * CG + rank;
+                const int a_row = (p.m_base + m) * BM, b_row = n * BN + rank * (BN / CG);
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, S::kStageBytes);
-                    tma_load_2d(sbase + S::a_hi(stage), &tm_qhi, full, kb * BK, (p.m_base + m) * BM);
-                    tma_load_2d(sbase + S::b_hi(stage), &tm_bhi, full, kb * BK, n * BN);
-                    if constexpr (TERMS == 3) {
-                        tma_load_2d(sbase + S::a_lo(stage), &tm_qlo, full, kb * BK, (p.m_base + m) * BM);
-                        tma_load_2d(sbase + S::b_lo(stage), &tm_blo, full, kb * BK, n * BN);
+                    if constexpr (CG == 2) {
+                        const uint32_t full = map_to_cta(bar_full + 8 * stage, 0);  // the leader's barrier
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * S::kStageBytes);
+                        tma_load_2d_pair(sbase + S::a_hi(stage), &tm_qhi, full, kb * BK, a_row);
+                        tma_load_2d_pair(sbase + S::b_hi(stage), &tm_bhi, full, kb * BK, b_row);
+                        if constexpr (TERMS == 3) {
+                            tma_load_2d_pair(sbase + S::a_lo(stage), &tm_qlo, full, kb * BK, a_row);
+                            tma_load_2d_pair(sbase + S::b_lo(stage), &tm_blo, full, kb * BK, b_row);
+                        }
+                    } else {
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_expect_tx(full, S::kStageBytes);
+                        tma_load_2d(sbase + S::a_hi(stage), &tm_qhi, full, kb * BK, a_row);
+                        tma_load_2d(sbase + S::b_hi(stage), &tm_bhi, full, kb * BK, b_row);
+                        if constexpr (TERMS == 3) {
+                            tma_load_2d(sbase + S::a_lo(stage), &tm_qlo, full, kb * BK, a_row);
+                            tma_load_2d(sbase + S::b_lo(stage), &tm_blo, full, kb * BK, b_row);
+                        }
                     }
                     if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        // ================= MMA issuer (one thread; in a pair only the leader CTA issues) =================
+        if (lane == 0 && rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int j = 0;
-            for (TileIter it(p.mt, stride); it.next(p.mt, p.nt); ++j) {
+            for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, p.nt); ++j) {
                 const int buf = j & 1;
                 mbar_wait(bar_tempty + 8 * buf, ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -303,47 +378,78 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                         const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
-                        umma_f16(tmem_d, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) != 0);
-                        if constexpr (TERMS == 3) {
-                            umma_f16(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1);
-                            umma_f16(tmem_d, a_lo + adv, b_hi + adv, kIdesc, 1);
+                        if constexpr (CG == 2) {
+                            umma_f16_pair(tmem_d, a_hi + adv, b_hi + adv, kIdescPair, (kb | ks) != 0);
+                            if constexpr (TERMS == 3) {
+                                umma_f16_pair(tmem_d, a_hi + adv, b_lo + adv, kIdescPair, 1);
+                                umma_f16_pair(tmem_d, a_lo + adv, b_hi + adv, kIdescPair, 1);
+                            }
+                        } else {
+                            umma_f16(tmem_d, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) != 0);
+                            if constexpr (TERMS == 3) {
+                                umma_f16(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1);
+                                umma_f16(tmem_d, a_lo + adv, b_hi + adv, kIdesc, 1);
+                            }
                         }
                     }
-                    umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (CG == 2) umma_commit_pair(bar_empty + 8 * stage);
+                    else umma_commit(bar_empty + 8 * stage);
                     if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
-                umma_commit(bar_tfull + 8 * buf);  // accumulator complete
+                // accumulator complete
+                if constexpr (CG == 2) umma_commit_pair(bar_tfull + 8 * buf);
+                else umma_commit(bar_tfull + 8 * buf);
             }
         }
     } else if (warp >= 4) {
         // ================= epilogue: EG groups of 4 warps; thread == (query row, column group) =================
         // A warp may only touch the TMEM lane quarter warp % 4, so group g (warps 4+4g .. 7+4g) takes columns
         // [g, g+1) * 256/EG of every accumulator.  Each group owns a separate running list (no merge needed: the refine
-        // kernels treat every (CTA, group) as one producer).
+        // kernels treat every (CTA, group) as one producer).  In a pair each CTA's TMEM holds the accumulator rows of its
+        // own 128 queries against all 256 bank rows of the tile.
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;        // column group of the accumulator
         const int row = quarter * 32 + lane;     // row inside the M tile
         const int et = threadIdx.x - kGemmCtlThreads;  // 0 .. 128*EG-1
         constexpr int kHalfCols = BN / EG;
         float4 *my_state = state + (size_t)half * p.cand_stride;
+        const uint32_t tempty_leader = CG == 2 ? map_to_cta(bar_tempty, 0) : bar_tempty;
+        auto release_tmem = [&](int buf) {  // one arrival per warp on the (leader's) tmem_empty barrier
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * buf);
+                else mbar_arrive(bar_tempty + 8 * buf);
+            }
+        };
         int j = 0;
-        for (TileIter it(p.mt, stride); it.next(p.mt, p.nt); ++j) {
-            const int n = it.n, m_local = p.m_base + it.m;
+        for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, p.nt); ++j) {
+            const int n = it.n, m_tile = it.m * CG + rank;
+            const bool valid = m_tile < p.mt;    // odd M-tile count: the pair's last second tile does not exist
+            const int m_local = p.m_base + m_tile;
             const int buf = j & 1;
             float *bn = bnorm_s + buf * BN;
             // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
 #pragma unroll
             for (int g = 0; g < 2 / EG; ++g) bn[et + g * 128 * EG] = __ldg(p.bnorm + (size_t)n * BN + et + g * 128 * EG);
-            // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
-            const float c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + m_local * BM + row)));
-            // two independent running top-2 lists (even / odd columns) halve the dependent min/select chain; list A
-            // continues this producer's state for the query, list B starts empty and is merged into A after the tile
-            const float4 st = my_state[m_local * BM + row];
-            Top2 ta{st.x, st.z, __float_as_int(st.y), __float_as_int(st.w)};
-            Top2 tb{INFINITY, INFINITY, -1, -1};
+            float c = 0.f;
+            Top2 ta{INFINITY, INFINITY, -1, -1}, tb{INFINITY, INFINITY, -1, -1};
+            if (valid) {
+                // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
+                c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + m_local * BM + row)));
+                // two independent running top-2 lists (even / odd columns) halve the dependent min/select chain; list A
+                // continues this producer's state for the query, list B starts empty and is merged into A after the tile
+                const float4 st = my_state[m_local * BM + row];
+                ta = Top2{st.x, st.z, __float_as_int(st.y), __float_as_int(st.w)};
+            }
             mbar_wait(bar_tfull + 8 * buf, (j >> 1) & 1);
             tc_fence_after();
             asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");  // bn[] visible to all epilogue warps
+            if (!valid) {
+                release_tmem(buf);
+                continue;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * kHalfCols;
             const int col0 = n * BN + half * kHalfCols;
             const float *bnh = bn + half * kHalfCols;
@@ -356,13 +462,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
                 tmem_ld32(taddr + (ch + 1) * 32, rb);
                 top2_chunk(ra, c, bnh + ch * 32, col0 + ch * 32, ta, tb);
                 tmem_ld_wait();
-                if (ch + 2 < kHalfCols / 32) {
-                    tmem_ld32(taddr + (ch + 2) * 32, ra);
-                } else {  // this warp's part of the accumulator is in registers: hand the TMEM buffer back early
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-                }
+                if (ch + 2 < kHalfCols / 32) tmem_ld32(taddr + (ch + 2) * 32, ra);
+                else release_tmem(buf);  // this warp's part of the accumulator is in registers: hand the buffer back early
                 top2_chunk(rb, c, bnh + (ch + 1) * 32, col0 + (ch + 1) * 32, ta, tb);
             }
             top2_insert(ta, tb.b1, tb.i1);
@@ -372,9 +473,11 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the very end
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -477,6 +580,8 @@ static int make_map(void **slot, const __half *base, long long rows, int dim, in
 int score_make_tensor_maps(cmdb_bank *b) {
     CMDB_CHECK(make_map(&b->tmap_hi, b->hi, b->fin_rows_pad, b->dim, BN));
     CMDB_CHECK(make_map(&b->tmap_lo, b->lo, b->fin_rows_pad, b->dim, BN));
+    CMDB_CHECK(make_map(&b->tmap_hi2, b->hi, b->fin_rows_pad, b->dim, BN / 2));  // half tiles for the CTA-pair kernels
+    CMDB_CHECK(make_map(&b->tmap_lo2, b->lo, b->fin_rows_pad, b->dim, BN / 2));
     return CMDB_OK;
 }
 
@@ -630,19 +735,40 @@ int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_c
     p.m_base = row0 / BM;
     p.m_count = compact ? s.fail_ctl + 2 : nullptr;
     const int eg_env = score_gemm_groups();
-    auto launch = [&](auto kern, size_t smem, int threads) -> int {
+    // CTA pairs (cta_group::2): CMDB_GEMM_PAIR=0/1 forces a choice for every launch with >= 2 M tiles
+    static const int pair_env = [] {
+        const char *e = getenv("CMDB_GEMM_PAIR");
+        return e ? atoi(e) : -1;
+    }();
+    // measured at 16 images x 200k x 768: the 3-term kernel gains 5 % from pairs (7.84 -> 7.42 ms), the 1-term pre-filter
+    // loses 3 % (2.81 -> 2.90 ms; it is not limited by shared-memory reads, and a pair halves the producers per query)
+    const bool pair = !compact && eg_env == 2 && b->num_sms % 2 == 0 &&
+                      ((p.mt >= 2 && pair_env == 1) || (pair_env < 0 && terms == 3 && p.mt >= 8));
+    if (!compact && row0 == 0) s.sched_pair = pair;   // the first-pass schedule (the exact rescan needs it)
+    s.sched_pair_last = pair;
+    const int threads = kGemmCtlThreads + 128 * eg_env;
+    auto launch = [&](auto kern, size_t smem, bool cluster2) -> int {
         CMDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<b->num_sms, threads, smem, st>>>(
-            *reinterpret_cast<CUtensorMap *>(s.tmap_qhi), *reinterpret_cast<CUtensorMap *>(s.tmap_qlo),
-            *reinterpret_cast<CUtensorMap *>(b->tmap_hi), *reinterpret_cast<CUtensorMap *>(b->tmap_lo), p);
-        CMDB_CUDA(cudaGetLastError());
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(b->num_sms), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cluster2 ? 2 : 1, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr, cfg.numAttrs = 1;
+        // the pair kernels load HALF bank tiles (box of 128 rows)
+        const CUtensorMap &mh = *reinterpret_cast<CUtensorMap *>(cluster2 ? b->tmap_hi2 : b->tmap_hi);
+        const CUtensorMap &ml = *reinterpret_cast<CUtensorMap *>(cluster2 ? b->tmap_lo2 : b->tmap_lo);
+        CMDB_CUDA(cudaLaunchKernelEx(&cfg, kern, *reinterpret_cast<CUtensorMap *>(s.tmap_qhi),
+                                     *reinterpret_cast<CUtensorMap *>(s.tmap_qlo), mh, ml, p));
         return CMDB_OK;
     };
-    const int threads = kGemmCtlThreads + 128 * eg_env;
-    if (terms == 1 && eg_env == 2) CMDB_CHECK(launch(score_gemm_kernel<1, 2>, GemmSmem<1>::total + 1024, threads));
-    else if (terms == 1) CMDB_CHECK(launch(score_gemm_kernel<1, 1>, GemmSmem<1>::total + 1024, threads));
-    else if (eg_env == 2) CMDB_CHECK(launch(score_gemm_kernel<3, 2>, GemmSmem<3>::total + 1024, threads));
-    else CMDB_CHECK(launch(score_gemm_kernel<3, 1>, GemmSmem<3>::total + 1024, threads));
+    if (pair) {
+        if (terms == 1) CMDB_CHECK(launch(score_gemm_kernel<1, 2, 2>, GemmSmem<1, 2>::total + 1024, true));
+        else CMDB_CHECK(launch(score_gemm_kernel<3, 2, 2>, GemmSmem<3, 2>::total + 1024, true));
+    } else if (terms == 1 && eg_env == 2) CMDB_CHECK(launch(score_gemm_kernel<1, 2, 1>, GemmSmem<1, 1>::total + 1024, false));
+    else if (terms == 1) CMDB_CHECK(launch(score_gemm_kernel<1, 1, 1>, GemmSmem<1, 1>::total + 1024, false));
+    else if (eg_env == 2) CMDB_CHECK(launch(score_gemm_kernel<3, 2, 1>, GemmSmem<3, 1>::total + 1024, false));
+    else CMDB_CHECK(launch(score_gemm_kernel<3, 1, 1>, GemmSmem<3, 1>::total + 1024, false));
     *n_cand_out = eg_env * b->num_sms;  // (CTA, column group) producers
     return CMDB_OK;
 }

@@ -246,17 +246,19 @@ __device__ __forceinline__ int producer_first_tile(int c, int m, int G, int stri
 
 __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ work, const int *__restrict__ n_items_ptr,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
-                                                     long long rows, int G, int EG, int nt, int chunk_tiles, int mt_total,
-                                                     int stride_full, int stride_last, unsigned long long *best_key) {
+                                                     long long rows, int n_units, int cg, int EG, int nt, int chunk_tiles,
+                                                     int mt_total, int stride_full, int stride_last,
+                                                     unsigned long long *best_key) {
     __shared__ unsigned long long red[8];
     const int n_items = min(*n_items_ptr, kWorkCap);
-    const int tiles_per = (nt + G - 1) / G;
+    // n_units scheduling units (CTAs, or CTA pairs when cg == 2) share the N tiles of one M tile (pair)
+    const int tiles_per = (nt + n_units - 1) / n_units;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cols = kScoreBN / EG;
     constexpr int kUnitRows = 32;  // rows per block and step: 4 per warp, so a handful of pairs still fills the GPU
     const int units_per_tile = cols / kUnitRows;
-    const long long n_units = (long long)n_items * tiles_per * units_per_tile;
-    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const long long n_work = (long long)n_items * tiles_per * units_per_tile;
+    for (long long u = blockIdx.x; u < n_work; u += gridDim.x) {
         const int item = (int)(u / (tiles_per * units_per_tile));
         const int rem = (int)(u % (tiles_per * units_per_tile));
         const int k = rem / units_per_tile, sub = rem % units_per_tile;
@@ -265,7 +267,8 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
         // the first-pass GEMM ran in chunks of chunk_tiles M tiles (the last one may be shorter), each with its own schedule
         const int mtile = qi / kScoreBM, chunk = mtile / chunk_tiles;
         const bool last = (chunk + 1) * chunk_tiles >= mt_total;
-        const int n = producer_first_tile(c, mtile - chunk * chunk_tiles, G, last ? stride_last : stride_full) + k * G;
+        const int m_in = mtile - chunk * chunk_tiles;  // pair mode: CTA 2u + r handled the M tiles 2*mp + r of pair u
+        const int n = producer_first_tile(c / cg, m_in / cg, n_units, last ? stride_last : stride_full) + k * n_units;
         unsigned long long key = ~0ULL;
         if (n < nt) {
             const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows;
@@ -416,11 +419,12 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     fallback_decide_kernel<<<1, 1, 0, st>>>(s.fail_ctl);
     CMDB_CUDA(cudaGetLastError());
     // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
-    const int G = b->num_sms, EG = score_gemm_groups();
+    const int cg = s.sched_pair ? 2 : 1, n_units = b->num_sms / cg, EG = score_gemm_groups();
     const int last_tiles = s.mt_total - (s.mt_total - 1) / s.chunk_tiles * s.chunk_tiles;
-    rescan_kernel<<<b->num_sms * 8, 256, 0, st>>>(s.work_list, s.fail_ctl + 3, s.q_f32, b->data, b->dim, b->fin_rows, G, EG,
+    rescan_kernel<<<b->num_sms * 8, 256, 0, st>>>(s.work_list, s.fail_ctl + 3, s.q_f32, b->data, b->dim, b->fin_rows, n_units, cg, EG,
                                                   (int)(b->fin_rows_pad / kScoreBN), s.chunk_tiles, s.mt_total,
-                                                  score_tile_stride(s.chunk_tiles, G), score_tile_stride(last_tiles, G), s.best_key);
+                                                  score_tile_stride((s.chunk_tiles + cg - 1) / cg, n_units),
+                                                  score_tile_stride((last_tiles + cg - 1) / cg, n_units), s.best_key);
     CMDB_CUDA(cudaGetLastError());
     rescan_finish_kernel<<<8, 256, 0, st>>>(s.fail_list, s.fail_ctl + 4, s.best_key, P_img, b->row_offset, s.min_val, s.min_idx,
                                             s.s_key);
@@ -754,7 +758,7 @@ struct ReweightCertParams {
     int dim;
     const float *q_norm, *q_eps;     // of the m_star rows (q_split_kernel)
     float bmax, eb_max, acc_model;
-    int G, EG, stride, nt;           // tile schedule of the GEMM launch (mt = 1)
+    int n_units, cg, EG, stride, nt; // tile schedule of the GEMM launch (mt = 1): units = CTAs or CTA pairs
     const unsigned long long *s_key;
     unsigned long long *top3;
     TailResult *res;
@@ -831,12 +835,12 @@ __global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p
     };
     const int n_rows = n_rows_sh, n_bad = n_bad_sh;
     for (int i = warp; i < n_rows; i += 8) visit(cand_rows[i]);
-    const int cols = kScoreBN / p.EG, tiles_per = (p.nt + p.G - 1) / p.G;
+    const int cols = kScoreBN / p.EG, tiles_per = (p.nt + p.n_units - 1) / p.n_units;
     for (int i = 0; i < n_bad; ++i) {
         const int c = bad_prod[i] / p.EG, g = bad_prod[i] % p.EG;
-        const int n0 = producer_first_tile(c, 0, p.G, p.stride);
+        const int n0 = producer_first_tile(c / p.cg, 0, p.n_units, p.stride);
         for (int j = warp; j < tiles_per * cols; j += 8) {
-            const int n = n0 + (j / cols) * p.G;
+            const int n = n0 + (j / cols) * p.n_units;
             const long long r = (long long)n * kScoreBN + g * cols + j % cols;
             if (n < p.nt && r < p.rows) visit(r);
         }
@@ -1068,7 +1072,8 @@ static int score_reweight_tensor(cmdb_bank *b, int B, int P_img, bool fused) {
     p.m_star = s.m_star, p.m_test = s.m_test, p.bank = b->data, p.rows = b->fin_rows, p.row_offset = b->row_offset;
     p.dim = b->dim, p.q_norm = s.q_norm, p.q_eps = s.q_eps;
     p.bmax = b->cert_bmax, p.eb_max = b->cert_eb_max, p.acc_model = (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f;
-    p.G = b->num_sms, p.EG = score_gemm_groups(), p.stride = score_tile_stride(1, b->num_sms);
+    p.cg = s.sched_pair_last ? 2 : 1, p.n_units = b->num_sms / p.cg, p.EG = score_gemm_groups();
+    p.stride = score_tile_stride(1, p.n_units);
     p.nt = (int)(b->fin_rows_pad / kScoreBN);
     p.s_key = s.s_key, p.top3 = s.top3, p.res = reinterpret_cast<TailResult *>(s.tail), p.fuse_final = fused ? 1 : 0;
     CMDB_REQUIRE(n_cand <= 320, CMDB_ERR_UNSUPPORTED, "scoring: %d GEMM producers exceed reweight_cert_kernel's limit", n_cand);
