@@ -381,8 +381,12 @@ def run_ours(args):
                                           f"score_restated: torch.cdist + min + topk + bilinear + blur), {ms:.0f} ms/image"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    # device / pinned tensors go before the bank (whose stream they were used on), the bank before the process group
+    torch.cuda.synchronize()
+    del dev, host, imgs
     bank.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

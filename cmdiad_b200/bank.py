@@ -342,7 +342,9 @@ class Bank:
         lo, hi = min(rows, rank * per), min(rows, (rank + 1) * per)
         part = torch.empty(per, D, dtype=torch.float32, device=dev)
         if hi > lo:
-            part[:hi - lo].copy_(flat[lo:hi], non_blocking=True)
+            # a blocking copy on purpose: torch's pinned-memory allocator would otherwise remember the handle's stream for
+            # this host block and touch it when the block is freed -- possibly after the bank (and its stream) is closed
+            part[:hi - lo].copy_(flat[lo:hi], non_blocking=False)
         if hi - lo < per:
             part[hi - lo:].zero_()
         full = torch.empty(per * world, D, dtype=torch.float32, device=dev)
@@ -368,6 +370,9 @@ class Bank:
             for b0 in range(0, Btot, step):
                 chunk = patches[b0:b0 + step]
                 B = chunk.shape[0]
+                # host-side allocations first: everything below is enqueued without waiting, and the GPU should not idle
+                # between two phases while numpy allocates the result arrays
+                res, outs, _ = self._alloc_out(B, P, out_hw, full)
                 if not chunk.is_cuda and world > 1 and B * P >= 1024:
                     chunk = self._stage_sharded(chunk, dev, world, rank, group)
                 keys = torch.empty(B * P, dtype=torch.int64, device=dev)
@@ -383,7 +388,6 @@ class Bank:
                 nn_rows = torch.empty(B * 3 * self.dim, dtype=torch.float32, device=dev)
                 L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), world, B, _ptr(nn_rows)))
                 dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
-                res, outs, _ = self._alloc_out(B, P, out_hw, full)
                 # image i of this round has global index b0 + i and belongs to rank (b0 + i) % world
                 first, stride = ((rank - b0) % world, world) if distribute else (0, 1)
                 L.check(self._lib.cmdb_score_shard_finish(self._h, _ptr(nn_rows), B, P, int(fh), int(fw), int(out_hw),
