@@ -331,7 +331,8 @@ class Bank:
         patch = _as_f32(patch)
         return self.score_sharded_batch(patch.unsqueeze(0), feature_map_dims, out_hw, full, group)[0]
 
-    def _stage_sharded(self, chunk, dev, world, rank, group):
+    @staticmethod
+    def _stage_sharded(chunk, dev, world, rank, group):
         """Host queries of a sharded round: every rank copies only its 1/world slice of the rows over PCIe and the
         slices are all-gathered over NVLink (every rank needs all queries, but NVLink is ~10x the host link)."""
         import torch.distributed as dist

@@ -110,3 +110,35 @@ def test_key_packing_properties():
             lo, hi = sharding.shard_range(n, r, w)
             if hi > lo:
                 assert (sharding.owner_of(np.arange(lo, hi), n, w) == r).all()
+
+
+def _stage_worker(rank, world, port, B, P, D, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cmdiad_b200.bank import Bank
+    x = torch.from_numpy(np.stack([synth.patches(P, D, seed=40 + i, dist="G") for i in range(B)]))
+    full = Bank._stage_sharded(x, torch.device("cpu"), world, rank, None)
+    ok = bool((full == x).all()) and tuple(full.shape) == (B, P, D)
+    ret.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("B,P", [(4, 96), (3, 49)])   # 384 rows split evenly, 147 rows with a padded last slice
+def test_cooperative_query_staging_over_gloo(B, P):
+    """Bank._stage_sharded: every rank contributes 1/world of the query rows, the all-gather must reproduce the batch on
+    every rank (row counts that do not divide by the world size are padded and cut again)."""
+    world, D = 2, 64
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stage_worker, args=(r, world, port, B, P, D, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(ret.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: True, 1: True}
