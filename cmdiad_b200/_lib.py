@@ -67,6 +67,7 @@ SYMBOLS = {
     "cmdb_bank_stream": (_I, [_VP, ctypes.POINTER(_VP)]),
     "cmdb_bank_get_timings": (_I, [_VP, c_f32_p]),
     "cmdb_bank_score_stats": (_I, [_VP, _VP]),
+    "cmdb_bank_build_knn": (_I, [_VP]),
     "cmdb_coreset_select": (_I, [_VP, _I64, _VP, _VP, _VP, _I, _I, _VP]),
     "cmdb_comm_create": (_I, [_I, _I, _I, ctypes.c_size_t, ctypes.POINTER(_VP)]),
     "cmdb_comm_handle_bytes": (_I, []),

@@ -138,6 +138,12 @@ class Bank:
         FP32-equivalent GEMM; 3: FP32-equivalent GEMM for every query; 1: uncertified pre-filter (diagnostics)."""
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_PREFILTER_TERMS, int(terms)))
 
+    def build_knn(self):
+        """Precompute the three nearest bank rows of every bank row (exact; the bank against itself through the
+        certified pre-filter GEMM).  The re-weighting step of score / score_batch then becomes a table lookup with
+        identical results.  Un-sharded banks only; call after finalize()."""
+        L.check(self._lib.cmdb_bank_build_knn(self._h))
+
     def score_stats(self):
         """Counters of the last scoring call on this handle: queries, GEMM mode that ran, and for the certified
         pre-filter how many queries it could not certify, how many (query, producer) pairs were rescanned exactly,

@@ -427,6 +427,15 @@ int cmdb_debug_read_candidates(cmdb_bank *b, float *out_host, int n_cta, int n_q
     return CMDB_OK;
 }
 
+// test hook (not in the public header): rows [r0, r0 + n) of the neighbour table as packed (d^2 bits << 32 | row) keys
+int cmdb_debug_read_knn(cmdb_bank *b, unsigned long long *out_host, long long r0, long long n) {
+    CMDB_REQUIRE(b && out_host && b->knn_table && r0 >= 0 && n >= 1 && r0 + n <= b->fin_rows, CMDB_ERR_INVALID,
+                 "cmdb_debug_read_knn: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaMemcpy(out_host, b->knn_table + (size_t)r0 * 3, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+    return CMDB_OK;
+}
+
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host, float *out_pre_host,
                        uint8_t *out_u8_host) {
     CMDB_REQUIRE(map_host && out_host && fh > 0 && fw > 0, CMDB_ERR_INVALID, "cmdb_upsample_blur: bad arguments");

@@ -265,6 +265,8 @@ static void free_scoring_layout(cmdb_bank *b) {
     cudaFree(b->hi);
     cudaFree(b->lo);
     cudaFree(b->norm);
+    cudaFree(b->knn_table);
+    b->knn_table = nullptr;
     b->hi = b->lo = nullptr;
     b->norm = nullptr;
     free(b->tmap_hi);
@@ -375,6 +377,16 @@ int cmdb_bank_get_timings(cmdb_bank *b, float *out_ms) {
     CMDB_REQUIRE(b->timing && b->ev_valid, CMDB_ERR_STATE, "cmdb_bank_get_timings: enable CMDB_OPT_TIMING and call cmdb_score first");
     for (int i = 0; i < CMDB_T_COUNT; ++i) CMDB_CUDA(cudaEventElapsedTime(out_ms + i, b->ev[i], b->ev[i + 1]));
     return CMDB_OK;
+}
+
+int cmdb_bank_build_knn(cmdb_bank *b) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_build_knn: bank is NULL");
+    CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "cmdb_bank_build_knn: call cmdb_bank_finalize first");
+    CMDB_REQUIRE(b->row_offset == 0, CMDB_ERR_UNSUPPORTED,
+                 "cmdb_bank_build_knn: the table needs every bank row on this GPU (row-sharded handles re-weight on the fly)");
+    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "cmdb_bank_build_knn: a submitted batch is outstanding");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    return score_build_knn_table(b);
 }
 
 int cmdb_bank_score_stats(cmdb_bank *b, int64_t *out6) {

@@ -123,6 +123,9 @@ struct cmdb_bank {
     float cert_bmax = 0.f;    // max ||b||
     float cert_eb_max = 0.f;  // max ||b - b_hi * 2^-scale_exp||
     unsigned int *cert_buf = nullptr;  // device [2]: the two maxima as float bits
+    // optional table of the three nearest bank rows of every bank row, as packed (d^2 bits << 32 | row) keys
+    // (cmdb_bank_build_knn): turns the per-image w_dist pass into a lookup
+    unsigned long long *knn_table = nullptr;  // [fin_rows][3]
     // statistics of the last scoring call / adaptive fallback to the direct 3-term GEMM
     int64_t last_queries = 0;
     int last_mode = 0;           // GEMM mode the last call actually ran
@@ -226,6 +229,7 @@ int score_refine(cmdb_bank *b, int B, int P_img, int n_cand, bool compact);
 int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand);
 int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star);
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused);
+int score_build_knn_table(cmdb_bank *b);
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B);
 int score_final(cmdb_bank *b, int B);
 int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,

@@ -691,11 +691,12 @@ int score_query_prep(cmdb_bank *b, int P, bool compact, int row0) {
     return CMDB_OK;
 }
 
-// fp16 split (+ norms for the certificate) of n <= 128 explicit rows into rows 0..127 of the query operand
+// fp16 split (+ norms for the certificate) of n explicit rows (n <= cap_p) into rows 0.. of the query operand
 void q_split_rows(cmdb_bank *b, const float *rows_dev, int n) {
     ScoreScratch &s = b->ss;
-    q_split_kernel<<<BM / 8, 256, 0, b->stream>>>(rows_dev, n, BM, b->dim, s.q_hi, s.q_lo, s.q_scale_exp, s.q_norm, s.q_eps, nullptr,
-                                                  nullptr);
+    const int p_pad = (n + BM - 1) / BM * BM;
+    q_split_kernel<<<std::min(b->num_sms * 2, p_pad / 8), 256, 0, b->stream>>>(rows_dev, n, p_pad, b->dim, s.q_hi, s.q_lo, s.q_scale_exp,
+                                                                              s.q_norm, s.q_eps, nullptr, nullptr);
 }
 
 int score_gemm_groups() {

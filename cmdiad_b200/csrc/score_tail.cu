@@ -838,7 +838,8 @@ __global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p
     const int cols = kScoreBN / p.EG, tiles_per = (p.nt + p.n_units - 1) / p.n_units;
     for (int i = 0; i < n_bad; ++i) {
         const int c = bad_prod[i] / p.EG, g = bad_prod[i] % p.EG;
-        const int n0 = producer_first_tile(c / p.cg, 0, p.n_units, p.stride);
+        // M tile of this query row inside the GEMM launch (0 for the re-weighting of a batch; the table build has many)
+        const int n0 = producer_first_tile(c / p.cg, (b / kScoreBM) / p.cg, p.n_units, p.stride);
         for (int j = warp; j < tiles_per * cols; j += 8) {
             const int n = n0 + (j / cols) * p.n_units;
             const long long r = (long long)n * kScoreBN + g * cols + j % cols;
@@ -854,10 +855,10 @@ __global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p
             const unsigned long long key = wkeys[w][k];
             if (key != f[0] && key != f[1] && key != f[2]) top3_insert(f, key);
         }
-    const unsigned long long skey = p.s_key[b];
-    const float s_star = __uint_as_float((unsigned int)(skey >> 32));
+    float s_star = 0.f;
     float knn[2] = {NAN, NAN};
     if (p.fuse_final) {  // features.py:275-283: m_star_knn = ||m_test - bank[nn_idx[1:]]||, m_test = patch[s_idx]
+        s_star = __uint_as_float((unsigned int)(p.s_key[b] >> 32));
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (f[1 + k] != ~0ULL)
@@ -865,8 +866,9 @@ __global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p
                                            p.bank + (size_t)((long long)(f[1 + k] & 0xffffffffULL) - p.row_offset) * dim, dim4, lane));
     }
     if (lane == 0) {
+        p.top3[(size_t)b * 3 + 0] = f[0], p.top3[(size_t)b * 3 + 1] = f[1], p.top3[(size_t)b * 3 + 2] = f[2];
+        if (!p.res) return;  // table build: only the keys
         TailResult *res = p.res + b;
-        p.top3[b * 3 + 0] = f[0], p.top3[b * 3 + 1] = f[1], p.top3[b * 3 + 2] = f[2];
         for (int k = 0; k < 3; ++k) res->nn_idx[k] = f[k] == ~0ULL ? -1 : (long long)(f[k] & 0xffffffffULL);
         if (p.fuse_final) {
             const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))  (features.py:285)
@@ -876,6 +878,37 @@ __global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p
             res->s = w * s_star;  // features.py:290
             res->knn0 = knn[0], res->knn1 = knn[1];
         }
+    }
+}
+
+// re-weighting with the bank's precomputed neighbour table (cmdb_bank_build_knn): image b = blockIdx.x, 2 warps.
+// m_star is bank row res[b].m_star_row (select_kernel), so its three nearest rows are table[m_star_row]; what is left of
+// features.py:239-290 is m_star_knn = ||m_test - bank[nn_idx[1:]]||, w and s.
+__global__ void __launch_bounds__(64) reweight_lookup_kernel(const unsigned long long *__restrict__ table, const float *__restrict__ m_test,
+                                                            const float *__restrict__ bank, int dim,
+                                                            const unsigned long long *__restrict__ s_key, unsigned long long *top3,
+                                                            TailResult *res_all) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float knn[2];
+    TailResult *res = res_all + b;
+    const unsigned long long *keys3 = table + (size_t)res->m_star_row * 3;
+    const unsigned long long key = keys3[1 + warp];
+    float v = NAN;
+    if (key != ~0ULL) v = sqrtf(warp_sqdist(m_test + (size_t)b * dim, bank + (size_t)(key & 0xffffffffULL) * dim, dim >> 2, lane));
+    if (lane == 0) knn[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float s_star = __uint_as_float((unsigned int)(s_key[b] >> 32));
+        for (int k = 0; k < 3; ++k) {
+            top3[b * 3 + k] = keys3[k];
+            res->nn_idx[k] = keys3[k] == ~0ULL ? -1 : (long long)(keys3[k] & 0xffffffffULL);
+        }
+        const float Dn = sqrtf((float)dim);  // torch.sqrt(torch.tensor(patch.shape[1]))  (features.py:285)
+        const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
+        const float w = 1.f - expf(s_star / Dn) / den;  // features.py:287
+        res->w = w;
+        res->s = w * s_star;  // features.py:290
+        res->knn0 = knn[0], res->knn1 = knn[1];
     }
 }
 
@@ -1082,7 +1115,49 @@ static int score_reweight_tensor(cmdb_bank *b, int B, int P_img, bool fused) {
     return CMDB_OK;
 }
 
+// three nearest bank rows of every bank row.  The bank is its own query set: chunks of rows go through the
+// fp16 split, the certified pre-filter GEMM and reweight_cert_kernel (one block per row, keys only).
+int score_build_knn_table(cmdb_bank *b) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    const int chunk = 64 * kScoreBM;  // 8192 rows: 64 M tiles per GEMM launch
+    // scratch for `chunk` query rows; sized like a 32-image batch so that later scoring calls do not have to grow it
+    CMDB_CHECK(score_scratch_alloc(b, 32, chunk / 32, s.map_stride ? (int)lround(sqrt((double)s.map_stride)) : 224));
+    score_select_slot(b, 0);
+    if (!b->knn_table) CMDB_CUDA(cudaMalloc(&b->knn_table, sizeof(unsigned long long) * 3 * (size_t)b->fin_rows));
+    for (long long r0 = 0; r0 < b->fin_rows; r0 += chunk) {
+        const int n = (int)std::min<long long>(chunk, b->fin_rows - r0);
+        const float *rows = b->data + (size_t)r0 * b->dim;
+        q_split_rows(b, rows, n);
+        CMDB_CUDA(cudaGetLastError());
+        int n_cand = 0;
+        CMDB_CHECK(score_gemm_candidates(b, n, 1, false, &n_cand));
+        ReweightCertParams p{};
+        p.cand = s.cand, p.n_cand = n_cand, p.cand_stride = s.cap_p;
+        p.m_star = rows, p.m_test = nullptr, p.bank = b->data, p.rows = b->fin_rows, p.row_offset = 0;
+        p.dim = b->dim, p.q_norm = s.q_norm, p.q_eps = s.q_eps;
+        p.bmax = b->cert_bmax, p.eb_max = b->cert_eb_max, p.acc_model = (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f;
+        p.cg = s.sched_pair_last ? 2 : 1, p.n_units = b->num_sms / p.cg, p.EG = score_gemm_groups();
+        const int mt = (n + kScoreBM - 1) / kScoreBM;
+        p.stride = score_tile_stride((mt + p.cg - 1) / p.cg, p.n_units);
+        p.nt = (int)(b->fin_rows_pad / kScoreBN);
+        p.s_key = nullptr, p.top3 = b->knn_table + (size_t)r0 * 3, p.res = nullptr, p.fuse_final = 0;
+        CMDB_REQUIRE(n_cand <= 320, CMDB_ERR_UNSUPPORTED, "scoring: %d GEMM producers exceed reweight_cert_kernel's limit", n_cand);
+        reweight_cert_kernel<<<n, 256, 0, st>>>(p);
+        CMDB_CUDA(cudaGetLastError());
+    }
+    CMDB_CUDA(cudaStreamSynchronize(st));
+    return CMDB_OK;
+}
+
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused) {
+    if (fused && b->knn_table && b->row_offset == 0) {  // the bank's neighbour table: the w_dist pass is a lookup
+        CMDB_CHECK(score_select(b, B, P_img, true));
+        reweight_lookup_kernel<<<B, 64, 0, b->stream>>>(b->knn_table, b->ss.m_test, b->data, b->dim, b->ss.s_key, b->ss.top3,
+                                                        reinterpret_cast<TailResult *>(b->ss.tail));
+        CMDB_CUDA(cudaGetLastError());
+        return CMDB_OK;
+    }
     // a single image: the one-launch CUDA-core sweep is as fast as a one-tile GEMM over the whole bank; batches go to the
     // tensor cores, whose cost does not grow with B (identical keys either way).  CMDB_REWEIGHT_TENSOR=0/1 forces one path (tests).
     static const int force = [] {

@@ -232,6 +232,8 @@ class Features(torch.nn.Module):
                 setattr(self, f"patch_{m}_lib", DeviceLib(self._banks[m]))
         for m in self._score_modals():
             self._banks[m].finalize()
+            # the w_dist top-3 of features.py:239-254 only depends on the bank -> precomputed per bank row
+            self._banks[m].build_knn()
         self._host_copies = {m: [] for m in _MODALS}
 
     # ---- scoring of one sample: shared by late fusion and predict ------------------------------------------------
@@ -341,6 +343,8 @@ class Features(torch.nn.Module):
             bank, meta = Bank.load(os.path.join(directory, f"bank_{m}.npz"), device=self.cuda_device,
                                    finalize=m in self._score_modals())
             self._banks[m] = bank
+            if m in self._score_modals():
+                bank.build_knn()   # not stored: rebuilding the neighbour table takes milliseconds
             setattr(self, f"{m}_mean", torch.tensor(np.float32(meta["mean"])))
             setattr(self, f"{m}_std", torch.tensor(np.float32(meta["std"])))
             setattr(self, f"patch_{m}_lib", DeviceLib(bank))

@@ -103,6 +103,12 @@ int cmdb_bank_stream(cmdb_bank *bank, void **out_stream);
 /* milliseconds of each stage (CMDB_T_*) of the last cmdb_score call on this handle; needs CMDB_OPT_TIMING = 1.
  * out_ms: float [CMDB_T_COUNT].  Measured with CUDA events on the handle's stream. */
 int cmdb_bank_get_timings(cmdb_bank *bank, float *out_ms);
+/* Optional: the three nearest bank rows of EVERY bank row, computed once after cmdb_bank_finalize with the
+ * certified pre-filter GEMM of the bank against itself (exact keys, same order and ties as the per-image w_dist top-3 of
+ * features.py:239-254, whose query m_star is always a bank row).  With the table the re-weighting of cmdb_score /
+ * cmdb_score_batch is a lookup instead of a pass over the bank; results are unchanged.  Un-sharded banks only (the table
+ * needs all rows on one GPU); freed by the next cmdb_bank_finalize. */
+int cmdb_bank_build_knn(cmdb_bank *bank);
 /* statistics of the last scoring call on this handle (waits for the handle's stream): out6[0] = query rows, out6[1] = GEMM
  * mode that ran (0 / 1 / 3, see CMDB_OPT_PREFILTER_TERMS); mode 0 only: out6[2] = query rows the pre-filter could not
  * certify, out6[3] = (query, producer) pairs queued for the exact rescan, out6[4] = 1 if there were too many pairs and

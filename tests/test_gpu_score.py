@@ -124,6 +124,42 @@ def test_score_batch_equals_single_calls(env, B, P, fm, D):
     b.close()
 
 
+@pytest.mark.parametrize("R,D,dist", [(3000, 768, "G"), (20000, 768, "C"), (700, 128, "G")])
+def test_bank_knn_table(env, R, D, dist):
+    """cmdb_bank_build_knn: the table of every bank row's three nearest rows must equal a brute force, and
+    scoring with the table (re-weighting = lookup) must reproduce scoring without it bit for bit."""
+    import ctypes
+    from cmdiad_b200 import synth
+    cent = synth.centroids(D, 128) if dist == "C" else None
+    lib = synth.patches(R, D, seed=81, dist=dist, cent=cent)
+    P, fm = (784, 28) if D == 768 else (100, 10)
+    patches = np.stack([synth.patches(P, D, seed=600 + i, dist=dist, anomalous_frac=0.01, cent=cent) for i in range(6)])
+    b = _bank(env, lib)
+    before_batch = b.score_batch(patches, (fm, fm), 224, full=True)
+    before_single = b.score(patches[0], (fm, fm), 224, full=True)
+    b.build_knn()
+    n_chk = min(R, 1500)
+    keys = np.zeros((n_chk, 3), np.uint64)
+    assert b._lib.cmdb_debug_read_knn(b._h, keys.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(0), ctypes.c_longlong(n_chk)) == 0
+    rows = (keys & np.uint64(0xffffffff)).astype(np.int64)
+    d2 = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    t = torch.from_numpy(lib).double()
+    ref_d2 = torch.cdist(t[:n_chk], t, compute_mode="donot_use_mm_for_euclid_dist") ** 2
+    ref_v, ref_i = torch.topk(ref_d2, 3, dim=1, largest=False)
+    assert (rows[:, 0] == np.arange(n_chk)).all() and (d2[:, 0] == 0).all()       # a row is its own nearest neighbour
+    np.testing.assert_allclose(d2, ref_v.numpy(), rtol=1e-5, atol=1e-6)
+    agree = (np.sort(rows, 1) == np.sort(ref_i.numpy(), 1)).all(1)
+    gap_ok = (ref_d2.gather(1, ref_i)[:, 2] * (1 + 1e-5) >= torch.sort(ref_d2, 1).values[:, 3]).numpy()  # 3rd/4th near-tie
+    assert (agree | gap_ok).all(), int((~(agree | gap_ok)).sum())
+    _assert_same_results(before_batch, b.score_batch(patches, (fm, fm), 224, full=True), "table vs tensor-core re-weighting")
+    after_single = b.score(patches[0], (fm, fm), 224, full=True)
+    for name in _RESULT_FIELDS:
+        assert (getattr(before_single, name) == getattr(after_single, name)).all(), name
+    b.finalize()          # a new finalize drops the table
+    _assert_same_results(before_batch, b.score_batch(patches, (fm, fm), 224, full=True), "after re-finalize")
+    b.close()
+
+
 def test_async_submit_wait_pipeline(env):
     """cmdb_score_batch_submit / _wait: two batches outstanding (double-buffered query / result blocks); results equal
     the synchronous call, in submission order and out of order, host and device inputs; a third submit is refused."""
