@@ -2,20 +2,23 @@
 //
 // torch.cdist computes d^2 = ||a||^2 + ||b||^2 - 2 a.b with a float32 GEMM and the reference then takes min/argmin over
 // the materialised [P,R] matrix.  Here the contraction runs on the 5th-generation tensor cores and the distance matrix
-// never exists:
-//   * FP32-equivalent operands: every float32 value (scaled by a power of two) is split into fp16 hi + fp16 lo
-//     (22 significand bits); a.b ~= hi.hi + hi.lo + lo.hi, three kind::f16 MMAs per K step into ONE fp32 TMEM
-//     accumulator -- 1.5x the tensor time of a plain fp16 GEMM and half that of 3xTF32;
-//   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer (SWIZZLE_128B tiles of q_hi/q_lo/b_hi/b_lo
-//     into a 2-stage ring), warp 1 = single-thread tcgen05.mma issuer (M=128 queries x N=256 bank rows, accumulators
-//     double-buffered in all 512 TMEM columns), warps 4-7 = epilogue;
+// never exists; the tensor cores only PROPOSE candidates, every returned distance / index comes from an exact float32
+// re-check (score_tail.cu):
+//   * TERMS = 1 (default): fp16 roundings of the power-of-two-scaled operands, one kind::f16 MMA per K step.  The
+//     certificate in refine_cert_kernel bounds the error and proves which rows cannot be the nearest neighbour.
+//     TERMS = 3: FP32-equivalent split, every value = fp16 hi + fp16 lo (22 significand bits), a.b ~= hi.hi + hi.lo +
+//     lo.hi, three MMAs per K step into ONE fp32 TMEM accumulator (1.5x the tensor time of a plain fp16 GEMM, half that
+//     of 3xTF32) -- selectable mode and fallback of the default mode;
+//   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer (SWIZZLE_128B tiles into a 4- / 2-stage
+//     ring), warp 1 = single-thread tcgen05.mma issuer (M=128 queries x N=256 bank rows, accumulators double-buffered in
+//     all 512 TMEM columns), warp 2 = TMEM allocation, warps 4-11 = two epilogue groups (column halves);
+//     CG = 2: CTA pairs (cluster of 2, cta_group::2, M = 256), each CTA stages its query tile and half of the bank tile;
 //   * epilogue: tcgen05.ld 32 columns at a time, val = ||b||^2 - 2 a.b (the per-query ||a||^2 is constant under argmin),
-//     branch-free per-thread top-2 (value, bank row) carried across all tiles of the CTA in a per-CTA list in L2
-//     (148 x P x 16 B, 2 KB read + written per tile); one thread == one query row, so no cross-lane reduction is
-//     needed.  refine_kernel (score_tail.cu) re-checks the best candidates with exact float32 differences.
+//     two branch-free top-2 chains per thread (value, bank row), carried across all tiles of the producer in a list in
+//     L2 (296 producers x P x 16 B); one thread == one query row, so no cross-lane reduction is needed;
 //   * one launch sweeps all M tiles of a batch in n-major order: the bank streams from HBM exactly once per launch and
-//     the (small) query operand is re-read from L2.
-// Algorithmic work: 2*P*R*D FLOP per image; tensor work is 3x that.
+//     the (small) query operand is re-read from L2; the tile schedule spreads every query's rows over all CTAs.
+// Algorithmic work: 2*P*R*D FLOP per image (TERMS = 3 issues 3x that).
 #include <cuda.h>
 
 #include <cstdlib>

@@ -1,11 +1,14 @@
 // Everything of compute_single_s_s_map (reference features.py:225-297) after the distance GEMM:
-//   refine      exact float32 re-check of the GEMM epilogue's per-CTA top-2 candidates -> min_val / min_idx (:227),
-//               and the packed argmax key of min_val -> s_star / s_idx (:228-231)
+//   refine_cert certificate of the pre-filter GEMM + exact float32 re-check of every candidate inside the error band
+//               -> min_val / min_idx (:227) and the packed argmax key of min_val -> s_star / s_idx (:228-231);
+//               rescan / fallback_decide / rescan_finish: exact rescan of producers the certificate could not clear
+//   refine      (3-term and diagnostics modes) exact re-check of the 4 best candidates
 //   select      m_test = patch[s_idx], m_star = bank[min_idx[s_idx]] (:235-251)
-//   reweight    w_dist = ||m_star - bank_r|| for every bank row, 3 smallest (:239-254; HBM bound, R*D*4 bytes), with
-//               the m_star selection as prologue and m_star_knn, w, s (:275-290) as last-block epilogue
+//   reweight    w_dist = ||m_star - bank_r|| for every bank row, 3 smallest (:239-254), m_star_knn, w, s (:275-290):
+//               reweight_lookup (bank neighbour table), reweight_cert (batch through the tensor cores) or reweight_kernel
+//               (CUDA-core sweep of the float32 bank)
 //   upsample_blur  bilinear 28^2/56^2 -> 224^2 (:293-294) + KNNGaussianBlur (utils/utils.py:71-83): /max, 8-bit
-//               truncation, Pillow's 3+3 pass integer box blur, /255, *max -- one CTA, whole image in shared memory
+//               truncation, Pillow's 3+3 pass integer box blur, /255, *max -- 16 row bands / 16 column bands per image
 #include <math.h>
 
 #include <cstdlib>
