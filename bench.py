@@ -133,8 +133,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
+    # one step = one 784-patch image on the host cores (0.3 s on the GPU box's 16 cores): bounded so the arm ends in < 1 min
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
     val, ms = cpu_reference_leg(steps, warm)
     cores = torch.get_num_threads()
     line = {"metric": METRIC, "value": val, "unit": "patch-NN scores/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
