@@ -32,6 +32,10 @@ t0 = b.score_batch_async(p, (14, 14), 64)
 t1 = b.score_batch_async(torch.from_numpy(p).cuda(), (14, 14), 64, full=True)
 ra, rb = t0.wait(), t1.wait()
 print("async ok", ra[0].s, rb[0].s, b.score_stats())
+b.build_knn()   # neighbour table: reweight_cert_kernel in table mode, then the lookup path
+rk = b.score_batch(p, (14, 14), 64, full=True)
+assert all((rk[i].nn_idx == rb[i].nn_idx).all() and rk[i].s[0] == rb[i].s[0] for i in range(3))
+print("knn table ok", rk[0].nn_idx)
 b.set_score_impl(L.SCORE_SIMT)
 r2 = b.score(p[0], (14, 14), 64)
 print("score ok", r[0].s, r2.s)
