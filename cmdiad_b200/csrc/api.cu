@@ -427,6 +427,10 @@ int cmdb_debug_read_candidates(cmdb_bank *b, float *out_host, int n_cta, int n_q
     return CMDB_OK;
 }
 
+// host-only test hooks (not in the public header): the GEMM's tile-schedule stride and the fallback-tier rule
+int cmdb_debug_tile_stride(int mt, int G) { return score_tile_stride(mt, G); }
+int cmdb_debug_fallback_use_rescan(int fails, int pairs) { return fallback_use_rescan(fails, pairs) ? 1 : 0; }
+
 // test hook (not in the public header): rows [r0, r0 + n) of the neighbour table as packed (d^2 bits << 32 | row) keys
 int cmdb_debug_read_knn(cmdb_bank *b, unsigned long long *out_host, long long r0, long long n) {
     CMDB_REQUIRE(b && out_host && b->knn_table && r0 >= 0 && n >= 1 && r0 + n <= b->fin_rows, CMDB_ERR_INVALID,

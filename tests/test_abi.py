@@ -79,3 +79,65 @@ def test_methods_mirror_reference_interface():
     assert set(M.METHODS) == {"DINO", "Point_MAE", "DINO+Point_MAE", "WithHallucination", "WithHallucinationFromFeature"}
     d = M.DoubleRGBPointFeatures
     assert d.mean_from == {"xyz": "xyz", "rgb": "xyz"} and d.std_from == {"xyz": "rgb", "rgb": "rgb"}  # the quirk
+
+
+def test_tile_schedule_covers_every_query_on_every_cta(built):
+    """The certificate of the pre-filter relies on the GEMM's tile schedule: tile (n, m) runs on CTA (n*s + m) mod G with
+    s >= mt coprime to G.  Checked here on the host: the stride the library picks, exact-once coverage, balance, and that
+    every CTA (producer) sees rows of every query tile once nt >= G -- for the M-tile counts of the bench (98), one image
+    (7), the re-weighting launch (1), the CTA-pair launches (49 pairs on 74 units) and awkward gcds."""
+    from math import gcd
+    from cmdiad_b200 import _lib as L
+    lib = L.load()
+    for mt, nt, G in [(98, 782, 148), (7, 782, 148), (1, 782, 148), (74, 157, 148), (148, 300, 148), (296, 40, 148),
+                      (49, 782, 74), (37, 200, 74), (3, 5, 148), (64, 782, 148)]:
+        s = lib.cmdb_debug_tile_stride(mt, G)
+        assert s >= mt and gcd(s % G or G, G) == 1 and s < mt + G
+        owner = {}
+        per_cta = [0] * G
+        for n in range(nt):
+            for m in range(mt):
+                c = (n * s + m) % G
+                owner[(n, m)] = c
+                per_cta[c] += 1
+        assert len(owner) == nt * mt
+        assert max(per_cta) - min(per_cta) <= mt // G + 1 + (nt % G != 0) * (mt // G + 1)
+        if nt >= G:
+            for m in (0, mt // 2, mt - 1):
+                assert len({owner[(n, m)] for n in range(nt)}) == G, (mt, nt, G, m)
+        # the device iterator walks n in order and steps m by G inside a tile row: same tiles, same order
+        smod = s % G
+        for c in (0, 1, G // 2, G - 1):
+            got, n, m, base = [], -1, mt, (c + smod) % G
+            while True:
+                m += G
+                done = False
+                while m >= mt:
+                    n += 1
+                    if n >= nt:
+                        done = True
+                        break
+                    base -= smod
+                    if base < 0:
+                        base += G
+                    m = base
+                if done:
+                    break
+                got.append((n, m))
+            assert got == sorted(k for k, v in owner.items() if v == c)
+
+
+def test_fallback_tier_rule(built):
+    """few uncertified (query, producer) pairs -> exact rescan; many -> 3-term GEMM over the uncertified queries"""
+    from cmdiad_b200 import _lib as L
+    lib = L.load()
+    assert lib.cmdb_debug_fallback_use_rescan(75, 75) == 1           # the bench's steady state
+    assert lib.cmdb_debug_fallback_use_rescan(0, 0) == 1
+    assert lib.cmdb_debug_fallback_use_rescan(600, 700) == 1         # one pair per query: rescan is cheaper per query
+    assert lib.cmdb_debug_fallback_use_rescan(784, 40000) == 0       # near-duplicate banks: hundreds of pairs per query
+    assert lib.cmdb_debug_fallback_use_rescan(10, 9000) == 0         # beyond the work list
+    prev = 1
+    for pairs in range(0, 20000, 50):                                # monotone in the number of pairs
+        cur = lib.cmdb_debug_fallback_use_rescan(500, pairs)
+        assert cur <= prev
+        prev = cur
