@@ -270,9 +270,10 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "patch-NN scores/s", "h2d_bytes_per_step": B * P * DIM * 4,
                     "d2h_bytes_per_step": B * (OUT_HW * OUT_HW * 4 + P * 12 + 64)},
             # per step: q_split, GEMM, certified refine, decide, rescan, rescan-finish, GEMM-fallback chain (q_split, GEMM,
-            # refine: sized on the device, empty unless many certificates fail), reweight, 2 blur kernels (+ pack/unpack/
+            # refine: sized on the device, empty unless many certificates fail), select + neighbour-table lookup (N = 1;
+            # re-weighting GEMM chain when sharded), 2 blur kernels (+ pack/unpack/
             # select/merge/final/contrib in the sharded protocol); two timed loops (device-resident and host inputs)
-            "gpu_launches": args.steps * 2 * (12 if world == 1 else 18),
+            "gpu_launches": args.steps * 2 * (13 if world == 1 else 18),
             "clocks": clk.summary()}
     if sync_call:
         line["sync_call"] = sync_call
