@@ -55,7 +55,7 @@ if __name__ == "__main__":
     g = "gpurun_out"
     if os.path.exists(f"{g}/launches.csv"):
         launches(f"{g}/launches.csv", f"profiles/{TAG}_launches_bench.txt",
-                 "ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 python bench.py --steps 2 --warmup 3 --skip-cpu")
+                 "ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 python bench.py --steps 2 --warmup 3 --skip-cpu")
     for rep, title in (("prof_gemm", "ncu --set full --clock-control none, score_gemm_kernel, batch of 16 images x 784 patches vs 200k x 768 bank"),
                        ("prof_coreset", "ncu --set full --clock-control none, coreset_kernel<__half,3>, 200k x 301, 300 picks"),
                        ("prof_reweight", "ncu --set full --clock-control none, reweight_kernel<6>, batch of 16, 200k x 768 bank")):
