@@ -309,19 +309,25 @@ class Features(torch.nn.Module):
         mask = torch.as_tensor(mask)
         self.image_preds.append(s.numpy())
         self.image_labels.append(label)
-        self.pixel_preds.extend(s_map.flatten().numpy())
-        self.pixel_labels.extend(mask.flatten().numpy())
+        # the reference extends two Python lists by 50 176 scalars per image (multiple_features.py:998-999); the same
+        # values are kept as one array per image here and concatenated once in calculate_metrics
+        self.pixel_preds.append(s_map.flatten().numpy())
+        self.pixel_labels.append(mask.flatten().numpy())
         self.predictions.append(s_map.detach().cpu().squeeze().numpy())
         self.gts.append(mask.detach().cpu().squeeze().numpy())
         self.img_name.append(rgb_path)
 
-    # ---- features.py:302-324 (AU-PRO is out of scope) -------------------------------------------------
+    # ---- features.py:302-324 (vectorised on the host, cmdiad_b200/metrics.py) ------------------------
     def calculate_metrics(self):
+        from . import metrics
         self.image_preds = np.stack(self.image_preds)
         self.image_labels = np.stack(self.image_labels)
-        self.pixel_preds = np.array(self.pixel_preds)
+        self.pixel_preds = np.concatenate(self.pixel_preds) if len(self.pixel_preds) else np.zeros(0)
+        self.pixel_labels = np.concatenate(self.pixel_labels) if len(self.pixel_labels) else np.zeros(0)
         self.image_rocauc = roc_auc_score(self.image_labels, self.image_preds)
         self.pixel_rocauc = roc_auc_score(self.pixel_labels, self.pixel_preds)
+        self.au_pro, _ = metrics.au_pro(self.gts, self.predictions)            # features.py:323
+        self.au_pro_001, _ = metrics.au_pro(self.gts, self.predictions, 0.01)  # features.py:324
 
     # ---- persistence of the fitted state (banks after run_coreset, statistics, late-fusion head) ----------------------
     def save_state(self, directory):

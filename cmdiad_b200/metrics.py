@@ -1,0 +1,69 @@
+"""Evaluation metrics of the reference's calculate_metrics (features.py:302-324), vectorised.
+
+The reference accumulates 50 176 Python scalars per test image (`pixel_preds.extend`, multiple_features.py:998) and
+walks every ground-truth component once per threshold in Python (utils/au_pro_util.py:157-201).  Here predictions stay
+numpy arrays and the PRO curve is evaluated with one `searchsorted` per component for all thresholds at once.  The
+arithmetic (which counts are taken, the order of the float64 additions, the trapezoid with its interpolated last
+segment) follows the reference, so the values are bit-identical -- tests/test_metrics.py checks that against the
+unmodified reference module.
+"""
+import numpy as np
+from scipy.ndimage import label
+from sklearn.metrics import roc_auc_score
+
+
+def pro_curve(predictions, gts, num_thresholds=100):
+    """PRO curve (utils/au_pro_util.py:104-201): false-positive rates and mean per-region overlaps at `num_thresholds`
+    thresholds taken at equidistant ranks of the sorted anomaly-free scores.  predictions / gts: sequences of 2-D arrays."""
+    assert len(predictions) == len(gts)
+    structure = np.ones((3, 3), dtype=int)        # 8-connectivity (au_pro_util.py:129)
+    ok_scores, components = [], []
+    for gt, pred in zip(gts, predictions):
+        gt, pred = np.asarray(gt), np.asarray(pred)
+        labeled, n = label(gt, structure)
+        ok_scores.append(pred[labeled == 0])
+        for k in range(n):
+            components.append(np.sort(pred[labeled == (k + 1)]))
+    # the reference collects the anomaly-free scores in a float64 buffer (np.zeros default dtype) before sorting
+    ok = np.sort(np.concatenate(ok_scores).astype(np.float64)) if ok_scores else np.zeros(0)
+    pos = np.linspace(0, len(ok) - 1, num=num_thresholds, dtype=int)
+    thr = ok[pos]
+    fprs = 1.0 - (pos + 1) / len(ok)
+    # overlap of a component at threshold t = 1 - #{scores <= t} / size  (GroundTruthComponent.compute_overlap)
+    overlaps = np.empty((len(components), len(thr)), dtype=np.float64)
+    for i, c in enumerate(components):
+        overlaps[i] = 1.0 - np.searchsorted(c, thr, side="right") / len(c)
+    # `pro += overlap` over the components in order, then `/= len`: a sequential float64 sum
+    pros = (np.cumsum(overlaps, axis=0)[-1] if len(components) else np.zeros(len(thr))) / max(1, len(components))
+    fprs = np.concatenate([[1.0], fprs])[::-1]
+    pros = np.concatenate([[1.0], pros])[::-1]
+    return fprs, pros
+
+
+def trapezoid(x, y, x_max=None):
+    """au_pro_util.py:52-101: trapezoid rule with an interpolated last segment at x_max (non-finite points dropped)"""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    keep = np.isfinite(x) & np.isfinite(y)
+    x, y = x[keep], y[keep]
+    correction = 0.0
+    if x_max is not None:
+        if x_max not in x:
+            ins = int(np.searchsorted(x, x_max, side="right"))   # bisect.bisect
+            assert 0 < ins < len(x)
+            y_interp = y[ins - 1] + ((y[ins] - y[ins - 1]) * (x_max - x[ins - 1]) / (x[ins] - x[ins - 1]))
+            correction = 0.5 * (y_interp + y[ins - 1]) * (x_max - x[ins - 1])
+        m = x <= x_max
+        x, y = x[m], y[m]
+    return np.sum(0.5 * (y[1:] + y[:-1]) * (x[1:] - x[:-1])) + correction
+
+
+def au_pro(gts, predictions, integration_limit=0.3, num_thresholds=100):
+    """calculate_au_pro (au_pro_util.py:204-224): area under the PRO curve up to `integration_limit`, normalised"""
+    fprs, pros = pro_curve(predictions, gts, num_thresholds)
+    return trapezoid(fprs, pros, x_max=integration_limit) / integration_limit, (fprs, pros)
+
+
+def image_and_pixel_rocauc(image_labels, image_preds, pixel_labels, pixel_preds):
+    """features.py:314-319"""
+    return (roc_auc_score(np.asarray(image_labels), np.asarray(image_preds)),
+            roc_auc_score(np.asarray(pixel_labels).reshape(-1), np.asarray(pixel_preds).reshape(-1)))

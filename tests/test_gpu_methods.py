@@ -49,7 +49,7 @@ def test_rgb_features_fp16_pipeline_vs_oracle(env):
     patch = ((torch.from_numpy(test) - m.rgb_mean) / m.rgb_std).numpy()
     ref = O.score_restated(patch, lib[ref_idx], (28, 28), 224)
     np.testing.assert_allclose(m.last_score.s[0], ref["s"], rtol=1e-4)
-    assert m.predictions[0].shape == (224, 224) and len(m.pixel_preds) == 224 * 224
+    assert m.predictions[0].shape == (224, 224) and sum(len(a) for a in m.pixel_preds) == 224 * 224
     s_ref = m.detect_fuser.score_samples(np.array([[m.args.rgb_s_lambda * ref["s"]]]))
     np.testing.assert_allclose(m.image_preds[0], s_ref, rtol=1e-4)
     # persistence: a fresh object restored from disk predicts identically without re-running the coreset
@@ -103,6 +103,7 @@ def test_hallucination_class_wiring(env, main):
         assert (m.predictions[n_before + i] == m.predictions[i]).all()
     m.calculate_metrics()
     assert 0.0 <= m.image_rocauc <= 1.0 and 0.0 <= m.pixel_rocauc <= 1.0
+    assert 0.0 <= m.au_pro <= 1.0 and 0.0 <= m.au_pro_001 <= 1.0 and m.pixel_preds.shape == m.pixel_labels.shape
     with pytest.raises(NotImplementedError):
         m.args.dist_method_s = "l1"
         m.calculate_dist(torch.zeros(2, 2), torch.zeros(2, 2))
