@@ -38,6 +38,22 @@ class ScoreOut(ctypes.Structure):
                 ("s_map_pre", c_f32_p), ("s_map_u8", c_u8_p)]
 
 
+class FusionHead(ctypes.Structure):
+    """struct cmdb_fusion_head"""
+    _fields_ = [("n_modal", ctypes.c_int), ("s_lambda", ctypes.c_float * 3), ("smap_lambda", ctypes.c_float * 3),
+                ("detect_coef", ctypes.c_double * 3), ("detect_offset", ctypes.c_double),
+                ("seg_coef", ctypes.c_double * 3), ("seg_offset", ctypes.c_double)]
+
+
+class FusedOut(ctypes.Structure):
+    """struct cmdb_fused_out"""
+    _fields_ = [("s", c_f64_p), ("s_map", c_f64_p), ("s_modal", c_f32_p), ("min_val", c_f32_p * 3), ("min_idx", c_i64_p * 3)]
+
+
+FUSED_KEEP_ON_DEVICE = 1
+FUSED_NO_HOST_MAPS = 2
+
+
 class CmdbError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"cmdiad_b200 error {status}: {message}")
@@ -89,6 +105,26 @@ SYMBOLS = {
     "cmdb_score_shard_nn": (_I, [_VP, _VP, _I, _I, _VP]),
     "cmdb_score_shard_finish": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(ScoreOut)]),
     "cmdb_upsample_blur": (_I, [_I, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "cmdb_bank_set_query_norm": (_I, [_VP, ctypes.c_float, ctypes.c_float, _I]),
+    "cmdb_bank_build_knn_rows": (_I, [_VP, _I64, _I64]),
+    "cmdb_bank_read_knn": (_I, [_VP, _I64, _I64, _VP, _I]),
+    "cmdb_bank_set_knn_table": (_I, [_VP, _VP, _I64, _I]),
+    "cmdb_score_shard_lookup": (_I, [_VP, _VP, _I, _I, _VP]),
+    "cmdb_score_shard_finish_submit": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, ctypes.c_uint, ctypes.POINTER(ctypes.c_int64)]),
+    "cmdb_score_shard_wait": (_I, [_VP, ctypes.c_int64, ctypes.POINTER(ScoreOut)]),
+    "cmdb_bank_stage_h2d": (_I, [_VP, _VP, _VP, ctypes.c_size_t]),
+    "cmdb_bank_read_device": (_I, [_VP, _I64, _I64, _VP]),
+    "cmdb_score_fused_batch_submit": (_I, [ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_I), ctypes.POINTER(_I),
+                                           ctypes.POINTER(_I), _I, _I, _I, ctypes.POINTER(FusionHead), ctypes.c_uint,
+                                           ctypes.POINTER(ctypes.c_int64)]),
+    "cmdb_score_fused_batch_wait": (_I, [_VP, ctypes.c_int64, ctypes.POINTER(FusedOut)]),
+    "cmdb_score_fused_batch": (_I, [ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_I), ctypes.POINTER(_I),
+                                    ctypes.POINTER(_I), _I, _I, _I, ctypes.POINTER(FusionHead), ctypes.c_uint,
+                                    ctypes.POINTER(FusedOut)]),
+    "cmdb_eval_reserve": (_I, [_VP, _I64, _I]),
+    "cmdb_eval_reset": (_I, [_VP]),
+    "cmdb_eval_count": (_I, [_VP, c_i64_p]),
+    "cmdb_eval_read": (_I, [_VP, _I64, _I64, _VP, _VP]),
 }
 # test hook exported by the library but deliberately not part of the public header
 DEBUG_SYMBOLS = {

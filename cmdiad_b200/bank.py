@@ -138,11 +138,81 @@ class Bank:
         FP32-equivalent GEMM; 3: FP32-equivalent GEMM for every query; 1: uncertified pre-filter (diagnostics)."""
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_PREFILTER_TERMS, int(terms)))
 
+    def set_query_norm(self, mean, std, enabled=True):
+        """enabled: scoring calls take RAW patches and compute (patch - mean) / std on the device (float32, bit-identical
+        to the reference's host expression, multiple_features.py:90)"""
+        L.check(self._lib.cmdb_bank_set_query_norm(self._h, float(mean), float(std), int(bool(enabled))))
+
     def build_knn(self):
         """Precompute the three nearest bank rows of every bank row (exact; the bank against itself through the
         certified pre-filter GEMM).  The re-weighting step of score / score_batch then becomes a table lookup with
         identical results.  Un-sharded banks only; call after finalize()."""
         L.check(self._lib.cmdb_bank_build_knn(self._h))
+
+    def build_knn_rows(self, row_first, n_rows):
+        """neighbour-table entries of rows [row_first, row_first + n_rows) only (the others stay empty)"""
+        L.check(self._lib.cmdb_bank_build_knn_rows(self._h, int(row_first), int(n_rows)))
+
+    def read_knn(self, row_first, n_rows, out=None):
+        """packed (d^2 bits << 32 | global row) keys [n_rows, 3] of the neighbour table; out: int64 tensor (host or device)"""
+        if out is None:
+            out = torch.empty((n_rows, 3), dtype=torch.int64)
+        assert out.is_contiguous() and out.numel() >= 3 * n_rows
+        L.check(self._lib.cmdb_bank_read_knn(self._h, int(row_first), int(n_rows), _ptr(out), int(out.is_cuda)))
+        return out
+
+    def set_knn_table(self, keys, n_rows_total):
+        """installs a replicated table covering ALL global rows on this (row-sharded) handle"""
+        assert keys.dtype == torch.int64 and keys.is_contiguous() and keys.numel() == 3 * n_rows_total
+        self._order_after_producer(keys)
+        if keys.is_cuda:
+            torch.cuda.current_stream(keys.device).synchronize()
+        L.check(self._lib.cmdb_bank_set_knn_table(self._h, _ptr(keys), int(n_rows_total), int(keys.is_cuda)))
+        self._knn_replicated = True
+
+    def read_device(self, row0=0, n_rows=None, out=None):
+        n_rows = self.rows - row0 if n_rows is None else n_rows
+        if out is None:
+            out = torch.empty((n_rows, self.dim), dtype=torch.float32, device=torch.device("cuda", self.device))
+        L.check(self._lib.cmdb_bank_read_device(self._h, int(row0), int(n_rows), _ptr(out)))
+        return out
+
+    def build_knn_sharded(self, group=None):
+        """Row-sharded bank: builds the REPLICATED neighbour table (SURVEY 8f-1 for sharded banks).  Collective: the fp32
+        shards are all-gathered over NVLink into a temporary un-sharded handle on every rank, each rank computes the table
+        entries of the rows it owns (R/world x R distance work per rank, through the same certified GEMM), and the
+        24-byte-per-row slices are all-gathered.  Afterwards score_sharded_batch needs two small collectives per round
+        instead of four and no re-weighting pass over the bank."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", self.device)
+        rows = self.rows
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = rows
+        dist.all_reduce(counts, group=group)
+        counts = counts.cpu().tolist()
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        n_total, max_rows = int(offs[-1]), int(max(counts))
+        assert int(offs[rank]) == self._row_offset(), "shards must be contiguous blocks in rank order"
+        mine = torch.zeros((max_rows, self.dim), dtype=torch.float32, device=dev)
+        self.read_device(0, rows, out=mine)
+        gathered = torch.empty((world * max_rows, self.dim), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        torch.cuda.current_stream(dev).synchronize()
+        del mine
+        full = Bank(self.dim, n_total, device=self.device)
+        for r in range(world):
+            full.append(gathered[r * max_rows:r * max_rows + counts[r]])
+        del gathered
+        full.finalize()
+        full.build_knn_rows(int(offs[rank]), rows)
+        keys_mine = torch.full((max_rows, 3), -1, dtype=torch.int64, device=dev)
+        full.read_knn(int(offs[rank]), rows, out=keys_mine)
+        full.close()
+        all_keys = torch.empty((world * max_rows, 3), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_keys, keys_mine, group=group)
+        table = torch.cat([all_keys[r * max_rows:r * max_rows + counts[r]] for r in range(world)]).contiguous()
+        self.set_knn_table(table, n_total)
 
     def score_stats(self):
         """Counters of the last scoring call on this handle: queries, GEMM mode that ran, and for the certified
@@ -164,14 +234,28 @@ class Bank:
 
     def stream(self):
         """torch view of the handle's CUDA stream (for event timing on the stream the kernels run on)"""
-        p = ctypes.c_void_p()
-        L.check(self._lib.cmdb_bank_stream(self._h, ctypes.byref(p)))
-        return torch.cuda.ExternalStream(p.value, device=torch.device("cuda", self.device))
+        st = getattr(self, "_stream", None)
+        if st is None:
+            p = ctypes.c_void_p()
+            L.check(self._lib.cmdb_bank_stream(self._h, ctypes.byref(p)))
+            st = self._stream = torch.cuda.ExternalStream(p.value, device=torch.device("cuda", self.device))
+        return st
+
+    def _order_after_producer(self, t):
+        """Device inputs: the library reads `t` on the handle's own (non-blocking) stream, so that stream first has to
+        wait for whatever torch stream is producing it (ordering contract of `*_is_device = 1`, include/cmdiad_b200.h);
+        record_stream keeps torch's caching allocator from recycling the block while the handle still reads it."""
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            st = self.stream()
+            st.wait_stream(torch.cuda.current_stream(t.device))
+            t.record_stream(st)
+        return t
 
     # ---- storage ---------------------------------------------------------------------------------------------
     def append(self, rows):
         rows = _as_f32(rows)
         assert rows.dim() == 2 and rows.shape[1] == self.dim, f"expected [n,{self.dim}], got {tuple(rows.shape)}"
+        self._order_after_producer(rows)
         L.check(self._lib.cmdb_bank_append(self._h, _ptr(rows), rows.shape[0], int(rows.is_cuda)))
 
     def stats(self):
@@ -304,6 +388,7 @@ class Bank:
         B, P = patches.shape[0], patches.shape[1]
         fh, fw = feature_map_dims
         results, outs, _ = self._alloc_out(B, P, out_hw, full)
+        self._order_after_producer(patches)
         L.check(self._lib.cmdb_score_batch(self._h, _ptr(patches), B, P, int(fh), int(fw), int(out_hw), int(patches.is_cuda),
                                            outs))
         return results
@@ -325,6 +410,7 @@ class Bank:
         B, P = patches.shape[0], patches.shape[1]
         fh, fw = feature_map_dims
         ticket = ctypes.c_int64()
+        self._order_after_producer(patches)
         L.check(self._lib.cmdb_score_batch_submit(self._h, _ptr(patches), B, P, int(fh), int(fw), int(out_hw),
                                                   int(patches.is_cuda), 3 if full else 0, ctypes.byref(ticket)))
         return _Ticket(self, ticket.value, patches, B, P, out_hw, full)
@@ -337,62 +423,142 @@ class Bank:
         patch = _as_f32(patch)
         return self.score_sharded_batch(patch.unsqueeze(0), feature_map_dims, out_hw, full, group)[0]
 
-    @staticmethod
-    def _stage_sharded(chunk, dev, world, rank, group):
-        """Host queries of a sharded round: every rank copies only its 1/world slice of the rows over PCIe and the
-        slices are all-gathered over NVLink (every rank needs all queries, but NVLink is ~10x the host link)."""
+    def _shard_buf(self, name, slot, shape, dtype):
+        """device buffers of the sharded rounds, cached per result slot (no allocator traffic per round)"""
+        cache = self.__dict__.setdefault("_shard_bufs", {})
+        key = (name, slot, tuple(shape), dtype)
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = torch.empty(shape, dtype=dtype, device=torch.device("cuda", self.device))
+        return t
+
+    def _stage_sharded(self, chunk, slot, world, rank, group):
+        """Host queries of a sharded round: every rank copies only its 1/world slice of the rows over PCIe (on the
+        handle's copy stream) and the slices are all-gathered over NVLink -- every rank needs all queries, but NVLink is
+        ~10x the host link.  The buffers are double-buffered per result slot."""
         import torch.distributed as dist
+        from .sharding import stage_slice
         B, P, D = chunk.shape
         rows = B * P
-        per = (rows + world - 1) // world
         flat = chunk.reshape(rows, D)
-        lo, hi = min(rows, rank * per), min(rows, (rank + 1) * per)
-        part = torch.empty(per, D, dtype=torch.float32, device=dev)
+        per, lo, hi = stage_slice(rows, world, rank)
+        part = self._shard_buf("part", slot, (per, D), torch.float32)
         if hi > lo:
-            # a blocking copy on purpose: torch's pinned-memory allocator would otherwise remember the handle's stream for
-            # this host block and touch it when the block is freed -- possibly after the bank (and its stream) is closed
-            part[:hi - lo].copy_(flat[lo:hi], non_blocking=False)
+            src = flat[lo:hi]
+            L.check(self._lib.cmdb_bank_stage_h2d(self._h, _ptr(part), _ptr(src), src.numel() * 4))
         if hi - lo < per:
             part[hi - lo:].zero_()
-        full = torch.empty(per * world, D, dtype=torch.float32, device=dev)
+        full = self._shard_buf("full", slot, (per * world, D), torch.float32)
         dist.all_gather_into_tensor(full, part, group=group)
         return full[:rows].view(B, P, D)
 
-    def score_sharded_batch(self, patches, feature_map_dims, out_hw=224, full=False, group=None, distribute=False):
-        """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; the five phases
-        of include/cmdiad_b200.h with torch.distributed (NCCL over NVLink) collectives in between.  Kernels and
-        collectives are all enqueued on the handle's stream, so there is no host synchronisation between the phases,
-        and the collectives are per round of up to 32 images, not per image.
-        distribute=False: every rank returns all results.  distribute=True: rank r finishes (blur, device->host) only
-        images r, r+world, ... and returns None for the others."""
+    def score_sharded_async(self, patches, feature_map_dims, out_hw=224, full=False, group=None, distribute=False,
+                            img_base=0, phase_events=None):
+        """One pipelined round (<= max_shard_batch() images) of row-sharded scoring with the replicated neighbour table
+        (build_knn_sharded): min -> MIN all-reduce -> lookup -> SUM all-reduce -> finish, all enqueued on the handle's
+        stream without waiting.  Returns a ticket; ticket.wait() -> BatchResult.  Two rounds may be outstanding, so the
+        caller submits round k + 1 before waiting for round k.  Collective: every rank calls it with the same images.
+        distribute: rank r runs the blur and the device->host copy only for the images i with (img_base + i) % world == r
+        (the scalars of all images are replicated)."""
+        import torch.distributed as dist
+        assert getattr(self, "_knn_replicated", False), "call build_knn_sharded() first"
+        patches = _as_f32(patches)
+        B, P = patches.shape[0], patches.shape[1]
+        assert B <= self.max_shard_batch()
+        fh, fw = feature_map_dims
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        slot = self.__dict__.setdefault("_shard_round", 0) & 1
+        self._shard_round += 1
+        evs = phase_events
+
+        def mark():
+            if evs is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.stream())
+                evs.append(e)
+
+        self._order_after_producer(patches)
+        # host-side allocations first: everything below is enqueued without waiting, and the GPU should not idle between
+        # two phases while numpy allocates the result arrays
+        res, outs, _ = self._alloc_out(B, P, out_hw, full)
+        with torch.cuda.stream(self.stream()):
+            mark()
+            chunk = patches
+            if not chunk.is_cuda and world > 1 and B * P >= 1024:
+                chunk = self._stage_sharded(chunk, slot, world, rank, group)
+            mark()
+            keys = self._shard_buf("keys", slot, (B * P,), torch.int64)
+            L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
+            mark()
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+            mark()
+            d2 = self._shard_buf("d2", slot, (B * 2,), torch.float32)
+            L.check(self._lib.cmdb_score_shard_lookup(self._h, _ptr(keys), B, P, _ptr(d2)))
+            mark()
+            dist.all_reduce(d2, op=dist.ReduceOp.SUM, group=group)
+            mark()
+            first, stride = ((rank - img_base) % world, world) if distribute else (0, 1)
+            ticket = ctypes.c_int64()
+            L.check(self._lib.cmdb_score_shard_finish_submit(self._h, _ptr(d2), B, P, int(fh), int(fw), int(out_hw), int(first),
+                                                             int(stride), 3 if full else 0, ctypes.byref(ticket)))
+            mark()
+        return _ShardTicket(self, ticket.value, patches, res, outs, first, stride, B)
+
+    PHASES = ("stage", "local_min", "allreduce_min", "lookup", "allreduce_sum", "finish")
+
+    def score_sharded_batch(self, patches, feature_map_dims, out_hw=224, full=False, group=None, distribute=False,
+                            phase_events=None):
+        """Row-sharded scoring: one process per GPU, each holding a contiguous block of bank rows; torch.distributed
+        (NCCL over NVLink) collectives between the phases of include/cmdiad_b200.h.  Kernels and collectives are all
+        enqueued on the handle's stream: nothing synchronises the host between the phases, and the collectives are per
+        round of up to 32 images, not per image.
+        With the replicated neighbour table (build_knn_sharded): three phases / two collectives per round, and two
+        rounds are kept in flight (score_sharded_async).  Without it: the five-phase protocol with the re-weighting
+        sweep over the shards, one round at a time.
+        distribute=False: every rank returns all maps.  distribute=True: rank r finishes (blur, device->host) only images
+        r, r+world, ... and returns None for the others.
+        phase_events (table path): optional list; gets one list of torch events per round, recorded on the handle's
+        stream around the phases named in Bank.PHASES."""
         import torch.distributed as dist
         patches = _as_f32(patches)
         Btot, P = patches.shape[0], patches.shape[1]
         fh, fw = feature_map_dims
-        dev = torch.device("cuda", self.device)
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         results = []
         step = self.max_shard_batch()
-        with torch.cuda.stream(self.stream()):
+        if getattr(self, "_knn_replicated", False):
+            pending = None
             for b0 in range(0, Btot, step):
+                evs = [] if phase_events is not None else None
+                t = self.score_sharded_async(patches[b0:b0 + step], feature_map_dims, out_hw, full, group, distribute, b0, evs)
+                if phase_events is not None:
+                    phase_events.append(evs)
+                if pending is not None:
+                    results.extend(pending.wait())
+                pending = t
+            if pending is not None:
+                results.extend(pending.wait())
+            return results
+        self._order_after_producer(patches)
+        with torch.cuda.stream(self.stream()):
+            for k, b0 in enumerate(range(0, Btot, step)):
                 chunk = patches[b0:b0 + step]
                 B = chunk.shape[0]
-                # host-side allocations first: everything below is enqueued without waiting, and the GPU should not idle
-                # between two phases while numpy allocates the result arrays
+                slot = k & 1
                 res, outs, _ = self._alloc_out(B, P, out_hw, full)
                 if not chunk.is_cuda and world > 1 and B * P >= 1024:
-                    chunk = self._stage_sharded(chunk, dev, world, rank, group)
-                keys = torch.empty(B * P, dtype=torch.int64, device=dev)
+                    chunk = self._stage_sharded(chunk, slot, world, rank, group)
+                keys = self._shard_buf("keys", slot, (B * P,), torch.int64)
                 L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
                 dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
-                m_star = torch.empty(B * self.dim, dtype=torch.float32, device=dev)
+                m_star = self._shard_buf("m_star", slot, (B * self.dim,), torch.float32)
                 L.check(self._lib.cmdb_score_shard_select(self._h, _ptr(keys), B, P, _ptr(m_star)))
                 dist.all_reduce(m_star, op=dist.ReduceOp.SUM, group=group)
-                top = torch.empty(B * 3, dtype=torch.int64, device=dev)
+                top = self._shard_buf("top", slot, (B * 3,), torch.int64)
                 L.check(self._lib.cmdb_score_shard_topk(self._h, _ptr(m_star), B, P, _ptr(top)))
-                gathered = torch.empty(world * B * 3, dtype=torch.int64, device=dev)
+                gathered = self._shard_buf("gathered", slot, (world * B * 3,), torch.int64)
                 dist.all_gather_into_tensor(gathered, top, group=group)
-                nn_rows = torch.empty(B * 3 * self.dim, dtype=torch.float32, device=dev)
+                nn_rows = self._shard_buf("nn_rows", slot, (B * 3 * self.dim,), torch.float32)
                 L.check(self._lib.cmdb_score_shard_nn(self._h, _ptr(gathered), world, B, _ptr(nn_rows)))
                 dist.all_reduce(nn_rows, op=dist.ReduceOp.SUM, group=group)
                 # image i of this round has global index b0 + i and belongs to rank (b0 + i) % world
@@ -403,6 +569,24 @@ class Bank:
                     res.owned = set(range(first, B, stride))
                 results.extend(res)
         return results
+
+
+class _ShardTicket:
+    """An outstanding score_sharded_async round (keeps inputs and result arrays alive until the results are fetched)."""
+
+    def __init__(self, bank, ticket, patches, res, outs, first, stride, B):
+        self._bank, self._ticket, self._patches = bank, ticket, patches
+        self._res, self._outs, self._sub = res, outs, (first, stride, B)
+        self._done = False
+
+    def wait(self):
+        if not self._done:
+            L.check(self._bank._lib.cmdb_score_shard_wait(self._bank._h, self._ticket, self._outs))
+            first, stride, B = self._sub
+            if stride > 1:
+                self._res.owned = set(range(first, B, stride))
+            self._done, self._patches, self._outs = True, None, None
+        return self._res
 
 
 class _Ticket:

@@ -2,6 +2,8 @@
 // row-sharded phases), stand-alone upsample+blur.  Declarations and reference citations: include/cmdiad_b200.h.
 #include <math.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace cmdb {
@@ -74,28 +76,30 @@ static unsigned want_mask_of(const cmdb_score_out *outs, int B, int first = 0, i
     return w;
 }
 
-// host block of a slot -> the caller's buffers
-static void scatter_outputs(const cmdb_bank *b, const unsigned char *h, int B, int P, int out_hw, cmdb_score_out *outs,
-                            int img_first = 0, int img_step = 1) {
+// host block of a slot -> the caller's buffers (maps = false: only the scalars and per-patch arrays of image i)
+static void scatter_one(const cmdb_bank *b, const unsigned char *h, int i, int P, int out_hw, cmdb_score_out *out, bool maps = true) {
     const ScoreScratch &s = b->ss;
     const size_t npix = (size_t)out_hw * out_hw;
-    for (int i = img_first; i < B; i += img_step) {
-        cmdb_score_out *out = outs + i;
-        TailResult tr;
-        memcpy(&tr, h + sizeof(TailResult) * i, sizeof(tr));
-        if (out->min_val) memcpy(out->min_val, h + s.off_min_val + sizeof(float) * (size_t)i * P, sizeof(float) * P);
-        if (out->min_idx) memcpy(out->min_idx, h + s.off_min_idx + sizeof(long long) * (size_t)i * P, sizeof(long long) * P);
+    TailResult tr;
+    memcpy(&tr, h + sizeof(TailResult) * i, sizeof(tr));
+    if (out->min_val) memcpy(out->min_val, h + s.off_min_val + sizeof(float) * (size_t)i * P, sizeof(float) * P);
+    if (out->min_idx) memcpy(out->min_idx, h + s.off_min_idx + sizeof(long long) * (size_t)i * P, sizeof(long long) * P);
+    if (maps) {
         if (out->s_map) memcpy(out->s_map, h + s.off_map_out + sizeof(float) * s.map_stride * i, sizeof(float) * npix);
         if (out->s_map_pre) memcpy(out->s_map_pre, h + s.off_map_pre + sizeof(float) * s.map_stride * i, sizeof(float) * npix);
         if (out->s_map_u8) memcpy(out->s_map_u8, h + s.off_map_u8 + s.map_stride * i, npix);
-        if (out->s) *out->s = tr.s;
-        if (out->s_star) *out->s_star = tr.s_star;
-        if (out->s_idx) *out->s_idx = tr.s_idx;
-        if (out->w) *out->w = tr.w;
-        if (out->m_star_knn) out->m_star_knn[0] = tr.knn0, out->m_star_knn[1] = tr.knn1;
-        if (out->nn_idx)
-            for (int k = 0; k < 3; ++k) out->nn_idx[k] = tr.nn_idx[k];
     }
+    if (out->s) *out->s = tr.s;
+    if (out->s_star) *out->s_star = tr.s_star;
+    if (out->s_idx) *out->s_idx = tr.s_idx;
+    if (out->w) *out->w = tr.w;
+    if (out->m_star_knn) out->m_star_knn[0] = tr.knn0, out->m_star_knn[1] = tr.knn1;
+    if (out->nn_idx)
+        for (int k = 0; k < 3; ++k) out->nn_idx[k] = tr.nn_idx[k];
+}
+static void scatter_outputs(const cmdb_bank *b, const unsigned char *h, int B, int P, int out_hw, cmdb_score_out *outs,
+                            int img_first = 0, int img_step = 1) {
+    for (int i = img_first; i < B; i += img_step) scatter_one(b, h, i, P, out_hw, outs + i);
 }
 
 // sharded finish: device->host copy of the result block (all images: ONE copy; a strided subset -- this rank owns images
@@ -131,6 +135,65 @@ static int blur_batch(cmdb_bank *b, int B, int fh, int fw, int out_hw, int img_f
                                 s.map_out, s.map_u8, s.map_tmp, s.map_max);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// late-fusion head (multiple_features.py:986-994): lambda scaling in float32, SGDOneClassSVM.score_samples in float64
+//   X @ coef_ on 2 columns: dgemv evaluates fma(x0, c0, x1 * c1) for the [npix, 2] map matrix and the ddot of a single
+//   row fma(x1, c1, x0 * c0) (OpenBLAS as shipped with numpy/scipy in this image; pinned by tests against sklearn).
+// grid (pixel blocks, images)
+// ---------------------------------------------------------------------------------------------------------------
+struct FuseParams {
+    int n_modal, B, npix;
+    const float *maps[3];
+    size_t map_stride[3];
+    const TailResult *tails[3];
+    float s_lambda[3], smap_lambda[3];
+    double det_coef[3], det_off, seg_coef[3], seg_off;
+    double *out_s;        // [B]
+    float *out_s_modal;   // [B][3]
+    double *out_map;      // [B][npix] or nullptr
+    double *acc_map;      // [B][npix] slice of the device-side result store, or nullptr
+    double *acc_s;        // [B] or nullptr
+};
+
+__global__ void __launch_bounds__(256) fuse_head_kernel(FuseParams p) {
+    const int b = blockIdx.y;
+    const float *m0 = p.maps[0] + (size_t)b * p.map_stride[0];
+    const float *m1 = p.n_modal > 1 ? p.maps[1] + (size_t)b * p.map_stride[1] : nullptr;
+    const float *m2 = p.n_modal > 2 ? p.maps[2] + (size_t)b * p.map_stride[2] : nullptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.npix; i += gridDim.x * blockDim.x) {
+        // lambda * s_map in float32 (python float * float32 tensor), then sklearn's float64 copy
+        const double x0 = (double)__fmul_rn(p.smap_lambda[0], m0[i]);
+        double v;
+        if (p.n_modal == 1) {
+            v = __dmul_rn(x0, p.seg_coef[0]);
+        } else {
+            const double x1 = (double)__fmul_rn(p.smap_lambda[1], m1[i]);
+            if (p.n_modal == 2) {
+                v = __fma_rn(x0, p.seg_coef[0], __dmul_rn(x1, p.seg_coef[1]));
+            } else {
+                const double x2 = (double)__fmul_rn(p.smap_lambda[2], m2[i]);
+                v = __fma_rn(x0, p.seg_coef[0], __fma_rn(x1, p.seg_coef[1], __dmul_rn(x2, p.seg_coef[2])));
+            }
+        }
+        v = __dadd_rn(__dsub_rn(v, p.seg_off), p.seg_off);  // decision_function(X) + offset_
+        if (p.out_map) p.out_map[(size_t)b * p.npix + i] = v;
+        if (p.acc_map) p.acc_map[(size_t)b * p.npix + i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double x[3] = {0.0, 0.0, 0.0};
+        for (int m = 0; m < p.n_modal; ++m) {
+            const float sm = __fmul_rn(p.s_lambda[m], p.tails[m][b].s);
+            p.out_s_modal[b * 3 + m] = sm;
+            x[m] = (double)sm;
+        }
+        double v = __dmul_rn(x[0], p.det_coef[0]);  // a single row goes through ddot: sequential fma over the columns
+        for (int m = 1; m < p.n_modal; ++m) v = __fma_rn(x[m], p.det_coef[m], v);
+        v = __dadd_rn(__dsub_rn(v, p.det_off), p.det_off);
+        p.out_s[b] = v;
+        if (p.acc_s) p.acc_s[b] = v;
+    }
+}
+
 }  // namespace cmdb
 
 using namespace cmdb;
@@ -154,8 +217,11 @@ int cmdb_project(cmdb_bank *b, const int32_t *indptr, const int32_t *indices, co
     return CMDB_OK;
 }
 
-// 16-byte key header + one 8-byte flagged word per two halves of the row
-static unsigned int mailbox_slot_stride(int d) { return 16u + 8u * (unsigned int)((d + 1) / 2 + 1); }
+// FP16: 16-byte key header + one 8-byte flagged word per two halves of the row
+// FP64: 32-byte key header (3 flagged words) + two 8-byte flagged words per element
+static unsigned int mailbox_slot_stride(int d, int dtype_mode = CMDB_CORESET_FP64) {
+    return dtype_mode == CMDB_CORESET_FP16 ? 16u + 8u * (unsigned int)((d + 1) / 2 + 1) : 32u + 16u * (unsigned int)(d + 1);
+}
 
 static int coreset_impl(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices, const double *data,
                         int d_proj, int dtype_mode, int64_t *out_idx_host, const int64_t *force_idx, void *out_min_last,
@@ -215,7 +281,7 @@ int cmdb_coreset_select_sharded(cmdb_bank *b, cmdb_comm *comm, int64_t n_total_r
     unsigned char *local = nullptr;
     CMDB_CHECK(comm_info(comm, &sh.rank, &sh.world, &local, sh.peers, &mb_bytes));
     sh.row_offset = b->row_offset, sh.n_total = n_total_rows, sh.z0_host = z0_host;
-    sh.slot_stride = mailbox_slot_stride(d_proj);
+    sh.slot_stride = mailbox_slot_stride(d_proj, dtype_mode);
     CMDB_REQUIRE(mb_bytes >= cmdb_coreset_mailbox_bytes(sh.world, d_proj), CMDB_ERR_INVALID,
                  "cmdb_coreset_select_sharded: mailbox has %zu bytes, need %zu", mb_bytes,
                  cmdb_coreset_mailbox_bytes(sh.world, d_proj));
@@ -232,7 +298,7 @@ int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host,
 // Enqueue one sub-batch (<= score_max_batch images) on buffer slot `slot`: staging, GEMM + certificate, maps, re-weighting
 // and the device->host copies of the results (on the d2h stream, the maps as soon as the blur is done).  No host sync.
 static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int bc, int P, int fh, int fw, int out_hw,
-                            unsigned want, int slot) {
+                            unsigned want, int slot, bool host_maps = true) {
 #define CMDB_MARK(i)                                                   \
     do {                                                               \
         if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[i], b->stream)); \
@@ -250,7 +316,8 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
     CMDB_CUDA(cudaEventRecord(b->ev_chunk[0], st));
     CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_chunk[0], 0));
     CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + s.off_min_val, s.out_block + s.off_min_val,
-                              out_block_extent(b, bc, want) - s.off_min_val, cudaMemcpyDeviceToHost, b->d2h_stream));
+                              (host_maps ? out_block_extent(b, bc, want) : s.off_map_out) - s.off_min_val, cudaMemcpyDeviceToHost,
+                              b->d2h_stream));
     CMDB_MARK(CMDB_T_REWEIGHT);
     CMDB_CHECK(score_reweight(b, bc, P, true));
     CMDB_MARK(CMDB_T_OUT);
@@ -261,7 +328,7 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
     if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->d2h_stream));
 #undef CMDB_MARK
     cmdb_bank::Pending &pd = b->pending[slot];
-    pd.active = true, pd.B = bc, pd.P = P, pd.out_hw = out_hw, pd.want = want;
+    pd.active = true, pd.B = bc, pd.P = P, pd.out_hw = out_hw, pd.want = want, pd.host_maps = host_maps;
     return CMDB_OK;
 }
 
@@ -349,11 +416,25 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_REQUIRE(keys_device, CMDB_ERR_INVALID, "cmdb_score_shard_min: keys_device is NULL");
     CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_shard_min: out_hw=%d not in [8,256]", out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
-    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
-                 "cmdb_score_shard_min: a submitted batch is outstanding on this handle; wait for it first");
+    if (b->pending[0].active || b->pending[1].active) {
+        // pipelined rounds (cmdb_score_shard_finish_submit / cmdb_score_shard_wait): the other result slot is used
+        CMDB_REQUIRE((size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
+                     "cmdb_score_shard_min: out_hw changes while a submitted round is outstanding; wait for it first");
+        const int slot = b->next_slot;
+        CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
+                     "cmdb_score_shard_min: two submitted rounds are outstanding on this handle; wait for one first");
+        CMDB_CHECK(stage_alloc(b, B, P, out_hw));  // fails with CMDB_ERR_STATE if the scratch would have to grow
+        score_select_slot(b, slot);
+        b->shard_slot = slot;
+        CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
+        pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
+        CMDB_CUDA(cudaGetLastError());
+        return CMDB_OK;
+    }
     if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
     CMDB_CHECK(stage_alloc(b, B, P, out_hw));
     score_select_slot(b, 0);
+    b->shard_slot = 0;
     CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1));
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
@@ -416,6 +497,110 @@ int cmdb_score_shard_finish(cmdb_bank *b, const float *nn_rows_device, int B, in
     return copy_outputs(b, B, P, out_hw, outs, img_first, img_step);
 }
 
+// ---- sharded rounds with the replicated neighbour table: min -> [MIN all-reduce] -> lookup -> [SUM all-reduce] -> finish ----
+
+int cmdb_score_shard_lookup(cmdb_bank *b, const int64_t *reduced_keys_device, int B, int P, float *knn_d2_contrib_device) {
+    CMDB_CHECK(check_score_args(b, reduced_keys_device, B, P, "cmdb_score_shard_lookup"));
+    CMDB_REQUIRE(knn_d2_contrib_device && B * P <= b->ss.cap_p && B <= b->ss.cap_b, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_lookup: bad arguments (call cmdb_score_shard_min first)");
+    CMDB_REQUIRE(b->knn_table && b->knn_rows >= b->row_offset + b->fin_rows, CMDB_ERR_STATE,
+                 "cmdb_score_shard_lookup: install the replicated neighbour table first (cmdb_bank_set_knn_table)");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = b->stream;
+    CMDB_CUDA(cudaMemsetAsync(b->ss.s_key, 0, sizeof(unsigned long long) * B, st));
+    unpack_keys_kernel<<<(B * P + 255) / 256, 256, 0, st>>>((const long long *)reduced_keys_device, B * P, P, b->ss.min_val,
+                                                            b->ss.min_idx, b->ss.s_key);
+    CMDB_CHECK(score_select(b, B, P, false));  // m_test, s*, s_idx, m_star_row (a global row: no bank access needed)
+    return score_shard_lookup(b, B, knn_d2_contrib_device);
+}
+
+int cmdb_score_shard_finish_submit(cmdb_bank *b, const float *knn_d2_sum_device, int B, int P, int fh, int fw, int out_hw,
+                                   int img_first, int img_step, unsigned want_maps, int64_t *out_ticket) {
+    CMDB_CHECK(check_score_args(b, knn_d2_sum_device, B, P, "cmdb_score_shard_finish_submit"));
+    CMDB_REQUIRE(out_ticket && fh > 0 && fw > 0 && fh * fw == P && B * P <= b->ss.cap_p && B <= b->ss.cap_b, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_finish_submit: bad arguments");
+    CMDB_REQUIRE((size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_finish_submit: out_hw differs from cmdb_score_shard_min");
+    CMDB_REQUIRE(img_first >= 0 && img_step >= 1, CMDB_ERR_INVALID, "cmdb_score_shard_finish_submit: bad image subset");
+    const int slot = b->shard_slot;
+    CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE, "cmdb_score_shard_finish_submit: this round's slot is still outstanding");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    CMDB_CHECK(score_shard_final(b, B, knn_d2_sum_device));
+    CMDB_CHECK(blur_batch(b, B, fh, fw, out_hw, img_first, img_step));
+    CMDB_CUDA(cudaEventRecord(b->ev_compute[slot], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
+    // scalar / per-patch prefix of ALL images in one copy, then the maps of the images this rank finished
+    const size_t npix = (size_t)out_hw * out_hw;
+    want_maps &= 3u;
+    if (img_first == 0 && img_step == 1) {
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, out_block_extent(b, B, want_maps), cudaMemcpyDeviceToHost, b->d2h_stream));
+    } else {
+        CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_map_out, cudaMemcpyDeviceToHost, b->d2h_stream));
+        for (int i = img_first; i < B; i += img_step) {
+            const size_t o1 = s.off_map_out + sizeof(float) * s.map_stride * i, o2 = s.off_map_pre + sizeof(float) * s.map_stride * i;
+            const size_t o3 = s.off_map_u8 + s.map_stride * i;
+            CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o1, s.out_block + o1, sizeof(float) * npix, cudaMemcpyDeviceToHost, b->d2h_stream));
+            if (want_maps & 1u) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o2, s.out_block + o2, sizeof(float) * npix, cudaMemcpyDeviceToHost, b->d2h_stream));
+            if (want_maps & 2u) CMDB_CUDA(cudaMemcpyAsync(s.out_block_host + o3, s.out_block + o3, npix, cudaMemcpyDeviceToHost, b->d2h_stream));
+        }
+    }
+    CMDB_CUDA(cudaEventRecord(b->ev_done[slot], b->d2h_stream));
+    cmdb_bank::Pending &pd = b->pending[slot];
+    pd.active = true, pd.B = B, pd.P = P, pd.out_hw = out_hw, pd.want = want_maps, pd.host_maps = true;
+    pd.img_first = img_first, pd.img_step = img_step;
+    pd.ticket = ++b->ticket_counter;
+    b->next_slot = slot ^ 1;
+    *out_ticket = pd.ticket;
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_wait(cmdb_bank *b, int64_t ticket, cmdb_score_out *outs) {
+    CMDB_REQUIRE(b && outs, CMDB_ERR_INVALID, "cmdb_score_shard_wait: NULL argument");
+    for (int slot = 0; slot < 2; ++slot) {
+        cmdb_bank::Pending &pd = b->pending[slot];
+        if (!pd.active || pd.ticket != ticket) continue;
+        CMDB_CUDA(cudaSetDevice(b->device));
+        CMDB_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+        pd.active = false;
+        // maps: the images this rank finished; the scalars and per-patch arrays are replicated, so every image gets those
+        for (int i = 0; i < pd.B; ++i) {
+            const bool mine = i >= pd.img_first && (i - pd.img_first) % pd.img_step == 0;
+            scatter_one(b, b->ss.out_block_host_buf[slot], i, pd.P, pd.out_hw, outs + i, mine);
+        }
+        return CMDB_OK;
+    }
+    set_error("cmdb_score_shard_wait: ticket %lld is not outstanding", (long long)ticket);
+    return CMDB_ERR_STATE;
+}
+
+// plain host -> device copy on the handle's stream (stream-ordered with the phases that follow); used by the Python side to
+// stage its slice of a round's queries without involving torch's pinned-memory bookkeeping
+int cmdb_bank_stage_h2d(cmdb_bank *b, void *dst_device, const void *src_host, size_t bytes) {
+    CMDB_REQUIRE(b && dst_device && src_host, CMDB_ERR_INVALID, "cmdb_bank_stage_h2d: NULL argument");
+    if (bytes == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    // on the copy stream, so that it overlaps the kernels already queued on the compute stream; the compute stream picks the
+    // data up through an event.  (The caller guarantees that dst_device is not read by earlier, still running work.)
+    CMDB_CUDA(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, b->copy_stream));
+    CMDB_CUDA(cudaEventRecord(b->ev_stage, b->copy_stream));
+    CMDB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_stage, 0));
+    return CMDB_OK;
+}
+
+int cmdb_bank_read_device(cmdb_bank *b, int64_t row0, int64_t n_rows, float *out_device) {
+    CMDB_REQUIRE(b && out_device && row0 >= 0 && n_rows >= 0 && row0 + n_rows <= b->rows, CMDB_ERR_INVALID,
+                 "cmdb_bank_read_device: rows [%lld,%lld) outside [0,%lld)", (long long)row0, (long long)(row0 + n_rows),
+                 b ? (long long)b->rows : 0LL);
+    if (n_rows == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaMemcpyAsync(out_device, b->data + row0 * b->dim, sizeof(float) * (size_t)n_rows * b->dim, cudaMemcpyDeviceToDevice,
+                              b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    return CMDB_OK;
+}
+
 // test hook (not in the public header): the GEMM epilogue's per-CTA top-2 lists of the last call, [n_cta][n_q][4] floats
 int cmdb_debug_read_candidates(cmdb_bank *b, float *out_host, int n_cta, int n_q) {
     CMDB_REQUIRE(b && out_host && b->ss.cand && n_cta >= 1 && n_cta <= 2 * b->num_sms && n_q >= 1 && n_q <= b->ss.cap_p,
@@ -437,6 +622,207 @@ int cmdb_debug_read_knn(cmdb_bank *b, unsigned long long *out_host, long long r0
                  "cmdb_debug_read_knn: bad arguments");
     CMDB_CUDA(cudaSetDevice(b->device));
     CMDB_CUDA(cudaMemcpy(out_host, b->knn_table + (size_t)r0 * 3, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+    return CMDB_OK;
+}
+
+
+// ---- late-fusion head on the device -------------------------------------------------------------------------------
+
+static size_t fused_off_modal(int cap_b) { return (sizeof(double) * cap_b + 255) & ~size_t(255); }
+static size_t fused_off_map(int cap_b) { return fused_off_modal(cap_b) + ((sizeof(float) * 3 * cap_b + 255) & ~size_t(255)); }
+constexpr int kFusedCapB = 32;
+
+static int fused_alloc(cmdb_bank *b0, int out_hw) {
+    cmdb_bank::Fused &f = b0->fused;
+    const size_t need = fused_off_map(kFusedCapB) + sizeof(double) * (size_t)out_hw * out_hw * kFusedCapB;
+    if (f.cap_bytes >= need) return CMDB_OK;
+    CMDB_REQUIRE(!f.active[0] && !f.active[1], CMDB_ERR_STATE, "fused scoring: out_hw grows while a submitted batch is outstanding");
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(f.dev[i]);
+        if (f.host[i]) cudaFreeHost(f.host[i]);
+        f.dev[i] = f.host[i] = nullptr;
+        CMDB_CUDA(cudaMalloc(&f.dev[i], need));
+        CMDB_CUDA(cudaMallocHost(&f.host[i], need));
+        if (!f.ev_done[i]) CMDB_CUDA(cudaEventCreateWithFlags(&f.ev_done[i], cudaEventDisableTiming));
+    }
+    f.cap_bytes = need;
+    return CMDB_OK;
+}
+
+int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *patches, const int *P, const int *fh,
+                                  const int *fw, int B, int out_hw, int patch_is_device, const cmdb_fusion_head *head,
+                                  unsigned flags, int64_t *out_ticket) {
+    CMDB_REQUIRE(banks && patches && P && fh && fw && head && out_ticket, CMDB_ERR_INVALID, "cmdb_score_fused_batch_submit: NULL argument");
+    const int M = head->n_modal;
+    CMDB_REQUIRE(M >= 1 && M <= 3, CMDB_ERR_INVALID, "cmdb_score_fused_batch_submit: n_modal=%d not in [1,3]", M);
+    for (int m = 0; m < M; ++m) {
+        CMDB_REQUIRE(banks[m], CMDB_ERR_INVALID, "cmdb_score_fused_batch_submit: banks[%d] is NULL", m);
+        CMDB_REQUIRE(banks[m]->device == banks[0]->device, CMDB_ERR_INVALID, "cmdb_score_fused_batch_submit: all banks must live on one GPU");
+        for (int k = 0; k < m; ++k)
+            CMDB_REQUIRE(banks[k] != banks[m], CMDB_ERR_INVALID, "cmdb_score_fused_batch_submit: one handle per modality");
+        CMDB_CHECK(check_batch_args(banks[m], patches[m], B, P[m], fh[m], fw[m], out_hw, "cmdb_score_fused_batch_submit"));
+        CMDB_REQUIRE(B <= score_max_batch(banks[m]) && B <= kFusedCapB, CMDB_ERR_INVALID,
+                     "cmdb_score_fused_batch_submit: batch=%d exceeds the per-call limit %d", B, std::min(kFusedCapB, score_max_batch(banks[m])));
+        CMDB_REQUIRE(!banks[m]->pending[banks[m]->next_slot].active, CMDB_ERR_STATE,
+                     "cmdb_score_fused_batch_submit: two batches are already outstanding; wait for one first");
+    }
+    cmdb_bank *b0 = banks[0];
+    cmdb_bank::Fused &f = b0->fused;
+    CMDB_CUDA(cudaSetDevice(b0->device));
+    CMDB_CHECK(fused_alloc(b0, out_hw));
+    const int fs = b0->next_slot;  // the fused block shares the slot parity of modality 0
+    CMDB_REQUIRE(!f.active[fs], CMDB_ERR_STATE, "cmdb_score_fused_batch_submit: fused slot still outstanding");
+    const int npix = out_hw * out_hw;
+    const bool keep = (flags & CMDB_FUSED_KEEP_ON_DEVICE) != 0, host_maps = (flags & CMDB_FUSED_NO_HOST_MAPS) == 0;
+    if (keep) {
+        CMDB_REQUIRE(f.acc_maps && f.acc_npix == npix && f.acc_n + B <= f.acc_cap, CMDB_ERR_CAPACITY,
+                     "cmdb_score_fused_batch_submit: device-side result store missing or full (%lld + %d > %lld); call cmdb_eval_reserve",
+                     f.acc_n, B, f.acc_cap);
+    }
+    FuseParams fp{};
+    fp.n_modal = M, fp.B = B, fp.npix = npix;
+    for (int m = 0; m < M; ++m) {
+        cmdb_bank *bm = banks[m];
+        const int slot = bm->next_slot;
+        bm->next_slot ^= 1;
+        CMDB_CHECK(submit_sub_batch(bm, patches[m], patch_is_device, B, P[m], fh[m], fw[m], out_hw, 0u, slot, false));
+        bm->pending[slot].ticket = ++bm->ticket_counter;
+        f.banks[fs][m] = bm, f.slots[fs][m] = slot;
+        fp.maps[m] = reinterpret_cast<const float *>(bm->ss.out_block_buf[slot] + bm->ss.off_map_out);
+        fp.map_stride[m] = bm->ss.map_stride;
+        fp.tails[m] = reinterpret_cast<const TailResult *>(bm->ss.out_block_buf[slot]);
+        fp.s_lambda[m] = head->s_lambda[m], fp.smap_lambda[m] = head->smap_lambda[m];
+        fp.det_coef[m] = head->detect_coef[m], fp.seg_coef[m] = head->seg_coef[m];
+        if (m > 0) CMDB_CUDA(cudaStreamWaitEvent(b0->stream, bm->ev_compute[slot], 0));
+    }
+    fp.det_off = head->detect_offset, fp.seg_off = head->seg_offset;
+    unsigned char *blk = f.dev[fs];
+    fp.out_s = reinterpret_cast<double *>(blk);
+    fp.out_s_modal = reinterpret_cast<float *>(blk + fused_off_modal(kFusedCapB));
+    fp.out_map = host_maps ? reinterpret_cast<double *>(blk + fused_off_map(kFusedCapB)) : nullptr;
+    if (keep) {
+        fp.acc_map = f.acc_maps + (size_t)f.acc_n * npix;
+        fp.acc_s = f.acc_scores + f.acc_n;
+        f.acc_n += B;
+    }
+    fuse_head_kernel<<<dim3((npix + 1023) / 1024, B), 256, 0, b0->stream>>>(fp);
+    CMDB_CUDA(cudaGetLastError());
+    // results of this slot: scalars (+ maps) on the d2h stream; the next batch's kernels may already run meanwhile
+    CMDB_CUDA(cudaEventRecord(b0->ev_chunk[1], b0->stream));
+    CMDB_CUDA(cudaStreamWaitEvent(b0->d2h_stream, b0->ev_chunk[1], 0));
+    const size_t bytes = host_maps ? fused_off_map(kFusedCapB) + sizeof(double) * (size_t)npix * B : fused_off_map(kFusedCapB);
+    CMDB_CUDA(cudaMemcpyAsync(f.host[fs], blk, bytes, cudaMemcpyDeviceToHost, b0->d2h_stream));
+    CMDB_CUDA(cudaEventRecord(f.ev_done[fs], b0->d2h_stream));
+    // the fuse kernel read the other banks' result blocks: their slots may only be reused after it (they wait on it through
+    // the ticket: a slot is busy until cmdb_score_fused_batch_wait returned)
+    f.active[fs] = true, f.n_modal[fs] = M, f.B[fs] = B, f.out_hw[fs] = out_hw;
+    f.ticket[fs] = b0->pending[f.slots[fs][0]].ticket;
+    *out_ticket = f.ticket[fs];
+    return CMDB_OK;
+}
+
+int cmdb_score_fused_batch_wait(cmdb_bank *b0, int64_t ticket, cmdb_fused_out *outs) {
+    CMDB_REQUIRE(b0 && outs, CMDB_ERR_INVALID, "cmdb_score_fused_batch_wait: NULL argument");
+    cmdb_bank::Fused &f = b0->fused;
+    for (int fs = 0; fs < 2; ++fs) {
+        if (!f.active[fs] || f.ticket[fs] != ticket) continue;
+        CMDB_CUDA(cudaSetDevice(b0->device));
+        CMDB_CUDA(cudaEventSynchronize(f.ev_done[fs]));
+        const int B = f.B[fs], M = f.n_modal[fs], npix = f.out_hw[fs] * f.out_hw[fs];
+        std::vector<cmdb_score_out> tmp((size_t)B);
+        for (int m = 0; m < M; ++m) {
+            for (int i = 0; i < B; ++i) {
+                tmp[i] = cmdb_score_out{};
+                tmp[i].min_val = outs[i].min_val[m], tmp[i].min_idx = outs[i].min_idx[m];
+            }
+            CMDB_CHECK(wait_slot(f.banks[fs][m], f.slots[fs][m], tmp.data()));
+        }
+        const unsigned char *h = f.host[fs];
+        const double *hs = reinterpret_cast<const double *>(h);
+        const float *hm = reinterpret_cast<const float *>(h + fused_off_modal(kFusedCapB));
+        const double *hmap = reinterpret_cast<const double *>(h + fused_off_map(kFusedCapB));
+        for (int i = 0; i < B; ++i) {
+            if (outs[i].s) *outs[i].s = hs[i];
+            if (outs[i].s_modal)
+                for (int m = 0; m < M; ++m) outs[i].s_modal[m] = hm[i * 3 + m];
+            if (outs[i].s_map) memcpy(outs[i].s_map, hmap + (size_t)i * npix, sizeof(double) * npix);
+        }
+        f.active[fs] = false;
+        return CMDB_OK;
+    }
+    set_error("cmdb_score_fused_batch_wait: ticket %lld is not outstanding", (long long)ticket);
+    return CMDB_ERR_STATE;
+}
+
+int cmdb_score_fused_batch(cmdb_bank *const *banks, const float *const *patches, const int *P, const int *fh, const int *fw,
+                           int B, int out_hw, int patch_is_device, const cmdb_fusion_head *head, unsigned flags,
+                           cmdb_fused_out *outs) {
+    CMDB_REQUIRE(banks && patches && P && head && outs && B >= 1, CMDB_ERR_INVALID, "cmdb_score_fused_batch: bad arguments");
+    const int M = head->n_modal;
+    CMDB_REQUIRE(M >= 1 && M <= 3, CMDB_ERR_INVALID, "cmdb_score_fused_batch: n_modal=%d not in [1,3]", M);
+    int bc_max = kFusedCapB;
+    for (int m = 0; m < M; ++m) {
+        CMDB_REQUIRE(banks[m] && patches[m], CMDB_ERR_INVALID, "cmdb_score_fused_batch: NULL bank / patches");
+        bc_max = std::min(bc_max, score_max_batch(banks[m]));
+    }
+    // sub-batches are pipelined: batch k + 1 is submitted before the host waits for batch k
+    int64_t prev_ticket = 0;
+    int prev_b0 = -1;
+    for (int b0 = 0; b0 < B; b0 += bc_max) {
+        const int bc = std::min(bc_max, B - b0);
+        const float *pp[3] = {nullptr, nullptr, nullptr};
+        for (int m = 0; m < M; ++m) pp[m] = patches[m] + (size_t)b0 * P[m] * banks[m]->dim;
+        int64_t t = 0;
+        CMDB_CHECK(cmdb_score_fused_batch_submit(banks, pp, P, fh, fw, bc, out_hw, patch_is_device, head, flags, &t));
+        if (prev_b0 >= 0) CMDB_CHECK(cmdb_score_fused_batch_wait(banks[0], prev_ticket, outs + prev_b0));
+        prev_ticket = t, prev_b0 = b0;
+    }
+    return cmdb_score_fused_batch_wait(banks[0], prev_ticket, outs + prev_b0);
+}
+
+
+// ---- device-side result store: replaces pixel_preds.extend / predictions.append of 50 176 scalars per image
+//      (multiple_features.py:996-1001); the fused maps stay in HBM until cmdb_eval_* consumes them ----
+
+int cmdb_eval_reserve(cmdb_bank *b, int64_t n_images, int out_hw) {
+    CMDB_REQUIRE(b && n_images >= 1 && out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_eval_reserve: bad arguments");
+    cmdb_bank::Fused &f = b->fused;
+    CMDB_REQUIRE(!f.active[0] && !f.active[1], CMDB_ERR_STATE, "cmdb_eval_reserve: a submitted batch is outstanding");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    cudaFree(f.acc_maps), cudaFree(f.acc_scores);
+    f.acc_maps = f.acc_scores = nullptr, f.acc_cap = f.acc_n = 0, f.acc_npix = out_hw * out_hw;
+    CMDB_CUDA(cudaMalloc(&f.acc_maps, sizeof(double) * (size_t)n_images * f.acc_npix));
+    CMDB_CUDA(cudaMalloc(&f.acc_scores, sizeof(double) * (size_t)n_images));
+    f.acc_cap = n_images;
+    return CMDB_OK;
+}
+
+int cmdb_eval_count(cmdb_bank *b, int64_t *out_n) {
+    CMDB_REQUIRE(b && out_n, CMDB_ERR_INVALID, "cmdb_eval_count: bad arguments");
+    *out_n = b->fused.acc_n;
+    return CMDB_OK;
+}
+
+int cmdb_eval_reset(cmdb_bank *b) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_eval_reset: bank is NULL");
+    CMDB_REQUIRE(!b->fused.active[0] && !b->fused.active[1], CMDB_ERR_STATE, "cmdb_eval_reset: a submitted batch is outstanding");
+    b->fused.acc_n = 0;
+    return CMDB_OK;
+}
+
+int cmdb_eval_read(cmdb_bank *b, int64_t first, int64_t n, double *maps_host, double *scores_host) {
+    cmdb_bank::Fused &f = b->fused;
+    CMDB_REQUIRE(b && first >= 0 && n >= 0 && first + n <= f.acc_n, CMDB_ERR_INVALID, "cmdb_eval_read: images [%lld,%lld) outside [0,%lld)",
+                 (long long)first, (long long)(first + n), (long long)f.acc_n);
+    if (n == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    if (maps_host)
+        CMDB_CUDA(cudaMemcpyAsync(maps_host, f.acc_maps + (size_t)first * f.acc_npix, sizeof(double) * (size_t)n * f.acc_npix,
+                                  cudaMemcpyDeviceToHost, b->stream));
+    if (scores_host)
+        CMDB_CUDA(cudaMemcpyAsync(scores_host, f.acc_scores + first, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
     return CMDB_OK;
 }
 

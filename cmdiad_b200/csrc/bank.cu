@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(256) split_rows_kernel_impl(const float *__res
     }
 }
 
+void launch_normalize(cudaStream_t stream, int num_sms, float *x, int64_t n, float mean, float stdv) {
+    if (n <= 0) return;
+    int grid = (int)std::min<int64_t>((n / 4 + 511) / 512 + 1, (int64_t)num_sms * 4);
+    normalize_kernel<<<grid, 512, 0, stream>>>(x, n, mean, stdv);
+}
+
 void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t n_rows, int64_t n_pad, int dim,
                        int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm, unsigned int *cert_buf) {
     int grid = (int)std::min<int64_t>((n_pad + 7) / 8, (int64_t)num_sms * 8);
@@ -245,6 +251,7 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_compute[i], cudaEventDisableTiming);
     }
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fail, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_stage, cudaEventDisableTiming);
     for (auto &e : b->ev_chunk)
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaMalloc(&b->data, sizeof(float) * (size_t)capacity_rows * dim);
@@ -266,7 +273,7 @@ static void free_scoring_layout(cmdb_bank *b) {
     cudaFree(b->lo);
     cudaFree(b->norm);
     cudaFree(b->knn_table);
-    b->knn_table = nullptr;
+    b->knn_table = nullptr, b->knn_rows = 0;
     b->hi = b->lo = nullptr;
     b->norm = nullptr;
     free(b->tmap_hi);
@@ -285,6 +292,12 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
     if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
     free_scoring_layout(b);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(b->fused.dev[i]);
+        if (b->fused.host[i]) cudaFreeHost(b->fused.host[i]);
+        if (b->fused.ev_done[i]) cudaEventDestroy(b->fused.ev_done[i]);
+    }
+    cudaFree(b->fused.acc_maps), cudaFree(b->fused.acc_scores);
     cudaFree(b->data);
     cudaFree(b->stats_buf);
     cudaFree(b->absmax_buf);
@@ -299,6 +312,7 @@ void cmdb_bank_destroy(cmdb_bank *b) {
         if (b->ev_compute[i]) cudaEventDestroy(b->ev_compute[i]);
     }
     if (b->ev_fail) cudaEventDestroy(b->ev_fail);
+    if (b->ev_stage) cudaEventDestroy(b->ev_stage);
     for (auto &e : b->ev_chunk)
         if (e) cudaEventDestroy(e);
     delete b;
@@ -366,6 +380,15 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
     return CMDB_ERR_INVALID;
 }
 
+int cmdb_bank_set_query_norm(cmdb_bank *b, float mean, float stdv, int enabled) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_set_query_norm: bank is NULL");
+    CMDB_REQUIRE(!enabled || (isfinite(mean) && isfinite(stdv) && stdv != 0.f), CMDB_ERR_INVALID,
+                 "cmdb_bank_set_query_norm: need finite mean and a finite non-zero std");
+    b->q_norm_enabled = enabled != 0;
+    b->q_mean = mean, b->q_std = stdv;
+    return CMDB_OK;
+}
+
 int cmdb_bank_stream(cmdb_bank *b, void **out_stream) {
     CMDB_REQUIRE(b && out_stream, CMDB_ERR_INVALID, "cmdb_bank_stream: bad arguments");
     *out_stream = (void *)b->stream;
@@ -379,14 +402,58 @@ int cmdb_bank_get_timings(cmdb_bank *b, float *out_ms) {
     return CMDB_OK;
 }
 
-int cmdb_bank_build_knn(cmdb_bank *b) {
-    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_build_knn: bank is NULL");
-    CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "cmdb_bank_build_knn: call cmdb_bank_finalize first");
+static int build_knn_checks(cmdb_bank *b, const char *fn) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "%s: bank is NULL", fn);
+    CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "%s: call cmdb_bank_finalize first", fn);
     CMDB_REQUIRE(b->row_offset == 0, CMDB_ERR_UNSUPPORTED,
-                 "cmdb_bank_build_knn: the table needs every bank row on this GPU (row-sharded handles re-weight on the fly)");
-    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "cmdb_bank_build_knn: a submitted batch is outstanding");
+                 "%s: the table is computed on a handle that holds every bank row (row-sharded handles install a replicated "
+                 "table with cmdb_bank_set_knn_table)", fn);
+    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "%s: a submitted batch is outstanding", fn);
     CMDB_CUDA(cudaSetDevice(b->device));
-    return score_build_knn_table(b);
+    return CMDB_OK;
+}
+
+int cmdb_bank_build_knn(cmdb_bank *b) {
+    CMDB_CHECK(build_knn_checks(b, "cmdb_bank_build_knn"));
+    return score_build_knn_table(b, 0, b->fin_rows);
+}
+
+int cmdb_bank_build_knn_rows(cmdb_bank *b, int64_t row_first, int64_t n_rows) {
+    CMDB_CHECK(build_knn_checks(b, "cmdb_bank_build_knn_rows"));
+    CMDB_REQUIRE(row_first >= 0 && n_rows >= 0 && row_first + n_rows <= b->fin_rows, CMDB_ERR_INVALID,
+                 "cmdb_bank_build_knn_rows: rows [%lld,%lld) outside [0,%lld)", (long long)row_first,
+                 (long long)(row_first + n_rows), (long long)b->fin_rows);
+    return score_build_knn_table(b, row_first, n_rows);
+}
+
+int cmdb_bank_read_knn(cmdb_bank *b, int64_t row_first, int64_t n_rows, uint64_t *out_keys, int out_is_device) {
+    CMDB_REQUIRE(b && out_keys && b->knn_table && row_first >= 0 && n_rows >= 0 && row_first + n_rows <= b->knn_rows,
+                 CMDB_ERR_INVALID, "cmdb_bank_read_knn: no table, or rows outside it");
+    if (n_rows == 0) return CMDB_OK;
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaMemcpyAsync(out_keys, b->knn_table + (size_t)row_first * 3, sizeof(uint64_t) * 3 * (size_t)n_rows,
+                              out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    return CMDB_OK;
+}
+
+int cmdb_bank_set_knn_table(cmdb_bank *b, const uint64_t *keys, int64_t n_rows_total, int keys_is_device) {
+    CMDB_REQUIRE(b && keys && n_rows_total >= 1, CMDB_ERR_INVALID, "cmdb_bank_set_knn_table: bad arguments");
+    CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "cmdb_bank_set_knn_table: call cmdb_bank_finalize first");
+    CMDB_REQUIRE(b->row_offset + b->fin_rows <= n_rows_total, CMDB_ERR_INVALID,
+                 "cmdb_bank_set_knn_table: the table must cover all GLOBAL rows (this shard ends at %lld, table has %lld)",
+                 (long long)(b->row_offset + b->fin_rows), (long long)n_rows_total);
+    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "cmdb_bank_set_knn_table: a submitted batch is outstanding");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    cudaFree(b->knn_table);
+    b->knn_table = nullptr, b->knn_rows = 0;
+    CMDB_CUDA(cudaMalloc(&b->knn_table, sizeof(uint64_t) * 3 * (size_t)n_rows_total));
+    CMDB_CUDA(cudaMemcpyAsync(b->knn_table, keys, sizeof(uint64_t) * 3 * (size_t)n_rows_total,
+                              keys_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
+    CMDB_CUDA(cudaStreamSynchronize(b->stream));
+    b->knn_rows = n_rows_total;
+    return CMDB_OK;
 }
 
 int cmdb_bank_score_stats(cmdb_bank *b, int64_t *out6) {

@@ -125,7 +125,10 @@ struct cmdb_bank {
     unsigned int *cert_buf = nullptr;  // device [2]: the two maxima as float bits
     // optional table of the three nearest bank rows of every bank row, as packed (d^2 bits << 32 | row) keys
     // (cmdb_bank_build_knn): turns the per-image w_dist pass into a lookup
-    unsigned long long *knn_table = nullptr;  // [fin_rows][3]
+    unsigned long long *knn_table = nullptr;  // [knn_rows][3]
+    // rows the table covers: fin_rows for a table built on this handle (cmdb_bank_build_knn); the GLOBAL row count for a
+    // replicated table installed on a row-sharded handle (cmdb_bank_set_knn_table)
+    long long knn_rows = 0;
     // statistics of the last scoring call / adaptive fallback to the direct 3-term GEMM
     int64_t last_queries = 0;
     int last_mode = 0;           // GEMM mode the last call actually ran
@@ -138,14 +141,40 @@ struct cmdb_bank {
     cudaEvent_t ev_done[2] = {};          // slot's results are in the pinned host block
     cudaEvent_t ev_compute[2] = {};       // slot's kernels are done (its q_f32 may be overwritten)
     cudaEvent_t ev_fail = nullptr;        // the certificate counters of the last certified call are on the host
+    cudaEvent_t ev_stage = nullptr;       // cmdb_bank_stage_h2d: the staged bytes are on the device
     struct Pending {
         bool active = false;
         int B = 0, P = 0, out_hw = 0;
         unsigned want = 0;
+        bool host_maps = true;   // false: the per-modality maps stay in HBM (fused late-fusion head), only scalars travel
+        int img_first = 0, img_step = 1;  // sharded rounds: the images whose maps this rank finished
         long long ticket = 0;
     } pending[2];
+    // queries are normalised on the device right after staging: (q - q_mean) / q_std, one IEEE subtract + one IEEE divide
+    // like the reference's torch expression (multiple_features.py:90, 976-977); cmdb_bank_set_query_norm
+    bool q_norm_enabled = false;
+    float q_mean = 0.f, q_std = 1.f;
+    // late-fusion head on the device (cmdb_score_fused_batch*; this handle is modality 0 of the fused call): per slot the
+    // fused float64 maps / image scores / lambda-scaled per-modality s in one device block mirrored by a pinned host block
+    struct Fused {
+        unsigned char *dev[2] = {nullptr, nullptr};
+        unsigned char *host[2] = {nullptr, nullptr};
+        size_t cap_bytes = 0;
+        cudaEvent_t ev_done[2] = {};
+        bool active[2] = {false, false};
+        int n_modal[2] = {0, 0}, B[2] = {0, 0}, out_hw[2] = {0, 0};
+        cmdb_bank *banks[2][3] = {};
+        int slots[2][3] = {};
+        long long ticket[2] = {0, 0};
+        // device-resident accumulation of the fused maps over predict calls (cmdb_eval_*)
+        double *acc_maps = nullptr;     // [acc_cap][npix]
+        double *acc_scores = nullptr;   // [acc_cap]
+        long long acc_cap = 0, acc_n = 0;
+        int acc_npix = 0;
+    } fused;
     long long ticket_counter = 0;
     int next_slot = 0;
+    int shard_slot = 0;   // result slot of the sharded round in progress (cmdb_score_shard_min .. finish)
     float *data = nullptr;  // [capacity, dim] float32 row-major
     // scoring layout (cmdb_bank_finalize)
     bool finalized = false;
@@ -172,6 +201,7 @@ namespace cmdb {
 // bank.cu
 int bank_max_abs(cmdb_bank *b, const float *x, int64_t n, float *out_host);
 int pick_scale_exp(float absmax);
+void launch_normalize(cudaStream_t stream, int num_sms, float *x, int64_t n, float mean, float stdv);
 void launch_split_rows(cudaStream_t stream, int num_sms, const float *x, int64_t n_rows, int64_t n_pad, int dim,
                        int scale_exp, __half *hi, __half *lo, float *norm, float pad_norm, unsigned int *cert_buf);
 
@@ -229,7 +259,9 @@ int score_refine(cmdb_bank *b, int B, int P_img, int n_cand, bool compact);
 int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand);
 int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star);
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused);
-int score_build_knn_table(cmdb_bank *b);
+int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count);
+int score_shard_lookup(cmdb_bank *b, int B, float *contrib_dev);
+int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev);
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B);
 int score_final(cmdb_bank *b, int B);
 int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,

@@ -68,6 +68,7 @@ struct Traits<__half> {
     static __device__ __forceinline__ __half from_acc(float a) { return __float2half_rn(sqrtf(a)); }
     static __device__ __forceinline__ __half zero() { return __ushort_as_half((unsigned short)0); }
     static __device__ __forceinline__ __half from_bits(unsigned short b) { return __ushort_as_half(b); }
+    static __device__ __forceinline__ __half from_bits64(unsigned long long) { return zero(); }  // float64 mailbox only
     static __device__ __forceinline__ bool lt(__half a, __half b) { return __half2float(a) < __half2float(b); }
     static __device__ __forceinline__ bool gt(__half a, __half b) { return __half2float(a) > __half2float(b); }
 };
@@ -77,7 +78,8 @@ struct Traits<double> {
     static __device__ __forceinline__ unsigned long long bits(double v) { return (unsigned long long)__double_as_longlong(v); }
     static __device__ __forceinline__ double from_acc(double a) { return sqrt(a); }
     static __device__ __forceinline__ double zero() { return 0.0; }
-    static __device__ __forceinline__ double from_bits(unsigned short) { return 0.0; }  // sharded loop is half-only
+    static __device__ __forceinline__ double from_bits(unsigned short) { return 0.0; }  // half mailbox only
+    static __device__ __forceinline__ double from_bits64(unsigned long long b) { return __longlong_as_double((long long)b); }
     static __device__ __forceinline__ bool lt(double a, double b) { return a < b; }
     static __device__ __forceinline__ bool gt(double a, double b) { return a > b; }
 };
@@ -279,6 +281,8 @@ struct CoresetParams {
     const void *last0;                  // [d] global row 0 in storage type (pick 1 measures distances to it)
     unsigned int *abort_flag;           // set when a peer did not answer in time
     long long spin_limit;               // clock64() ticks to wait for a peer
+    size_t *l2_prev_limit;              // host side only: persisting-L2 carve-out found before the launch ...
+    bool *l2_changed;                   // ... and whether launch_coreset enlarged it (restored by coreset_greedy_dev)
 };
 
 // per-warp constants of the streaming loop: every warp handles ONE alignment class (rows with row % 4 == warp % 4 of
@@ -327,6 +331,7 @@ template <typename T, int NV, bool DYN>
 __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p) {
     using acc_t = typename Traits<T>::acc_t;
     constexpr int RB = Batch<T>::rows;
+    constexpr unsigned int kMbHdr = sizeof(T) == 2 ? 16u : 32u;  // key header of a mailbox slot, then the row words
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: tile [kCsWarps][32][33] acc_t | last_sh [d] T | red (val,row) [32] | mind [rows_per_cta] T
     acc_t *tile_all = reinterpret_cast<acc_t *>(smem_raw);
@@ -393,9 +398,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = reinterpret_cast<const T *>(p.last0)[e];
         } else if (p.world > 1) {
             // sel is a GLOBAL row: its values are the winner's row words in the local mailbox (flagged with pick - 1)
-            const unsigned char *src = p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) * p.mb_slot_stride + 16;
+            const unsigned char *src = p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) * p.mb_slot_stride + kMbHdr;
             const long long t0 = clock64();
-            for (int w2 = threadIdx.x; w2 < ((d + 1) >> 1); w2 += kCsThreads) {
+            auto wait_word = [&](int w2) {
                 unsigned long long word;
                 for (;;) {
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src + 8 * w2) : "memory");
@@ -405,8 +410,19 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
                         break;
                     }
                 }
-                last_sh[2 * w2] = Traits<T>::from_bits((unsigned short)(word & 0xffffu));
-                if (2 * w2 + 1 < d) last_sh[2 * w2 + 1] = Traits<T>::from_bits((unsigned short)((word >> 16) & 0xffffu));
+                return word;
+            };
+            if constexpr (sizeof(T) == 2) {
+                for (int w2 = threadIdx.x; w2 < ((d + 1) >> 1); w2 += kCsThreads) {
+                    const unsigned long long word = wait_word(w2);
+                    last_sh[2 * w2] = Traits<T>::from_bits((unsigned short)(word & 0xffffu));
+                    if (2 * w2 + 1 < d) last_sh[2 * w2 + 1] = Traits<T>::from_bits((unsigned short)((word >> 16) & 0xffffu));
+                }
+            } else {  // float64: two flagged words per element (low half, high half)
+                for (int e = threadIdx.x; e < d; e += kCsThreads) {
+                    const unsigned long long lo = wait_word(2 * e) & 0xffffffffULL, hi = wait_word(2 * e + 1) & 0xffffffffULL;
+                    last_sh[e] = Traits<T>::from_bits64((hi << 32) | lo);
+                }
             }
         } else {
             for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
@@ -608,53 +624,82 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             //   row words: [63:32] pick          | [31:0] two consecutive halves of the candidate row
             const unsigned int slot = (unsigned int)((pick & 1) * p.world + p.rank) * p.mb_slot_stride;
             const bool have = br != ~0ULL;
+            const unsigned long long grow = have ? (unsigned long long)(br + p.row_offset) : 0xffffffffULL;
             if (blockIdx.x == 0) {
-                const int n_words = (d + 1) >> 1;
-                for (int w2 = threadIdx.x; w2 < n_words; w2 += kCsThreads) {
-                    unsigned int lo16 = 0, hi16 = 0;
-                    if (have) {
-                        lo16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2)) & 0xffffu;
-                        if (2 * w2 + 1 < d) hi16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2 + 1)) & 0xffffu;
+                if constexpr (sizeof(T) == 2) {
+                    const int n_words = (d + 1) >> 1;
+                    for (int w2 = threadIdx.x; w2 < n_words; w2 += kCsThreads) {
+                        unsigned int lo16 = 0, hi16 = 0;
+                        if (have) {
+                            lo16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2)) & 0xffffu;
+                            if (2 * w2 + 1 < d) hi16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2 + 1)) & 0xffffu;
+                        }
+                        const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | (hi16 << 16) | lo16;
+                        for (int r = 0; r < p.world; ++r)
+                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + kMbHdr + 8 * w2), "l"(word) : "memory");
                     }
-                    const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | (hi16 << 16) | lo16;
-                    for (int r = 0; r < p.world; ++r)
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + 16 + 8 * w2), "l"(word) : "memory");
-                }
-                if (threadIdx.x < p.world) {
-                    const unsigned long long grow = have ? (unsigned long long)(br + p.row_offset) : 0xffffffffULL;
-                    const unsigned long long key = ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) |
-                                                   (0xffffffffULL - (grow & 0xffffffffULL));
-                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[threadIdx.x] + slot), "l"(key) : "memory");
+                    if (threadIdx.x < p.world) {
+                        const unsigned long long key = ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) |
+                                                       (0xffffffffULL - (grow & 0xffffffffULL));
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[threadIdx.x] + slot), "l"(key) : "memory");
+                    }
+                } else {
+                    // float64:  row words [63:32] pick | [31:0] low / high half of element w2 / 2
+                    //           key words 0..2: [63:32] pick | value low half, value high half, ~global_row
+                    for (int w2 = threadIdx.x; w2 < 2 * d; w2 += kCsThreads) {
+                        const unsigned long long bits = have ? Traits<T>::bits(__ldg(z + (long long)br * d + (w2 >> 1))) : 0ULL;
+                        const unsigned long long part = (w2 & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
+                        const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | part;
+                        for (int r = 0; r < p.world; ++r)
+                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + kMbHdr + 8 * w2), "l"(word) : "memory");
+                    }
+                    if (threadIdx.x < 3 * p.world) {
+                        const int r = threadIdx.x / 3, k = threadIdx.x % 3;
+                        const unsigned long long part = k == 0 ? (bv & 0xffffffffULL) : k == 1 ? (bv >> 32) : (0xffffffffULL - (grow & 0xffffffffULL));
+                        const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | part;
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + 8 * k), "l"(word) : "memory");
+                    }
                 }
             }
             if (warp == 0) {
-                unsigned long long key = 0ULL;
+                unsigned long long kval = 0ULL, kinv = 0ULL;  // value bits and ~global_row of rank `lane`
                 int ok = 1;
                 if (lane < p.world) {
                     const unsigned long long *kp = reinterpret_cast<const unsigned long long *>(
                         p.mb_peer[p.rank] + (size_t)((pick & 1) * p.world + lane) * p.mb_slot_stride);
                     const long long t0 = clock64();
-                    for (;;) {
-                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(key) : "l"(kp) : "memory");
-                        if ((key >> 48) == (unsigned long long)(pick & 0xffff)) break;
-                        if (clock64() - t0 > p.spin_limit || ld_volatile(p.abort_flag)) {
-                            ok = 0;
-                            break;
+                    auto poll = [&](const unsigned long long *q, int shift, unsigned long long want) {
+                        unsigned long long w = 0ULL;
+                        for (;;) {
+                            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(q) : "memory");
+                            if ((w >> shift) == want) break;
+                            if (clock64() - t0 > p.spin_limit || ld_volatile(p.abort_flag)) {
+                                ok = 0;
+                                break;
+                            }
                         }
+                        return w;
+                    };
+                    if constexpr (sizeof(T) == 2) {
+                        const unsigned long long key = poll(kp, 48, (unsigned long long)(pick & 0xffff));
+                        kval = (key >> 32) & 0xffffULL, kinv = key & 0xffffffffULL;
+                    } else {
+                        const unsigned long long want = (unsigned long long)(unsigned int)pick;
+                        const unsigned long long w0 = poll(kp, 32, want), w1 = poll(kp + 1, 32, want), w2 = poll(kp + 2, 32, want);
+                        kval = ((w1 & 0xffffffffULL) << 32) | (w0 & 0xffffffffULL), kinv = w2 & 0xffffffffULL;
                     }
                 }
                 if (lane == 0 && ld_volatile(p.abort_flag)) ok = 0;
                 ok = __all_sync(0xffffffffu, ok);
-                unsigned long long best = lane < p.world ? key : 0ULL;
                 int brank = lane;
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {  // kMaxRanks == 8 lanes
-                    const unsigned long long ok2 = __shfl_xor_sync(0xffffffffu, best, o);
+                for (int o = 4; o > 0; o >>= 1) {  // kMaxRanks == 8 lanes: max value, ties -> lowest global row (largest ~row)
+                    const unsigned long long ov = __shfl_xor_sync(0xffffffffu, kval, o), oi = __shfl_xor_sync(0xffffffffu, kinv, o);
                     const int or2 = __shfl_xor_sync(0xffffffffu, brank, o);
-                    if (ok2 > best) best = ok2, brank = or2;
+                    if (ov > kval || (ov == kval && oi > kinv)) kval = ov, kinv = oi, brank = or2;
                 }
                 if (lane == 0) {
-                    xkey_sh = (best & 0xffffffffULL) | ((unsigned long long)brank << 32);
+                    xkey_sh = (kinv & 0xffffffffULL) | ((unsigned long long)brank << 32);
                     abort_sh = !ok;
                     if (!ok) *p.abort_flag = 1u;
                 }
@@ -770,7 +815,12 @@ static int launch_coreset(cmdb_bank *b, CoresetParams p) {
         cudaStreamAttrValue attr{};
         if (want_persist && max_persist > 0 && max_window > 0) {
             const size_t carve = std::min<size_t>(z_bytes, (size_t)max_persist);
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+            // the carve-out is process-wide device state: only ever GROW it here (another component of the host program
+            // may have configured its own) and let coreset_greedy_dev restore the previous value when the loop is done
+            size_t prev = 0;
+            (void)cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize);
+            if (prev >= carve || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                if (prev < carve && p.l2_prev_limit) *p.l2_prev_limit = prev, *p.l2_changed = true;
                 attr.accessPolicyWindow.base_ptr = const_cast<void *>(p.z);
                 attr.accessPolicyWindow.num_bytes = std::min<size_t>(z_bytes, (size_t)max_window);
                 attr.accessPolicyWindow.hitRatio =
@@ -818,8 +868,8 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     CMDB_REQUIRE(n_total < (1LL << 32) - 1, CMDB_ERR_UNSUPPORTED, "coreset: N must fit 32 bits");
     CMDB_REQUIRE(dtype_mode == CMDB_CORESET_FP16 || dtype_mode == CMDB_CORESET_FP64, CMDB_ERR_INVALID,
                  "coreset: unknown dtype_mode %d", dtype_mode);
-    CMDB_REQUIRE(!sharded || (dtype_mode == CMDB_CORESET_FP16 && !force_idx_host && N > 0), CMDB_ERR_UNSUPPORTED,
-                 "coreset: the row-sharded loop supports FP16 mode on non-empty shards only");
+    CMDB_REQUIRE(!sharded || (!force_idx_host && N > 0), CMDB_ERR_UNSUPPORTED,
+                 "coreset: the row-sharded loop needs non-empty shards and does not support teacher forcing");
     cudaStream_t st = b->stream;
     long long *idx_dev = nullptr, *force_dev = nullptr;
     PickSlot *slots = nullptr;
@@ -828,7 +878,17 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     unsigned int *abort_dev = nullptr;
     void *mind = nullptr;
     int rc = CMDB_OK;
-    auto cleanup = [&]() {
+    size_t l2_prev = 0;
+    bool l2_changed = false;
+    auto cleanup = [&]() {  // every exit path: error returns included
+        if (l2_changed) {
+            // hand the persisting-L2 carve-out back exactly as it was found (cudaDeviceSetLimit is process-wide state);
+            // lines other code had pinned are left alone -- only our own window was ever marked persisting
+            (void)cudaStreamSynchronize(st);
+            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_prev);
+            (void)cudaGetLastError();
+            l2_changed = false;
+        }
         cudaFree(idx_dev), cudaFree(force_dev), cudaFree(slots), cudaFree(zh_alloc), cudaFree(mind);
         cudaFree(last0_h), cudaFree(z0_dev), cudaFree(abort_dev);
     };
@@ -858,6 +918,7 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     CoresetParams p{};
     p.N = N, p.d = d, p.n_select = n_select, p.out_idx = idx_dev, p.force_idx = force_dev, p.slots = slots;
     p.chunk_ctr = abort_dev + 1;
+    p.l2_prev_limit = &l2_prev, p.l2_changed = &l2_changed;
     p.world = 1, p.rank = 0, p.row_offset = 0, p.abort_flag = abort_dev, p.spin_limit = 20LL * 1000 * 1000 * 1000;  // ~10 s
     const double *first_row = z_dev;  // pick 0 = global row 0
     if (sharded) {
@@ -865,10 +926,14 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
         for (int r = 0; r < kMaxRanks; ++r) p.mb_peer[r] = sh->peers[r];
         CS_TRY(cudaMalloc(&z0_dev, sizeof(double) * d));
         CS_TRY(cudaMemcpyAsync(z0_dev, sh->z0_host, sizeof(double) * d, cudaMemcpyHostToDevice, st));
-        CS_TRY(cudaMalloc(&last0_h, sizeof(__half) * d));
-        to_half_kernel<<<1, 512, 0, st>>>(z0_dev, d, last0_h);
-        CS_TRY(cudaGetLastError());
-        p.last0 = last0_h;
+        if (dtype_mode == CMDB_CORESET_FP16) {
+            CS_TRY(cudaMalloc(&last0_h, sizeof(__half) * d));
+            to_half_kernel<<<1, 512, 0, st>>>(z0_dev, d, last0_h);
+            CS_TRY(cudaGetLastError());
+            p.last0 = last0_h;
+        } else {
+            p.last0 = z0_dev;
+        }
         first_row = z0_dev;
     }
     if (dtype_mode == CMDB_CORESET_FP16) {
@@ -886,7 +951,7 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
         }
     } else {
         CS_TRY(cudaMalloc(&mind, sizeof(double) * (size_t)N));
-        rc = launch_rownorm<double>(st, b->num_sms, z_dev, z_dev, N, d, reinterpret_cast<double *>(mind), nullptr);
+        rc = launch_rownorm<double>(st, b->num_sms, z_dev, first_row, N, d, reinterpret_cast<double *>(mind), nullptr, p.row_offset);
         if (rc == CMDB_OK) {
             p.z = z_dev, p.mind = mind;
             rc = launch_coreset<double>(b, p);
@@ -912,9 +977,6 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
                                (dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double)) * (size_t)N,
                                cudaMemcpyDeviceToHost, st));
     CS_TRY(cudaStreamSynchronize(st));
-    (void)cudaCtxResetPersistingL2Cache();
-    (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-    (void)cudaGetLastError();
 #undef CS_TRY
     cleanup();
     if (aborted) {

@@ -457,6 +457,7 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     if (b->score_impl != CMDB_SCORE_TCGEN05) {
         b->last_mode = 3;
         CMDB_CUDA(cudaMemcpyAsync(s.q_f32, src, sizeof(float) * P * D, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        if (b->q_norm_enabled) launch_normalize(st, b->num_sms, s.q_f32, (int64_t)P * D, b->q_mean, b->q_std);
         CMDB_CHECK(mark(ev_gemm));
         CMDB_CHECK(score_simt_candidates(b, P, &n_cand));
         CMDB_CHECK(mark(ev_refine));
@@ -517,6 +518,9 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     for (int c = 0; c < n_chunks; ++c) {
         const int row0 = c * chunk_tiles * kScoreBM, rows = std::min(P, (c + 1) * chunk_tiles * kScoreBM) - row0;
         if (via_copy_stream) CMDB_CUDA(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
+        // (patch - mean) / std on the device (multiple_features.py:90): without chunking the one copy above covers all rows
+        if (b->q_norm_enabled)
+            launch_normalize(st, b->num_sms, s.q_f32 + (size_t)row0 * D, (int64_t)(via_copy_stream ? rows : P) * D, b->q_mean, b->q_std);
         CMDB_CHECK(score_query_prep(b, rows, false, row0));
         if (c == 0) CMDB_CHECK(mark(ev_gemm));
         CMDB_CHECK(score_gemm_candidates(b, rows, mode == 3 ? 3 : 1, false, &n_cand, row0));
@@ -915,6 +919,46 @@ __global__ void __launch_bounds__(64) reweight_lookup_kernel(const unsigned long
     }
 }
 
+// sharded mode with the REPLICATED neighbour table (every rank holds the keys of all global rows; the bank rows themselves
+// stay sharded): image b = blockIdx.x, 2 warps.  m_star's three nearest rows are table[m_star_row]; this rank contributes
+// the exact squared distance ||m_test - bank[nn_k]||^2 (k = 1, 2) for the neighbour rows it owns and 0 for the others, so
+// that a float SUM all-reduce over the ranks reproduces warp_sqdist's value bit for bit (x + 0 + ... + 0).
+__global__ void __launch_bounds__(64) shard_lookup_kernel(const unsigned long long *__restrict__ table, const float *__restrict__ m_test,
+                                                         const float *__restrict__ bank, long long rows, long long row_offset,
+                                                         int dim, unsigned long long *top3, TailResult *res_all,
+                                                         float *__restrict__ contrib) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TailResult *res = res_all + b;
+    const unsigned long long *keys3 = table + (size_t)res->m_star_row * 3;
+    const unsigned long long key = keys3[1 + warp];
+    const long long l = (long long)(key & 0xffffffffULL) - row_offset;
+    float v = 0.f;
+    if (key != ~0ULL && l >= 0 && l < rows) v = warp_sqdist(m_test + (size_t)b * dim, bank + (size_t)l * dim, dim >> 2, lane);
+    if (lane == 0) contrib[b * 2 + warp] = v;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 3; ++k) {
+            top3[b * 3 + k] = keys3[k];
+            res->nn_idx[k] = keys3[k] == ~0ULL ? -1 : (long long)(keys3[k] & 0xffffffffULL);
+        }
+}
+
+// ... and after the SUM all-reduce: m_star_knn, w, s (features.py:275-290) from the summed squared distances
+__global__ void shard_final_kernel(const unsigned long long *__restrict__ top3, const float *__restrict__ d2_sum, int dim, int B,
+                                   TailResult *res_all) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    TailResult *res = res_all + b;
+    float knn[2];
+    for (int k = 0; k < 2; ++k) knn[k] = top3[b * 3 + 1 + k] == ~0ULL ? NAN : sqrtf(d2_sum[b * 2 + k]);
+    const float Dn = sqrtf((float)dim);
+    const float s_star = res->s_star;
+    const float den = expf(knn[0] / Dn) + expf(knn[1] / Dn);
+    const float w = 1.f - expf(s_star / Dn) / den;
+    res->w = w;
+    res->s = w * s_star;
+    res->knn0 = knn[0], res->knn1 = knn[1];
+}
+
 // sharded mode, after the all-gather: image b = blockIdx.x merges the keys of all ranks ([rank][B][3] layout)
 __global__ void __launch_bounds__(32) merge_top3_kernel(const unsigned long long *__restrict__ gathered, int n_ranks, int B,
                                                         unsigned long long *__restrict__ out3) {
@@ -1120,16 +1164,23 @@ static int score_reweight_tensor(cmdb_bank *b, int B, int P_img, bool fused) {
 
 // three nearest bank rows of every bank row.  The bank is its own query set: chunks of rows go through the
 // fp16 split, the certified pre-filter GEMM and reweight_cert_kernel (one block per row, keys only).
-int score_build_knn_table(cmdb_bank *b) {
+int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count) {
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     const int chunk = 64 * kScoreBM;  // 8192 rows: 64 M tiles per GEMM launch
     // scratch for `chunk` query rows; sized like a 32-image batch so that later scoring calls do not have to grow it
     CMDB_CHECK(score_scratch_alloc(b, 32, chunk / 32, s.map_stride ? (int)lround(sqrt((double)s.map_stride)) : 224));
     score_select_slot(b, 0);
-    if (!b->knn_table) CMDB_CUDA(cudaMalloc(&b->knn_table, sizeof(unsigned long long) * 3 * (size_t)b->fin_rows));
-    for (long long r0 = 0; r0 < b->fin_rows; r0 += chunk) {
-        const int n = (int)std::min<long long>(chunk, b->fin_rows - r0);
+    if (!b->knn_table || b->knn_rows != b->fin_rows) {
+        cudaFree(b->knn_table);
+        b->knn_table = nullptr;
+        CMDB_CUDA(cudaMalloc(&b->knn_table, sizeof(unsigned long long) * 3 * (size_t)b->fin_rows));
+        CMDB_CUDA(cudaMemsetAsync(b->knn_table, 0xff, sizeof(unsigned long long) * 3 * (size_t)b->fin_rows, st));
+        b->knn_rows = b->fin_rows;
+    }
+    const long long row_end = row_first + row_count;
+    for (long long r0 = row_first; r0 < row_end; r0 += chunk) {
+        const int n = (int)std::min<long long>(chunk, row_end - r0);
         const float *rows = b->data + (size_t)r0 * b->dim;
         q_split_rows(b, rows, n);
         CMDB_CUDA(cudaGetLastError());
@@ -1154,7 +1205,7 @@ int score_build_knn_table(cmdb_bank *b) {
 }
 
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused) {
-    if (fused && b->knn_table && b->row_offset == 0) {  // the bank's neighbour table: the w_dist pass is a lookup
+    if (fused && b->knn_table && b->row_offset == 0 && b->knn_rows == b->fin_rows) {  // the bank's neighbour table: the w_dist pass is a lookup
         CMDB_CHECK(score_select(b, B, P_img, true));
         reweight_lookup_kernel<<<B, 64, 0, b->stream>>>(b->knn_table, b->ss.m_test, b->data, b->dim, b->ss.s_key, b->ss.top3,
                                                         reinterpret_cast<TailResult *>(b->ss.tail));
@@ -1191,6 +1242,19 @@ int score_reweight(cmdb_bank *b, int B, int P_img, bool fused) {
             return CMDB_ERR_UNSUPPORTED;
     }
 #undef CMDB_RW
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
+int score_shard_lookup(cmdb_bank *b, int B, float *contrib_dev) {
+    shard_lookup_kernel<<<B, 64, 0, b->stream>>>(b->knn_table, b->ss.m_test, b->data, b->fin_rows, b->row_offset, b->dim, b->ss.top3,
+                                                 reinterpret_cast<TailResult *>(b->ss.tail), contrib_dev);
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
+int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev) {
+    shard_final_kernel<<<1, 64, 0, b->stream>>>(b->ss.top3, d2_sum_dev, b->dim, B, reinterpret_cast<TailResult *>(b->ss.tail));
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }

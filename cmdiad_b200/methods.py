@@ -88,8 +88,10 @@ class Features(torch.nn.Module):
     mean_from = {}
     std_from = {}
 
-    def __init__(self, args=None, device=0, feature_fn=None, parity_stats=False, bank_capacity_rows=None, verbose=False):
+    def __init__(self, args=None, device=0, feature_fn=None, parity_stats=False, bank_capacity_rows=None, verbose=False,
+                 device_head=True):
         super().__init__()
+        self.device_head = device_head
         self.args = args if args is not None else default_args()
         self.cuda_device = int(device)
         self.feature_fn = feature_fn
@@ -123,6 +125,8 @@ class Features(torch.nn.Module):
                                                      max_iter=self.args.ocsvm_maxiter)
         self.s_lib, self.s_map_lib = [], []
         self.coreset_idx = None
+        self._fusion = None
+        self._pinned = {}
 
     # ---- storage ---------------------------------------------------------------------------------------------
     def _patches(self, sample):
@@ -132,7 +136,9 @@ class Features(torch.nn.Module):
     def _append(self, modal, patch):
         patch = torch.as_tensor(patch, dtype=torch.float32)
         if modal not in self._banks:
-            cap = self.bank_capacity_rows or int(self.args.max_sample) * patch.shape[0]
+            # the reference's fit loop admits max_sample + 1 samples (cmdiad_runner.py:46-52: `flag += 1; if flag >
+            # self.count: break` after the append)
+            cap = self.bank_capacity_rows or (int(self.args.max_sample) + 1) * patch.shape[0]
             self._banks[modal] = Bank(patch.shape[1], cap, device=self.cuda_device)
         self._banks[modal].append(patch)
         if self.parity_stats is True:
@@ -165,6 +171,7 @@ class Features(torch.nn.Module):
         self.s_map_lib = torch.cat(self.s_map_lib, 0)
         self.detect_fuser.fit(self.s_lib)
         self.seg_fuser.fit(self.s_map_lib)
+        self._fusion = None  # the device-side head is rebuilt from the new coef_ / offset_ on first use
 
     # ---- features.py:360-425 -----------------------------------------------------------------------------------
     def get_coreset_idx_randomp(self, z_lib, n=1000, eps=0.90, coreset_dtype="FP16", force_cpu=False, lib=""):
@@ -193,7 +200,9 @@ class Features(torch.nn.Module):
                 print(f"   DONE.                 Transformed dim = ({bank.rows}, {c.shape[0]}).")
         except ValueError:
             print("   Error: could not project vectors. Please increase `eps`.")
-        idx = bank.coreset_select(n, csr, mode)
+        # n = int(f_coreset * rows) may be 0 for tiny banks: the reference's `range(n - 1)` loop is then empty and it
+        # returns [0] (features.py:372, 401, 425)
+        idx = bank.coreset_select(max(1, int(n)), csr, mode)
         return torch.from_numpy(idx)
 
     # ---- run_coreset: one implementation for the six variants ----------------------------------------------------
@@ -235,6 +244,7 @@ class Features(torch.nn.Module):
             # the w_dist top-3 of features.py:239-254 only depends on the bank -> precomputed per bank row
             self._banks[m].build_knn()
         self._host_copies = {m: [] for m in _MODALS}
+        self._fusion = None
 
     # ---- scoring of one sample: shared by late fusion and predict ------------------------------------------------
     score_modals = ()  # order of the columns of s / s_map
@@ -267,19 +277,47 @@ class Features(torch.nn.Module):
         self.s_map_lib.append(s_map)
 
     def predict(self, sample, mask, label, rgb_path):
-        self.compute_s_s_map(self._patches(sample), mask, label, rgb_path)
+        """one test image (cmdiad_runner.py:84).  device_head (default): normalisation, scoring, lambda scaling and the two
+        linear heads all run behind the ABI (predict_batch with one image); otherwise the mirror of the reference's
+        compute_s_s_map with sklearn's score_samples on the host."""
+        if self.device_head:
+            self.predict_batch([sample], [mask], [label], [rgb_path])
+        else:
+            self.compute_s_s_map(self._patches(sample), mask, label, rgb_path)
 
-    # ---- batch forms (SURVEY 8f): same per-image results, one cmdb_score_batch call per modality ------------------
+    # ---- batch forms (SURVEY 8f): same per-image results, one device call per batch ---------------------------------
+    def _stack(self, patch_dicts, m, slot=0):
+        """[B,P,D] batch of RAW patches of modality m: device samples are stacked on the device, host samples are gathered
+        into a reused pinned block (two alternating blocks, so that a pipelined caller may fill one while the other is
+        still being copied)"""
+        first = patch_dicts[0][m]
+        if first.is_cuda:
+            return torch.stack([pd[m] for pd in patch_dicts])
+        key = (m, len(patch_dicts), tuple(first.shape), slot)
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = self._pinned[key] = torch.empty((len(patch_dicts),) + tuple(first.shape), dtype=torch.float32).pin_memory()
+        for i, pd in enumerate(patch_dicts):
+            buf[i].copy_(pd[m])
+        return buf
+
+    def _set_query_norm(self, enabled):
+        for m in self._score_modals():
+            self._banks[m].set_query_norm(float(getattr(self, f"{m}_mean")), float(getattr(self, f"{m}_std")), enabled)
+
     def _score_samples(self, patch_dicts):
         """[(s [1,m], s_map [gt*gt,m])] for a list of samples: the reference's per-image loop (cmdiad_runner.py:58-65,
-        80-85) collapsed into one batched device call per modality"""
+        80-85) collapsed into one batched device call per modality; (patch - mean) / std runs on the device"""
         cols = []
-        for m in self._score_modals():
-            mean, std = getattr(self, f"{m}_mean"), getattr(self, f"{m}_std")
-            batch = torch.stack([(pd[m] - mean) / std for pd in patch_dicts])
-            side = int(math.sqrt(batch.shape[1]))
-            res = self._lib(m).bank.score_batch(batch, (side, side), out_hw=self.gt_size)
-            cols.append((getattr(self.args, f"{m}_s_lambda"), getattr(self.args, f"{m}_smap_lambda"), res))
+        self._set_query_norm(True)
+        try:
+            for m in self._score_modals():
+                batch = self._stack(patch_dicts, m)
+                side = int(math.sqrt(batch.shape[1]))
+                res = self._lib(m).bank.score_batch(batch, (side, side), out_hw=self.gt_size)
+                cols.append((getattr(self.args, f"{m}_s_lambda"), getattr(self.args, f"{m}_smap_lambda"), res))
+        finally:
+            self._set_query_norm(False)
         out = []
         for i in range(len(patch_dicts)):
             s = torch.tensor([[lam_s * torch.tensor(res[i].s[0]) for lam_s, _, res in cols]])
@@ -292,10 +330,55 @@ class Features(torch.nn.Module):
             self.s_lib.append(s)
             self.s_map_lib.append(s_map)
 
-    def predict_batch(self, samples, masks, labels, rgb_paths):
-        scored = self._score_samples([self._patches(x) for x in samples])
-        for (s, s_map), mask, label, path in zip(scored, masks, labels, rgb_paths):
-            self._record(s, s_map, mask, label, path)
+    def fusion(self):
+        """the fitted late-fusion head on the device: built once after run_late_fusion"""
+        if getattr(self, "_fusion", None) is None:
+            from .fusion import LateFusion
+            mods = self._score_modals()
+            self._fusion = LateFusion.from_sklearn([self._banks[m] for m in mods],
+                                                   [getattr(self.args, f"{m}_s_lambda") for m in mods],
+                                                   [getattr(self.args, f"{m}_smap_lambda") for m in mods],
+                                                   self.detect_fuser, self.seg_fuser)
+        return self._fusion
+
+    def predict_batch(self, samples, masks, labels, rgb_paths, keep_on_device=False):
+        """predict() for a list of samples with everything after the backbones on the device: normalisation, distance
+        GEMM, re-weighting, maps, lambda scaling and the two linear One-Class-SVM heads (multiple_features.py:976-994).
+        Batches larger than the per-call limit are pipelined (batch k + 1 is staged and submitted before the host waits
+        for batch k).  keep_on_device: the fused maps are also appended to the device-side result store (reserve it with
+        self.fusion().eval_reserve(n_images) first) for calculate_metrics_device."""
+        fus = self.fusion()
+        mods = self._score_modals()
+        step = fus.max_batch()
+        pds = [self._patches(x) for x in samples]
+        self._set_query_norm(True)
+        try:
+            pending = None
+            for k, b0 in enumerate(range(0, len(pds), step)):
+                chunk = pds[b0:b0 + step]
+                batches = [self._stack(chunk, m, slot=k & 1) for m in mods]
+                dims = [(int(math.sqrt(b.shape[1])),) * 2 for b in batches]
+                t = fus.score_batch_async(batches, dims, out_hw=self.gt_size, keep_on_device=keep_on_device)
+                if pending is not None:
+                    self._record_fused(pending[0].wait(), *pending[1])
+                pending = (t, (masks[b0:b0 + step], labels[b0:b0 + step], rgb_paths[b0:b0 + step]))
+            if pending is not None:
+                self._record_fused(pending[0].wait(), *pending[1])
+        finally:
+            self._set_query_norm(False)
+
+    def _record_fused(self, res, masks, labels, rgb_paths):
+        """result bookkeeping of multiple_features.py:996-1003 for a fused batch (per-image arrays, not scalar lists)"""
+        self.last_fused = res
+        for i in range(len(res)):
+            mask = torch.as_tensor(masks[i])
+            self.image_preds.append(res.s[i:i + 1].copy())
+            self.image_labels.append(labels[i])
+            self.pixel_preds.append(res.s_map[i].reshape(-1))
+            self.pixel_labels.append(mask.flatten().numpy())
+            self.predictions.append(res.s_map[i])
+            self.gts.append(mask.detach().cpu().squeeze().numpy())
+            self.img_name.append(rgb_paths[i])
 
     def compute_s_s_map(self, patches, mask, label, rgb_path=None):
         s, s_map = self._score_sample(patches)
@@ -322,6 +405,13 @@ class Features(torch.nn.Module):
         from . import metrics
         self.image_preds = np.stack(self.image_preds)
         self.image_labels = np.stack(self.image_labels)
+        self.img_name = np.stack(self.img_name)
+        if self.args.save_raw_results:  # features.py:316-318
+            import os
+            d = f"./visualization/{getattr(self.args, 'experiment_note', '')}"
+            os.makedirs(d, exist_ok=True)
+            txt_to_save = np.concatenate((self.image_preds, self.image_labels, self.img_name), axis=1)
+            np.savetxt(f"{d}/{self.class_name}_raw_results.csv", txt_to_save, delimiter=",", fmt="%s")
         self.pixel_preds = np.concatenate(self.pixel_preds) if len(self.pixel_preds) else np.zeros(0)
         self.pixel_labels = np.concatenate(self.pixel_labels) if len(self.pixel_labels) else np.zeros(0)
         self.image_rocauc = roc_auc_score(self.image_labels, self.image_preds)
@@ -331,20 +421,25 @@ class Features(torch.nn.Module):
 
     # ---- persistence of the fitted state (banks after run_coreset, statistics, late-fusion head) ----------------------
     def save_state(self, directory):
-        """after run_coreset (and optionally run_late_fusion): one .npz per bank + the scalars; load_state restores a
-        ready-to-predict object without re-running the coreset selection"""
+        """after run_coreset (and optionally run_late_fusion): one .npz per bank + the scalars + the parameters of the two
+        linear One-Class-SVM heads; load_state restores a ready-to-predict object without re-running the coreset selection.
+        Plain arrays only -- nothing in a state directory is unpickled."""
         import os
-        import pickle
         os.makedirs(directory, exist_ok=True)
         for m in self.bank_modals:
             self._banks[m].save(os.path.join(directory, f"bank_{m}.npz"), mean=np.float32(getattr(self, f"{m}_mean")),
                                 std=np.float32(getattr(self, f"{m}_std")))
-        with open(os.path.join(directory, "fusers.pkl"), "wb") as f:
-            pickle.dump({"detect": self.detect_fuser, "seg": self.seg_fuser, "coreset_idx": self.coreset_idx}, f)
+        heads = {}
+        for name, f in (("detect", self.detect_fuser), ("seg", self.seg_fuser)):
+            if hasattr(f, "coef_"):
+                heads[f"{name}_coef"] = np.asarray(f.coef_, np.float64)
+                heads[f"{name}_offset"] = np.asarray(f.offset_, np.float64)
+        if self.coreset_idx is not None:
+            heads["coreset_idx"] = np.asarray(self.coreset_idx, np.int64)
+        np.savez(os.path.join(directory, "heads.npz"), **heads)
 
     def load_state(self, directory):
         import os
-        import pickle
         for m in self.bank_modals:
             bank, meta = Bank.load(os.path.join(directory, f"bank_{m}.npz"), device=self.cuda_device,
                                    finalize=m in self._score_modals())
@@ -354,9 +449,14 @@ class Features(torch.nn.Module):
             setattr(self, f"{m}_mean", torch.tensor(np.float32(meta["mean"])))
             setattr(self, f"{m}_std", torch.tensor(np.float32(meta["std"])))
             setattr(self, f"patch_{m}_lib", DeviceLib(bank))
-        with open(os.path.join(directory, "fusers.pkl"), "rb") as f:
-            d = pickle.load(f)
-        self.detect_fuser, self.seg_fuser, self.coreset_idx = d["detect"], d["seg"], d["coreset_idx"]
+        with np.load(os.path.join(directory, "heads.npz"), allow_pickle=False) as d:
+            for name, f in (("detect", self.detect_fuser), ("seg", self.seg_fuser)):
+                if f"{name}_coef" in d.files:  # score_samples is linear: coef_ / offset_ are the whole fitted state
+                    f.coef_ = d[f"{name}_coef"].copy()
+                    f.offset_ = d[f"{name}_offset"].copy()
+                    f.n_features_in_ = int(f.coef_.reshape(-1).shape[0])
+            self.coreset_idx = torch.from_numpy(d["coreset_idx"].copy()) if "coreset_idx" in d.files else None
+        self._fusion = None
 
     def close(self):
         for b in self._banks.values():

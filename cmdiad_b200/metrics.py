@@ -34,7 +34,9 @@ def pro_curve(predictions, gts, num_thresholds=100):
     for i, c in enumerate(components):
         overlaps[i] = 1.0 - np.searchsorted(c, thr, side="right") / len(c)
     # `pro += overlap` over the components in order, then `/= len`: a sequential float64 sum
-    pros = (np.cumsum(overlaps, axis=0)[-1] if len(components) else np.zeros(len(thr))) / max(1, len(components))
+    if not components:  # the reference divides by len(ground_truth_components) (au_pro_util.py:192): same error here
+        raise ZeroDivisionError("float division by zero: no ground-truth component in any mask")
+    pros = np.cumsum(overlaps, axis=0)[-1] / len(components)
     fprs = np.concatenate([[1.0], fprs])[::-1]
     pros = np.concatenate([[1.0], pros])[::-1]
     return fprs, pros

@@ -43,3 +43,24 @@ def contribution(rows_local, row_offset, wanted_global_rows):
     ok = (loc >= 0) & (loc < rows_local.shape[0])
     out[ok] = rows_local[loc[ok]]
     return out
+
+
+def stage_slice(n_rows, world, rank):
+    """cooperative staging of a round's host queries (Bank._stage_sharded): rank r copies rows [lo, hi) over PCIe into
+    a `per`-row block (zero padded), the blocks are all-gathered and cut back to n_rows.  Returns (per, lo, hi)."""
+    per = (n_rows + world - 1) // world
+    return per, min(n_rows, rank * per), min(n_rows, (rank + 1) * per)
+
+
+def knn_d2_contribution(rows_local, row_offset, m_test, nn_global_rows):
+    """three-phase protocol with the replicated neighbour table (cmdb_score_shard_lookup): this shard's contribution to
+    ||m_test - bank[nn_k]||^2 -- the float32 squared distance for the neighbour rows it owns, 0 for the others.  A float
+    SUM all-reduce then yields the owner's value exactly (x + 0 + ... + 0)."""
+    nn = np.asarray(nn_global_rows, dtype=np.int64)
+    out = np.zeros(len(nn), dtype=np.float32)
+    loc = nn - row_offset
+    for k, l in enumerate(loc):
+        if 0 <= l < rows_local.shape[0]:
+            d = (np.asarray(m_test, np.float32) - rows_local[l]).astype(np.float32)
+            out[k] = np.float32(np.sum(d.astype(np.float64) ** 2))
+    return out

@@ -11,6 +11,12 @@
  *   - every function returns 0 on success or a negative cmdb_status; nothing throws across the ABI.
  *     cmdb_last_error() returns a thread-local, NUL-terminated description of the last failure on this thread.
  *   - `*_is_device` flags: 0 = the pointer is host memory (pageable or pinned), 1 = device memory on the bank's GPU.
+ *     ORDERING CONTRACT for device pointers: the library reads them on the handle's own non-blocking stream
+ *     (cmdb_bank_stream), which does NOT implicitly follow the caller's streams.  Before the call, the work that
+ *     produces the buffer must either be complete or be ordered before that stream (record an event on the producer
+ *     stream and cudaStreamWaitEvent it on cmdb_bank_stream; the Python wrapper does this with
+ *     stream.wait_stream(torch.cuda.current_stream()) + tensor.record_stream()).  The buffer must stay valid until the
+ *     call -- or, for submit / wait pairs, the matching wait -- has returned.
  *   - calls on one handle are serialised by the caller (the reference is single-threaded per method object); distinct
  *     handles may be used from different threads.  Each handle owns one CUDA stream; host-visible results are complete
  *     when the call returns.
@@ -96,6 +102,8 @@ int cmdb_bank_normalize(cmdb_bank *bank, float mean, float std);
 int cmdb_bank_gather(cmdb_bank *bank, const int64_t *idx_host, int64_t n);
 /* copies rows [row0, row0+n_rows) back to the host (to refill self.patch_*_lib, which features.py:238-283 index) */
 int cmdb_bank_read(cmdb_bank *bank, int64_t row0, int64_t n_rows, float *out_host);
+/* the same into DEVICE memory on the bank's GPU (e.g. to all-gather the shards of a row-sharded bank over NCCL) */
+int cmdb_bank_read_device(cmdb_bank *bank, int64_t row0, int64_t n_rows, float *out_device);
 /* Builds the scoring layout (fp16 hi/lo split, row norms) for the current rows. Must precede cmdb_score*. */
 int cmdb_bank_finalize(cmdb_bank *bank);
 /* the cudaStream_t every kernel of this handle is launched on (for event timing by the caller) */
@@ -109,6 +117,16 @@ int cmdb_bank_get_timings(cmdb_bank *bank, float *out_ms);
  * cmdb_score_batch is a lookup instead of a pass over the bank; results are unchanged.  Un-sharded banks only (the table
  * needs all rows on one GPU); freed by the next cmdb_bank_finalize. */
 int cmdb_bank_build_knn(cmdb_bank *bank);
+/* Row-sharded banks: the table itself is small (24 B per row: 4.8 MB at 200k rows, 96 MB at 4M), so every rank keeps a
+ * REPLICATED copy covering all global rows while the bank rows stay sharded.  Building it: gather the shards into a
+ * temporary un-sharded handle on every rank, cmdb_bank_build_knn_rows for the rows this rank owns (the R x R work is
+ * split evenly over the ranks), cmdb_bank_read_knn, all-gather the slices (any transport), cmdb_bank_set_knn_table on
+ * the sharded handle (Bank.build_knn_sharded does exactly this over NCCL).  Keys hold GLOBAL rows. */
+int cmdb_bank_build_knn_rows(cmdb_bank *bank, int64_t row_first, int64_t n_rows);
+int cmdb_bank_read_knn(cmdb_bank *bank, int64_t row_first, int64_t n_rows, uint64_t *out_keys /* [n_rows][3] */,
+                       int out_is_device);
+int cmdb_bank_set_knn_table(cmdb_bank *bank, const uint64_t *keys /* [n_rows_total][3] */, int64_t n_rows_total,
+                            int keys_is_device);
 /* statistics of the last scoring call on this handle (waits for the handle's stream): out6[0] = query rows, out6[1] = GEMM
  * mode that ran (0 / 1 / 3, see CMDB_OPT_PREFILTER_TERMS); mode 0 only: out6[2] = query rows the pre-filter could not
  * certify, out6[3] = (query, producer) pairs queued for the exact rescan, out6[4] = 1 if there were too many pairs and
@@ -137,7 +155,8 @@ int cmdb_coreset_select(cmdb_bank *bank, int64_t n_select, const int32_t *csr_in
  * mailbox_bytes >= cmdb_coreset_mailbox_bytes(world, d_proj_max).
  * cmdb_coreset_select_sharded: z0_host = the float64 projection of GLOBAL row 0 (cmdb_project on the owning rank,
  * broadcast by the caller); n_total_rows = rows of all shards; out_idx_host gets the same n_select GLOBAL rows on every
- * rank, bit-identical to the single-GPU cmdb_coreset_select on the un-sharded bank.  FP16 mode only in this version.
+ * rank, bit-identical to the single-GPU cmdb_coreset_select on the un-sharded bank.  Both dtype modes (FP16: one flagged
+ * 8-byte word per two halves of the exchanged row; float64: two flagged words per element).
  * All ranks must call it together (it waits for its peers inside the kernel, with a timeout).
  */
 int cmdb_comm_create(int device, int rank, int world, size_t mailbox_bytes, cmdb_comm **out);
@@ -233,6 +252,93 @@ int cmdb_score_shard_nn(cmdb_bank *bank, const int64_t *gathered_keys_device, in
                         float *nn_rows_contrib_device);
 int cmdb_score_shard_finish(cmdb_bank *bank, const float *nn_rows_device, int B, int P, int fh, int fw, int out_hw,
                             int img_first, int img_step, cmdb_score_out *outs);
+
+/*
+ * Query normalisation on the device: with enabled != 0 every scoring entry point of this handle takes RAW patches and
+ * applies (patch - mean) / std in float32 (one IEEE subtract, one IEEE divide == torch's CPU result) right after staging
+ * them, i.e. the first line of compute_s_s_map (multiple_features.py:90, 976-977) moves behind the ABI.
+ */
+int cmdb_bank_set_query_norm(cmdb_bank *bank, float mean, float std, int enabled);
+
+/*
+ * Late-fusion head on the device: what compute_s_s_map does after compute_single_s_s_map
+ * (multiple_features.py:986-994 and the five sibling classes) for up to 3 modalities:
+ *     s      = detect_fuser.score_samples([[lambda_s[0] * s_0, lambda_s[1] * s_1, ...]])
+ *     s_map  = seg_fuser.score_samples(stack_m(lambda_map[m] * s_map_m))            [out_hw^2], float64
+ * with SGDOneClassSVM.score_samples(X) = (X @ coef_ - offset_) + offset_ evaluated in float64 on the float32 products
+ * lambda * value exactly as sklearn does on the reference's float32 tensors (features.py:114-115, 352-358).
+ */
+typedef struct cmdb_fusion_head {
+    int n_modal;             /* columns of s / s_map = number of bank handles of the call (1..3), in column order */
+    float s_lambda[3];       /* args.{xyz,rgb,fusion}_s_lambda    (main.py:114-125) */
+    float smap_lambda[3];    /* args.{xyz,rgb,fusion}_smap_lambda */
+    double detect_coef[3];   /* detect_fuser.coef_ */
+    double detect_offset;    /* detect_fuser.offset_ */
+    double seg_coef[3];      /* seg_fuser.coef_ */
+    double seg_offset;       /* seg_fuser.offset_ */
+} cmdb_fusion_head;
+
+typedef struct cmdb_fused_out {
+    /* HOST buffers owned by the caller; NULL = not wanted */
+    double *s;        /* [1]        fused image score  (multiple_features.py:990) */
+    double *s_map;    /* [out_hw^2] fused pixel map    (multiple_features.py:992-994) */
+    float *s_modal;   /* [n_modal]  lambda_s[m] * s_m: the row add_sample_to_late_fusion_mem_bank appends to s_lib */
+    /* per-modality per-patch results, as in cmdb_score_out (optional) */
+    float *min_val[3];
+    int64_t *min_idx[3];
+} cmdb_fused_out;
+
+#define CMDB_FUSED_KEEP_ON_DEVICE 1u /* append the fused maps / scores to the handle's device-side result store (cmdb_eval_*) */
+#define CMDB_FUSED_NO_HOST_MAPS 2u   /* do not copy the fused maps to the host (outs[].s_map is ignored) */
+
+/*
+ * Scores B images against n_modal banks (one handle per modality, all on the same GPU; patches[m]: float32
+ * [B, P[m], dim_m]) and applies the late-fusion head.  The per-modality maps never leave HBM; per image one float64 map
+ * and one float64 score travel to the host.  submit / wait follow cmdb_score_batch_submit / _wait (two batches may be in
+ * flight; B <= the per-call limit of every bank); cmdb_score_fused_batch = submit + wait, any B.
+ * The ticket belongs to banks[0].
+ */
+int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *patches, const int *P, const int *fh,
+                                  const int *fw, int B, int out_hw, int patch_is_device, const cmdb_fusion_head *head,
+                                  unsigned flags, int64_t *out_ticket);
+int cmdb_score_fused_batch_wait(cmdb_bank *bank0, int64_t ticket, cmdb_fused_out *outs);
+int cmdb_score_fused_batch(cmdb_bank *const *banks, const float *const *patches, const int *P, const int *fh, const int *fw,
+                           int B, int out_hw, int patch_is_device, const cmdb_fusion_head *head, unsigned flags,
+                           cmdb_fused_out *outs);
+
+/*
+ * Device-side result store.  The reference extends Python lists by 50 176 scalars per test image
+ * (pixel_preds / predictions, multiple_features.py:996-1001) and evaluates them with sklearn / numpy on the host
+ * (features.py:321-324, utils/au_pro_util.py:157-224).  With CMDB_FUSED_KEEP_ON_DEVICE the fused float64 maps and image
+ * scores of every cmdb_score_fused_batch* call are appended, in call order, to a pre-allocated store on banks[0]'s GPU.
+ */
+int cmdb_eval_reserve(cmdb_bank *bank, int64_t n_images, int out_hw); /* (re)allocates and empties the store */
+int cmdb_eval_reset(cmdb_bank *bank);                                 /* empties it */
+int cmdb_eval_count(cmdb_bank *bank, int64_t *out_n_images);
+int cmdb_eval_read(cmdb_bank *bank, int64_t first, int64_t n, double *maps_host /* [n, out_hw^2] or NULL */,
+                   double *scores_host /* [n] or NULL */);
+
+/*
+ * Row-sharded scoring with the replicated neighbour table (cmdb_bank_set_knn_table): three phases and TWO small collectives
+ * per round, and a submit / wait finish so that two rounds can be in flight per handle (the result copy of round k and the
+ * host work for round k + 1 overlap the kernels of the other round; nothing synchronises the host between the phases):
+ *   1. cmdb_score_shard_min            as above                                                     -> all-reduce MIN (int64[B*P])
+ *   2. cmdb_score_shard_lookup         decodes the reduced keys (min_val, min_idx, s*, s_idx, m_star row), reads the three
+ *      nearest rows of m_star from the table and writes, per image, the exact SQUARED distances ||m_test - bank[nn_k]||^2
+ *      (k = 1, 2; features.py:275-283) for the neighbour rows this rank owns, 0 for the others     -> all-reduce SUM (float[B*2])
+ *   3. cmdb_score_shard_finish_submit  m_star_knn = sqrt(sum), w, s for all images; upsample + blur + device->host copy of
+ *      the maps of images img_first, img_first + img_step, ...; returns a ticket without waiting.
+ *      cmdb_score_shard_wait(ticket, outs[B]) blocks until the round is complete: every outs[i] gets the scalars and
+ *      per-patch arrays (replicated on all ranks), the maps are filled for the images this rank finished.
+ * Results are bit-identical to cmdb_score_batch on the un-sharded bank.
+ */
+int cmdb_score_shard_lookup(cmdb_bank *bank, const int64_t *reduced_keys_device, int B, int P, float *knn_d2_contrib_device);
+int cmdb_score_shard_finish_submit(cmdb_bank *bank, const float *knn_d2_sum_device, int B, int P, int fh, int fw, int out_hw,
+                                   int img_first, int img_step, unsigned want_maps, int64_t *out_ticket);
+int cmdb_score_shard_wait(cmdb_bank *bank, int64_t ticket, cmdb_score_out *outs);
+/* cudaMemcpyAsync(host -> device) on the handle's copy stream; everything enqueued on the handle afterwards sees the data.
+ * dst_device must not be in use by work queued earlier (double-buffer it across rounds). */
+int cmdb_bank_stage_h2d(cmdb_bank *bank, void *dst_device, const void *src_host, size_t bytes);
 
 /* Stand-alone score-map post-processing (features.py:293-295, utils/utils.py:71-83): map [fh*fw] -> [out_hw^2]. */
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host,

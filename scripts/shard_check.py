@@ -1,4 +1,8 @@
-"""torchrun --nproc-per-node N scripts/shard_check.py : row-sharded scoring == single-GPU scoring, bit for bit."""
+"""torchrun --nproc-per-node N scripts/shard_check.py : row-sharded scoring == single-GPU scoring, bit for bit.
+
+Covers both sharded protocols (five phases with the re-weighting sweep; three phases with the replicated neighbour
+table, pipelined rounds), replicated and distributed finishing, host and device queries, several rounds per call.
+Prints one line per check and a final SHARD CHECK OK / FAILED (rank 0); exit code 1 on failure."""
 import os
 import sys
 
@@ -22,33 +26,53 @@ shard.finalize()
 full = Bank(D, R, device=local)
 full.append(lib)
 full.finalize()
+full.build_knn()
+NAMES = ("min_idx", "min_val", "s", "s_star", "s_idx", "nn_idx", "m_star_knn", "w", "s_map")
 bad = 0
-# batch form: 5 images per round of collectives
-pb = np.stack([synth.patches(P, D, seed=80 + t, anomalous_frac=0.01, cent=cent) for t in range(5)])
-ab = shard.score_sharded_batch(pb, (28, 28), 224, full=True)
-bb = full.score_batch(pb, (28, 28), 224, full=True)
-for t in range(5):
-    same = all((getattr(ab[t], n) == getattr(bb[t], n)).all() for n in ("min_idx", "min_val", "s", "s_idx", "nn_idx", "s_map", "w"))
-    bad += int(not same)
-    if rank == 0:
-        print(f"batch image {t}: sharded == single-GPU: {same}", flush=True)
-# distributed finish: rank r returns only images r, r + world, ...
-dd = shard.score_sharded_batch(pb, (28, 28), 224, full=True, distribute=True)
-for t in range(5):
-    mine = t % world == rank
-    ok = (dd[t] is not None) == mine and (not mine or all((getattr(dd[t], n) == getattr(bb[t], n)).all() for n in ("min_idx", "s", "s_map", "nn_idx")))
+
+
+def same(a, b, names=NAMES):
+    return all((getattr(a, n) == getattr(b, n)).all() for n in names)
+
+
+def report(what, ok):
+    global bad
     bad += int(not ok)
-for t in range(3):
-    patch = synth.patches(P, D, seed=50 + t, anomalous_frac=0.01, cent=cent)
-    a = shard.score_sharded(patch, (28, 28), 224, full=True)
-    b = full.score(patch, (28, 28), 224, full=True)
-    same = ((a.min_idx == b.min_idx).all() and (a.min_val == b.min_val).all() and a.s[0] == b.s[0]
-            and int(a.s_idx[0]) == int(b.s_idx[0]) and (a.nn_idx == b.nn_idx).all() and (a.s_map == b.s_map).all())
-    bad += int(not same)
     if rank == 0:
-        print(f"image {t}: sharded == single-GPU: {same}; s={a.s[0]:.6f}/{b.s[0]:.6f} nn={a.nn_idx}/{b.nn_idx}", flush=True)
+        print(f"{what}: sharded == single-GPU: {ok}", flush=True)
+
+
+n_img = 70  # three rounds of <= 32 images
+pb = np.stack([synth.patches(P, D, seed=80 + t, anomalous_frac=0.01, cent=cent) for t in range(n_img)])
+bb = full.score_batch(pb, (28, 28), 224, full=True)
+for table in (False, True):
+    if table:
+        shard.build_knn_sharded()
+        keys_sh = shard.read_knn(0, R).numpy()
+        keys_1 = full.read_knn(0, R).numpy()
+        report("replicated neighbour table == single-GPU table", bool((keys_sh == keys_1).all()))
+    tag = "table/pipelined" if table else "five-phase"
+    for src_name, src in (("host", pb), ("device", torch.from_numpy(pb).cuda())):
+        ab = shard.score_sharded_batch(src, (28, 28), 224, full=True)
+        report(f"[{tag}] {n_img} images, {src_name} queries, replicated finish", all(same(ab[t], bb[t]) for t in range(n_img)))
+    dd = shard.score_sharded_batch(pb, (28, 28), 224, full=True, distribute=True)
+    ok = True
+    for t in range(n_img):
+        mine = t % world == rank
+        ok &= (dd[t] is not None) == mine and (not mine or same(dd[t], bb[t]))
+    report(f"[{tag}] distributed finish (rank r returns images r, r+{world}, ...)", ok)
+    if table:  # scalars of the images finished elsewhere are replicated
+        arr = shard.score_sharded_batch(pb[:5], (28, 28), 224, distribute=True)
+        ok = all(float(arr[0].s[0]) == float(bb[0].s[0]) for _ in range(1)) if rank == 0 else True
+        report(f"[{tag}] scalars available on every rank", ok)
+    for t in range(2):
+        a = shard.score_sharded(pb[t], (28, 28), 224, full=True)
+        report(f"[{tag}] single image {t}", same(a, bb[t]))
 t = torch.tensor([bad], device="cuda")
 dist.all_reduce(t)
 if rank == 0:
-    print("SHARD CHECK", "OK" if int(t) == 0 else f"FAILED on {int(t)} rank-images", flush=True)
+    print("SHARD CHECK", "OK" if int(t) == 0 else f"FAILED on {int(t)} rank-checks", f"(world {world})", flush=True)
+shard.close()
+full.close()
 dist.destroy_process_group()
+sys.exit(0 if int(t) == 0 else 1)

@@ -48,7 +48,8 @@ def test_rgb_features_fp16_pipeline_vs_oracle(env):
     m.predict({"rgb": test}, torch.zeros(1, 224, 224), 1, ["x.png"])
     patch = ((torch.from_numpy(test) - m.rgb_mean) / m.rgb_std).numpy()
     ref = O.score_restated(patch, lib[ref_idx], (28, 28), 224)
-    np.testing.assert_allclose(m.last_score.s[0], ref["s"], rtol=1e-4)
+    # predict() runs the late-fusion head on the device: last_fused.s_modal = lambda * s per modality
+    np.testing.assert_allclose(m.last_fused.s_modal[0, 0], np.float32(m.args.rgb_s_lambda) * ref["s"], rtol=1e-4)
     assert m.predictions[0].shape == (224, 224) and sum(len(a) for a in m.pixel_preds) == 224 * 224
     s_ref = m.detect_fuser.score_samples(np.array([[m.args.rgb_s_lambda * ref["s"]]]))
     np.testing.assert_allclose(m.image_preds[0], s_ref, rtol=1e-4)
@@ -155,6 +156,16 @@ def test_sharded_entry_points_with_one_rank(env):
         for i in range(3):
             for name in ("s", "s_idx", "min_val", "min_idx", "nn_idx", "m_star_knn", "w", "s_map"):
                 assert (getattr(a[i], name) == getattr(c[i], name)).all(), (i, name)
+        # replicated neighbour table + pipelined rounds (three phases, two collectives per round); 40 images = 2 rounds
+        b.build_knn_sharded()
+        many = np.stack([env["synth"].patches(784, 768, 170 + i, anomalous_frac=0.01, k=64) for i in range(40)])
+        a = b.score_sharded_batch(many, (28, 28), 224, full=True)
+        c = b.score_batch(many, (28, 28), 224, full=True)
+        d = b.score_sharded_batch(torch.from_numpy(many).cuda(), (28, 28), 224, full=True, distribute=True)
+        for i in range(40):
+            for name in ("s", "s_idx", "min_val", "min_idx", "nn_idx", "m_star_knn", "w", "s_map", "s_map_pre"):
+                assert (getattr(a[i], name) == getattr(c[i], name)).all(), (i, name)
+                assert (getattr(d[i], name) == getattr(c[i], name)).all(), (i, name)
         b.close()
     finally:
         dist.destroy_process_group()

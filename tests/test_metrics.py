@@ -71,9 +71,12 @@ def test_trapezoid_and_edge_cases():
     y03 = 0.6 + (0.9 - 0.6) * (0.3 - 0.2) / (0.5 - 0.2)
     np.testing.assert_allclose(metrics.trapezoid(x, y, x_max=0.3), full_to_02 + 0.5 * (0.6 + y03) * 0.1, rtol=1e-15)
     assert metrics.trapezoid(x, y, x_max=0.2) == metrics.trapezoid(x[:3], y[:3])
-    # no anomalous region at all: the curve is defined (all-zero PRO) instead of a ZeroDivisionError
+    # no anomalous region at all: the reference divides by the component count (au_pro_util.py:192) -> same error here
     gts, preds = [np.zeros((8, 8), np.float32)], [np.arange(64, dtype=np.float32).reshape(8, 8)]
-    v, (f, p) = metrics.au_pro(gts, preds)
-    assert v >= 0 and len(f) == 101 and p[0] == 0.0 and p[-1] == 1.0
+    with pytest.raises(ZeroDivisionError):
+        metrics.au_pro(gts, preds)
+    if R.reference_available():
+        with pytest.raises(ZeroDivisionError):
+            _reference_au_pro().calculate_au_pro(gts, preds)
     img, pix = metrics.image_and_pixel_rocauc([0, 1, 1, 0], [0.1, 0.9, 0.8, 0.3], [[0, 1], [1, 0]], [[0.2, 0.7], [0.9, 0.1]])
     assert img == 1.0 and pix == 1.0
