@@ -81,6 +81,39 @@ class DeviceLib:
         return self.bank.rows
 
 
+def coreset_idx_randomp(bank, n, eps=0.90, coreset_dtype="FP16", random_state=None, dist_method="l2", verbose=False):
+    """Features.get_coreset_idx_randomp (features.py:360-425) on a device bank: sklearn draws the sparse projection
+    matrix on the host exactly as the reference does, the projection and the whole greedy loop run on the GPU.
+    Returns a CPU LongTensor [n] of LOCAL rows with idx[0] == 0."""
+    if dist_method != "l2":
+        raise NotImplementedError  # l1 / dot / cos_dist branches of features.py:379-384 are out of scope
+    if coreset_dtype == "FP16":
+        mode = L.CORESET_FP16
+    elif coreset_dtype == "TF32":
+        mode = L.CORESET_FP64  # the reference only flips a matmul flag; its data stays float64
+    else:
+        raise NotImplementedError  # features.py:394-395
+    if verbose:
+        print(f"   Fitting random projections. Start dim = {(bank.rows, bank.dim)}.")
+    csr = None
+    try:
+        transformer = random_projection.SparseRandomProjection(eps=eps, random_state=random_state)
+        # fit() reads only X.shape / X.dtype; the reference's torch float32 input is validated to float64, so the
+        # components stay float64 with unsorted indices.  A zero-stride float64 dummy reproduces that (and consumes
+        # numpy's global RNG identically when random_state is None) without touching the bank.
+        transformer.fit(np.broadcast_to(np.zeros((1, 1)), (bank.rows, bank.dim)))
+        c = transformer.components_
+        csr = (c.indptr, c.indices, c.data, c.shape[0])
+        if verbose:
+            print(f"   DONE.                 Transformed dim = ({bank.rows}, {c.shape[0]}).")
+    except ValueError:
+        print("   Error: could not project vectors. Please increase `eps`.")
+    # n = int(f_coreset * rows) may be 0 for tiny banks: the reference's `range(n - 1)` loop is then empty and it returns
+    # [0] (features.py:372, 401, 425)
+    idx = bank.coreset_select(max(1, int(n)), csr, mode)
+    return torch.from_numpy(idx)
+
+
 class Features(torch.nn.Module):
     """Base class (features.py:21-121, hot-path attributes only)."""
     # per-class wiring, see the subclasses
@@ -176,34 +209,8 @@ class Features(torch.nn.Module):
     # ---- features.py:360-425 -----------------------------------------------------------------------------------
     def get_coreset_idx_randomp(self, z_lib, n=1000, eps=0.90, coreset_dtype="FP16", force_cpu=False, lib=""):
         """z_lib: DeviceLib (the normalised bank in HBM).  Returns a CPU LongTensor [n] with idx[0] == 0."""
-        if self.args.dist_method_coreset != "l2":
-            raise NotImplementedError  # l1 / dot / cos_dist branches of features.py:379-384 are out of scope
-        if coreset_dtype == "FP16":
-            mode = L.CORESET_FP16
-        elif coreset_dtype == "TF32":
-            mode = L.CORESET_FP64  # the reference only flips a matmul flag; its data stays float64
-        else:
-            raise NotImplementedError
-        bank = z_lib.bank
-        if self.verbose:
-            print(f"   Fitting random projections. Start dim = {tuple(z_lib.shape)}.")
-        csr = None
-        try:
-            transformer = random_projection.SparseRandomProjection(eps=eps, random_state=self.random_state)
-            # fit() reads only X.shape / X.dtype; the reference's torch float32 input is validated to float64, so the
-            # components stay float64 with unsorted indices.  A zero-stride float64 dummy reproduces that (and consumes
-            # numpy's global RNG identically when random_state is None) without touching the bank.
-            transformer.fit(np.broadcast_to(np.zeros((1, 1)), (bank.rows, bank.dim)))
-            c = transformer.components_
-            csr = (c.indptr, c.indices, c.data, c.shape[0])
-            if self.verbose:
-                print(f"   DONE.                 Transformed dim = ({bank.rows}, {c.shape[0]}).")
-        except ValueError:
-            print("   Error: could not project vectors. Please increase `eps`.")
-        # n = int(f_coreset * rows) may be 0 for tiny banks: the reference's `range(n - 1)` loop is then empty and it
-        # returns [0] (features.py:372, 401, 425)
-        idx = bank.coreset_select(max(1, int(n)), csr, mode)
-        return torch.from_numpy(idx)
+        return coreset_idx_randomp(z_lib.bank, n, eps, coreset_dtype, self.random_state, self.args.dist_method_coreset,
+                                   self.verbose)
 
     # ---- run_coreset: one implementation for the six variants ----------------------------------------------------
     def _normalised_modals(self):
