@@ -125,6 +125,7 @@ SYMBOLS = {
     "cmdb_eval_reset": (_I, [_VP]),
     "cmdb_eval_count": (_I, [_VP, c_i64_p]),
     "cmdb_eval_read": (_I, [_VP, _I64, _I64, _VP, _VP]),
+    "cmdb_eval_pixel_metrics": (_I, [_VP, _VP, _I64, _VP, _I, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64), c_i64_p, c_i64_p]),
 }
 # test hook exported by the library but deliberately not part of the public header
 DEBUG_SYMBOLS = {

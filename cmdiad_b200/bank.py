@@ -243,12 +243,13 @@ class Bank:
 
     def _order_after_producer(self, t):
         """Device inputs: the library reads `t` on the handle's own (non-blocking) stream, so that stream first has to
-        wait for whatever torch stream is producing it (ordering contract of `*_is_device = 1`, include/cmdiad_b200.h);
-        record_stream keeps torch's caching allocator from recycling the block while the handle still reads it."""
+        wait for whatever torch stream is producing it (ordering contract of `*_is_device = 1`, include/cmdiad_b200.h).
+        The tensor is kept alive by the caller / the ticket until the library has consumed it (synchronous calls return
+        after that point), so torch's caching allocator cannot recycle the block early; tensor.record_stream is
+        deliberately NOT used: it would make the allocator touch the handle's stream when the tensor dies, possibly after
+        the bank (and its stream) has been closed."""
         if isinstance(t, torch.Tensor) and t.is_cuda:
-            st = self.stream()
-            st.wait_stream(torch.cuda.current_stream(t.device))
-            t.record_stream(st)
+            self.stream().wait_stream(torch.cuda.current_stream(t.device))
         return t
 
     # ---- storage ---------------------------------------------------------------------------------------------

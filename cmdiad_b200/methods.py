@@ -426,6 +426,21 @@ class Features(torch.nn.Module):
         self.au_pro, _ = metrics.au_pro(self.gts, self.predictions)            # features.py:323
         self.au_pro_001, _ = metrics.au_pro(self.gts, self.predictions, 0.01)  # features.py:324
 
+    def calculate_metrics_device(self):
+        """calculate_metrics (features.py:302-324) with the pixel-level part on the GPU: the fused maps were kept in the
+        device-side result store by predict_batch(..., keep_on_device=True); one radix sort of all (score, label) pairs
+        yields the pixel AUROC and the counts behind both AU-PRO values (cmdb_eval_pixel_metrics).  au_pro / au_pro_001
+        are bit-identical to the host path, pixel_rocauc agrees to float64 rounding (exact U statistic vs sklearn's
+        trapezoids)."""
+        from . import metrics
+        self.image_preds = np.stack(self.image_preds)
+        self.image_labels = np.stack(self.image_labels)
+        self.image_rocauc = roc_auc_score(self.image_labels, self.image_preds)
+        r = metrics.device_pixel_metrics(self.fusion(), self.gts)
+        self.pixel_rocauc = r["pixel_rocauc"]
+        self.au_pro, self.au_pro_001 = r["au_pro"][0.3], r["au_pro"][0.01]
+        return r
+
     # ---- persistence of the fitted state (banks after run_coreset, statistics, late-fusion head) ----------------------
     def save_state(self, directory):
         """after run_coreset (and optionally run_late_fusion): one .npz per bank + the scalars + the parameters of the two

@@ -69,3 +69,53 @@ def image_and_pixel_rocauc(image_labels, image_preds, pixel_labels, pixel_preds)
     """features.py:314-319"""
     return (roc_auc_score(np.asarray(image_labels), np.asarray(image_preds)),
             roc_auc_score(np.asarray(pixel_labels).reshape(-1), np.asarray(pixel_preds).reshape(-1)))
+
+
+# ---- device-side evaluation (SURVEY 8f-3): cmdb_eval_pixel_metrics does the sorting / counting on the GPU ----------------
+def label_components(gts):
+    """scipy.ndimage.label with the 8-connectivity structure of au_pro_util.py:129 for every mask, numbered through the
+    whole set in image order.  Returns (int32 labels [n, H*W], n_components)."""
+    structure = np.ones((3, 3), dtype=int)
+    out, base = [], 0
+    for gt in gts:
+        labeled, n = label(np.asarray(gt), structure)
+        lab = labeled.astype(np.int32)
+        lab[lab > 0] += base
+        out.append(lab.reshape(-1))
+        base += n
+    return np.stack(out), base
+
+
+def pro_curve_from_counts(pos, n_ok, le_counts, sizes):
+    """the PRO curve of utils/au_pro_util.py:157-201 from exact integer counts (same float64 operations, same order)"""
+    if len(sizes) == 0:
+        raise ZeroDivisionError("float division by zero: no ground-truth component in any mask")
+    fprs = 1.0 - (pos + 1) / n_ok
+    overlaps = 1.0 - le_counts / sizes[:, None]                       # 1.0 - index / len(scores) per component
+    pros = np.cumsum(overlaps, axis=0)[-1] / len(sizes)               # pro += overlap in component order, then /= len
+    return np.concatenate([[1.0], fprs])[::-1], np.concatenate([[1.0], pros])[::-1]
+
+
+def device_pixel_metrics(fusion, gts, num_thresholds=100, limits=(0.3, 0.01)):
+    """pixel AUROC + AU-PRO (features.py:322-324) of the maps kept in `fusion`'s device-side result store (one per mask in
+    `gts`, in predict order).  Returns dict(pixel_rocauc, au_pro={limit: value}, curve=(fprs, pros))."""
+    import ctypes
+
+    from . import _lib as L
+    lib = L.load()
+    labels, n_comp = label_components(gts)
+    assert fusion.eval_count() == labels.shape[0], "one ground-truth mask per stored map"
+    labels = np.ascontiguousarray(labels)
+    n_ok = int((labels == 0).sum())
+    pos = np.linspace(0, n_ok - 1, num=num_thresholds, dtype=int).astype(np.int64)
+    thr = np.empty(num_thresholds, np.float64)
+    le = np.empty((max(1, n_comp), num_thresholds), np.int64)
+    sizes = np.empty(max(1, n_comp), np.int64)
+    two_u, n_pos, n_neg = ctypes.c_uint64(), ctypes.c_int64(), ctypes.c_int64()
+    L.check(lib.cmdb_eval_pixel_metrics(fusion.banks[0]._h, labels.ctypes.data, n_comp, pos.ctypes.data, num_thresholds,
+                                        thr.ctypes.data, le.ctypes.data, sizes.ctypes.data, ctypes.byref(two_u),
+                                        ctypes.byref(n_pos), ctypes.byref(n_neg)))
+    fprs, pros = pro_curve_from_counts(pos, n_ok, le[:n_comp], sizes[:n_comp])
+    auc = two_u.value / (2.0 * n_pos.value * n_neg.value) if n_pos.value and n_neg.value else float("nan")
+    return dict(pixel_rocauc=auc, au_pro={lim: trapezoid(fprs, pros, x_max=lim) / lim for lim in limits}, curve=(fprs, pros),
+                thresholds=thr, n_pos=n_pos.value, n_neg=n_neg.value)

@@ -15,7 +15,7 @@
  *     (cmdb_bank_stream), which does NOT implicitly follow the caller's streams.  Before the call, the work that
  *     produces the buffer must either be complete or be ordered before that stream (record an event on the producer
  *     stream and cudaStreamWaitEvent it on cmdb_bank_stream; the Python wrapper does this with
- *     stream.wait_stream(torch.cuda.current_stream()) + tensor.record_stream()).  The buffer must stay valid until the
+ *     stream.wait_stream(torch.cuda.current_stream()) and by holding the tensor until the call has consumed it).  The buffer must stay valid until the
  *     call -- or, for submit / wait pairs, the matching wait -- has returned.
  *   - calls on one handle are serialised by the caller (the reference is single-threaded per method object); distinct
  *     handles may be used from different threads.  Each handle owns one CUDA stream; host-visible results are complete
@@ -339,6 +339,25 @@ int cmdb_score_shard_wait(cmdb_bank *bank, int64_t ticket, cmdb_score_out *outs)
 /* cudaMemcpyAsync(host -> device) on the handle's copy stream; everything enqueued on the handle afterwards sees the data.
  * dst_device must not be in use by work queued earlier (double-buffer it across rounds). */
 int cmdb_bank_stage_h2d(cmdb_bank *bank, void *dst_device, const void *src_host, size_t bytes);
+
+/*
+ * Pixel-level evaluation of everything in the result store, on the device (features.py:321-324: pixel AUROC and the two
+ * AU-PRO values of utils/au_pro_util.py:104-224).  One stable radix sort of all (score, label) pairs, then:
+ *   out_two_u        exact integer 2U of the Mann-Whitney statistic (ties count 1/2): pixel AUROC = 2U / (2 n_pos n_neg),
+ *                    what sklearn's roc_auc_score computes by trapezoids;
+ *   out_thresholds   [n_thresholds] the anomaly-free scores at ranks ok_rank_pos_host[t] of their sorted order
+ *                    (np.linspace(0, n_ok - 1, num, dtype=int), au_pro_util.py:176);
+ *   out_component_le_counts [n_components][n_thresholds]  #{scores of ground-truth component c <= threshold t}
+ *                    (GroundTruthComponent.compute_overlap, :44-49), out_component_sizes [n_components].
+ * The counts are exact integers; the host finishes the PRO curve and its integral with the reference's own float64
+ * operations (cmdiad_b200/metrics.py), so au_pro / au_pro_001 are bit-identical to the reference.
+ * labels_host: int32 [n_images * out_hw^2], 0 = anomaly-free pixel, c in 1..n_components = pixel of ground-truth component
+ * c (scipy.ndimage.label per mask with the 8-connectivity structure of au_pro_util.py:129, numbered through the set in
+ * image order; the masks are host inputs of predict(), so labelling them stays on the host).
+ */
+int cmdb_eval_pixel_metrics(cmdb_bank *bank, const int32_t *labels_host, int64_t n_components, const int64_t *ok_rank_pos_host,
+                            int n_thresholds, double *out_thresholds, int64_t *out_component_le_counts,
+                            int64_t *out_component_sizes, uint64_t *out_two_u, int64_t *out_n_pos, int64_t *out_n_neg);
 
 /* Stand-alone score-map post-processing (features.py:293-295, utils/utils.py:71-83): map [fh*fw] -> [out_hw^2]. */
 int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int out_hw, float *out_host,

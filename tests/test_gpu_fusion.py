@@ -126,3 +126,37 @@ def test_bank_capacity_admits_max_sample_plus_one(env):
         m.add_sample_to_mem_bank({"rgb": env["synth"].patches(196, 768, 940 + i, k=64)})
     assert m._banks["rgb"].rows == 3 * 196
     m.close()
+
+
+def test_device_side_metrics_match_the_host_path(env):
+    """fused maps kept on the device, pixel AUROC + AU-PRO from one radix sort of (score, label) pairs
+    (cmdb_eval_pixel_metrics) against calculate_metrics on the host (sklearn roc_auc_score + the vectorised rewrite of
+    utils/au_pro_util.py, itself bit-identical to the reference module -- tests/test_metrics.py)."""
+    from cmdiad_b200 import RGBFeatures, default_args
+    sy = env["synth"]
+    train = [{"rgb": x} for x in sy.image_bank(4, 196, 768, 91, k=32)]
+    m = _fit(env, RGBFeatures, default_args(coreset_dtype="TF32", random_state=0, f_coreset=0.25), train, 4 * 196)
+    n_test = 12
+    g = np.random.Generator(np.random.PCG64(5))
+    tests, masks, labels = [], [], []
+    for i in range(n_test):
+        tests.append({"rgb": sy.patches(196, 768, 950 + i, anomalous_frac=0.05 if i % 2 else 0.0, k=32)})
+        mask = np.zeros((224, 224), np.float32)
+        for _ in range(i % 3):
+            cy, cx, r = g.integers(20, 200), g.integers(20, 200), g.integers(3, 15)
+            yy, xx = np.ogrid[:224, :224]
+            mask[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 1
+        if i == 4:
+            mask[5, 5] = mask[6, 6] = 1   # two pixels touching diagonally: one component under 8-connectivity
+        masks.append(torch.from_numpy(mask).view(1, 224, 224))
+        labels.append(int(mask.any()))
+    m.fusion().eval_reserve(n_test)
+    m.predict_batch(tests, masks, labels, [["t.png"]] * n_test, keep_on_device=True)
+    dev = m.calculate_metrics_device()
+    img_auc_dev = m.image_rocauc
+    au_dev, au001_dev, pix_dev = m.au_pro, m.au_pro_001, m.pixel_rocauc
+    m.calculate_metrics()   # host path over the same per-image arrays
+    assert m.au_pro == au_dev and m.au_pro_001 == au001_dev, (m.au_pro, au_dev, m.au_pro_001, au001_dev)
+    assert abs(m.pixel_rocauc - pix_dev) <= 1e-12 and m.image_rocauc == img_auc_dev
+    assert dev["n_pos"] == int(sum(float(k.sum()) for k in masks)) and dev["n_pos"] + dev["n_neg"] == n_test * 224 * 224
+    m.close()

@@ -80,3 +80,29 @@ def test_trapezoid_and_edge_cases():
             _reference_au_pro().calculate_au_pro(gts, preds)
     img, pix = metrics.image_and_pixel_rocauc([0, 1, 1, 0], [0.1, 0.9, 0.8, 0.3], [[0, 1], [1, 0]], [[0.2, 0.7], [0.9, 0.1]])
     assert img == 1.0 and pix == 1.0
+
+
+def test_pro_curve_from_integer_counts_equals_direct_evaluation():
+    """the host half of the device-side evaluation (metrics.device_pixel_metrics): given the exact integer counts the GPU
+    returns (emulated with numpy here), the curve and both integrals must equal the direct evaluation bit for bit"""
+    for seed, q in ((0, False), (1, True)):
+        gts, preds = _maps(seed, quantised=q)
+        preds = [p.astype(np.float64) for p in preds]
+        labels, n_comp = metrics.label_components(gts)
+        flat = np.stack([p.reshape(-1) for p in preds])
+        ok = np.sort(flat[labels == 0])
+        pos = np.linspace(0, len(ok) - 1, num=100, dtype=int)
+        thr = ok[pos]
+        le = np.stack([(flat[labels == c + 1][:, None] <= thr[None, :]).sum(0) for c in range(n_comp)])
+        sizes = np.array([(labels == c + 1).sum() for c in range(n_comp)])
+        fprs, pros = metrics.pro_curve_from_counts(pos, len(ok), le, sizes)
+        wf, wp = metrics.pro_curve(preds, gts)
+        assert (fprs == wf).all() and (pros == wp).all()
+        for lim in (0.3, 0.01):
+            assert metrics.trapezoid(fprs, pros, x_max=lim) / lim == metrics.au_pro(gts, preds, lim)[0]
+        # exact Mann-Whitney form of the pixel AUROC (what cmdb_eval_pixel_metrics returns as the integer 2U)
+        y, s = (labels > 0).reshape(-1), flat.reshape(-1)
+        neg = np.sort(s[~y])
+        two_u = int((np.searchsorted(neg, s[y], side="left") + np.searchsorted(neg, s[y], side="right")).sum())
+        from sklearn.metrics import roc_auc_score
+        assert abs(two_u / (2.0 * y.sum() * (~y).sum()) - roc_auc_score(y, s)) < 1e-12
