@@ -786,7 +786,7 @@ def dropin_leg(bank, imgs, B):
     masks = [torch.zeros(1, OUT_HW, OUT_HW)] * n_images
     out = {}
     for name, smp in (("host_samples", samples), ("device_samples", [{"rgb": s["rgb"].cuda()} for s in samples])):
-        m.predict_batch(smp[:B], masks[:B], [0] * B, [["w.png"]] * B)
+        m.predict_batch(smp, masks, [0] * n_images, [["w.png"]] * n_images)   # warm-up: pinned staging blocks, scratch
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         m.predict_batch(smp, masks, [0] * n_images, [["x.png"]] * n_images)

@@ -92,6 +92,7 @@ SYMBOLS = {
     "cmdb_comm_reset": (_I, [_VP]),
     "cmdb_comm_destroy": (None, [_VP]),
     "cmdb_coreset_mailbox_bytes": (ctypes.c_size_t, [_I, _I]),
+    "cmdb_coreset_comm_bytes": (ctypes.c_size_t, [_I, _I, _I64, _I]),
     "cmdb_coreset_select_sharded": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _VP, _I, _I, _VP, _VP]),
     "cmdb_project": (_I, [_VP, _VP, _VP, _VP, _I, _I64, _I64, _VP]),
     "cmdb_coreset_rownorms": (_I, [_I, _VP, _VP, _I64, _I, _I, _VP]),

@@ -32,27 +32,42 @@ class ScoreResult:
 
 
 class Comm:
-    """Peer mailboxes of this rank for the row-sharded coreset loop (CUDA IPC over NVLink, one process per GPU).
-    Collective constructor: every rank of `group` must create it together."""
+    """Peer-mapped buffer of this rank for the row-sharded coreset loop (CUDA IPC over NVLink, one process per GPU): key
+    slots for the per-pick exchange + a replica of the whole projected bank.  Collective constructor: every rank of
+    `group` must create it together; coreset_select_sharded grows it (collectively) when a bank needs more room."""
 
-    def __init__(self, device, d_proj_max=512, group=None):
+    def __init__(self, device, d_proj_max=512, group=None, rows_max=0, dtype_mode=L.CORESET_FP16):
         import torch.distributed as dist
         self._lib = L.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = int(device)
+        self.d_proj_max = int(d_proj_max)
         self._h = ctypes.c_void_p()
-        nbytes = self._lib.cmdb_coreset_mailbox_bytes(self.world, int(d_proj_max))
-        L.check(self._lib.cmdb_comm_create(int(device), self.rank, self.world, nbytes, ctypes.byref(self._h)))
+        self.bytes = 0
+        self._create(self._lib.cmdb_coreset_comm_bytes(self.world, int(d_proj_max), int(rows_max), int(dtype_mode)))
+
+    def _create(self, nbytes):
+        import torch.distributed as dist
+        self.close()
+        L.check(self._lib.cmdb_comm_create(self.device, self.rank, self.world, int(nbytes), ctypes.byref(self._h)))
         hb = self._lib.cmdb_comm_handle_bytes()
         mine = np.zeros(hb, np.uint8)
         L.check(self._lib.cmdb_comm_export(self._h, _ptr(mine)))
-        dev = torch.device("cuda", int(device))
+        dev = torch.device("cuda", self.device)
         gathered = torch.empty(self.world * hb, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, torch.from_numpy(mine).to(dev), group=group)
+        dist.all_gather_into_tensor(gathered, torch.from_numpy(mine).to(dev), group=self.group)
         handles = np.ascontiguousarray(gathered.cpu().numpy())
         L.check(self._lib.cmdb_comm_import(self._h, _ptr(handles)))
-        self.device = int(device)
-        self.d_proj_max = int(d_proj_max)
+        self.bytes = int(nbytes)
+
+    def ensure(self, nbytes):
+        """collective: every rank passes the same size"""
+        import torch.distributed as dist
+        if self.bytes < nbytes:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)   # nobody still uses the old mapping
+            self._create(nbytes)
 
     def reset_and_barrier(self):
         import torch.distributed as dist
@@ -63,6 +78,7 @@ class Comm:
         if getattr(self, "_h", None):
             self._lib.cmdb_comm_destroy(self._h)
             self._h = ctypes.c_void_p()
+            self.bytes = 0
 
     def __del__(self):
         try:
@@ -331,7 +347,7 @@ class Bank:
         bank; every rank calls this together and gets the same GLOBAL indices as the single-GPU coreset_select."""
         import torch.distributed as dist
         indptr, indices, data, d_proj = self._csr(csr)
-        assert d_proj <= comm.d_proj_max
+        comm.ensure(self._lib.cmdb_coreset_comm_bytes(comm.world, d_proj, int(n_total_rows), int(dtype_mode)))
         dev = torch.device("cuda", self.device)
         z0 = torch.zeros(d_proj, dtype=torch.float64, device=dev)
         if comm.rank == 0:  # rank 0 owns global row 0 (contiguous shards in rank order)

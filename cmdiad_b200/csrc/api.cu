@@ -217,12 +217,6 @@ int cmdb_project(cmdb_bank *b, const int32_t *indptr, const int32_t *indices, co
     return CMDB_OK;
 }
 
-// FP16: 16-byte key header + one 8-byte flagged word per two halves of the row
-// FP64: 32-byte key header (3 flagged words) + two 8-byte flagged words per element
-static unsigned int mailbox_slot_stride(int d, int dtype_mode = CMDB_CORESET_FP64) {
-    return dtype_mode == CMDB_CORESET_FP16 ? 16u + 8u * (unsigned int)((d + 1) / 2 + 1) : 32u + 16u * (unsigned int)(d + 1);
-}
-
 static int coreset_impl(cmdb_bank *b, int64_t n_select, const int32_t *indptr, const int32_t *indices, const double *data,
                         int d_proj, int dtype_mode, int64_t *out_idx_host, const int64_t *force_idx, void *out_min_last,
                         ShardCtx *sh = nullptr) {
@@ -268,7 +262,14 @@ int cmdb_coreset_select_debug(cmdb_bank *b, int64_t n_select, const int32_t *ind
 }
 
 size_t cmdb_coreset_mailbox_bytes(int world, int d_proj_max) {
-    return (size_t)2 * (size_t)(world > 0 ? world : 1) * mailbox_slot_stride(d_proj_max > 0 ? d_proj_max : 1);
+    (void)world, (void)d_proj_max;
+    return kCommHeaderBytes;  // flags + key slots; the replica of the projected bank follows (cmdb_coreset_comm_bytes)
+}
+
+size_t cmdb_coreset_comm_bytes(int world, int d_proj, int64_t n_total_rows, int dtype_mode) {
+    (void)world;
+    const size_t es = dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double);
+    return kCommHeaderBytes + es * (size_t)std::max<int64_t>(n_total_rows, 1) * (size_t)std::max(d_proj, 1) + 256;
 }
 
 int cmdb_coreset_select_sharded(cmdb_bank *b, cmdb_comm *comm, int64_t n_total_rows, int64_t n_select, const int32_t *indptr,
@@ -281,10 +282,10 @@ int cmdb_coreset_select_sharded(cmdb_bank *b, cmdb_comm *comm, int64_t n_total_r
     unsigned char *local = nullptr;
     CMDB_CHECK(comm_info(comm, &sh.rank, &sh.world, &local, sh.peers, &mb_bytes));
     sh.row_offset = b->row_offset, sh.n_total = n_total_rows, sh.z0_host = z0_host;
-    sh.slot_stride = mailbox_slot_stride(d_proj, dtype_mode);
-    CMDB_REQUIRE(mb_bytes >= cmdb_coreset_mailbox_bytes(sh.world, d_proj), CMDB_ERR_INVALID,
-                 "cmdb_coreset_select_sharded: mailbox has %zu bytes, need %zu", mb_bytes,
-                 cmdb_coreset_mailbox_bytes(sh.world, d_proj));
+    sh.comm_bytes = mb_bytes;
+    CMDB_REQUIRE(mb_bytes >= cmdb_coreset_comm_bytes(sh.world, d_proj, n_total_rows, dtype_mode), CMDB_ERR_INVALID,
+                 "cmdb_coreset_select_sharded: the peer buffer has %zu bytes, need %zu (cmdb_coreset_comm_bytes)", mb_bytes,
+                 cmdb_coreset_comm_bytes(sh.world, d_proj, n_total_rows, dtype_mode));
     CMDB_REQUIRE(b->row_offset + b->rows <= n_total_rows, CMDB_ERR_INVALID, "cmdb_coreset_select_sharded: shard exceeds n_total_rows");
     CMDB_CUDA(cudaSetDevice(b->device));
     return coreset_impl(b, n_select, indptr, indices, data, d_proj, dtype_mode, out_idx_host, nullptr, nullptr, &sh);

@@ -1,6 +1,8 @@
 // Peer mailboxes for the row-sharded coreset loop: every rank owns one device buffer that all ranks of the
 // box can write over NVLink (CUDA IPC mapping, one process per GPU).  The persistent coreset kernel uses it for the
 // per-pick exchange of (value,row) candidates and of the winning row itself -- no host launch, no NCCL call per pick.
+#include <algorithm>
+
 #include "common.cuh"
 
 struct cmdb_comm {
@@ -70,7 +72,8 @@ int cmdb_comm_import(cmdb_comm *c, const void *handles) {
 int cmdb_comm_reset(cmdb_comm *c) {
     CMDB_REQUIRE(c, CMDB_ERR_INVALID, "cmdb_comm_reset: comm is NULL");
     CMDB_CUDA(cudaSetDevice(c->device));
-    CMDB_CUDA(cudaMemset(c->local, 0, c->bytes));
+    // flags + key slots only: the replica region behind them is rewritten by every call anyway
+    CMDB_CUDA(cudaMemset(c->local, 0, std::min(c->bytes, kCommHeaderBytes)));
     CMDB_CUDA(cudaDeviceSynchronize());
     return CMDB_OK;
 }

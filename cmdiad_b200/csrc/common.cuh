@@ -85,6 +85,8 @@ struct ScoreScratch {
     int n_topk_blocks = 0;
     unsigned int *done_counter = nullptr;  // last-block-done counter of reweight_kernel
     float4 *cand = nullptr;         // [n_ctas, cap_p] per-CTA running top-2 (val1, idx1, val2, idx2) of the GEMM epilogue
+    size_t cand_window_bytes = 0;   // L2 access-policy window over cand (0 = persistence not available / disabled)
+    float cand_hit_ratio = 0.f;
     float *min_val = nullptr;       // [cap_p]
     long long *min_idx = nullptr;   // [cap_p]
     unsigned long long *s_key = nullptr;    // packed argmax key of min_val
@@ -213,11 +215,17 @@ int project_rows(cmdb_bank *b, const float *x_dev, int64_t n_rows, int D, const 
 int comm_info(cmdb_comm *c, int *rank, int *world, unsigned char **local, unsigned char **peers, size_t *bytes);
 
 // coreset.cu
+// layout of a rank's peer-mapped buffer (cmdb_comm): [0, 256) per-rank "shard arrived" flags | key slots
+// [parity][rank][CTA] x 32 B | at kCommHeaderBytes: replica of the whole projected bank in storage type
+constexpr unsigned int kCommReadyOff = 0;
+constexpr unsigned int kCommKeysOff = 256;
+constexpr unsigned int kCommMaxCtas = 192;
+constexpr size_t kCommHeaderBytes = 256 * 1024;  // >= 256 + 2 * kMaxRanks * kCommMaxCtas * 32
 struct ShardCtx {  // row-sharded coreset loop
     int world, rank;
     long long row_offset, n_total;
     unsigned char *peers[kMaxRanks];
-    unsigned int slot_stride;
+    size_t comm_bytes;
     const double *z0_host;  // float64 projection of global row 0
 };
 int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int64_t n_select, int dtype_mode,

@@ -275,10 +275,12 @@ struct CoresetParams {
     long long row_offset;
     int world, rank;
     unsigned char *mb_peer[kMaxRanks];  // mailbox of every rank (mb_peer[rank] is local memory)
-    unsigned int mb_slot_stride;        // bytes per (parity, source-rank) slot: 16-byte key header + row data
+    unsigned int mb_keys_off;           // byte offset of the key slots inside a mailbox: [parity][source rank][source CTA]
+    const void *z_full;                 // replica of the WHOLE projected bank [n_total, d] (storage type); local rows are a slice
     unsigned int *chunk_ctr;            // [3] dynamic scheduling: per-pick work counters (rotating, reset by CTA 0)
     int dynamic;                        // 1: warps pull 32-row chunks from a grid-wide queue instead of a static split
-    const void *last0;                  // [d] global row 0 in storage type (pick 1 measures distances to it)
+    unsigned int mb_ready_off;          // byte offset of the per-rank "shard has arrived in your replica" flags (8 bytes each)
+    unsigned long long ready_epoch;     // value those flags take for this call
     unsigned int *abort_flag;           // set when a peer did not answer in time
     long long spin_limit;               // clock64() ticks to wait for a peer
     size_t *l2_prev_limit;              // host side only: persisting-L2 carve-out found before the launch ...
@@ -331,7 +333,6 @@ template <typename T, int NV, bool DYN>
 __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p) {
     using acc_t = typename Traits<T>::acc_t;
     constexpr int RB = Batch<T>::rows;
-    constexpr unsigned int kMbHdr = sizeof(T) == 2 ? 16u : 32u;  // key header of a mailbox slot, then the row words
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: tile [kCsWarps][32][33] acc_t | last_sh [d] T | red (val,row) [32] | mind [rows_per_cta] T
     acc_t *tile_all = reinterpret_cast<acc_t *>(smem_raw);
@@ -386,46 +387,34 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
     const size_t rstride_b = (size_t)4 * d * sizeof(T);  // bytes between consecutive rows of this warp
 
     long long sel = 0;  // features.py:372 -- pick 0 is (global) row 0
-    int win_rank = 0;   // sharded mode: rank whose candidate won the previous pick
-    __shared__ unsigned long long xkey_sh;
-    __shared__ int abort_sh;
     if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[0] = 0;
+    if (p.world > 1) {
+        // the replica of the projected bank is complete once every rank's shard copy has landed: each rank's copy stream
+        // sets its flag in our mailbox right after its rows (stream order), so one poll per peer suffices
+        if (threadIdx.x < p.world) {
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(p.mb_peer[p.rank] + p.mb_ready_off) + threadIdx.x;
+            const long long t0 = clock64();
+            unsigned long long v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v == p.ready_epoch) break;
+                if (clock64() - t0 > p.spin_limit) {
+                    *p.abort_flag = 1u;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (ld_volatile(p.abort_flag)) return;
+    }
 
     for (long long pick = 1; pick < p.n_select; ++pick) {
         // ---- stage `last` = z[sel] in shared memory; owner CTA zeroes min_d[sel] (features.py:418-419) ----
         __syncthreads();
-        if (p.world > 1 && pick == 1) {
-            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = reinterpret_cast<const T *>(p.last0)[e];
-        } else if (p.world > 1) {
-            // sel is a GLOBAL row: its values are the winner's row words in the local mailbox (flagged with pick - 1)
-            const unsigned char *src = p.mb_peer[p.rank] + (size_t)(((pick - 1) & 1) * p.world + win_rank) * p.mb_slot_stride + kMbHdr;
-            const long long t0 = clock64();
-            auto wait_word = [&](int w2) {
-                unsigned long long word;
-                for (;;) {
-                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src + 8 * w2) : "memory");
-                    if ((word >> 32) == (unsigned long long)(unsigned int)(pick - 1)) break;
-                    if (clock64() - t0 > p.spin_limit) {  // reported through the key exchange of this pick
-                        *p.abort_flag = 1u;
-                        break;
-                    }
-                }
-                return word;
-            };
-            if constexpr (sizeof(T) == 2) {
-                for (int w2 = threadIdx.x; w2 < ((d + 1) >> 1); w2 += kCsThreads) {
-                    const unsigned long long word = wait_word(w2);
-                    last_sh[2 * w2] = Traits<T>::from_bits((unsigned short)(word & 0xffffu));
-                    if (2 * w2 + 1 < d) last_sh[2 * w2 + 1] = Traits<T>::from_bits((unsigned short)((word >> 16) & 0xffffu));
-                }
-            } else {  // float64: two flagged words per element (low half, high half)
-                for (int e = threadIdx.x; e < d; e += kCsThreads) {
-                    const unsigned long long lo = wait_word(2 * e) & 0xffffffffULL, hi = wait_word(2 * e + 1) & 0xffffffffULL;
-                    last_sh[e] = Traits<T>::from_bits64((hi << 32) | lo);
-                }
-            }
-        } else {
-            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(z + sel * d + e);
+        {
+            // sel is a GLOBAL row; row-sharded mode reads it from the local replica of the projected bank (no row exchange)
+            const T *zsel = p.world > 1 ? reinterpret_cast<const T *>(p.z_full) : z;
+            for (int e = threadIdx.x; e < d; e += kCsThreads) last_sh[e] = __ldg(zsel + sel * d + e);
         }
         {
             const long long sl = sel - p.row_offset;  // local row of the previous pick, if this shard owns it
@@ -561,6 +550,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
         }
         if (lane == 0) red_val[warp] = bv, red_row[warp] = br;
         __syncthreads();
+        long long argmax;
+        if (p.world == 1) {
         PickSlot *slots = p.slots + (pick & 1) * gridDim.x;
         if (warp == 0) {
             bv = lane < kCsWarps ? red_val[lane] : 0ULL;
@@ -614,100 +605,96 @@ __global__ void __launch_bounds__(kCsThreads, 1) coreset_kernel(CoresetParams p)
             const unsigned long long ov = red_val[w], orow = red_row[w];
             if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
         }
-        long long argmax = (long long)br;  // local row (or ~0 when this GPU has no rows)
-        if (p.world > 1) {
-            // ---- cross-GPU exchange: CTA 0 pushes this GPU's candidate key + row into every rank's mailbox (NVLink
-            //      stores), then every CTA polls its LOCAL mailbox for the keys of all ranks ----
-            // LL-style protocol: every 8-byte word carries its own flag (the pick number), so neither side needs a
-            // system-scope fence -- stores are fire-and-forget over NVLink and the receiver spins on the words it needs.
-            //   key word : [63:48] pick & 0xffff | [47:32] value (half bits) | [31:0] ~global_row
-            //   row words: [63:32] pick          | [31:0] two consecutive halves of the candidate row
-            const unsigned int slot = (unsigned int)((pick & 1) * p.world + p.rank) * p.mb_slot_stride;
-            const bool have = br != ~0ULL;
-            const unsigned long long grow = have ? (unsigned long long)(br + p.row_offset) : 0xffffffffULL;
-            if (blockIdx.x == 0) {
+        argmax = (long long)br;  // local row == global row
+        } else {
+            // ---- row-sharded: ONE flat exchange per pick.  Every CTA of every GPU writes its candidate key straight into
+            //      the mailboxes of all ranks (plain NVLink stores; the local rank's mailbox is written the same way), and
+            //      every CTA polls the world x grid keys in its LOCAL mailbox.  LL-style protocol: each 8-byte word carries
+            //      its own flag (the pick number), so neither side needs a system-scope fence, and slots are double-buffered
+            //      by pick parity.  No second hop: the winning row itself is read from the local replica next pick.
+            //        half  : one word   [63:48] pick & 0xffff | [47:32] value bits | [31:0] ~global_row
+            //        double: three words [63:32] pick | value low half / value high half / ~global_row
+            constexpr unsigned int kKeyBytes = sizeof(T) == 2 ? 8u : 32u;
+            const unsigned int n_cta = gridDim.x;
+            if (warp == 0) {
+                bv = lane < kCsWarps ? red_val[lane] : 0ULL;
+                br = lane < kCsWarps ? red_row[lane] : ~0ULL;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    unsigned long long ov = __shfl_xor_sync(0xffffffffu, bv, o), orow = __shfl_xor_sync(0xffffffffu, br, o);
+                    if (ov > bv || (ov == bv && orow < br)) bv = ov, br = orow;
+                }
+                const unsigned long long inv = br == ~0ULL ? 0ULL : 0xffffffffULL - (unsigned long long)(br + p.row_offset);
+                if (br == ~0ULL) bv = 0ULL;
+                const size_t slot = p.mb_keys_off + (size_t)(((pick & 1) * p.world + p.rank) * n_cta + blockIdx.x) * kKeyBytes;
                 if constexpr (sizeof(T) == 2) {
-                    const int n_words = (d + 1) >> 1;
-                    for (int w2 = threadIdx.x; w2 < n_words; w2 += kCsThreads) {
-                        unsigned int lo16 = 0, hi16 = 0;
-                        if (have) {
-                            lo16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2)) & 0xffffu;
-                            if (2 * w2 + 1 < d) hi16 = Traits<T>::bits(__ldg(z + (long long)br * d + 2 * w2 + 1)) & 0xffffu;
-                        }
-                        const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | (hi16 << 16) | lo16;
-                        for (int r = 0; r < p.world; ++r)
-                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + kMbHdr + 8 * w2), "l"(word) : "memory");
-                    }
-                    if (threadIdx.x < p.world) {
-                        const unsigned long long key = ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) |
-                                                       (0xffffffffULL - (grow & 0xffffffffULL));
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[threadIdx.x] + slot), "l"(key) : "memory");
+                    if (lane < p.world) {
+                        const unsigned long long key = ((unsigned long long)(pick & 0xffff) << 48) | ((bv & 0xffffULL) << 32) | inv;
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[lane] + slot), "l"(key) : "memory");
                     }
                 } else {
-                    // float64:  row words [63:32] pick | [31:0] low / high half of element w2 / 2
-                    //           key words 0..2: [63:32] pick | value low half, value high half, ~global_row
-                    for (int w2 = threadIdx.x; w2 < 2 * d; w2 += kCsThreads) {
-                        const unsigned long long bits = have ? Traits<T>::bits(__ldg(z + (long long)br * d + (w2 >> 1))) : 0ULL;
-                        const unsigned long long part = (w2 & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
-                        const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | part;
-                        for (int r = 0; r < p.world; ++r)
-                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + kMbHdr + 8 * w2), "l"(word) : "memory");
-                    }
-                    if (threadIdx.x < 3 * p.world) {
-                        const int r = threadIdx.x / 3, k = threadIdx.x % 3;
-                        const unsigned long long part = k == 0 ? (bv & 0xffffffffULL) : k == 1 ? (bv >> 32) : (0xffffffffULL - (grow & 0xffffffffULL));
+                    if (lane < 3 * p.world) {
+                        const int r = lane / 3, k = lane % 3;
+                        const unsigned long long part = k == 0 ? (bv & 0xffffffffULL) : k == 1 ? (bv >> 32) : inv;
                         const unsigned long long word = ((unsigned long long)(unsigned int)pick << 32) | part;
                         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.mb_peer[r] + slot + 8 * k), "l"(word) : "memory");
                     }
                 }
             }
-            if (warp == 0) {
-                unsigned long long kval = 0ULL, kinv = 0ULL;  // value bits and ~global_row of rank `lane`
-                int ok = 1;
-                if (lane < p.world) {
-                    const unsigned long long *kp = reinterpret_cast<const unsigned long long *>(
-                        p.mb_peer[p.rank] + (size_t)((pick & 1) * p.world + lane) * p.mb_slot_stride);
-                    const long long t0 = clock64();
-                    auto poll = [&](const unsigned long long *q, int shift, unsigned long long want) {
-                        unsigned long long w = 0ULL;
-                        for (;;) {
-                            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(q) : "memory");
-                            if ((w >> shift) == want) break;
-                            if (clock64() - t0 > p.spin_limit || ld_volatile(p.abort_flag)) {
-                                ok = 0;
-                                break;
-                            }
+            // poll the keys of all (rank, CTA) pairs in the local mailbox
+            unsigned long long kval = 0ULL, kinv = 0ULL;
+            int ok = 1;
+            {
+                const unsigned char *base = p.mb_peer[p.rank] + p.mb_keys_off + (size_t)((pick & 1) * p.world) * n_cta * kKeyBytes;
+                const long long t0 = clock64();
+                auto poll = [&](const unsigned char *q, int shift, unsigned long long want) {
+                    unsigned long long w = 0ULL;
+                    for (;;) {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(q) : "memory");
+                        if ((w >> shift) == want) break;
+                        if (clock64() - t0 > p.spin_limit || ld_volatile(p.abort_flag)) {
+                            ok = 0;
+                            break;
                         }
-                        return w;
-                    };
+                    }
+                    return w;
+                };
+                for (unsigned int k = threadIdx.x; k < (unsigned int)p.world * n_cta; k += kCsThreads) {
+                    unsigned long long ov, oi;
                     if constexpr (sizeof(T) == 2) {
-                        const unsigned long long key = poll(kp, 48, (unsigned long long)(pick & 0xffff));
-                        kval = (key >> 32) & 0xffffULL, kinv = key & 0xffffffffULL;
+                        const unsigned long long key = poll(base + (size_t)k * kKeyBytes, 48, (unsigned long long)(pick & 0xffff));
+                        ov = (key >> 32) & 0xffffULL, oi = key & 0xffffffffULL;
                     } else {
                         const unsigned long long want = (unsigned long long)(unsigned int)pick;
-                        const unsigned long long w0 = poll(kp, 32, want), w1 = poll(kp + 1, 32, want), w2 = poll(kp + 2, 32, want);
-                        kval = ((w1 & 0xffffffffULL) << 32) | (w0 & 0xffffffffULL), kinv = w2 & 0xffffffffULL;
+                        const unsigned char *q = base + (size_t)k * kKeyBytes;
+                        const unsigned long long w0 = poll(q, 32, want), w1 = poll(q + 8, 32, want), w2 = poll(q + 16, 32, want);
+                        ov = ((w1 & 0xffffffffULL) << 32) | (w0 & 0xffffffffULL), oi = w2 & 0xffffffffULL;
                     }
-                }
-                if (lane == 0 && ld_volatile(p.abort_flag)) ok = 0;
-                ok = __all_sync(0xffffffffu, ok);
-                int brank = lane;
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {  // kMaxRanks == 8 lanes: max value, ties -> lowest global row (largest ~row)
-                    const unsigned long long ov = __shfl_xor_sync(0xffffffffu, kval, o), oi = __shfl_xor_sync(0xffffffffu, kinv, o);
-                    const int or2 = __shfl_xor_sync(0xffffffffu, brank, o);
-                    if (ov > kval || (ov == kval && oi > kinv)) kval = ov, kinv = oi, brank = or2;
-                }
-                if (lane == 0) {
-                    xkey_sh = (kinv & 0xffffffffULL) | ((unsigned long long)brank << 32);
-                    abort_sh = !ok;
-                    if (!ok) *p.abort_flag = 1u;
+                    if (ov > kval || (ov == kval && oi > kinv)) kval = ov, kinv = oi;  // max value, ties -> lowest global row
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ov = __shfl_xor_sync(0xffffffffu, kval, o), oi = __shfl_xor_sync(0xffffffffu, kinv, o);
+                if (ov > kval || (ov == kval && oi > kinv)) kval = ov, kinv = oi;
+            }
+            ok = __all_sync(0xffffffffu, ok);
+            __syncthreads();  // red_* reads of the CTA stage are done
+            if (lane == 0) red_val[warp] = kval, red_row[warp] = kinv | (ok ? 0ULL : (1ULL << 63));
             __syncthreads();
-            if (abort_sh) return;  // every CTA of every rank reaches the same verdict within the timeout
-            win_rank = (int)(xkey_sh >> 32);
-            argmax = (long long)(0xffffffffULL - (xkey_sh & 0xffffffffULL));  // global row
+            kval = red_val[0], kinv = red_row[0] & 0xffffffffULL;
+            bool bad = (red_row[0] >> 63) != 0;
+#pragma unroll
+            for (int w = 1; w < kCsWarps; ++w) {
+                const unsigned long long ov = red_val[w], oi = red_row[w] & 0xffffffffULL;
+                bad |= (red_row[w] >> 63) != 0;
+                if (ov > kval || (ov == kval && oi > kinv)) kval = ov, kinv = oi;
+            }
+            if (bad) {  // a peer did not answer in time: every CTA of every rank reaches the same verdict within the timeout
+                if (threadIdx.x == 0) *p.abort_flag = 1u;
+                return;
+            }
+            argmax = (long long)(0xffffffffULL - kinv);  // global row
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) p.out_idx[pick] = argmax;
         sel = p.force_idx ? p.force_idx[pick] : argmax;
@@ -873,7 +860,7 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     cudaStream_t st = b->stream;
     long long *idx_dev = nullptr, *force_dev = nullptr;
     PickSlot *slots = nullptr;
-    __half *zh_alloc = nullptr, *last0_h = nullptr;
+    __half *zh_alloc = nullptr;
     double *z0_dev = nullptr;
     unsigned int *abort_dev = nullptr;
     void *mind = nullptr;
@@ -890,7 +877,7 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
             l2_changed = false;
         }
         cudaFree(idx_dev), cudaFree(force_dev), cudaFree(slots), cudaFree(zh_alloc), cudaFree(mind);
-        cudaFree(last0_h), cudaFree(z0_dev), cudaFree(abort_dev);
+        cudaFree(z0_dev), cudaFree(abort_dev);
     };
 #define CS_TRY(expr)                                                                                         \
     do {                                                                                                     \
@@ -921,31 +908,50 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
     p.l2_prev_limit = &l2_prev, p.l2_changed = &l2_changed;
     p.world = 1, p.rank = 0, p.row_offset = 0, p.abort_flag = abort_dev, p.spin_limit = 20LL * 1000 * 1000 * 1000;  // ~10 s
     const double *first_row = z_dev;  // pick 0 = global row 0
+    const size_t es = dtype_mode == CMDB_CORESET_FP16 ? sizeof(__half) : sizeof(double);
+    unsigned char *mine_in_replica = nullptr;  // this shard's rows inside the local replica of the projected bank
     if (sharded) {
-        p.world = sh->world, p.rank = sh->rank, p.row_offset = sh->row_offset, p.mb_slot_stride = sh->slot_stride;
+        p.world = sh->world, p.rank = sh->rank, p.row_offset = sh->row_offset;
+        p.mb_keys_off = kCommKeysOff, p.mb_ready_off = kCommReadyOff, p.ready_epoch = 1ULL;
         for (int r = 0; r < kMaxRanks; ++r) p.mb_peer[r] = sh->peers[r];
-        CS_TRY(cudaMalloc(&z0_dev, sizeof(double) * d));
+        CMDB_REQUIRE(b->num_sms <= (int)kCommMaxCtas, CMDB_ERR_UNSUPPORTED, "coreset: %d SMs exceed the mailbox layout", b->num_sms);
+        CS_TRY(cudaMalloc(&z0_dev, sizeof(double) * (d + 1)));
         CS_TRY(cudaMemcpyAsync(z0_dev, sh->z0_host, sizeof(double) * d, cudaMemcpyHostToDevice, st));
-        if (dtype_mode == CMDB_CORESET_FP16) {
-            CS_TRY(cudaMalloc(&last0_h, sizeof(__half) * d));
-            to_half_kernel<<<1, 512, 0, st>>>(z0_dev, d, last0_h);
-            CS_TRY(cudaGetLastError());
-            p.last0 = last0_h;
-        } else {
-            p.last0 = z0_dev;
-        }
+        CS_TRY(cudaMemcpyAsync(z0_dev + d, &p.ready_epoch, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         first_row = z0_dev;
+        p.z_full = sh->peers[sh->rank] + kCommHeaderBytes;
+        mine_in_replica = sh->peers[sh->rank] + kCommHeaderBytes + es * (size_t)sh->row_offset * d;
     }
+    // row-sharded: the kernel reads the local rows from the replica (the natural [n_total, d] layout, so address alignment ==
+    // global alignment class with no padding); every rank copies its slice into all peers' replicas over NVLink and then
+    // raises its flag there (stream order: the flag lands after the rows)
+    auto publish_shard = [&]() -> cudaError_t {
+        for (int r = 0; r < p.world; ++r) {
+            cudaError_t e = cudaSuccess;
+            if (r != p.rank)
+                e = cudaMemcpyAsync(sh->peers[r] + kCommHeaderBytes + es * (size_t)sh->row_offset * d, mine_in_replica,
+                                    es * (size_t)N * d, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(sh->peers[r] + kCommReadyOff + 8 * (size_t)p.rank, z0_dev + d, 8, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
     if (dtype_mode == CMDB_CORESET_FP16) {
-        const int pad = (int)((p.row_offset * d) & 3);  // keep address alignment == global alignment class
-        CS_TRY(cudaMalloc(&zh_alloc, sizeof(__half) * ((size_t)N * d + 4)));
-        __half *zh = zh_alloc + pad;
+        __half *zh;
+        if (sharded) {
+            zh = reinterpret_cast<__half *>(mine_in_replica);
+        } else {
+            CS_TRY(cudaMalloc(&zh_alloc, sizeof(__half) * ((size_t)N * d + 4)));
+            zh = zh_alloc;
+        }
         CS_TRY(cudaMalloc(&mind, sizeof(__half) * (size_t)std::max<int64_t>(N, 1)));
         // features.py:378 initial distances in float64, then .half() (:389-391)
         rc = launch_rownorm<double>(st, b->num_sms, z_dev, first_row, N, d, nullptr, reinterpret_cast<__half *>(mind), p.row_offset);
         if (rc == CMDB_OK) {
             to_half_kernel<<<b->num_sms * 4, 512, 0, st>>>(z_dev, (long long)N * d, zh);
             CS_TRY(cudaGetLastError());
+            if (sharded) CS_TRY(publish_shard());
             p.z = zh, p.mind = mind;
             rc = launch_coreset<__half>(b, p);
         }
@@ -954,6 +960,11 @@ int coreset_greedy_dev(cmdb_bank *b, const double *z_dev, int64_t N, int d, int6
         rc = launch_rownorm<double>(st, b->num_sms, z_dev, first_row, N, d, reinterpret_cast<double *>(mind), nullptr, p.row_offset);
         if (rc == CMDB_OK) {
             p.z = z_dev, p.mind = mind;
+            if (sharded) {
+                CS_TRY(cudaMemcpyAsync(mine_in_replica, z_dev, es * (size_t)N * d, cudaMemcpyDeviceToDevice, st));
+                CS_TRY(publish_shard());
+                p.z = mine_in_replica;
+            }
             rc = launch_coreset<double>(b, p);
         }
     }

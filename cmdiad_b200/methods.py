@@ -300,13 +300,15 @@ class Features(torch.nn.Module):
         first = patch_dicts[0][m]
         if first.is_cuda:
             return torch.stack([pd[m] for pd in patch_dicts])
-        key = (m, len(patch_dicts), tuple(first.shape), slot)
+        key = (m, tuple(first.shape), slot)
         buf = self._pinned.get(key)
-        if buf is None:
-            buf = self._pinned[key] = torch.empty((len(patch_dicts),) + tuple(first.shape), dtype=torch.float32).pin_memory()
+        if buf is None or buf.shape[0] < len(patch_dicts):
+            # pinned allocations cost tens of milliseconds: one block per (modality, slot), sized for the largest batch
+            cap = max(len(patch_dicts), 32)
+            buf = self._pinned[key] = torch.empty((cap,) + tuple(first.shape), dtype=torch.float32).pin_memory()
         for i, pd in enumerate(patch_dicts):
             buf[i].copy_(pd[m])
-        return buf
+        return buf[:len(patch_dicts)]
 
     def _set_query_norm(self, enabled):
         for m in self._score_modals():

@@ -148,15 +148,19 @@ int cmdb_coreset_select(cmdb_bank *bank, int64_t n_select, const int32_t *csr_in
 
 /*
  * Row-sharded coreset selection over the GPUs of one NVSwitch box (one process per GPU).  Every rank holds a
- * contiguous block of bank rows (cmdb_bank_set_row_offset) and runs the same persistent kernel on its shard; per pick
- * the ranks exchange their local (value,row) candidate AND the candidate row through peer-mapped mailboxes (CUDA IPC
- * over NVLink) from inside the kernel -- there is no host round trip and no NCCL call per pick.  Setup, once:
- *   cmdb_comm_create on every rank -> cmdb_comm_export -> all-gather the handles (any host transport) -> cmdb_comm_import.
- * mailbox_bytes >= cmdb_coreset_mailbox_bytes(world, d_proj_max).
+ * contiguous block of bank rows (cmdb_bank_set_row_offset) and runs the same persistent kernel on its shard.  The ranks
+ * share through peer-mapped buffers (CUDA IPC over NVLink, one per rank):
+ *   - a REPLICA of the whole projected bank in the loop's storage type (half: 2 * n_total * d' bytes -- 120 MB at
+ *     200k x 301, 3 GB at 4M x 375), filled once per call: every rank copies its projected slice into all peers' replicas;
+ *   - key slots [parity][rank][CTA]: per pick every CTA of every GPU stores its candidate (value, global row) as
+ *     self-flagged 8-byte words straight into all ranks' slots and polls the world x CTAs keys of its LOCAL buffer -- one
+ *     NVLink hop per pick, no system-scope fence, no NCCL call, no host round trip; the winning row is then read from the
+ *     local replica.
+ * Setup, once:  cmdb_comm_create on every rank -> cmdb_comm_export -> all-gather the handles (any host transport) ->
+ * cmdb_comm_import.  mailbox_bytes >= cmdb_coreset_comm_bytes(world, d_proj, n_total_rows, dtype_mode).
  * cmdb_coreset_select_sharded: z0_host = the float64 projection of GLOBAL row 0 (cmdb_project on the owning rank,
  * broadcast by the caller); n_total_rows = rows of all shards; out_idx_host gets the same n_select GLOBAL rows on every
- * rank, bit-identical to the single-GPU cmdb_coreset_select on the un-sharded bank.  Both dtype modes (FP16: one flagged
- * 8-byte word per two halves of the exchanged row; float64: two flagged words per element).
+ * rank, bit-identical to the single-GPU cmdb_coreset_select on the un-sharded bank, in both dtype modes.
  * All ranks must call it together (it waits for its peers inside the kernel, with a timeout).
  */
 int cmdb_comm_create(int device, int rank, int world, size_t mailbox_bytes, cmdb_comm **out);
@@ -166,7 +170,8 @@ int cmdb_comm_import(cmdb_comm *comm, const void *handles /* [world][cmdb_comm_h
 /* clears the local mailbox; every rank calls it, then the ranks barrier, before each cmdb_coreset_select_sharded */
 int cmdb_comm_reset(cmdb_comm *comm);
 void cmdb_comm_destroy(cmdb_comm *comm);
-size_t cmdb_coreset_mailbox_bytes(int world, int d_proj_max);
+size_t cmdb_coreset_mailbox_bytes(int world, int d_proj_max); /* flags + key slots only */
+size_t cmdb_coreset_comm_bytes(int world, int d_proj, int64_t n_total_rows, int dtype_mode); /* + the replica */
 int cmdb_coreset_select_sharded(cmdb_bank *bank, cmdb_comm *comm, int64_t n_total_rows, int64_t n_select,
                                 const int32_t *csr_indptr, const int32_t *csr_indices, const double *csr_data, int d_proj,
                                 int dtype_mode, const double *z0_host, int64_t *out_idx_host);

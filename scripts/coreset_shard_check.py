@@ -1,4 +1,6 @@
-"""torchrun --nproc-per-node N scripts/coreset_shard_check.py : row-sharded coreset == single-GPU coreset == oracle."""
+"""torchrun --nproc-per-node N scripts/coreset_shard_check.py : row-sharded coreset == single-GPU coreset, both dtype modes.
+
+Prints one line per case and CORESET SHARD CHECK OK / FAILED (rank 0); exit code 1 on failure."""
 import os
 import sys
 import time
@@ -17,7 +19,9 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 comm = Comm(local, d_proj_max=512)
 ok_all = True
-for (N, D, n, seed) in ((7841, 768, 500, 3), (30011, 768, 300, 4), (200_000, 768, 2000, 5)):
+for (N, D, n, seed, mode) in ((7841, 768, 500, 3, L.CORESET_FP16), (7841, 768, 500, 3, L.CORESET_FP64),
+                              (30011, 768, 300, 4, L.CORESET_FP16), (30011, 1152, 300, 6, L.CORESET_FP64),
+                              (200_000, 768, 2000, 5, L.CORESET_FP16), (200_000, 768, 500, 5, L.CORESET_FP64)):
     from sklearn import random_projection
     tr = random_projection.SparseRandomProjection(eps=0.9, random_state=0)
     tr.fit(np.broadcast_to(np.zeros((1, 1)), (N, D)))
@@ -29,17 +33,18 @@ for (N, D, n, seed) in ((7841, 768, 500, 3), (30011, 768, 300, 4), (200_000, 768
     lo, hi = shard_range(N, rank, world)
     shard = Bank(D, hi - lo, device=local, row_offset=lo)
     shard.append(lib[lo:hi])
+    shard.coreset_select_sharded(comm, N, 16, csr, mode)  # warm-up: module load, peer-buffer growth
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    idx_sh = shard.coreset_select_sharded(comm, N, n, csr)
+    idx_sh = shard.coreset_select_sharded(comm, N, n, csr, mode)
     t_sh = time.perf_counter() - t0
     full = Bank(D, N, device=local)
     full.append(lib)
-    full.coreset_select(16, csr)
+    full.coreset_select(16, csr, mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    idx_1 = full.coreset_select(n, csr)
+    idx_1 = full.coreset_select(n, csr, mode)
     t_1 = time.perf_counter() - t0
     same = bool((idx_sh == idx_1).all())
     t = torch.tensor([int(same)], device="cuda")
@@ -47,11 +52,13 @@ for (N, D, n, seed) in ((7841, 768, 500, 3), (30011, 768, 300, 4), (200_000, 768
     ok_all &= bool(int(t))
     if rank == 0:
         first = np.nonzero(idx_sh != idx_1)[0][:1]
-        print(f"N={N} d'={csr[3]} n={n}: sharded({world}) == single: {bool(int(t))} (first diff {first}); "
-              f"{t_sh * 1e6 / n:.1f} us/pick sharded vs {t_1 * 1e6 / n:.1f} us/pick single", flush=True)
+        print(f"N={N} D={D} d'={csr[3]} n={n} {'FP16' if mode == L.CORESET_FP16 else 'FP64'}: sharded({world}) == single: "
+              f"{bool(int(t))} (first diff {first}); {t_sh * 1e6 / n:.1f} us/pick sharded vs {t_1 * 1e6 / n:.1f} us/pick single",
+              flush=True)
     shard.close()
     full.close()
 if rank == 0:
-    print("CORESET SHARD CHECK", "OK" if ok_all else "FAILED", flush=True)
+    print("CORESET SHARD CHECK", "OK" if ok_all else "FAILED", f"(world {world})", flush=True)
 comm.close()
 dist.destroy_process_group()
+sys.exit(0 if ok_all else 1)

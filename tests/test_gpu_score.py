@@ -318,18 +318,15 @@ def test_rescan_tier_under_load(env):
     b.close()
 
 
-def test_prefilter_error_model(env):
-    """The certificate rests on (a) Cauchy-Schwarz bounds of the fp16 operand rounding -- mathematics -- and (b) a model
-    of the tensor-core accumulation error, (D/16 + 1) * 17 * 2^-23 * ||q_hi|| ||b_hi||.  (b) is measured here: the GEMM
-    epilogue's values are compared with a float64 evaluation of the same fp16 operands."""
+def _measure_error_model(env, lib, patch, fm):
+    """(accumulation error / model, total error / certificate bound) of the pre-filter GEMM's epilogue values, measured
+    against a float64 evaluation of the same fp16 operands; also returns the bank for further checks"""
     import ctypes
-    from cmdiad_b200 import synth
-    D, R, P = 768, 20000, 784
-    lib = synth.patches(R, D, seed=91)
-    patch = synth.patches(P, D, seed=92, anomalous_frac=0.02)
+    R, D = lib.shape
+    P = patch.shape[0]
     b = _bank(env, lib)
     b.set_prefilter_terms(1)
-    b.score(patch, (28, 28), 224)
+    b.score(patch, (fm, fm), 224)
     n_cta = 296   # producers = (CTA, accumulator column half)
     cand = np.zeros((n_cta, P, 4), np.float32)
     rc = b._lib.cmdb_debug_read_candidates(b._h, cand.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_cta), ctypes.c_int(P))
@@ -339,10 +336,11 @@ def test_prefilter_error_model(env):
     ok = idx >= 0
     assert ok.any()
     # the fp16 operands exactly as the library builds them (power-of-two scales, round to nearest even)
-    eb = 13 - int(np.frexp(np.abs(lib).max())[1])
-    bh = (lib * np.float32(2.0 ** eb)).astype(np.float16).astype(np.float64) * 2.0 ** -eb
-    eq = 13 - np.frexp(np.abs(patch).max(1))[1].astype(np.int64)
-    qh = (patch * (2.0 ** eq)[:, None].astype(np.float32)).astype(np.float16).astype(np.float64) * (2.0 ** -eq)[:, None]
+    with np.errstate(over="ignore", under="ignore"):
+        eb = 13 - int(np.frexp(np.abs(lib).max())[1])
+        bh = (lib * np.float32(2.0 ** eb)).astype(np.float16).astype(np.float64) * 2.0 ** -eb
+        eq = 13 - np.frexp(np.abs(patch).max(1))[1].astype(np.int64)
+        qh = (patch * (2.0 ** eq)[:, None].astype(np.float32)).astype(np.float16).astype(np.float64) * (2.0 ** -eq)[:, None]
     bn = (lib.astype(np.float64) ** 2).sum(1).astype(np.float32).astype(np.float64)
     qhn, bhn = np.linalg.norm(qh, axis=1), np.linalg.norm(bh, axis=1)
     worst_acc, worst_total = 0.0, 0.0
@@ -364,9 +362,71 @@ def test_prefilter_error_model(env):
         E = 2 * (qe[qs] * (bmax + ebmax) + qn[qs] * ebmax + acc_model * (qn[qs] + qe[qs]) * (bmax + ebmax)) \
             + (D + 16) * 2.0 ** -24 * (qn[qs] + bmax) ** 2
         worst_total = max(worst_total, float((np.abs(val[c, qs] + qn[qs] ** 2 - exact) / E).max()))
+    return worst_acc, worst_total, b
+
+
+def test_prefilter_error_model(env):
+    """The certificate rests on (a) Cauchy-Schwarz bounds of the fp16 operand rounding -- mathematics -- and (b) a model
+    of the tensor-core accumulation error, (D/16 + 1) * 17 * 2^-23 * ||q_hi|| ||b_hi||.  (b) is measured here: the GEMM
+    epilogue's values are compared with a float64 evaluation of the same fp16 operands."""
+    from cmdiad_b200 import synth
+    D, R, P = 768, 20000, 784
+    lib = synth.patches(R, D, seed=91)
+    patch = synth.patches(P, D, seed=92, anomalous_frac=0.02)
+    worst_acc, worst_total, b = _measure_error_model(env, lib, patch, 28)
     print(f"accumulation error / model = {worst_acc:.4f}, total error / certificate bound = {worst_total:.4f}")
     assert worst_acc < 0.25, worst_acc      # the model keeps >= 4x margin over what the hardware does
     assert worst_total < 0.5, worst_total
+    b.close()
+
+
+def _adversarial(kind, R, P, D, seed):
+    """inputs built to stress the certificate: the accumulation model is empirical, so it is probed
+    where alignment / truncation inside the tensor core hurts most"""
+    g = np.random.Generator(np.random.PCG64(seed))
+    if kind == "wide_range":      # 2^-14 .. 1 inside every row: small addends are aligned against large partial sums
+        lib = g.standard_normal((R, D), dtype=np.float32) * np.exp2(-14 * g.random((R, D), dtype=np.float32))
+        patch = g.standard_normal((P, D), dtype=np.float32) * np.exp2(-14 * g.random((P, D), dtype=np.float32))
+    elif kind == "subnormal_residue":  # one spike per row: everything else lands in fp16's subnormal range after scaling
+        lib = g.standard_normal((R, D), dtype=np.float32) * np.float32(3e-8)
+        patch = g.standard_normal((P, D), dtype=np.float32) * np.float32(3e-8)
+        lib[np.arange(R), g.integers(0, D, R)] = g.choice([-1.0, 1.0], R).astype(np.float32)
+        patch[np.arange(P), g.integers(0, D, P)] = g.choice([-1.0, 1.0], P).astype(np.float32)
+    elif kind == "cancelling":    # products alternate in sign and cancel: a.b ~ 0 with |a||b| large
+        half = D // 2
+        x = g.standard_normal((P, half), dtype=np.float32) + 3
+        y = g.standard_normal((R, half), dtype=np.float32) + 3
+        patch = np.concatenate([x, -x], 1)[:, g.permutation(D)]
+        lib = np.concatenate([y, y * (1 + 1e-3 * g.standard_normal((R, half), dtype=np.float32))], 1)[:, g.permutation(D)]
+        patch = np.ascontiguousarray(patch, dtype=np.float32)
+        lib = np.ascontiguousarray(lib, dtype=np.float32)
+    elif kind == "near_duplicates":   # many rows within float32 noise of each other: the band never empties
+        base = g.standard_normal((R // 8, D), dtype=np.float32)
+        lib = np.repeat(base, 8, 0) * (1 + 1e-6 * g.standard_normal((R, 1), dtype=np.float32))
+        patch = base[g.integers(0, R // 8, P)] + 1e-3 * g.standard_normal((P, D), dtype=np.float32)
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(lib, np.float32), np.ascontiguousarray(patch, np.float32)
+
+
+@pytest.mark.parametrize("D", [768, 1920])
+@pytest.mark.parametrize("kind", ["wide_range", "subnormal_residue", "cancelling", "near_duplicates"])
+def test_certificate_under_adversarial_inputs(env, kind, D):
+    """mode 0 (certified pre-filter, tensor cores) must equal the exact CUDA-core scan bit for bit on inputs chosen to
+    break an optimistic accumulation model, and the measured error must stay below half of the certificate's bound"""
+    L = env["L"]
+    R, P, fm = 6000, 256, 16
+    lib, patch = _adversarial(kind, R, P, D, seed=sum(map(ord, kind)) + D)
+    worst_acc, worst_total, b = _measure_error_model(env, lib, patch, fm)
+    print(f"{kind} D={D}: accumulation error / model = {worst_acc:.4f}, total error / certificate bound = {worst_total:.4f}")
+    assert worst_acc < 0.5 and worst_total < 0.5, (worst_acc, worst_total)
+    b.set_prefilter_terms(0)
+    cert = b.score(patch, (fm, fm), 224)
+    stats = b.score_stats()
+    b.set_score_impl(L.SCORE_SIMT)
+    exact = b.score(patch, (fm, fm), 224)
+    assert (cert.min_idx == exact.min_idx).all() and (cert.min_val == exact.min_val).all(), (kind, D, stats)
+    assert (cert.s_map == exact.s_map).all() and cert.s[0] == exact.s[0] and (cert.nn_idx == exact.nn_idx).all()
     b.close()
 
 
