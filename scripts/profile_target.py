@@ -11,13 +11,19 @@ import bench  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "score"
 torch.cuda.set_device(0)
-bank = bench.build_bank(0, 1)
+bank = bench.build_bank(0, bench.BANK_ROWS, 0)
 if what == "score":
     bank.finalize()
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     patches = torch.stack(bench.test_patches(B)).cuda()
+    bank.build_knn()
+    bank.score_batch(patches, (28, 28), 224)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()   # ncu --profile-from-start off: only the calls below are visible to the profiler
     for i in range(3):
         bank.score_batch(patches, (28, 28), 224)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 else:
     from sklearn import random_projection
     tr = random_projection.SparseRandomProjection(eps=0.9, random_state=0)

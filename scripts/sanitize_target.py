@@ -41,4 +41,24 @@ r2 = b.score(p[0], (14, 14), 64)
 print("score ok", r[0].s, r2.s)
 out, pre, u8 = upsample_blur(np.abs(p[0][:, :1].reshape(14, 14)) + 1, 64)
 print("blur ok", out.shape)
+# round 2: query normalisation + late-fusion head + device-side result store + pixel metrics (radix sort) on two banks
+from cmdiad_b200 import metrics  # noqa: E402
+from cmdiad_b200.fusion import LateFusion  # noqa: E402
+b.set_score_impl(L.SCORE_TCGEN05)
+b2 = Bank(D, 600)
+b2.append(lib[:600] * 1.5)
+b2.finalize()
+b2.build_knn()
+b.set_query_norm(0.1, 1.3, True)
+b2.set_query_norm(-0.2, 0.9, True)
+fus = LateFusion([b, b2], [1.0, 0.1], [1.0, 0.1], [0.8, 0.9], [2.0], [0.7, 1.1], [3.0])
+fus.eval_reserve(6, 64)
+for _ in range(2):
+    rf = fus.score_batch([p, p * 0.5], [(14, 14), (14, 14)], 64, keep_on_device=True, want_patch=True)
+gts = [np.zeros((64, 64), np.float32) for _ in range(6)]
+gts[1][10:20, 10:20] = 1
+gts[4][40:44, 30:50] = 1
+ev = metrics.device_pixel_metrics(fus, gts)
+print("fused + eval ok", rf.s, ev["pixel_rocauc"], ev["au_pro"])
 b.close()
+b2.close()

@@ -48,6 +48,23 @@ def full(rep, out, title):
         for i, h in enumerate(hdr):
             if h in KEYS:
                 f.write(f"{h:92s} {units[i]:16s} {vals[i]}\n")
+    return {h: (units[i], vals[i]) for i, h in enumerate(hdr)}
+
+
+def to_bytes(unit, val):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    return float(val.replace(",", "")) * scale
+
+
+def gemm_traffic(metrics, images, source, out="profiles/gemm_traffic.json"):
+    """bench.py reads roofline.traffic from this file: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the
+    dominant kernel, from the ncu --set full capture named in `source`"""
+    import json
+    rd = to_bytes(*metrics["dram__bytes_read.sum"])
+    wr = to_bytes(*metrics["dram__bytes_write.sum"])
+    json.dump({"kernel": metrics["Kernel Name"][1], "images_per_launch": images, "dram_bytes_read": rd, "dram_bytes_write": wr,
+               "duration_ms_under_ncu": to_bytes("byte", metrics["gpu__time_duration.sum"][1]) * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}[metrics["gpu__time_duration.sum"][0]],
+               "source": source}, open(out, "w"), indent=1)
 
 
 if __name__ == "__main__":
@@ -60,4 +77,7 @@ if __name__ == "__main__":
                        ("prof_coreset", "ncu --set full --clock-control none, coreset_kernel<__half,3>, 200k x 301, 300 picks"),
                        ("prof_reweight", "ncu --set full --clock-control none, reweight_kernel<6>, batch of 16, 200k x 768 bank")):
         if os.path.exists(f"{g}/{rep}.ncu-rep"):
-            full(f"{g}/{rep}.ncu-rep", f"profiles/{TAG}_{rep}.txt", title)
+            m = full(f"{g}/{rep}.ncu-rep", f"profiles/{TAG}_{rep}.txt", title)
+            if rep == "prof_gemm":
+                gemm_traffic(m, 16, f"profiles/{TAG}_prof_gemm.txt (gpurun_out/prof_gemm.ncu-rep: ncu --set full --clock-control none "
+                                    f"-k regex:score_gemm -s 1 -c 1 python scripts/profile_target.py score 16)")
