@@ -613,6 +613,35 @@ int cmdb_debug_read_candidates(cmdb_bank *b, float *out_host, int n_cta, int n_q
     return CMDB_OK;
 }
 
+// test hook (not in the public header): exact float32 scan of the whole bank with the arithmetic of the re-check kernels
+// (warp_sqdist, lowest row on ties) -- what the certified pre-filter must reproduce bit for bit
+int cmdb_debug_exact_min(cmdb_bank *b, const float *patch_host, int P, float *min_val_out, int64_t *min_idx_out) {
+    CMDB_REQUIRE(b && patch_host && min_val_out && min_idx_out && P >= 1 && b->finalized, CMDB_ERR_INVALID, "cmdb_debug_exact_min: bad arguments");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    float *q = nullptr;
+    unsigned long long *keys = nullptr;
+    std::vector<unsigned long long> h((size_t)P);
+    cudaError_t e = cudaMalloc(&q, sizeof(float) * (size_t)P * b->dim);
+    if (e == cudaSuccess) e = cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)P);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, patch_host, sizeof(float) * (size_t)P * b->dim, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * (size_t)P, b->stream);
+    int rc = CMDB_OK;
+    if (e == cudaSuccess) rc = score_exact_scan(b, q, P, keys);
+    if (e == cudaSuccess && rc == CMDB_OK) e = cudaMemcpyAsync(h.data(), keys, sizeof(unsigned long long) * (size_t)P, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess && rc == CMDB_OK) e = cudaStreamSynchronize(b->stream);
+    cudaFree(q), cudaFree(keys);
+    if (rc != CMDB_OK) return rc;
+    CMDB_CUDA(e);
+    for (int i = 0; i < P; ++i) {
+        const unsigned int bits = (unsigned int)(h[i] >> 32);
+        float d2;
+        memcpy(&d2, &bits, sizeof(d2));
+        min_val_out[i] = sqrtf(d2);
+        min_idx_out[i] = (int64_t)(h[i] & 0xffffffffULL) + b->row_offset;
+    }
+    return CMDB_OK;
+}
+
 // host-only test hooks (not in the public header): the GEMM's tile-schedule stride and the fallback-tier rule
 int cmdb_debug_tile_stride(int mt, int G) { return score_tile_stride(mt, G); }
 int cmdb_debug_fallback_use_rescan(int fails, int pairs) { return fallback_use_rescan(fails, pairs) ? 1 : 0; }

@@ -268,6 +268,7 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand);
 int score_select(cmdb_bank *b, int B, int P_img, bool local_m_star);
 int score_reweight(cmdb_bank *b, int B, int P_img, bool fused);
 int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count);
+int score_exact_scan(cmdb_bank *b, const float *q_dev, int P, unsigned long long *keys_dev);
 int score_shard_lookup(cmdb_bank *b, int B, float *contrib_dev);
 int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev);
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B);

@@ -293,6 +293,31 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
     }
 }
 
+// test hook: the exact scan the certificate promises equality with -- every (query, bank row) distance by warp_sqdist, smallest
+// (d^2 bits, row) key per query.  grid (row chunks, query groups of 8); one warp per query.
+__global__ void __launch_bounds__(256) exact_scan_kernel(const float *__restrict__ q, int P, const float *__restrict__ bank,
+                                                         long long rows, int dim, long long chunk,
+                                                         unsigned long long *__restrict__ best_key) {
+    const int lane = threadIdx.x & 31, qi = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (qi >= P) return;
+    const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+    unsigned long long key = ~0ULL;
+    for (long long r = r0; r < r1; ++r) {
+        const float d2 = warp_sqdist(q + (size_t)qi * dim, bank + (size_t)r * dim, dim >> 2, lane);
+        const unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)r;
+        key = kk < key ? kk : key;
+    }
+    if (lane == 0 && key != ~0ULL) atomicMin(best_key + qi, key);
+}
+
+int score_exact_scan(cmdb_bank *b, const float *q_dev, int P, unsigned long long *keys_dev) {
+    const long long chunk = std::max<long long>(64, (b->fin_rows + 4 * b->num_sms - 1) / (4 * b->num_sms));
+    const int gx = (int)((b->fin_rows + chunk - 1) / chunk);
+    exact_scan_kernel<<<dim3(gx, (P + 7) / 8), 256, 0, b->stream>>>(q_dev, P, b->data, b->fin_rows, b->dim, chunk, keys_dev);
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
 __global__ void rescan_finish_kernel(const int *__restrict__ fail_list, const int *__restrict__ count_ptr,
                                      const unsigned long long *__restrict__ best_key, int P_img, long long row_offset,
                                      float *__restrict__ min_val, long long *__restrict__ min_idx, unsigned long long *s_key) {
