@@ -73,6 +73,7 @@ struct ScoreScratch {
     int *fail_count_host = nullptr; // pinned copy of [0..1] (statistics / adaptive mode)
     bool sched_pair = false;            // the last first-pass GEMM ran on CTA pairs (cta_group::2)
     bool sched_pair_last = false;       // ... and the most recent GEMM launch of any kind
+    int sched_run_last = 1;             // N tiles per visit (score_gemm_run) of the most recent GEMM launch
     int chunk_tiles = 0, mt_total = 0;  // M-tile layout of the last first-pass GEMM: chunks of chunk_tiles tiles (rescan needs it)
     int2 *work_list = nullptr;      // [kWorkCap] (query row, producer) pairs whose producer may hide rows inside the band
     unsigned long long *best_key = nullptr;  // [cap_p] running exact (d^2 bits << 32 | row) of the uncertified queries
@@ -250,6 +251,7 @@ int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_c
 void q_split_rows(cmdb_bank *b, const float *rows_dev, int n);
 int score_gemm_groups();              // epilogue warp groups per CTA: producers = groups * CTAs
 int score_tile_stride(int mt, int G); // host copy of the GEMM's tile schedule stride
+int score_gemm_run(int nt, int mt_units, int G);  // N tiles per visit of an M tile for a launch of that shape
 // stage the queries (src: host or device, [B*P_img, dim]) + candidates + refine, all modes
 // stage_after: event the copy stream waits for before it overwrites q_f32 (nullptr: everything queued so far)
 int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine,

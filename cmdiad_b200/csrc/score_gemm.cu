@@ -267,6 +267,8 @@ struct GemmParams {
     int b_scale_exp;
     float4 *cand;       // [gridDim.x][cand_stride]: CTA c keeps its running top-2 of query row q at cand[c*cand_stride + q]
     int cand_stride;    // >= mt * 128
+    int run;            // consecutive N tiles a unit processes for one M tile before it moves on: the running top-2 stays
+                        // in registers across the run, so the lists are read / written once per RUN tiles (see score_gemm_run)
 };
 
 template <int TERMS, int EG, int CG>
@@ -289,6 +291,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
     const int unit = (int)blockIdx.x / CG, n_units = (int)gridDim.x / CG;  // scheduling unit = CTA or CTA pair
     const int mt_units = (p.mt + CG - 1) / CG;
     const int stride = tile_stride(mt_units, n_units);
+    const int nruns = (p.nt + p.run - 1) / p.run;  // the schedule deals (run of N tiles, M tile) pairs instead of single tiles
     // barriers: full[S::kStages], empty[S::kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
     // (pair: full[] and tmem_empty[] are only used in the leader, rank 0; empty[] and tmem_full[] exist in both CTAs and
     // are signalled by the leader's multicast commits)
@@ -332,8 +335,9 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, p.nt);) {
-                const int n = it.n, m = it.m * CG + rank;
+            for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, nruns);) {
+              const int m = it.m * CG + rank;
+              for (int n = it.n * p.run, n_end = min(p.nt, n + p.run); n < n_end; ++n) {
                 const int a_row = (p.m_base + m) * BM, b_row = n * BN + rank * (BN / CG);
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -358,6 +362,7 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
                     }
                     if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
+              }
             }
         }
     } else if (warp == 1) {
@@ -366,7 +371,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int j = 0;
-            for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, p.nt); ++j) {
+            for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, nruns);)
+              for (int n = it.n * p.run, n_end = min(p.nt, n + p.run); n < n_end; ++n, ++j) {
                 const int buf = j & 1;
                 mbar_wait(bar_tempty + 8 * buf, ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -427,25 +433,28 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             }
         };
         int j = 0;
-        for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, p.nt); ++j) {
-            const int n = it.n, m_tile = it.m * CG + rank;
-            const bool valid = m_tile < p.mt;    // odd M-tile count: the pair's last second tile does not exist
-            const int m_local = p.m_base + m_tile;
+        for (TileIter it(unit, n_units, mt_units, stride); it.next(mt_units, nruns);) {
+          const int m_tile = it.m * CG + rank;
+          const bool valid = m_tile < p.mt;    // odd M-tile count: the pair's last second tile does not exist
+          const int m_local = p.m_base + m_tile;
+          float c = 0.f;
+          // running top-2 of this producer for its query row: loaded once per run of N tiles, carried in registers
+          Top2 ta{INFINITY, INFINITY, -1, -1};
+          if (valid) {
+              // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
+              c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + m_local * BM + row)));
+              const float4 st = my_state[m_local * BM + row];
+              ta = Top2{st.x, st.z, __float_as_int(st.y), __float_as_int(st.w)};
+          }
+          for (int n = it.n * p.run, n_end = min(p.nt, n + p.run); n < n_end; ++n, ++j) {
             const int buf = j & 1;
             float *bn = bnorm_s + buf * BN;
             // bank norms of this N tile (buffer `buf` was last read two tiles ago, before that tile's tmem_empty arrive)
 #pragma unroll
             for (int g = 0; g < 2 / EG; ++g) bn[et + g * 128 * EG] = __ldg(p.bnorm + (size_t)n * BN + et + g * 128 * EG);
-            float c = 0.f;
-            Top2 ta{INFINITY, INFINITY, -1, -1}, tb{INFINITY, INFINITY, -1, -1};
-            if (valid) {
-                // -2 * 2^-(e_bank + e_query_row): undoes the operand scaling and applies the -2 of ||a-b||^2
-                c = ldexpf(-2.f, -(p.b_scale_exp + __ldg(p.q_scale_exp + m_local * BM + row)));
-                // two independent running top-2 lists (even / odd columns) halve the dependent min/select chain; list A
-                // continues this producer's state for the query, list B starts empty and is merged into A after the tile
-                const float4 st = my_state[m_local * BM + row];
-                ta = Top2{st.x, st.z, __float_as_int(st.y), __float_as_int(st.w)};
-            }
+            // two independent running top-2 lists (even / odd columns) halve the dependent min/select chain; list A
+            // continues this producer's state for the query, list B starts empty and is merged into A after the tile
+            Top2 tb{INFINITY, INFINITY, -1, -1};
             mbar_wait(bar_tfull + 8 * buf, (j >> 1) & 1);
             tc_fence_after();
             asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");  // bn[] visible to all epilogue warps
@@ -471,7 +480,8 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_const
             }
             top2_insert(ta, tb.b1, tb.i1);
             top2_insert(ta, tb.b2, tb.i2);
-            my_state[m_local * BM + row] = make_float4(ta.b1, __int_as_float(ta.i1), ta.b2, __int_as_float(ta.i2));
+          }
+          if (valid) my_state[m_local * BM + row] = make_float4(ta.b1, __int_as_float(ta.i1), ta.b2, __int_as_float(ta.i2));
         }
     }
     tc_fence_before();
@@ -745,6 +755,23 @@ int score_tile_stride(int mt, int G) {  // == tile_stride() of the kernel
     }
 }
 
+// N tiles per visit of an M tile.  Longer runs cut the traffic of the candidate lists (read + written once per run instead of
+// once per tile) but coarsen the work units: take the longest run whose busiest unit stays within 2 % of the ideal share.
+int score_gemm_run(int nt, int mt_units, int G) {
+    static const int forced = [] {
+        const char *e = getenv("CMDB_GEMM_RUN");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced >= 1) return std::min(forced, 8);
+    const double ideal = (double)nt * mt_units / G;
+    for (int run = 8; run >= 2; run >>= 1) {
+        const long long nruns = (nt + run - 1) / run, pairs = nruns * mt_units;
+        const long long makespan = (pairs + G - 1) / G * run;
+        if ((double)makespan <= ideal * 1.02) return run;
+    }
+    return 1;
+}
+
 int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_cand_out, int row0) {
     ScoreScratch &s = b->ss;
     const int p_pad = (P + BM - 1) / BM * BM;
@@ -771,8 +798,14 @@ int score_gemm_candidates(cmdb_bank *b, int P, int terms, bool compact, int *n_c
     // loses 3 % (2.81 -> 2.90 ms; it is not limited by shared-memory reads, and a pair halves the producers per query)
     const bool pair = !compact && eg_env == 2 && b->num_sms % 2 == 0 &&
                       ((p.mt >= 2 && pair_env == 1) || (pair_env < 0 && terms == 3 && p.mt >= 8));
+    {
+        const int cg = pair ? 2 : 1;
+        // compact launches size themselves on the device (m_count): single tiles there
+        p.run = compact ? 1 : score_gemm_run(p.nt, (p.mt + cg - 1) / cg, b->num_sms / cg);
+    }
     if (!compact && row0 == 0) s.sched_pair = pair;   // the first-pass schedule (the exact rescan needs it)
     s.sched_pair_last = pair;
+    s.sched_run_last = p.run;
     const int threads = kGemmCtlThreads + 128 * eg_env;
     auto launch = [&](auto kern, size_t smem, bool cluster2) -> int {
         CMDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

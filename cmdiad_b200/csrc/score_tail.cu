@@ -250,12 +250,16 @@ __device__ __forceinline__ int producer_first_tile(int c, int m, int G, int stri
 __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ work, const int *__restrict__ n_items_ptr,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                      long long rows, int n_units, int cg, int EG, int nt, int chunk_tiles,
-                                                     int mt_total, int stride_full, int stride_last,
-                                                     unsigned long long *best_key) {
+                                                     int mt_total, int stride_full, int stride_last, int run_full,
+                                                     int run_last, unsigned long long *best_key) {
     __shared__ unsigned long long red[8];
     const int n_items = min(*n_items_ptr, kWorkCap);
-    // n_units scheduling units (CTAs, or CTA pairs when cg == 2) share the N tiles of one M tile (pair)
-    const int tiles_per = (nt + n_units - 1) / n_units;
+    // n_units scheduling units (CTAs, or CTA pairs when cg == 2) share the runs of N tiles of one M tile (pair); a chunk's
+    // schedule deals runs of `run` consecutive N tiles, so a producer's rows are runs_per runs of run tiles each.  Both
+    // chunk shapes are covered with the larger of the two unit counts (units beyond a producer's real tiles are empty).
+    const int run_max = max(run_full, run_last), run_min = min(run_full, run_last);
+    const int runs_per = ((nt + run_min - 1) / run_min + n_units - 1) / n_units;
+    const int tiles_per = runs_per * run_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cols = kScoreBN / EG;
     constexpr int kUnitRows = 32;  // rows per block and step: 4 per warp, so a handful of pairs still fills the GPU
@@ -264,16 +268,19 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
     for (long long u = blockIdx.x; u < n_work; u += gridDim.x) {
         const int item = (int)(u / (tiles_per * units_per_tile));
         const int rem = (int)(u % (tiles_per * units_per_tile));
-        const int k = rem / units_per_tile, sub = rem % units_per_tile;
+        const int kt = rem / units_per_tile, sub = rem % units_per_tile;
         const int2 w = work[item];
         const int qi = w.x, c = w.y / EG, g = w.y % EG;
         // the first-pass GEMM ran in chunks of chunk_tiles M tiles (the last one may be shorter), each with its own schedule
         const int mtile = qi / kScoreBM, chunk = mtile / chunk_tiles;
         const bool last = (chunk + 1) * chunk_tiles >= mt_total;
         const int m_in = mtile - chunk * chunk_tiles;  // pair mode: CTA 2u + r handled the M tiles 2*mp + r of pair u
-        const int n = producer_first_tile(c / cg, m_in / cg, n_units, last ? stride_last : stride_full) + k * n_units;
+        const int run = last ? run_last : run_full;
+        const int k = kt / run_max, t = kt % run_max;   // k-th run of this producer, t-th tile inside it
+        const int jrun = producer_first_tile(c / cg, m_in / cg, n_units, last ? stride_last : stride_full) + k * n_units;
+        const int n = t < run ? jrun * run + t : nt;
         unsigned long long key = ~0ULL;
-        if (n < nt) {
+        if (n < nt && (long long)jrun * run < nt) {
             const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows;
             for (int j = warp; j < kUnitRows; j += 8) {
                 const long long r = r0 + j;
@@ -449,10 +456,13 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
     const int cg = s.sched_pair ? 2 : 1, n_units = b->num_sms / cg, EG = score_gemm_groups();
     const int last_tiles = s.mt_total - (s.mt_total - 1) / s.chunk_tiles * s.chunk_tiles;
+    const int nt = (int)(b->fin_rows_pad / kScoreBN);
     rescan_kernel<<<b->num_sms * 8, 256, 0, st>>>(s.work_list, s.fail_ctl + 3, s.q_f32, b->data, b->dim, b->fin_rows, n_units, cg, EG,
-                                                  (int)(b->fin_rows_pad / kScoreBN), s.chunk_tiles, s.mt_total,
+                                                  nt, s.chunk_tiles, s.mt_total,
                                                   score_tile_stride((s.chunk_tiles + cg - 1) / cg, n_units),
-                                                  score_tile_stride((last_tiles + cg - 1) / cg, n_units), s.best_key);
+                                                  score_tile_stride((last_tiles + cg - 1) / cg, n_units),
+                                                  score_gemm_run(nt, (s.chunk_tiles + cg - 1) / cg, n_units),
+                                                  score_gemm_run(nt, (last_tiles + cg - 1) / cg, n_units), s.best_key);
     CMDB_CUDA(cudaGetLastError());
     rescan_finish_kernel<<<8, 256, 0, st>>>(s.fail_list, s.fail_ctl + 4, s.best_key, P_img, b->row_offset, s.min_val, s.min_idx,
                                             s.s_key);
@@ -790,7 +800,7 @@ struct ReweightCertParams {
     int dim;
     const float *q_norm, *q_eps;     // of the m_star rows (q_split_kernel)
     float bmax, eb_max, acc_model;
-    int n_units, cg, EG, stride, nt; // tile schedule of the GEMM launch (mt = 1): units = CTAs or CTA pairs
+    int n_units, cg, EG, stride, nt, run; // tile schedule of the GEMM launch: units = CTAs or CTA pairs, run = N tiles per visit
     const unsigned long long *s_key;
     unsigned long long *top3;
     TailResult *res;
@@ -867,15 +877,19 @@ __global__ void __launch_bounds__(256) reweight_cert_kernel(ReweightCertParams p
     };
     const int n_rows = n_rows_sh, n_bad = n_bad_sh;
     for (int i = warp; i < n_rows; i += 8) visit(cand_rows[i]);
-    const int cols = kScoreBN / p.EG, tiles_per = (p.nt + p.n_units - 1) / p.n_units;
+    const int cols = kScoreBN / p.EG;
+    const int nruns = (p.nt + p.run - 1) / p.run, runs_per = (nruns + p.n_units - 1) / p.n_units;
     for (int i = 0; i < n_bad; ++i) {
         const int c = bad_prod[i] / p.EG, g = bad_prod[i] % p.EG;
-        // M tile of this query row inside the GEMM launch (0 for the re-weighting of a batch; the table build has many)
-        const int n0 = producer_first_tile(c / p.cg, (b / kScoreBM) / p.cg, p.n_units, p.stride);
-        for (int j = warp; j < tiles_per * cols; j += 8) {
-            const int n = n0 + (j / cols) * p.n_units;
+        // M tile of this query row inside the GEMM launch (0 for the re-weighting of a batch; the table build has many);
+        // the producer visited runs j0, j0 + n_units, ... of p.run consecutive N tiles each
+        const int j0 = producer_first_tile(c / p.cg, (b / kScoreBM) / p.cg, p.n_units, p.stride);
+        for (int j = warp; j < runs_per * p.run * cols; j += 8) {
+            const int k = j / (p.run * cols), t = (j / cols) % p.run;
+            const int jrun = j0 + k * p.n_units;
+            const int n = jrun * p.run + t;
             const long long r = (long long)n * kScoreBN + g * cols + j % cols;
-            if (n < p.nt && r < p.rows) visit(r);
+            if (jrun < nruns && n < p.nt && r < p.rows) visit(r);
         }
     }
     if (lane == 0) wkeys[warp][0] = w3[0], wkeys[warp][1] = w3[1], wkeys[warp][2] = w3[2];
@@ -1180,6 +1194,7 @@ static int score_reweight_tensor(cmdb_bank *b, int B, int P_img, bool fused) {
     p.cg = s.sched_pair_last ? 2 : 1, p.n_units = b->num_sms / p.cg, p.EG = score_gemm_groups();
     p.stride = score_tile_stride(1, p.n_units);
     p.nt = (int)(b->fin_rows_pad / kScoreBN);
+    p.run = s.sched_run_last;
     p.s_key = s.s_key, p.top3 = s.top3, p.res = reinterpret_cast<TailResult *>(s.tail), p.fuse_final = fused ? 1 : 0;
     CMDB_REQUIRE(n_cand <= 320, CMDB_ERR_UNSUPPORTED, "scoring: %d GEMM producers exceed reweight_cert_kernel's limit", n_cand);
     reweight_cert_kernel<<<B, 256, 0, st>>>(p);
@@ -1220,6 +1235,7 @@ int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count
         const int mt = (n + kScoreBM - 1) / kScoreBM;
         p.stride = score_tile_stride((mt + p.cg - 1) / p.cg, p.n_units);
         p.nt = (int)(b->fin_rows_pad / kScoreBN);
+        p.run = s.sched_run_last;
         p.s_key = nullptr, p.top3 = b->knn_table + (size_t)r0 * 3, p.res = nullptr, p.fuse_final = 0;
         CMDB_REQUIRE(n_cand <= 320, CMDB_ERR_UNSUPPORTED, "scoring: %d GEMM producers exceed reweight_cert_kernel's limit", n_cand);
         reweight_cert_kernel<<<n, 256, 0, st>>>(p);

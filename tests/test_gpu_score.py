@@ -27,6 +27,15 @@ def _bank(env, lib, impl=None):
     return b
 
 
+# Post-blur tolerance against the reference's final map, in 8-bit quantisation steps of the map (max / 255).  Our
+# min_val is the exact direct-form float32 distance, the reference's is the mm-form of torch.cdist (|a|^2 + |b|^2 - 2ab,
+# relative error ~1e-6 from cancellation): pixels whose pre-blur value sits within that noise of an 8-bit boundary land
+# one level apart, and the integer blur spreads such a pixel over its neighbourhood with per-pass rounding.  Measured on
+# the golden cases and at the 200k headline size (bench.py parity block): <= 2 steps on <= 0.01 % of the pixels.
+MAP_MAX_LSB = 2.5
+MAP_FRAC_OVER_HALF_LSB = 0.002
+
+
 def _check_map(env, r, ref_map):
     """The blur quantises to 8 bits, so ulp-level differences of the pre-blur map move whole contour lines by one
     level.  Exactness is asserted where it is attainable (integer blur given the same 8-bit image: blur(my pre-blur
@@ -35,7 +44,9 @@ def _check_map(env, r, ref_map):
     assert (mine == r.s_map).all()
     lsb = ref_map.max() / 255.0
     diff = np.abs(r.s_map - ref_map)
-    assert diff.max() <= 3.0 * lsb and (diff > 0.5 * lsb).mean() <= 0.02
+    print(f"post-blur map vs reference: max {diff.max() / lsb:.3f} LSB, pixels > 0.5 LSB: {(diff > 0.5 * lsb).mean():.5%}, "
+          f">= 1.5 LSB: {(diff >= 1.5 * lsb).mean():.5%}")
+    assert diff.max() <= MAP_MAX_LSB * lsb and (diff > 0.5 * lsb).mean() <= MAP_FRAC_OVER_HALF_LSB
 
 
 def _check_against_oracle(env, r, ref, P):
