@@ -232,8 +232,11 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
 
 
-def parity_vs_oracle(results, patches_host, n_images=2):
-    """our results of the first n_images of a scored batch against oracle.score_restated on the SAME 200k x 768 bank"""
+def parity_vs_oracle(results, patches_host, n_images=2, exact_bank=None):
+    """our results of the first n_images of a scored batch against oracle.score_restated on the SAME 200k x 768 bank.
+    exact_bank: an un-sharded Bank of the same rows -- additionally compares min_val / min_idx bit for bit with the exact
+    float32 scan of the whole bank on the device (the arithmetic of the re-check kernels; test hook cmdb_debug_exact_min),
+    which separates our error from the float32 noise of the host's mm-form cdist."""
     from oracle import restate as O
     from tests.cases import tie_aware_idx_ok
     prev = torch.get_num_threads()
@@ -251,6 +254,18 @@ def parity_vs_oracle(results, patches_host, n_images=2):
             ok, nbad = tie_aware_idx_ok(r.min_idx, ref["min_idx"], ref["dist"].numpy())
             out["min_idx_strict_mismatch"] += int(nbad)
             out["min_idx_tie_aware_ok"] &= bool(ok)
+            rel_p = np.abs(r.min_val.astype(np.float64) - ref["min_val"]) / ref["min_val"]
+            if float(rel_p.max()) > out["min_val_max_rel"]:
+                w = int(rel_p.argmax())
+                out["min_val_worst"] = {"image": i, "patch": w, "ours": float(r.min_val[w]), "oracle": float(ref["min_val"][w]),
+                                        "row": int(r.min_idx[w]), "oracle_row": int(ref["min_idx"][w])}
+            if exact_bank is not None:
+                ex_val, ex_idx = np.empty(P, np.float32), np.empty(P, np.int64)
+                q = np.ascontiguousarray(patches_host[i].numpy())
+                rc = exact_bank._lib.cmdb_debug_exact_min(exact_bank._h, q.ctypes.data, P, ex_val.ctypes.data, ex_idx.ctypes.data)
+                out["equals_exact_device_scan"] = bool(out.get("equals_exact_device_scan", True) and rc == 0
+                                                       and (ex_val == r.min_val).all() and (ex_idx == r.min_idx).all())
+                out["oracle_vs_exact_scan_max_rel"] = max(out.get("oracle_vs_exact_scan_max_rel", 0.0), _rel(ref["min_val"], ex_val))
             out["min_val_max_rel"] = max(out["min_val_max_rel"], _rel(r.min_val, ref["min_val"]))
             out["s_max_rel"] = max(out["s_max_rel"], _rel(r.s[0], ref["s"]))
             out["s_star_max_rel"] = max(out["s_star_max_rel"], _rel(r.s_star[0], ref["s_star"]))
@@ -338,6 +353,7 @@ def large_bank_leg(rank, world, local, pk, steps, rows=1_000_000, picks=10_000, 
     t0 = time.perf_counter()
     if world > 1:
         bank.build_knn_sharded()
+        bank.attach_comm(comm)
     else:
         bank.build_knn()
     torch.cuda.synchronize()
@@ -479,6 +495,13 @@ def run_ours(args):
         bank.build_knn_sharded()
     torch.cuda.synchronize()
     knn_build_s = max_over_ranks(time.perf_counter() - t0)[0]
+    comm = None
+    if world > 1:
+        # peer-mapped buffers (CUDA IPC over NVLink): the sharded rounds exchange through them inside the kernels (no NCCL in
+        # the scoring data path); the sharded coreset loop uses the same object
+        from cmdiad_b200 import Comm
+        comm = Comm(local, d_proj_max=512)
+        bank.attach_comm(comm)
     bank.set_timing(world == 1)
     st = bank.stream()
     B = args.batch
@@ -561,11 +584,12 @@ def run_ours(args):
                  "config": {"workload": WORKLOAD, "bank_rows": BANK_ROWS, "dim": DIM, "patches_per_image": P,
                             "images_per_step": B,
                             "call": ("cmdb_score_batch_submit / _wait, two batches in flight" if world == 1 else
-                                     "cmdb_score_shard_min / _lookup / _finish_submit + _wait, two rounds in flight"),
+                                     "cmdb_score_shard_round_submit + cmdb_score_shard_wait, two rounds in flight"),
                             "sharding": "single GPU" if world == 1 else
-                            f"bank row-sharded over {world} GPUs, neighbour table replicated; per step 2 NCCL all-reduces (MIN over "
-                            f"{B * P} packed int64 keys, SUM over {2 * B} floats) + the all-gather of the cooperatively staged host "
-                            f"queries; map + device->host of image i on rank i % {world}",
+                            f"bank row-sharded over {world} GPUs, neighbour table replicated; per step 2 exchanges over peer-mapped "
+                            f"memory fused into the kernels (MIN over {B * P} packed int64 keys, SUM over {2 * B} floats; no NCCL call in "
+                            f"the scoring path) + the NCCL all-gather of the cooperatively staged host queries (e2e only); map + "
+                            f"device->host of image i on rank i % {world}",
                             "l2": "inputs larger than L2: the fp16 bank streams 307 MB per step and the candidate lists 59 MB vs 126 MB of L2"},
                  "e2e": {"value": e2e, "unit": "patch-NN scores/s",
                          "h2d_bytes_per_step": B * P * DIM * 4 // world if world > 1 else B * P * DIM * 4,
@@ -589,7 +613,10 @@ def run_ours(args):
                 traffic, traffic_src = gp["dram_bytes_read"] + gp["dram_bytes_write"], gp.get("source")
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
-                            "algorithmic_bytes": BANK_ROWS * DIM * 2 + B * P * DIM * 2, "kernel": "score_gemm_kernel<1,2,1>",
+                            "algorithmic_bytes": BANK_ROWS * DIM * 2 + B * P * DIM * 2 + 2 * 148 * B * P * 16,
+                            "algorithmic_bytes_note": "fp16 bank once + fp16 queries once (inputs) + the producers' candidate lists "
+                                                      "written once (output of the kernel: 296 x queries x 16 B)",
+                            "kernel": "score_gemm_kernel<1,2,1>",
                             "kernel_ms": gemm_ms,
                             "frac_of_sustained": achieved / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
                             "note": f"algorithmic 2*P*R*D FLOP per launch / CUDA-event time of the kernel on its stream; the "
@@ -614,13 +641,24 @@ def run_ours(args):
     full_res = submit(host[0], full=True).wait()
     single_r0 = None
     if world > 1:
+        # device time of one round at a time (CUDA events on the handle's stream): the peer-memory protocol as timed above, and
+        # the NCCL form of the same round (torch.distributed all-reduces between separate phase calls) with its phases
+        rounds = []
+        for _ in range(5):
+            evs = []
+            bank.score_sharded_async(devb[0], dims, OUT_HW, distribute=True, phase_events=evs).wait()
+            rounds.append(evs[1].elapsed_time(evs[-1]))
+        bank.attach_comm(None)
         ph = []
-        for _ in range(3):  # per-phase device times of one round at a time (CUDA events on the handle's stream)
+        for _ in range(4):
             evs = []
             bank.score_sharded_async(devb[0], dims, OUT_HW, distribute=True, phase_events=evs).wait()
             ph.append(evs)
+        bank.attach_comm(comm)
         torch.cuda.synchronize()
-        line["phase_ms"] = {n: float(np.median([p[i].elapsed_time(p[i + 1]) for p in ph])) for i, n in enumerate(Bank.PHASES)}
+        line["round_ms"] = {"peer_memory_exchange": float(np.median(rounds)),
+                            "nccl_exchange": float(np.median([p[1].elapsed_time(p[-1]) for p in ph[1:]]))}
+        line["phase_ms_nccl_form"] = {n: float(np.median([p[i].elapsed_time(p[i + 1]) for p in ph[1:]])) for i, n in enumerate(Bank.PHASES)}
         # sharded == single GPU: every rank holds a full replica of the bank for this check and compares the images it owns
         replica = build_bank(0, BANK_ROWS, local)
         replica.finalize()
@@ -652,10 +690,14 @@ def run_ours(args):
                                            "note": f"{world} independent replicas of the 200k bank, each rank scores its own batches from "
                                                    f"host buffers (no collective); NOT the headline: north_star shards the bank row-wise"}
         single_r0 = single if rank == 0 else None
-        replica.close()
+        if rank != 0:
+            replica.close()
     if rank == 0:
         src = full_res if world == 1 else single_r0
-        par.update(parity_vs_oracle(src, [host[0][i] for i in range(B)], n_images=1 if args.skip_cpu else 2))
+        par.update(parity_vs_oracle(src, [host[0][i] for i in range(B)], n_images=1 if args.skip_cpu else 2,
+                                    exact_bank=bank if world == 1 else replica))
+        if world > 1:
+            replica.close()
     line["parity"] = par
 
     # ---- the drop-in API: methods.predict_batch with everything behind the ABI -------------------------
@@ -663,10 +705,6 @@ def run_ours(args):
         line["predict_batch_e2e"] = dropin_leg(bank, imgs, B)
 
     # ---- coreset selection of 10 % of the same bank (BASELINE.json: "coreset-select seconds") ------------------------
-    comm = None
-    if world > 1:
-        from cmdiad_b200 import Comm
-        comm = Comm(local, d_proj_max=512)
     if not args.skip_coreset:
         csr = sparse_csr(BANK_ROWS, DIM)
         n_sel = BANK_ROWS // 10

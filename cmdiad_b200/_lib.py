@@ -114,6 +114,8 @@ SYMBOLS = {
     "cmdb_score_shard_finish_submit": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, ctypes.c_uint, ctypes.POINTER(ctypes.c_int64)]),
     "cmdb_score_shard_wait": (_I, [_VP, ctypes.c_int64, ctypes.POINTER(ScoreOut)]),
     "cmdb_bank_stage_h2d": (_I, [_VP, _VP, _VP, ctypes.c_size_t]),
+    "cmdb_bank_attach_comm": (_I, [_VP, _VP]),
+    "cmdb_score_shard_round_submit": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, ctypes.c_uint, ctypes.POINTER(ctypes.c_int64)]),
     "cmdb_bank_read_device": (_I, [_VP, _I64, _I64, _VP]),
     "cmdb_score_fused_batch_submit": (_I, [ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_I), ctypes.POINTER(_I),
                                            ctypes.POINTER(_I), _I, _I, _I, ctypes.POINTER(FusionHead), ctypes.c_uint,

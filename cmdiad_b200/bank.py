@@ -60,6 +60,9 @@ class Comm:
         handles = np.ascontiguousarray(gathered.cpu().numpy())
         L.check(self._lib.cmdb_comm_import(self._h, _ptr(handles)))
         self.bytes = int(nbytes)
+        for b in list(self.__dict__.get("_attached", ())):   # banks that exchange through this buffer follow it
+            if b._h:
+                L.check(self._lib.cmdb_bank_attach_comm(b._h, self._h))
 
     def ensure(self, nbytes):
         """collective: every rank passes the same size"""
@@ -76,6 +79,9 @@ class Comm:
 
     def close(self):
         if getattr(self, "_h", None):
+            for b in list(self.__dict__.get("_attached", ())):
+                if b._h:
+                    self._lib.cmdb_bank_attach_comm(b._h, None)
             self._lib.cmdb_comm_destroy(self._h)
             self._h = ctypes.c_void_p()
             self.bytes = 0
@@ -153,6 +159,17 @@ class Bank:
         """Distance-GEMM mode.  0 (default): certified hi.hi pre-filter, uncertified queries redone with the
         FP32-equivalent GEMM; 3: FP32-equivalent GEMM for every query; 1: uncertified pre-filter (diagnostics)."""
         L.check(self._lib.cmdb_bank_set_option(self._h, L.OPT_PREFILTER_TERMS, int(terms)))
+
+    def attach_comm(self, comm):
+        """Row-sharded scoring without NCCL: rounds exchange through `comm`'s peer-mapped buffers (the ones the sharded
+        coreset loop uses), fused into the kernels (cmdb_score_shard_round_submit).  None detaches."""
+        old = getattr(self, "_comm", None)
+        if old is not None and self in old.__dict__.get("_attached", []):
+            old._attached.remove(self)
+        L.check(self._lib.cmdb_bank_attach_comm(self._h, comm._h if comm is not None else None))
+        self._comm = comm
+        if comm is not None:
+            comm.__dict__.setdefault("_attached", []).append(self)
 
     def set_query_norm(self, mean, std, enabled=True):
         """enabled: scoring calls take RAW patches and compute (patch - mean) / std on the device (float32, bit-identical
@@ -504,6 +521,16 @@ class Bank:
             if not chunk.is_cuda and world > 1 and B * P >= 1024:
                 chunk = self._stage_sharded(chunk, slot, world, rank, group)
             mark()
+            first, stride = ((rank - img_base) % world, world) if distribute else (0, 1)
+            if getattr(self, "_comm", None) is not None:
+                # one call enqueues the whole round; the two exchanges run over peer-mapped memory inside the kernels
+                ticket = ctypes.c_int64()
+                L.check(self._lib.cmdb_score_shard_round_submit(self._h, _ptr(chunk), B, P, int(fh), int(fw), int(out_hw),
+                                                                int(chunk.is_cuda), int(first), int(stride), 3 if full else 0,
+                                                                ctypes.byref(ticket)))
+                for _ in range(5):
+                    mark()
+                return _ShardTicket(self, ticket.value, (patches, chunk), res, outs, first, stride, B)
             keys = self._shard_buf("keys", slot, (B * P,), torch.int64)
             L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
             mark()
@@ -514,7 +541,6 @@ class Bank:
             mark()
             dist.all_reduce(d2, op=dist.ReduceOp.SUM, group=group)
             mark()
-            first, stride = ((rank - img_base) % world, world) if distribute else (0, 1)
             ticket = ctypes.c_int64()
             L.check(self._lib.cmdb_score_shard_finish_submit(self._h, _ptr(d2), B, P, int(fh), int(fw), int(out_hw), int(first),
                                                              int(stride), 3 if full else 0, ctypes.byref(ticket)))

@@ -515,8 +515,16 @@ int cmdb_score_shard_lookup(cmdb_bank *b, const int64_t *reduced_keys_device, in
     return score_shard_lookup(b, B, knn_d2_contrib_device);
 }
 
+static int shard_finish_enqueue(cmdb_bank *b, const float *knn_d2_sum_device, int B, int P, int fh, int fw, int out_hw,
+                                int img_first, int img_step, unsigned want_maps, int64_t *out_ticket);
+
 int cmdb_score_shard_finish_submit(cmdb_bank *b, const float *knn_d2_sum_device, int B, int P, int fh, int fw, int out_hw,
                                    int img_first, int img_step, unsigned want_maps, int64_t *out_ticket) {
+    return shard_finish_enqueue(b, knn_d2_sum_device, B, P, fh, fw, out_hw, img_first, img_step, want_maps, out_ticket);
+}
+
+static int shard_finish_enqueue(cmdb_bank *b, const float *knn_d2_sum_device, int B, int P, int fh, int fw, int out_hw,
+                                int img_first, int img_step, unsigned want_maps, int64_t *out_ticket) {
     CMDB_CHECK(check_score_args(b, knn_d2_sum_device, B, P, "cmdb_score_shard_finish_submit"));
     CMDB_REQUIRE(out_ticket && fh > 0 && fw > 0 && fh * fw == P && B * P <= b->ss.cap_p && B <= b->ss.cap_b, CMDB_ERR_INVALID,
                  "cmdb_score_shard_finish_submit: bad arguments");
@@ -557,6 +565,67 @@ int cmdb_score_shard_finish_submit(cmdb_bank *b, const float *knn_d2_sum_device,
     return CMDB_OK;
 }
 
+// ---- NCCL-free sharded rounds: the two exchanges go through peer-mapped memory (cmdb_comm), fused into the kernels ----
+
+int cmdb_bank_attach_comm(cmdb_bank *b, cmdb_comm *comm) {
+    CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_attach_comm: bank is NULL");
+    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "cmdb_bank_attach_comm: a submitted round is outstanding");
+    b->comm = comm;
+    if (!comm) return CMDB_OK;
+    int rank = 0, world = 1;
+    size_t bytes = 0;
+    unsigned char *local = nullptr, *peers[kMaxRanks];
+    CMDB_CHECK(comm_info(comm, &rank, &world, &local, peers, &bytes));
+    CMDB_REQUIRE(bytes >= kCommHeaderBytes, CMDB_ERR_INVALID, "cmdb_bank_attach_comm: the peer buffer has %zu bytes, need >= %zu", bytes,
+                 (size_t)kCommHeaderBytes);
+    CMDB_CUDA(cudaSetDevice(b->device));
+    if (!b->shard_ctr) {
+        CMDB_CUDA(cudaMalloc(&b->shard_ctr, 4 * sizeof(unsigned int)));
+        CMDB_CUDA(cudaMemset(b->shard_ctr, 0, 4 * sizeof(unsigned int)));
+        CMDB_CUDA(cudaMalloc(&b->shard_d2, sizeof(float) * 4 * kShardD2Cap));
+        CMDB_CUDA(cudaHostAlloc(&b->shard_abort_host, sizeof(unsigned int), cudaHostAllocMapped));
+        *b->shard_abort_host = 0u;
+        CMDB_CUDA(cudaHostGetDevicePointer(&b->shard_abort_dev, b->shard_abort_host, 0));
+    }
+    return CMDB_OK;
+}
+
+int cmdb_score_shard_round_submit(cmdb_bank *b, const float *patches, int B, int P, int fh, int fw, int out_hw, int patch_is_device,
+                                  int img_first, int img_step, unsigned want_maps, int64_t *out_ticket) {
+    CMDB_CHECK(check_score_args(b, patches, B, P, "cmdb_score_shard_round_submit"));
+    CMDB_CHECK(check_shard_batch(b, B, "cmdb_score_shard_round_submit"));
+    CMDB_REQUIRE(b->comm, CMDB_ERR_STATE, "cmdb_score_shard_round_submit: attach the peer buffers first (cmdb_bank_attach_comm)");
+    CMDB_REQUIRE(b->knn_table && b->knn_rows >= b->row_offset + b->fin_rows, CMDB_ERR_STATE,
+                 "cmdb_score_shard_round_submit: install the replicated neighbour table first (cmdb_bank_set_knn_table)");
+    CMDB_REQUIRE(out_ticket && fh > 0 && fw > 0 && fh * fw == P && out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID,
+                 "cmdb_score_shard_round_submit: bad arguments");
+    int rank = 0, world = 1;
+    size_t bytes = 0;
+    unsigned char *local = nullptr;
+    PeerPtrs peers{};
+    CMDB_CHECK(comm_info(b->comm, &rank, &world, &local, peers.p, &bytes));
+    CMDB_CUDA(cudaSetDevice(b->device));
+    const bool busy = b->pending[0].active || b->pending[1].active;
+    if (!busy && (size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
+    CMDB_REQUIRE(!busy || (size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
+                 "cmdb_score_shard_round_submit: out_hw changes while a submitted round is outstanding; wait for it first");
+    const int slot = busy ? b->next_slot : 0;
+    CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
+                 "cmdb_score_shard_round_submit: two submitted rounds are outstanding on this handle; wait for one first");
+    CMDB_CHECK(stage_alloc(b, B, P, out_hw));
+    score_select_slot(b, slot);
+    b->shard_slot = slot;
+    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
+    const unsigned long long epoch = comm_next_score_epoch(b->comm);  // per buffer, not per bank: several banks may share it
+    const int xslot = (int)(epoch & 1ULL);
+    CMDB_CHECK(score_shard_exchange_keys(b, B, P, peers, world, rank, xslot, epoch));
+    CMDB_CHECK(score_select(b, B, P, false));
+    float *contrib = b->shard_d2 + xslot * kShardD2Cap, *d2_sum = b->shard_d2 + (2 + xslot) * kShardD2Cap;
+    CMDB_CHECK(score_shard_lookup(b, B, contrib));
+    CMDB_CHECK(score_shard_exchange_d2(b, B, peers, world, rank, xslot, epoch, contrib, d2_sum));
+    return shard_finish_enqueue(b, d2_sum, B, P, fh, fw, out_hw, img_first, img_step, want_maps, out_ticket);
+}
+
 int cmdb_score_shard_wait(cmdb_bank *b, int64_t ticket, cmdb_score_out *outs) {
     CMDB_REQUIRE(b && outs, CMDB_ERR_INVALID, "cmdb_score_shard_wait: NULL argument");
     for (int slot = 0; slot < 2; ++slot) {
@@ -565,6 +634,11 @@ int cmdb_score_shard_wait(cmdb_bank *b, int64_t ticket, cmdb_score_out *outs) {
         CMDB_CUDA(cudaSetDevice(b->device));
         CMDB_CUDA(cudaEventSynchronize(b->ev_done[slot]));
         pd.active = false;
+        if (b->shard_abort_host && *b->shard_abort_host) {
+            set_error("cmdb_score_shard_wait: a peer rank did not arrive at the exchange of this round within the timeout (all ranks "
+                      "must submit the same rounds in the same order)");
+            return CMDB_ERR_CUDA;
+        }
         // maps: the images this rank finished; the scalars and per-patch arrays are replicated, so every image gets those
         for (int i = 0; i < pd.B; ++i) {
             const bool mine = i >= pd.img_first && (i - pd.img_first) % pd.img_step == 0;

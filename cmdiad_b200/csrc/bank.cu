@@ -298,6 +298,8 @@ void cmdb_bank_destroy(cmdb_bank *b) {
         if (b->fused.ev_done[i]) cudaEventDestroy(b->fused.ev_done[i]);
     }
     cudaFree(b->fused.acc_maps), cudaFree(b->fused.acc_scores);
+    cudaFree(b->shard_ctr), cudaFree(b->shard_d2);
+    if (b->shard_abort_host) cudaFreeHost(b->shard_abort_host);
     cudaFree(b->data);
     cudaFree(b->stats_buf);
     cudaFree(b->absmax_buf);

@@ -11,6 +11,7 @@ struct cmdb_comm {
     unsigned char *local = nullptr;                 // this rank's mailbox (device memory)
     unsigned char *peer[cmdb::kMaxRanks] = {};      // every rank's mailbox as mapped into this process (peer[rank] == local)
     bool imported = false;
+    unsigned long long score_epoch = 0;  // round counter of the sharded-scoring exchange (monotone per buffer, same on every rank)
 };
 
 using namespace cmdb;
@@ -73,7 +74,7 @@ int cmdb_comm_reset(cmdb_comm *c) {
     CMDB_REQUIRE(c, CMDB_ERR_INVALID, "cmdb_comm_reset: comm is NULL");
     CMDB_CUDA(cudaSetDevice(c->device));
     // flags + key slots only: the replica region behind them is rewritten by every call anyway
-    CMDB_CUDA(cudaMemset(c->local, 0, std::min(c->bytes, kCommHeaderBytes)));
+    CMDB_CUDA(cudaMemset(c->local, 0, std::min(c->bytes, kCommCoresetBytes)));
     CMDB_CUDA(cudaDeviceSynchronize());
     return CMDB_OK;
 }
@@ -91,6 +92,8 @@ void cmdb_comm_destroy(cmdb_comm *c) {
 }  // extern "C"
 
 namespace cmdb {
+unsigned long long comm_next_score_epoch(cmdb_comm *c) { return ++c->score_epoch; }
+
 int comm_info(cmdb_comm *c, int *rank, int *world, unsigned char **local, unsigned char **peers, size_t *bytes) {
     CMDB_REQUIRE(c && (c->world == 1 || c->imported), CMDB_ERR_STATE, "comm: call cmdb_comm_import on every rank first");
     *rank = c->rank, *world = c->world, *local = c->local, *bytes = c->bytes;

@@ -178,6 +178,11 @@ struct cmdb_bank {
     long long ticket_counter = 0;
     int next_slot = 0;
     int shard_slot = 0;   // result slot of the sharded round in progress (cmdb_score_shard_min .. finish)
+    cmdb_comm *comm = nullptr;             // peer buffers for NCCL-free sharded rounds (cmdb_bank_attach_comm; not owned)
+    unsigned int *shard_ctr = nullptr;     // [0] device: last-block counter of the push kernels
+    unsigned int *shard_abort_host = nullptr;  // pinned + mapped: set by a kernel whose peers never arrived
+    unsigned int *shard_abort_dev = nullptr;   // device alias of shard_abort_host
+    float *shard_d2 = nullptr;             // device [2][kShardD2Cap]: local contributions / sums of the neighbour distances
     float *data = nullptr;  // [capacity, dim] float32 row-major
     // scoring layout (cmdb_bank_finalize)
     bool finalized = false;
@@ -214,6 +219,7 @@ int project_rows(cmdb_bank *b, const float *x_dev, int64_t n_rows, int D, const 
 
 // comm.cu
 int comm_info(cmdb_comm *c, int *rank, int *world, unsigned char **local, unsigned char **peers, size_t *bytes);
+unsigned long long comm_next_score_epoch(cmdb_comm *c);
 
 // coreset.cu
 // layout of a rank's peer-mapped buffer (cmdb_comm): [0, 256) per-rank "shard arrived" flags | key slots
@@ -221,7 +227,17 @@ int comm_info(cmdb_comm *c, int *rank, int *world, unsigned char **local, unsign
 constexpr unsigned int kCommReadyOff = 0;
 constexpr unsigned int kCommKeysOff = 256;
 constexpr unsigned int kCommMaxCtas = 192;
-constexpr size_t kCommHeaderBytes = 256 * 1024;  // >= 256 + 2 * kMaxRanks * kCommMaxCtas * 32
+constexpr size_t kCommCoresetBytes = 256 * 1024;  // coreset flags + key slots (>= 256 + 2 * kMaxRanks * kCommMaxCtas * 32); cleared by cmdb_comm_reset
+// row-sharded SCORING rounds exchange through the same buffer (never cleared: every word is rewritten with the round's epoch):
+//   flags  [2 slots][2 kinds][kMaxRanks] u64 at kCommScoreFlagsOff
+//   d2     [2 slots][kMaxRanks][kShardD2Cap] float at kCommScoreD2Off        (squared neighbour distances, 2 per image)
+//   keys   [2 slots][kMaxRanks][kShardKeysCap] int64 at kCommScoreKeysOff    (packed (min distance, global row) per query)
+constexpr size_t kCommScoreFlagsOff = kCommCoresetBytes;
+constexpr size_t kCommScoreD2Off = kCommScoreFlagsOff + 4096;
+constexpr int kShardD2Cap = 64;
+constexpr size_t kCommScoreKeysOff = kCommScoreD2Off + 8192;
+constexpr int kShardKeysCap = 128 * 1024;   // queries per round (32 images x 3136 patches = 100 352)
+constexpr size_t kCommHeaderBytes = 18 * 1024 * 1024;  // >= kCommScoreKeysOff + 2 * kMaxRanks * kShardKeysCap * 8; the replica follows
 struct ShardCtx {  // row-sharded coreset loop
     int world, rank;
     long long row_offset, n_total;
@@ -273,6 +289,13 @@ int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count
 int score_exact_scan(cmdb_bank *b, const float *q_dev, int P, unsigned long long *keys_dev);
 int score_shard_lookup(cmdb_bank *b, int B, float *contrib_dev);
 int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev);
+// peer-memory form of the two exchanges of a sharded round (no NCCL): see score_tail.cu
+struct PeerPtrs {
+    unsigned char *p[kMaxRanks];
+};
+int score_shard_exchange_keys(cmdb_bank *b, int B, int P_img, const PeerPtrs &peers, int world, int rank, int slot, unsigned long long epoch);
+int score_shard_exchange_d2(cmdb_bank *b, int B, const PeerPtrs &peers, int world, int rank, int slot, unsigned long long epoch,
+                            const float *contrib_dev, float *d2_sum_dev);
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B);
 int score_final(cmdb_bank *b, int B);
 int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,

@@ -763,8 +763,10 @@ int score_gemm_run(int nt, int mt_units, int G) {
         return e ? atoi(e) : 0;
     }();
     if (forced >= 1) return std::min(forced, 8);
+    // at least G runs per M tile, so that EVERY producer keeps seeing a share of every query's rows (the certificate wants the
+    // rows near a query's minimum spread over many producers; idle producers made 1.7x more queries need a rescan)
     const double ideal = (double)nt * mt_units / G;
-    for (int run = 8; run >= 2; run >>= 1) {
+    for (int run = std::min(8, std::max(1, nt / G)); run >= 2; --run) {
         const long long nruns = (nt + run - 1) / run, pairs = nruns * mt_units;
         const long long makespan = (pairs + G - 1) / G * run;
         if ((double)makespan <= ideal * 1.02) return run;

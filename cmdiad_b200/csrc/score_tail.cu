@@ -998,6 +998,143 @@ __global__ void shard_final_kernel(const unsigned long long *__restrict__ top3, 
     res->knn0 = knn[0], res->knn1 = knn[1];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL-free exchanges of a sharded round over peer-mapped memory (CUDA IPC / NVLink, cmdb_comm): the collective is fused
+// into the kernels on both sides of it.
+//   push   every rank packs its local (min distance, global row) keys and stores them straight into the round's slot
+//          [slot][rank][query] of EVERY rank's buffer (coalesced 8-byte NVLink stores); the last block to finish raises
+//          the rank's flag (the round's epoch) in every buffer: threadfence_system by all writers, then a release store
+//   reduce every rank waits for the world flags in its LOCAL buffer, takes the MIN over the world key arrays (non-negative
+//          distance bits << 32 | global row: integer MIN == argmin with lowest-row tie-break) and decodes min_val / min_idx /
+//          the per-image argmax key -- what ncclAllReduce(MIN) + unpack did in two launches and ~60 us at 8 ranks.
+// Slots alternate by round parity; a rank can be at most one round ahead of the slowest rank (it needs everybody's flag
+// of round r + 1 before it can finish that round), so a slot is never overwritten while someone still reads it.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) shard_push_keys_kernel(const float *__restrict__ min_val, const long long *__restrict__ min_idx,
+                                                              int n, PeerPtrs peers, int world, int rank, size_t keys_off,
+                                                              size_t flag_off, unsigned long long epoch, unsigned int *ctr) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long g = min_idx[i];
+        const long long key = g < 0 ? 0x7fffffffffffffffLL
+                                    : (long long)(((unsigned long long)__float_as_uint(min_val[i]) << 32) | (unsigned long long)g);
+        for (int r = 0; r < world; ++r)
+            reinterpret_cast<long long *>(peers.p[r] + keys_off)[(size_t)rank * kShardKeysCap + i] = key;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ctr, 1u) == gridDim.x - 1) {   // every block's stores are fenced: publish
+            __threadfence_system();
+            *ctr = 0u;
+            for (int r = 0; r < world; ++r)
+                st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.p[r] + flag_off) + rank, epoch);
+        }
+    }
+}
+
+// returns false on timeout (a peer never arrived): the abort word is set and the caller's results are invalid
+__device__ __forceinline__ bool wait_flags(const unsigned char *local, size_t flag_off, int world, unsigned long long epoch,
+                                           unsigned int *abort_word) {
+    __shared__ int ok_sh;
+    if (threadIdx.x == 0) ok_sh = 1;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned long long *f = reinterpret_cast<const unsigned long long *>(local + flag_off) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(f) < epoch) {
+            if (clock64() - t0 > 40LL * 1000 * 1000 * 1000) {  // ~20 s
+                ok_sh = 0;
+                *abort_word = 1u;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    return ok_sh != 0;
+}
+
+__global__ void __launch_bounds__(256) shard_reduce_keys_kernel(const unsigned char *__restrict__ local, size_t keys_off,
+                                                                size_t flag_off, int world, unsigned long long epoch, int n,
+                                                                int P_img, float *__restrict__ min_val,
+                                                                long long *__restrict__ min_idx, unsigned long long *s_key,
+                                                                unsigned int *abort_word) {
+    if (!wait_flags(local, flag_off, world, epoch, abort_word)) return;
+    const long long *keys = reinterpret_cast<const long long *>(local + keys_off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        long long k = 0x7fffffffffffffffLL;
+        for (int r = 0; r < world; ++r) {
+            const long long v = __ldcg(keys + (size_t)r * kShardKeysCap + i);
+            k = v < k ? v : k;
+        }
+        const float v = __uint_as_float((unsigned int)((unsigned long long)k >> 32));
+        min_val[i] = v;
+        min_idx[i] = (long long)((unsigned long long)k & 0xffffffffULL);
+        atomicMax(s_key + i / P_img, ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - (unsigned int)(i % P_img)));
+    }
+}
+
+// the second exchange: 2 squared neighbour distances per image, one non-zero contribution among the ranks
+__global__ void __launch_bounds__(64) shard_push_d2_kernel(const float *__restrict__ contrib, int n, PeerPtrs peers, int world, int rank,
+                                                          size_t d2_off, size_t flag_off, unsigned long long epoch) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        for (int r = 0; r < world; ++r) reinterpret_cast<float *>(peers.p[r] + d2_off)[rank * kShardD2Cap + i] = contrib[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int r = 0; r < world; ++r) st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.p[r] + flag_off) + rank, epoch);
+}
+
+__global__ void __launch_bounds__(64) shard_sum_d2_kernel(const unsigned char *__restrict__ local, size_t d2_off, size_t flag_off,
+                                                         int world, unsigned long long epoch, int n, float *__restrict__ d2_sum,
+                                                         unsigned int *abort_word) {
+    if (!wait_flags(local, flag_off, world, epoch, abort_word)) return;
+    const float *d = reinterpret_cast<const float *>(local + d2_off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float acc = 0.f;  // one owner contributes the value, the others 0: x + 0 + ... + 0 is exact in any order
+        for (int r = 0; r < world; ++r) acc += __ldcg(d + r * kShardD2Cap + i);
+        d2_sum[i] = acc;
+    }
+}
+
+static size_t shard_flag_off(int slot, int kind) { return kCommScoreFlagsOff + (size_t)((slot * 2 + kind) * kMaxRanks) * 8; }
+
+int score_shard_exchange_keys(cmdb_bank *b, int B, int P_img, const PeerPtrs &peers, int world, int rank, int slot,
+                              unsigned long long epoch) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
+    const int n = B * P_img;
+    CMDB_REQUIRE(n <= kShardKeysCap, CMDB_ERR_UNSUPPORTED, "sharded round: %d queries exceed the exchange slot (%d)", n, kShardKeysCap);
+    const size_t keys_off = kCommScoreKeysOff + (size_t)slot * kMaxRanks * kShardKeysCap * 8;
+    const int blocks = std::min((n + 255) / 256, 2 * b->num_sms);
+    shard_push_keys_kernel<<<blocks, 256, 0, st>>>(s.min_val, s.min_idx, n, peers, world, rank, keys_off, shard_flag_off(slot, 0), epoch,
+                                                   b->shard_ctr);
+    CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
+    shard_reduce_keys_kernel<<<blocks, 256, 0, st>>>(peers.p[rank], keys_off, shard_flag_off(slot, 0), world, epoch, n, P_img, s.min_val,
+                                                     s.min_idx, s.s_key, b->shard_abort_dev);
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
+int score_shard_exchange_d2(cmdb_bank *b, int B, const PeerPtrs &peers, int world, int rank, int slot, unsigned long long epoch,
+                            const float *contrib_dev, float *d2_sum_dev) {
+    cudaStream_t st = b->stream;
+    CMDB_REQUIRE(2 * B <= kShardD2Cap, CMDB_ERR_UNSUPPORTED, "sharded round: batch %d exceeds the exchange slot", B);
+    const size_t d2_off = kCommScoreD2Off + (size_t)slot * kMaxRanks * kShardD2Cap * 4;
+    shard_push_d2_kernel<<<1, 64, 0, st>>>(contrib_dev, 2 * B, peers, world, rank, d2_off, shard_flag_off(slot, 1), epoch);
+    shard_sum_d2_kernel<<<1, 64, 0, st>>>(peers.p[rank], d2_off, shard_flag_off(slot, 1), world, epoch, 2 * B, d2_sum_dev, b->shard_abort_dev);
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
 // sharded mode, after the all-gather: image b = blockIdx.x merges the keys of all ranks ([rank][B][3] layout)
 __global__ void __launch_bounds__(32) merge_top3_kernel(const unsigned long long *__restrict__ gathered, int n_ranks, int B,
                                                         unsigned long long *__restrict__ out3) {

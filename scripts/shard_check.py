@@ -45,13 +45,18 @@ def report(what, ok):
 n_img = 70  # three rounds of <= 32 images
 pb = np.stack([synth.patches(P, D, seed=80 + t, anomalous_frac=0.01, cent=cent) for t in range(n_img)])
 bb = full.score_batch(pb, (28, 28), 224, full=True)
-for table in (False, True):
-    if table:
+from cmdiad_b200 import Comm  # noqa: E402
+comm = Comm(local)
+for mode in ("five-phase", "table/nccl", "table/peer-memory"):
+    table = mode != "five-phase"
+    if mode == "table/nccl":
         shard.build_knn_sharded()
         keys_sh = shard.read_knn(0, R).numpy()
         keys_1 = full.read_knn(0, R).numpy()
         report("replicated neighbour table == single-GPU table", bool((keys_sh == keys_1).all()))
-    tag = "table/pipelined" if table else "five-phase"
+    if mode == "table/peer-memory":
+        shard.attach_comm(comm)   # exchanges fused into the kernels over peer-mapped memory: no NCCL in the scoring path
+    tag = mode
     for src_name, src in (("host", pb), ("device", torch.from_numpy(pb).cuda())):
         ab = shard.score_sharded_batch(src, (28, 28), 224, full=True)
         report(f"[{tag}] {n_img} images, {src_name} queries, replicated finish", all(same(ab[t], bb[t]) for t in range(n_img)))
@@ -74,5 +79,6 @@ if rank == 0:
     print("SHARD CHECK", "OK" if int(t) == 0 else f"FAILED on {int(t)} rank-checks", f"(world {world})", flush=True)
 shard.close()
 full.close()
+comm.close()
 dist.destroy_process_group()
 sys.exit(0 if int(t) == 0 else 1)

@@ -166,6 +166,15 @@ def test_sharded_entry_points_with_one_rank(env):
             for name in ("s", "s_idx", "min_val", "min_idx", "nn_idx", "m_star_knn", "w", "s_map", "s_map_pre"):
                 assert (getattr(a[i], name) == getattr(c[i], name)).all(), (i, name)
                 assert (getattr(d[i], name) == getattr(c[i], name)).all(), (i, name)
+        # the same rounds with the exchanges over peer-mapped memory instead of NCCL (cmdb_score_shard_round_submit)
+        comm2 = Comm(0)
+        b.attach_comm(comm2)
+        e = b.score_sharded_batch(many, (28, 28), 224, full=True, distribute=True)
+        for i in range(40):
+            for name in ("s", "s_idx", "min_val", "min_idx", "nn_idx", "m_star_knn", "w", "s_map", "s_map_pre"):
+                assert (getattr(e[i], name) == getattr(c[i], name)).all(), (i, name)
+        b.attach_comm(None)
+        comm2.close()
         b.close()
     finally:
         dist.destroy_process_group()
