@@ -58,11 +58,14 @@ typedef enum cmdb_status {
  *  0 (default) CERTIFIED PRE-FILTER: one hi.hi MMA per K step (11-bit operands) finds candidates; a per-query error bound
  *              (Cauchy-Schwarz on the operand rounding + a model of the tensor-core accumulation) proves for each query
  *              that every bank row outside the re-checked candidate set is strictly farther in float32 than the row
- *              returned.  Where the certificate fails, the rows it could not exclude are rescanned exactly (few cases) or
- *              the queries are redone with mode 3 (many cases) inside the same call.  min_val / min_idx are identical
- *              to mode 3; cmdb_bank_score_stats reports the counts, and a bank where most queries fail (dense
- *              near-duplicates) switches itself to mode 3 for the next 32 calls.
- *  3           FP32-equivalent split for every query: hi.hi + hi.lo + lo.hi, three MMAs per K step.
+ *              returned.  Where the certificate fails, the rows it could not exclude are rescanned exactly inside the same
+ *              call: min_val / min_idx then equal an exact float32 scan of the whole bank, lowest row on ties.  Only when
+ *              a call queues more than 16 384 unresolved (query, producer) pairs (banks dominated by rows float32 cannot
+ *              tell apart) are the uncertified queries redone with mode 3 instead; cmdb_bank_score_stats reports the
+ *              counts, and a bank where most queries end up there switches itself to mode 3 for the next 32 calls.
+ *  3           FP32-equivalent split for every query: hi.hi + hi.lo + lo.hi, three MMAs per K step, exact re-check of the
+ *              4 best candidates (no certificate: among more than 4 rows within float32 noise of the minimum it may return
+ *              another one of them -- same distance to 2e-6 relative, not necessarily the lowest row).
  *  1           uncertified hi.hi pre-filter + exact re-check of the 4 best candidates (diagnostics). */
 #define CMDB_OPT_PREFILTER_TERMS 3
 #define CMDB_OPT_TIMING 2 /* 1 = record CUDA events between the stages of cmdb_score (see cmdb_bank_get_timings) */

@@ -128,14 +128,16 @@ def test_tile_schedule_covers_every_query_on_every_cta(built):
 
 
 def test_fallback_tier_rule(built):
-    """few uncertified (query, producer) pairs -> exact rescan; many -> 3-term GEMM over the uncertified queries"""
+    """uncertified (query, producer) pairs that fit the work list -> exact rescan (rigorous); beyond it -> 3-term GEMM over
+    the uncertified queries"""
     from cmdiad_b200 import _lib as L
     lib = L.load()
     assert lib.cmdb_debug_fallback_use_rescan(75, 75) == 1           # the bench's steady state
     assert lib.cmdb_debug_fallback_use_rescan(0, 0) == 1
     assert lib.cmdb_debug_fallback_use_rescan(600, 700) == 1         # one pair per query: rescan is cheaper per query
     assert lib.cmdb_debug_fallback_use_rescan(784, 40000) == 0       # near-duplicate banks: hundreds of pairs per query
-    assert lib.cmdb_debug_fallback_use_rescan(10, 9000) == 0         # beyond the work list
+    assert lib.cmdb_debug_fallback_use_rescan(10, 9000) == 1         # many pairs per query, but they fit: stay rigorous
+    assert lib.cmdb_debug_fallback_use_rescan(10, 17000) == 0        # beyond the work list
     prev = 1
     for pairs in range(0, 20000, 50):                                # monotone in the number of pairs
         cur = lib.cmdb_debug_fallback_use_rescan(500, pairs)

@@ -271,9 +271,19 @@ def test_tiny_banks_all_paths_agree(env, R):
     b.close()
 
 
+def _exact_scan(b, patch):
+    P = patch.shape[0]
+    ex_val, ex_idx = np.empty(P, np.float32), np.empty(P, np.int64)
+    q = np.ascontiguousarray(patch, np.float32)
+    assert b._lib.cmdb_debug_exact_min(b._h, q.ctypes.data, P, ex_val.ctypes.data, ex_idx.ctypes.data) == 0
+    return ex_val, ex_idx
+
+
 def test_certificate_fallback_on_near_duplicates(env):
-    """Groups of near-duplicate bank rows defeat an 11-bit pre-filter: the certificate must notice (fallback > 0), the
-    answers must still equal the 3-term path, and a bank where most queries fail switches itself to the direct mode."""
+    """Groups of near-duplicate bank rows defeat an 11-bit pre-filter: the certificate must notice (fallback > 0).  While the
+    unresolved (query, producer) pairs fit the work list they are rescanned exactly and the answers equal the exact scan of
+    the whole bank; a bank with hundreds of indistinguishable rows per query overflows it, goes through the 3-term GEMM
+    tier and then switches itself to the direct mode."""
     from cmdiad_b200 import synth
     g = np.random.Generator(np.random.PCG64(5))
     unique = synth.patches(8000, 768, seed=49, dist="G")
@@ -284,19 +294,24 @@ def test_certificate_fallback_on_near_duplicates(env):
     near_dup = np.stack([base[g.integers(0, 200, 784)] + 0.05 * synth.patches(784, 768, seed=60 + i, dist="G") for i in range(2)])
     near_unique = unique[:784] + 0.05 * synth.patches(784, 768, seed=70, dist="G")
     b = _bank(env, lib)
-    # mixed batch first: image 0 keeps its certificate, image 1 falls back
+    # mixed batch: image 0 keeps its certificate, image 1 needs the exact rescan tier
     mixed = np.stack([near_unique, near_dup[0], near_unique[::-1].copy()])
     r_mixed = b.score_batch(mixed, (28, 28), 224, full=True)
     st = b.score_stats()
-    assert st["mode"] == 0 and 700 <= st["fallback_queries"] <= 784 + 80 and st["gemm_fallback"], st
+    assert st["mode"] == 0 and 700 <= st["fallback_queries"] <= 784 + 80 and not st["gemm_fallback"], st
     assert st["direct_calls_left"] == 0
-    b.set_prefilter_terms(3)
-    _assert_same_results(r_mixed, b.score_batch(mixed, (28, 28), 224, full=True), "mixed batch")
-    # mostly-failed call -> the next calls run the 3-term GEMM directly
-    b.set_prefilter_terms(0)
+    for i in range(3):
+        ex_val, ex_idx = _exact_scan(b, mixed[i])
+        assert (r_mixed[i].min_idx == ex_idx).all() and (r_mixed[i].min_val == ex_val).all(), i
+    b.close()
+    # 400 indistinguishable rows per query: far more pairs than the work list holds -> 3-term GEMM tier, then direct mode
+    dup = np.concatenate([base + 2e-4 * g.standard_normal(base.shape, dtype=np.float32) for _ in range(400)], 0)
+    lib = np.concatenate([unique, dup], 0)
+    lib = lib[g.permutation(lib.shape[0])]
+    b = _bank(env, lib)
     cert = b.score_batch(near_dup, (28, 28), 224, full=True)
     st = b.score_stats()
-    assert st["mode"] == 0 and st["fallback_queries"] > 0.5 * st["queries"], st
+    assert st["mode"] == 0 and st["fallback_queries"] > 0.5 * st["queries"] and st["gemm_fallback"], st
     again = b.score_batch(near_dup, (28, 28), 224, full=True)
     st2 = b.score_stats()
     assert st2["mode"] == 3 and st2["direct_calls_left"] == 31, st2
@@ -304,6 +319,8 @@ def test_certificate_fallback_on_near_duplicates(env):
     full = b.score_batch(near_dup, (28, 28), 224, full=True)
     _assert_same_results(cert, full, "certified(fallback) vs 3-term")
     _assert_same_results(again, full, "adaptive direct vs 3-term")
+    ex_val, _ = _exact_scan(b, near_dup[0])
+    np.testing.assert_allclose(cert[0].min_val, ex_val, rtol=2e-6)   # same distance, possibly another of the tied rows
     b.close()
 
 
@@ -438,9 +455,7 @@ def test_certificate_under_adversarial_inputs(env, kind, D):
     # the exact scan the certificate promises equality with: every (query, row) distance by the re-check arithmetic
     # (warp_sqdist), lowest row on ties.  (The CUDA-core diagnostics scorer is NOT that reference here: it re-checks only
     # its 4 best candidates, and these inputs have up to 8 rows within one float32 ulp of each other.)
-    ex_val, ex_idx = np.empty(P, np.float32), np.empty(P, np.int64)
-    rc = b._lib.cmdb_debug_exact_min(b._h, patch.ctypes.data, P, ex_val.ctypes.data, ex_idx.ctypes.data)
-    assert rc == 0
+    ex_val, ex_idx = _exact_scan(b, patch)
     bad = np.nonzero((cert.min_idx != ex_idx) | (cert.min_val != ex_val))[0]
     assert bad.size == 0, (kind, D, stats, bad[:5], cert.min_idx[bad[:5]], ex_idx[bad[:5]], cert.min_val[bad[:5]], ex_val[bad[:5]])
     # mode 3 (FP32-equivalent split, exact re-check of the 4 best candidates) carries no certificate: with more than 4 rows
