@@ -48,8 +48,8 @@ constexpr int kWorkCap = 16384;      // capacity of ScoreScratch::work_list
 // bound (~0.32 us per pair at 200k x 768) -- RIGOROUS: the result equals the exact float32 scan, lowest row on ties.
 // Tier 2, 3-term GEMM over the compacted uncertified queries + exact re-check of the 4 best candidates: at least one sweep
 // of the hi + lo bank (~0.25 ms), then ~0.55 us per query -- cheaper when a call queues very many pairs, but NOT certified:
-// among more than 4 rows within float32 noise of the minimum it may return another one of them (same distance to 2e-6,
-// not necessarily the lowest row).  Round 1 picked the cheaper tier; round 2 keeps the contract instead: tier 1 whenever the
+// among more than 4 rows within the float32 resolution of |a|^2 + |b|^2 - 2ab it may return another one of them (not
+// necessarily the exact minimum / lowest row).  Round 1 picked the cheaper tier; round 2 keeps the contract instead: tier 1 whenever the
 // pairs fit the work list (<= 5 ms of rescans in the worst case), tier 2 only beyond it (banks dominated by rows that
 // float32 cannot tell apart, where the reference's own mm-form argmin is arbitrary as well).
 __host__ __device__ inline bool fallback_use_rescan(int fails, int pairs) {

@@ -65,7 +65,7 @@ typedef enum cmdb_status {
  *              counts, and a bank where most queries end up there switches itself to mode 3 for the next 32 calls.
  *  3           FP32-equivalent split for every query: hi.hi + hi.lo + lo.hi, three MMAs per K step, exact re-check of the
  *              4 best candidates (no certificate: among more than 4 rows within float32 noise of the minimum it may return
- *              another one of them -- same distance to 2e-6 relative, not necessarily the lowest row).
+ *              another one of them -- equal up to the resolution of a float32 |a|^2 + |b|^2 - 2ab evaluation, not necessarily the lowest row).
  *  1           uncertified hi.hi pre-filter + exact re-check of the 4 best candidates (diagnostics). */
 #define CMDB_OPT_PREFILTER_TERMS 3
 #define CMDB_OPT_TIMING 2 /* 1 = record CUDA events between the stages of cmdb_score (see cmdb_bank_get_timings) */
