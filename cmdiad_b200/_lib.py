@@ -81,6 +81,7 @@ SYMBOLS = {
     "cmdb_bank_read": (_I, [_VP, _I64, _I64, _VP]),
     "cmdb_bank_finalize": (_I, [_VP]),
     "cmdb_bank_stream": (_I, [_VP, ctypes.POINTER(_VP)]),
+    "cmdb_bank_lane_streams": (_I, [_VP, ctypes.POINTER(_VP)]),
     "cmdb_bank_get_timings": (_I, [_VP, c_f32_p]),
     "cmdb_bank_score_stats": (_I, [_VP, _VP]),
     "cmdb_bank_build_knn": (_I, [_VP]),

@@ -265,24 +265,34 @@ class Bank:
         L.check(self._lib.cmdb_bank_get_timings(self._h, arr))
         return dict(zip(L.T_STAGES, [float(x) for x in arr]))
 
-    def stream(self):
-        """torch view of the handle's CUDA stream (for event timing on the stream the kernels run on)"""
-        st = getattr(self, "_stream", None)
+    def lane_streams(self):
+        """torch views of the handle's two lane streams (scoring calls alternate between them)"""
+        st = getattr(self, "_lanes", None)
         if st is None:
-            p = ctypes.c_void_p()
-            L.check(self._lib.cmdb_bank_stream(self._h, ctypes.byref(p)))
-            st = self._stream = torch.cuda.ExternalStream(p.value, device=torch.device("cuda", self.device))
+            arr = (ctypes.c_void_p * 2)()
+            L.check(self._lib.cmdb_bank_lane_streams(self._h, arr))
+            dev = torch.device("cuda", self.device)
+            st = self._lanes = {int(arr[i]): torch.cuda.ExternalStream(int(arr[i]), device=dev) for i in range(2)}
         return st
 
+    def stream(self):
+        """torch view of the CUDA stream the NEXT scoring call of this handle runs on (event timing, ordering of
+        collectives between the phases of a sharded round)"""
+        p = ctypes.c_void_p()
+        L.check(self._lib.cmdb_bank_stream(self._h, ctypes.byref(p)))
+        return self.lane_streams()[int(p.value)]
+
     def _order_after_producer(self, t):
-        """Device inputs: the library reads `t` on the handle's own (non-blocking) stream, so that stream first has to
+        """Device inputs: the library reads `t` on the handle's own (non-blocking) lane streams, so those first have to
         wait for whatever torch stream is producing it (ordering contract of `*_is_device = 1`, include/cmdiad_b200.h).
         The tensor is kept alive by the caller / the ticket until the library has consumed it (synchronous calls return
         after that point), so torch's caching allocator cannot recycle the block early; tensor.record_stream is
         deliberately NOT used: it would make the allocator touch the handle's stream when the tensor dies, possibly after
         the bank (and its stream) has been closed."""
         if isinstance(t, torch.Tensor) and t.is_cuda:
-            self.stream().wait_stream(torch.cuda.current_stream(t.device))
+            cur = torch.cuda.current_stream(t.device)
+            for st in self.lane_streams().values():
+                st.wait_stream(cur)
         return t
 
     # ---- storage ---------------------------------------------------------------------------------------------
@@ -504,18 +514,19 @@ class Bank:
         slot = self.__dict__.setdefault("_shard_round", 0) & 1
         self._shard_round += 1
         evs = phase_events
+        lane = self.stream()   # the lane this round runs on (the finish call below hands the handle to the other lane)
 
         def mark():
             if evs is not None:
                 e = torch.cuda.Event(enable_timing=True)
-                e.record(self.stream())
+                e.record(lane)
                 evs.append(e)
 
         self._order_after_producer(patches)
         # host-side allocations first: everything below is enqueued without waiting, and the GPU should not idle between
         # two phases while numpy allocates the result arrays
         res, outs, _ = self._alloc_out(B, P, out_hw, full)
-        with torch.cuda.stream(self.stream()):
+        with torch.cuda.stream(lane):
             mark()
             chunk = patches
             if not chunk.is_cuda and world > 1 and B * P >= 1024:

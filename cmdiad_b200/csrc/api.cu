@@ -360,6 +360,8 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
     CMDB_REQUIRE(outs, CMDB_ERR_INVALID, "cmdb_score_batch: outs is NULL");
     CMDB_CHECK(check_batch_args(b, patches, B, P, fh, fw, out_hw, "cmdb_score_batch"));
     const int bc_max = score_max_batch(b);
+    // sub-batches alternate between the two lanes: sub-batch k + 1 is enqueued before the host waits for sub-batch k
+    int prev_slot = -1, prev_b0 = 0;
     for (int b0 = 0; b0 < B; b0 += bc_max) {
         const int bc = std::min(bc_max, B - b0);
         const int slot = b->next_slot;
@@ -367,8 +369,10 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
         b->next_slot ^= 1;
         CMDB_CHECK(submit_sub_batch(b, patches + (size_t)b0 * P * b->dim, patch_is_device, bc, P, fh, fw, out_hw,
                                     want_mask_of(outs + b0, bc), slot));
-        CMDB_CHECK(wait_slot(b, slot, outs + b0));
+        if (prev_slot >= 0) CMDB_CHECK(wait_slot(b, prev_slot, outs + prev_b0));
+        prev_slot = slot, prev_b0 = b0;
     }
+    if (prev_slot >= 0) CMDB_CHECK(wait_slot(b, prev_slot, outs + prev_b0));
     return CMDB_OK;
 }
 
@@ -417,10 +421,13 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_REQUIRE(keys_device, CMDB_ERR_INVALID, "cmdb_score_shard_min: keys_device is NULL");
     CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_shard_min: out_hw=%d not in [8,256]", out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
-    if (b->pending[0].active || b->pending[1].active) {
-        // pipelined rounds (cmdb_score_shard_finish_submit / cmdb_score_shard_wait): the other result slot is used
-        CMDB_REQUIRE((size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
+    {
+        // the round runs on lane / result slot next_slot (what cmdb_bank_stream returns before this call); with the submit /
+        // wait finish two rounds may be in flight, one per lane
+        const bool busy = b->pending[0].active || b->pending[1].active;
+        CMDB_REQUIRE(!busy || (size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
                      "cmdb_score_shard_min: out_hw changes while a submitted round is outstanding; wait for it first");
+        if (!busy && (size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
         const int slot = b->next_slot;
         CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
                      "cmdb_score_shard_min: two submitted rounds are outstanding on this handle; wait for one first");
@@ -428,15 +435,7 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
         score_select_slot(b, slot);
         b->shard_slot = slot;
         CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
-        pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
-        CMDB_CUDA(cudaGetLastError());
-        return CMDB_OK;
     }
-    if ((size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
-    CMDB_CHECK(stage_alloc(b, B, P, out_hw));
-    score_select_slot(b, 0);
-    b->shard_slot = 0;
-    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1));
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;  // stream-ordered on the handle's stream (cmdb_bank_stream): run the collective there
@@ -582,7 +581,7 @@ int cmdb_bank_attach_comm(cmdb_bank *b, cmdb_comm *comm) {
     if (!b->shard_ctr) {
         CMDB_CUDA(cudaMalloc(&b->shard_ctr, 4 * sizeof(unsigned int)));
         CMDB_CUDA(cudaMemset(b->shard_ctr, 0, 4 * sizeof(unsigned int)));
-        CMDB_CUDA(cudaMalloc(&b->shard_d2, sizeof(float) * 4 * kShardD2Cap));
+        CMDB_CUDA(cudaMalloc(&b->shard_d2, sizeof(float) * 2 * kShardSlots * kShardD2Cap));
         CMDB_CUDA(cudaHostAlloc(&b->shard_abort_host, sizeof(unsigned int), cudaHostAllocMapped));
         *b->shard_abort_host = 0u;
         CMDB_CUDA(cudaHostGetDevicePointer(&b->shard_abort_dev, b->shard_abort_host, 0));
@@ -609,7 +608,7 @@ int cmdb_score_shard_round_submit(cmdb_bank *b, const float *patches, int B, int
     if (!busy && (size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
     CMDB_REQUIRE(!busy || (size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
                  "cmdb_score_shard_round_submit: out_hw changes while a submitted round is outstanding; wait for it first");
-    const int slot = busy ? b->next_slot : 0;
+    const int slot = b->next_slot;
     CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
                  "cmdb_score_shard_round_submit: two submitted rounds are outstanding on this handle; wait for one first");
     CMDB_CHECK(stage_alloc(b, B, P, out_hw));
@@ -617,10 +616,10 @@ int cmdb_score_shard_round_submit(cmdb_bank *b, const float *patches, int B, int
     b->shard_slot = slot;
     CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
     const unsigned long long epoch = comm_next_score_epoch(b->comm);  // per buffer, not per bank: several banks may share it
-    const int xslot = (int)(epoch & 1ULL);
+    const int xslot = (int)(epoch % kShardSlots);
     CMDB_CHECK(score_shard_exchange_keys(b, B, P, peers, world, rank, xslot, epoch));
     CMDB_CHECK(score_select(b, B, P, false));
-    float *contrib = b->shard_d2 + xslot * kShardD2Cap, *d2_sum = b->shard_d2 + (2 + xslot) * kShardD2Cap;
+    float *contrib = b->shard_d2 + xslot * kShardD2Cap, *d2_sum = b->shard_d2 + (kShardSlots + xslot) * kShardD2Cap;
     CMDB_CHECK(score_shard_lookup(b, B, contrib));
     CMDB_CHECK(score_shard_exchange_d2(b, B, peers, world, rank, xslot, epoch, contrib, d2_sum));
     return shard_finish_enqueue(b, d2_sum, B, P, fh, fw, out_hw, img_first, img_step, want_maps, out_ticket);

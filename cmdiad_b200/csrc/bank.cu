@@ -243,7 +243,9 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
     b->dim = dim;
     b->capacity = capacity_rows;
     cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, device);
-    cudaError_t err = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    cudaError_t err = cudaStreamCreateWithFlags(&b->lane_stream[0], cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->lane_stream[1], cudaStreamNonBlocking);
+    b->stream = b->lane_stream[0];
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2; ++i) {
@@ -288,7 +290,8 @@ static void free_scoring_layout(cmdb_bank *b) {
 void cmdb_bank_destroy(cmdb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto st : b->lane_stream)
+        if (st) cudaStreamSynchronize(st);
     if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
     if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
     free_scoring_layout(b);
@@ -306,7 +309,8 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     cudaFree(b->cert_buf);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
-    if (b->stream) cudaStreamDestroy(b->stream);
+    for (auto st : b->lane_stream)
+        if (st) cudaStreamDestroy(st);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     if (b->d2h_stream) cudaStreamDestroy(b->d2h_stream);
     for (int i = 0; i < 2; ++i) {
@@ -393,7 +397,13 @@ int cmdb_bank_set_query_norm(cmdb_bank *b, float mean, float stdv, int enabled) 
 
 int cmdb_bank_stream(cmdb_bank *b, void **out_stream) {
     CMDB_REQUIRE(b && out_stream, CMDB_ERR_INVALID, "cmdb_bank_stream: bad arguments");
-    *out_stream = (void *)b->stream;
+    *out_stream = (void *)b->lane_stream[b->next_slot];  // the lane the NEXT scoring call of this handle runs on
+    return CMDB_OK;
+}
+
+int cmdb_bank_lane_streams(cmdb_bank *b, void **out_streams2) {
+    CMDB_REQUIRE(b && out_streams2, CMDB_ERR_INVALID, "cmdb_bank_lane_streams: bad arguments");
+    out_streams2[0] = (void *)b->lane_stream[0], out_streams2[1] = (void *)b->lane_stream[1];
     return CMDB_OK;
 }
 
@@ -461,13 +471,13 @@ int cmdb_bank_set_knn_table(cmdb_bank *b, const uint64_t *keys, int64_t n_rows_t
 int cmdb_bank_score_stats(cmdb_bank *b, int64_t *out6) {
     CMDB_REQUIRE(b && out6, CMDB_ERR_INVALID, "cmdb_bank_score_stats: bad arguments");
     CMDB_CUDA(cudaSetDevice(b->device));
-    CMDB_CUDA(cudaStreamSynchronize(b->stream));
-    const bool cert = b->last_mode == 0 && b->ss.fail_count_host;
+    for (auto st : b->lane_stream) CMDB_CUDA(cudaStreamSynchronize(st));
+    const bool cert = b->last_mode == 0 && b->last_fail_host;
     out6[0] = b->last_queries;
     out6[1] = b->last_mode;
-    out6[2] = cert ? (int64_t)b->ss.fail_count_host[0] : 0;
-    out6[3] = cert ? (int64_t)b->ss.fail_count_host[1] : 0;
-    out6[4] = cert && !cmdb::fallback_use_rescan(b->ss.fail_count_host[0], b->ss.fail_count_host[1]);
+    out6[2] = cert ? (int64_t)b->last_fail_host[0] : 0;
+    out6[3] = cert ? (int64_t)b->last_fail_host[1] : 0;
+    out6[4] = cert && !cmdb::fallback_use_rescan(b->last_fail_host[0], b->last_fail_host[1]);
     out6[5] = b->direct_calls_left;
     return CMDB_OK;
 }

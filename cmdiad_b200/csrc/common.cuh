@@ -141,7 +141,14 @@ struct cmdb_bank {
     int last_mode = 0;           // GEMM mode the last call actually ran
     bool fail_pending = false;   // fail_count_host holds the count of a finished-or-in-flight call
     int direct_calls_left = 0;   // certified mode: calls to run directly with 3 terms before probing the pre-filter again
+    // Two compute LANES: scoring call k runs on lane k & 1 (its own stream and its own copy of every scratch buffer, ss_store),
+    // so the tail of a batch / round -- certificate, rescans, exchanges, re-weighting, maps -- overlaps the distance GEMM of
+    // the next one (the GEMM is one persistent CTA per SM; the small tail kernels fit beside it).  `stream` and `ss` are the
+    // lane currently selected (score_select_slot); everything that is not scoring runs on whichever lane is current.
     cudaStream_t stream = nullptr;
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cmdb::ScoreScratch ss_store[2];
+    int *last_fail_host = nullptr;   // pinned certificate counters of the most recent certified call (either lane)
     cudaStream_t copy_stream = nullptr;   // host -> device staging of query chunks, overlapped with the GEMM of earlier chunks
     cudaEvent_t ev_chunk[cmdb::kMaxStageChunks] = {};
     cudaStream_t d2h_stream = nullptr;    // device -> host copies of the results
@@ -233,15 +240,17 @@ constexpr unsigned int kCommKeysOff = 256;
 constexpr unsigned int kCommMaxCtas = 192;
 constexpr size_t kCommCoresetBytes = 256 * 1024;  // coreset flags + key slots (>= 256 + 2 * kMaxRanks * kCommMaxCtas * 32); cleared by cmdb_comm_reset
 // row-sharded SCORING rounds exchange through the same buffer (never cleared: every word is rewritten with the round's epoch):
-//   flags  [2 slots][2 kinds][kMaxRanks] u64 at kCommScoreFlagsOff
-//   d2     [2 slots][kMaxRanks][kShardD2Cap] float at kCommScoreD2Off        (squared neighbour distances, 2 per image)
-//   keys   [2 slots][kMaxRanks][kShardKeysCap] int64 at kCommScoreKeysOff    (packed (min distance, global row) per query)
+//   flags  [4 slots][2 kinds][kMaxRanks] u64 at kCommScoreFlagsOff
+//   d2     [4 slots][kMaxRanks][kShardD2Cap] float at kCommScoreD2Off        (squared neighbour distances, 2 per image)
+//   keys   [4 slots][kMaxRanks][kShardKeysCap] int64 at kCommScoreKeysOff    (packed (min distance, global row) per query)
+// (4 slots, round r uses slot r & 3: with two lanes per rank a rank may start round r + 2 while a peer still reads round r)
 constexpr size_t kCommScoreFlagsOff = kCommCoresetBytes;
 constexpr size_t kCommScoreD2Off = kCommScoreFlagsOff + 4096;
 constexpr int kShardD2Cap = 64;
-constexpr size_t kCommScoreKeysOff = kCommScoreD2Off + 8192;
+constexpr size_t kCommScoreKeysOff = kCommScoreD2Off + 16384;
 constexpr int kShardKeysCap = 128 * 1024;   // queries per round (32 images x 3136 patches = 100 352)
-constexpr size_t kCommHeaderBytes = 18 * 1024 * 1024;  // >= kCommScoreKeysOff + 2 * kMaxRanks * kShardKeysCap * 8; the replica follows
+constexpr int kShardSlots = 4;
+constexpr size_t kCommHeaderBytes = 34 * 1024 * 1024;  // >= kCommScoreKeysOff + kShardSlots * kMaxRanks * kShardKeysCap * 8; the replica follows
 struct ShardCtx {  // row-sharded coreset loop
     int world, rank;
     long long row_offset, n_total;

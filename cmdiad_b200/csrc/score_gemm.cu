@@ -598,17 +598,7 @@ int score_make_tensor_maps(cmdb_bank *b) {
     return CMDB_OK;
 }
 
-void score_scratch_free(cmdb_bank *b) {
-    ScoreScratch &s = b->ss;
-    // no copy may still be in flight into / out of the buffers
-    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
-    if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
-    if (b->stream) cudaStreamSynchronize(b->stream);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(s.q_f32_buf[i]), cudaFree(s.out_block_buf[i]);
-        if (s.out_block_host_buf[i]) cudaFreeHost(s.out_block_host_buf[i]);
-        b->pending[i].active = false;
-    }
+static void free_lane(ScoreScratch &s) {
     cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_scale_exp);
     cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys);
     cudaFree(s.map_tmp), cudaFree(s.map_max), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
@@ -617,7 +607,28 @@ void score_scratch_free(cmdb_bank *b) {
     cudaFree(s.work_list), cudaFree(s.best_key);
     if (s.fail_count_host) cudaFreeHost(s.fail_count_host);
     free(s.tmap_qhi), free(s.tmap_qlo);
-    s = ScoreScratch();
+}
+
+void score_scratch_free(cmdb_bank *b) {
+    // no copy or kernel may still be in flight into / out of the buffers
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
+    for (auto st : b->lane_stream)
+        if (st) cudaStreamSynchronize(st);
+    // query / result blocks are per SLOT and shared by both lane copies (slot i is only ever used by lane i)
+    ScoreScratch &s0 = b->ss_store[0];
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s0.q_f32_buf[i]), cudaFree(s0.out_block_buf[i]);
+        if (s0.out_block_host_buf[i]) cudaFreeHost(s0.out_block_host_buf[i]);
+        b->pending[i].active = false;
+    }
+    for (auto &s : b->ss_store) {
+        free_lane(s);
+        s = ScoreScratch();
+    }
+    b->ss = ScoreScratch();
+    b->last_fail_host = nullptr;
+    b->fail_pending = false;
 }
 
 int score_max_batch(const cmdb_bank *b) {
@@ -626,7 +637,10 @@ int score_max_batch(const cmdb_bank *b) {
     return std::max(1, std::min(32, by_smem));
 }
 
+// lane == slot: points b->ss / b->stream at that lane's scratch copy and stream, and at the slot's query / result blocks
 void score_select_slot(cmdb_bank *b, int slot) {
+    b->ss = b->ss_store[slot];
+    b->stream = b->lane_stream[slot];
     ScoreScratch &s = b->ss;
     s.q_f32 = s.q_f32_buf[slot];
     s.out_block = s.out_block_buf[slot];
@@ -640,79 +654,88 @@ void score_select_slot(cmdb_bank *b, int slot) {
 }
 
 int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
-    ScoreScratch &s = b->ss;
     const int p_pad = (B * P_img + BM - 1) / BM * BM;
     const int map_n = out_hw * out_hw;
-    if (s.cap_p >= p_pad && s.cap_b >= B && (int)s.map_stride >= map_n) return CMDB_OK;
+    {
+        const ScoreScratch &cur = b->ss_store[0];
+        if (cur.cap_p >= p_pad && cur.cap_b >= B && (int)cur.map_stride >= map_n) return CMDB_OK;
+    }
     CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
                  "scoring: the scratch buffers have to grow while a submitted batch is outstanding; wait for it first");
-    const int cap_p = std::max(p_pad, s.cap_p), cap_b = std::max(B, s.cap_b), map_cap = std::max(map_n, (int)s.map_stride);
+    const int cap_p = std::max(p_pad, b->ss_store[0].cap_p), cap_b = std::max(B, b->ss_store[0].cap_b);
+    const int map_cap = std::max(map_n, (int)b->ss_store[0].map_stride);
     score_scratch_free(b);
     const size_t D = b->dim;
-    s.n_topk_blocks = b->num_sms * 4;
-    for (int i = 0; i < 2; ++i) CMDB_CUDA(cudaMalloc(&s.q_f32_buf[i], sizeof(float) * cap_p * D));
-    CMDB_CUDA(cudaMalloc(&s.q_hi, sizeof(__half) * cap_p * D));
-    CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
-    CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int) * cap_p));
-    CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
-    CMDB_CUDA(cudaMalloc(&s.q_eps, sizeof(float) * cap_p));
-    CMDB_CUDA(cudaMalloc(&s.fail_list, sizeof(int) * cap_p));
-    CMDB_CUDA(cudaMalloc(&s.fail_ctl, 8 * sizeof(int)));
-    CMDB_CUDA(cudaMalloc(&s.work_list, sizeof(int2) * kWorkCap));
-    CMDB_CUDA(cudaMalloc(&s.best_key, sizeof(unsigned long long) * cap_p));
-    CMDB_CUDA(cudaMallocHost(&s.fail_count_host, 2 * sizeof(int)));
-    s.fail_count_host[0] = s.fail_count_host[1] = 0;
-    b->fail_pending = false;
-    CMDB_CUDA(cudaMalloc(&s.done_counter, sizeof(unsigned int)));
-    CMDB_CUDA(cudaMemset(s.done_counter, 0, sizeof(unsigned int)));
-    const size_t cand_bytes = sizeof(float4) * (size_t)cap_p * 2 * b->num_sms;
-    CMDB_CUDA(cudaMalloc(&s.cand, cand_bytes));
-    {
-        // L2 persistence for the candidate lists (see score_gemm_candidates).  The carve-out is process-wide device state:
-        // it is only ever GROWN here, never shrunk or reset, so a host program's own configuration survives.
-        static const bool enabled = [] {
-            const char *e = getenv("CMDB_CAND_L2PERSIST");
-            return !(e && e[0] == '0');
-        }();
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, b->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, b->device);
-        s.cand_window_bytes = 0, s.cand_hit_ratio = 0.f;
-        if (enabled && max_persist > 0 && max_window > 0) {
-            const size_t want = std::min<size_t>(cand_bytes, (size_t)max_persist);
-            size_t cur = 0;
-            (void)cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
-            if (cur >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-                s.cand_window_bytes = std::min<size_t>(cand_bytes, (size_t)max_window);
-                s.cand_hit_ratio = (float)std::min(1.0, (double)std::max(cur, want) / (double)s.cand_window_bytes);
-            }
-            (void)cudaGetLastError();
-        }
-    }
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
-    s.map_stride = map_cap;
-    s.off_min_val = up(sizeof(TailResult) * cap_b);
-    s.off_min_idx = s.off_min_val + up(sizeof(float) * cap_p);
-    s.off_map_out = s.off_min_idx + up(sizeof(long long) * cap_p);
-    s.off_map_pre = s.off_map_out + up(sizeof(float) * map_cap * cap_b);
-    s.off_map_u8 = s.off_map_pre + up(sizeof(float) * map_cap * cap_b);
-    s.out_block_bytes = s.off_map_u8 + up((size_t)map_cap * cap_b);
+    // shared per-slot blocks: queries in, results out (mirrored by a pinned host block)
+    ScoreScratch shared;
+    shared.map_stride = map_cap;
+    shared.off_min_val = up(sizeof(TailResult) * cap_b);
+    shared.off_min_idx = shared.off_min_val + up(sizeof(float) * cap_p);
+    shared.off_map_out = shared.off_min_idx + up(sizeof(long long) * cap_p);
+    shared.off_map_pre = shared.off_map_out + up(sizeof(float) * map_cap * cap_b);
+    shared.off_map_u8 = shared.off_map_pre + up(sizeof(float) * map_cap * cap_b);
+    shared.out_block_bytes = shared.off_map_u8 + up((size_t)map_cap * cap_b);
     for (int i = 0; i < 2; ++i) {
-        CMDB_CUDA(cudaMalloc(&s.out_block_buf[i], s.out_block_bytes));
-        CMDB_CUDA(cudaMallocHost(&s.out_block_host_buf[i], s.out_block_bytes));
+        CMDB_CUDA(cudaMalloc(&shared.q_f32_buf[i], sizeof(float) * cap_p * D));
+        CMDB_CUDA(cudaMalloc(&shared.out_block_buf[i], shared.out_block_bytes));
+        CMDB_CUDA(cudaMallocHost(&shared.out_block_host_buf[i], shared.out_block_bytes));
     }
+    for (int lane = 0; lane < 2; ++lane) {
+        ScoreScratch &s = b->ss_store[lane];
+        s = shared;
+        s.n_topk_blocks = b->num_sms * 4;
+        CMDB_CUDA(cudaMalloc(&s.q_hi, sizeof(__half) * cap_p * D));
+        CMDB_CUDA(cudaMalloc(&s.q_lo, sizeof(__half) * cap_p * D));
+        CMDB_CUDA(cudaMalloc(&s.q_scale_exp, sizeof(int) * cap_p));
+        CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
+        CMDB_CUDA(cudaMalloc(&s.q_eps, sizeof(float) * cap_p));
+        CMDB_CUDA(cudaMalloc(&s.fail_list, sizeof(int) * cap_p));
+        CMDB_CUDA(cudaMalloc(&s.fail_ctl, 8 * sizeof(int)));
+        CMDB_CUDA(cudaMalloc(&s.work_list, sizeof(int2) * kWorkCap));
+        CMDB_CUDA(cudaMalloc(&s.best_key, sizeof(unsigned long long) * cap_p));
+        CMDB_CUDA(cudaMallocHost(&s.fail_count_host, 2 * sizeof(int)));
+        s.fail_count_host[0] = s.fail_count_host[1] = 0;
+        CMDB_CUDA(cudaMalloc(&s.done_counter, sizeof(unsigned int)));
+        CMDB_CUDA(cudaMemset(s.done_counter, 0, sizeof(unsigned int)));
+        const size_t cand_bytes = sizeof(float4) * (size_t)cap_p * 2 * b->num_sms;
+        CMDB_CUDA(cudaMalloc(&s.cand, cand_bytes));
+        {
+            // optional L2 persistence for the candidate lists (CMDB_CAND_L2PERSIST=1; measured: no effect once the lists are
+            // touched once per run of tiles).  The carve-out is process-wide device state: only ever GROWN.
+            static const bool enabled = [] {
+                const char *e = getenv("CMDB_CAND_L2PERSIST");
+                return e && e[0] == '1';
+            }();
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, b->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, b->device);
+            s.cand_window_bytes = 0, s.cand_hit_ratio = 0.f;
+            if (enabled && max_persist > 0 && max_window > 0) {
+                const size_t want = std::min<size_t>(cand_bytes, (size_t)max_persist);
+                size_t cur = 0;
+                (void)cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+                if (cur >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    s.cand_window_bytes = std::min<size_t>(cand_bytes, (size_t)max_window);
+                    s.cand_hit_ratio = (float)std::min(1.0, (double)std::max(cur, want) / (double)s.cand_window_bytes);
+                }
+                (void)cudaGetLastError();
+            }
+        }
+        CMDB_CUDA(cudaMalloc(&s.map_tmp, (size_t)map_cap * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long) * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3 * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.m_star, sizeof(float) * D * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.nn_rows, sizeof(float) * 3 * D * cap_b));
+        s.cap_p = cap_p, s.cap_b = cap_b, s.map_cap = map_cap;
+        CMDB_CHECK(make_map(&s.tmap_qhi, s.q_hi, cap_p, b->dim, BM));
+        CMDB_CHECK(make_map(&s.tmap_qlo, s.q_lo, cap_p, b->dim, BM));
+    }
+    b->fail_pending = false;
     score_select_slot(b, 0);
-    CMDB_CUDA(cudaMalloc(&s.map_tmp, (size_t)map_cap * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long) * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3 * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.m_star, sizeof(float) * D * cap_b));
-    CMDB_CUDA(cudaMalloc(&s.nn_rows, sizeof(float) * 3 * D * cap_b));
-    s.cap_p = cap_p, s.cap_b = cap_b, s.map_cap = map_cap;
-    CMDB_CHECK(make_map(&s.tmap_qhi, s.q_hi, cap_p, b->dim, BM));
-    CMDB_CHECK(make_map(&s.tmap_qlo, s.q_lo, cap_p, b->dim, BM));
     return CMDB_OK;
 }
 

@@ -446,7 +446,8 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     cudaStream_t st = b->stream;
     CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
     CMDB_CUDA(cudaMemsetAsync(s.fail_ctl, 0, 8 * sizeof(int), st));
-    refine_cert_kernel<<<(P + 7) / 8, 256, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img, b->row_offset,
+    // 4 queries per block: 128 threads x 80 registers fit beside a resident GEMM CTA of the other lane (384 x 120 registers)
+    refine_cert_kernel<<<(P + 3) / 4, 128, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img, b->row_offset,
                                                     s.q_norm, s.q_eps, b->cert_bmax, b->cert_eb_max,
                                                     (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f, s.min_val, s.min_idx, s.s_key,
                                                     s.fail_list, s.fail_ctl, s.work_list, s.best_key);
@@ -504,10 +505,10 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
         // banks), run the FP32-equivalent GEMM directly for a while, then probe the pre-filter again
         // (the counters of the previous certified call; if their copy has not landed yet -- pipelined submits -- look again
         // next time instead of stalling the host)
-        if (b->fail_pending && cudaEventQuery(b->ev_fail) == cudaSuccess) {
+        if (b->fail_pending && b->last_fail_host && cudaEventQuery(b->ev_fail) == cudaSuccess) {
             b->fail_pending = false;
-            if (prev_queries > 0 && !fallback_use_rescan(s.fail_count_host[0], s.fail_count_host[1]) &&
-                (double)s.fail_count_host[0] > 0.5 * (double)prev_queries)
+            if (prev_queries > 0 && !fallback_use_rescan(b->last_fail_host[0], b->last_fail_host[1]) &&
+                (double)b->last_fail_host[0] > 0.5 * (double)prev_queries)
                 b->direct_calls_left = 32;
         }
         if (b->direct_calls_left > 0) {
@@ -566,6 +567,7 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     CMDB_CUDA(cudaMemcpyAsync(s.fail_count_host, s.fail_ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CMDB_CUDA(cudaEventRecord(b->ev_fail, st));
     b->fail_pending = true;
+    b->last_fail_host = s.fail_count_host;   // this lane's pinned counters
     // tier 2 (many uncertified pairs): FP32-equivalent GEMM over the compacted uncertified queries; every launch sizes
     // itself from the device-side control block and returns at once in the common case
     CMDB_CHECK(score_query_prep(b, P, true));
@@ -1106,6 +1108,9 @@ __global__ void __launch_bounds__(64) shard_sum_d2_kernel(const unsigned char *_
 }
 
 static size_t shard_flag_off(int slot, int kind) { return kCommScoreFlagsOff + (size_t)((slot * 2 + kind) * kMaxRanks) * 8; }
+static_assert(kCommScoreFlagsOff + kShardSlots * 2 * kMaxRanks * 8 <= kCommScoreD2Off, "flags overlap the d2 slots");
+static_assert(kCommScoreD2Off + (size_t)kShardSlots * kMaxRanks * kShardD2Cap * 4 <= kCommScoreKeysOff, "d2 slots overlap the key slots");
+static_assert(kCommScoreKeysOff + (size_t)kShardSlots * kMaxRanks * kShardKeysCap * 8 <= kCommHeaderBytes, "key slots exceed the header");
 
 int score_shard_exchange_keys(cmdb_bank *b, int B, int P_img, const PeerPtrs &peers, int world, int rank, int slot,
                               unsigned long long epoch) {
@@ -1116,7 +1121,7 @@ int score_shard_exchange_keys(cmdb_bank *b, int B, int P_img, const PeerPtrs &pe
     const size_t keys_off = kCommScoreKeysOff + (size_t)slot * kMaxRanks * kShardKeysCap * 8;
     const int blocks = std::min((n + 255) / 256, 2 * b->num_sms);
     shard_push_keys_kernel<<<blocks, 256, 0, st>>>(s.min_val, s.min_idx, n, peers, world, rank, keys_off, shard_flag_off(slot, 0), epoch,
-                                                   b->shard_ctr);
+                                                   b->shard_ctr + (slot & 1));  // consecutive rounds (= the two lanes) use different counters
     CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
     shard_reduce_keys_kernel<<<blocks, 256, 0, st>>>(peers.p[rank], keys_off, shard_flag_off(slot, 0), world, epoch, n, P_img, s.min_val,
                                                      s.min_idx, s.s_key, b->shard_abort_dev);

@@ -109,8 +109,11 @@ int cmdb_bank_read(cmdb_bank *bank, int64_t row0, int64_t n_rows, float *out_hos
 int cmdb_bank_read_device(cmdb_bank *bank, int64_t row0, int64_t n_rows, float *out_device);
 /* Builds the scoring layout (fp16 hi/lo split, row norms) for the current rows. Must precede cmdb_score*. */
 int cmdb_bank_finalize(cmdb_bank *bank);
-/* the cudaStream_t every kernel of this handle is launched on (for event timing by the caller) */
+/* A handle has two compute lanes (stream + private scratch each); scoring calls alternate between them so that the tail of
+ * one batch / round overlaps the distance GEMM of the next.  cmdb_bank_stream: the cudaStream_t the NEXT scoring call on this
+ * handle will run on (order producer work / collectives against it); cmdb_bank_lane_streams: both of them. */
 int cmdb_bank_stream(cmdb_bank *bank, void **out_stream);
+int cmdb_bank_lane_streams(cmdb_bank *bank, void **out_streams2);
 /* milliseconds of each stage (CMDB_T_*) of the last cmdb_score call on this handle; needs CMDB_OPT_TIMING = 1.
  * out_ms: float [CMDB_T_COUNT].  Measured with CUDA events on the handle's stream. */
 int cmdb_bank_get_timings(cmdb_bank *bank, float *out_ms);
