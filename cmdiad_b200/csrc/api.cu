@@ -305,9 +305,9 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
         if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[i], b->stream)); \
     } while (0)
     ScoreScratch &s = b->ss;
-    cudaStream_t st = b->stream;
     CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
     score_select_slot(b, slot);
+    cudaStream_t st = b->stream;  // the slot's lane (only valid after the selection)
     CMDB_MARK(CMDB_T_STAGE_IN);
     // this slot's q_f32 was last read by the batch submitted two calls ago
     CMDB_CHECK(score_local_min(b, src, is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE, b->ev_compute[slot]));

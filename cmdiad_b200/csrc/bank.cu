@@ -410,6 +410,7 @@ int cmdb_bank_lane_streams(cmdb_bank *b, void **out_streams2) {
 int cmdb_bank_get_timings(cmdb_bank *b, float *out_ms) {
     CMDB_REQUIRE(b && out_ms, CMDB_ERR_INVALID, "cmdb_bank_get_timings: bad arguments");
     CMDB_REQUIRE(b->timing && b->ev_valid, CMDB_ERR_STATE, "cmdb_bank_get_timings: enable CMDB_OPT_TIMING and call cmdb_score first");
+    CMDB_CUDA(cudaEventSynchronize(b->ev[CMDB_T_COUNT]));  // recorded right behind the event the wait call synchronised on
     for (int i = 0; i < CMDB_T_COUNT; ++i) CMDB_CUDA(cudaEventElapsedTime(out_ms + i, b->ev[i], b->ev[i + 1]));
     return CMDB_OK;
 }

@@ -1348,11 +1348,11 @@ static int score_reweight_tensor(cmdb_bank *b, int B, int P_img, bool fused) {
 // fp16 split, the certified pre-filter GEMM and reweight_cert_kernel (one block per row, keys only).
 int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count) {
     ScoreScratch &s = b->ss;
-    cudaStream_t st = b->stream;
     const int chunk = 64 * kScoreBM;  // 8192 rows: 64 M tiles per GEMM launch
     // scratch for `chunk` query rows; sized like a 32-image batch so that later scoring calls do not have to grow it
     CMDB_CHECK(score_scratch_alloc(b, 32, chunk / 32, s.map_stride ? (int)lround(sqrt((double)s.map_stride)) : 224));
     score_select_slot(b, 0);
+    cudaStream_t st = b->stream;  // lane 0 (only valid after the selection)
     if (!b->knn_table || b->knn_rows != b->fin_rows) {
         cudaFree(b->knn_table);
         b->knn_table = nullptr;
