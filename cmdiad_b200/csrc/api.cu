@@ -46,6 +46,15 @@ __global__ void contrib_rows_kernel(const float *__restrict__ bank, long long ro
     }
 }
 
+void api_prefer_carveout_fuse();
+void api_prefer_carveout() {
+    api_prefer_carveout_fuse();
+    CMDB_PREFER_MAX_SMEM(pack_keys_kernel);
+    CMDB_PREFER_MAX_SMEM(unpack_keys_kernel);
+    CMDB_PREFER_MAX_SMEM(contrib_rows_kernel);
+    (void)cudaGetLastError();
+}
+
 static int check_score_args(cmdb_bank *b, const void *patch, int B, int P, const char *fn) {
     CMDB_REQUIRE(b && patch, CMDB_ERR_INVALID, "%s: NULL argument", fn);
     CMDB_REQUIRE(b->finalized, CMDB_ERR_STATE, "%s: call cmdb_bank_finalize first", fn);
@@ -193,6 +202,8 @@ __global__ void __launch_bounds__(256) fuse_head_kernel(FuseParams p) {
         if (p.acc_s) p.acc_s[b] = v;
     }
 }
+
+void api_prefer_carveout_fuse() { CMDB_PREFER_MAX_SMEM(fuse_head_kernel); }
 
 }  // namespace cmdb
 
@@ -659,7 +670,7 @@ int cmdb_bank_stage_h2d(cmdb_bank *b, void *dst_device, const void *src_host, si
     // data up through an event.  (The caller guarantees that dst_device is not read by earlier, still running work.)
     CMDB_CUDA(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, b->copy_stream));
     CMDB_CUDA(cudaEventRecord(b->ev_stage, b->copy_stream));
-    CMDB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_stage, 0));
+    for (auto st : b->lane_stream) CMDB_CUDA(cudaStreamWaitEvent(st, b->ev_stage, 0));  // whichever lane runs the round
     return CMDB_OK;
 }
 

@@ -154,6 +154,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel_impl(const float *__res
     }
 }
 
+void bank_prefer_carveout() {
+    CMDB_PREFER_MAX_SMEM(normalize_kernel);
+    (void)cudaGetLastError();
+}
+
 void launch_normalize(cudaStream_t stream, int num_sms, float *x, int64_t n, float mean, float stdv) {
     if (n <= 0) return;
     int grid = (int)std::min<int64_t>((n / 4 + 511) / 512 + 1, (int64_t)num_sms * 4);

@@ -286,6 +286,16 @@ int score_gemm_run(int nt, int mt_units, int G);  // N tiles per visit of an M t
 int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, int P_img, int ev_gemm, int ev_refine,
                     cudaEvent_t stage_after = nullptr);
 
+// The distance GEMM keeps one persistent CTA per SM with ~200 KB of dynamic shared memory, i.e. the SM runs in its largest
+// shared-memory carve-out.  For the other lane's small kernels to become co-resident with it they must ask for the SAME
+// carve-out (an SM is only re-configured when it is idle); one function per translation unit sets that preference once.
+#define CMDB_PREFER_MAX_SMEM(kernel) \
+    (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+void tail_prefer_carveout();   // score_tail.cu
+void gemm_prefer_carveout();   // score_gemm.cu
+void api_prefer_carveout();    // api.cu
+void bank_prefer_carveout();   // bank.cu
+
 // score_tail.cu
 struct TailResult {  // device-side result block (ScoreScratch::tail)
     float s, s_star, w, knn0, knn1;

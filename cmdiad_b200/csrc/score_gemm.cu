@@ -598,6 +598,11 @@ int score_make_tensor_maps(cmdb_bank *b) {
     return CMDB_OK;
 }
 
+void gemm_prefer_carveout() {
+    CMDB_PREFER_MAX_SMEM(q_split_kernel);
+    (void)cudaGetLastError();
+}
+
 static void free_lane(ScoreScratch &s) {
     cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_scale_exp);
     cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys);
@@ -665,6 +670,13 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     const int cap_p = std::max(p_pad, b->ss_store[0].cap_p), cap_b = std::max(B, b->ss_store[0].cap_b);
     const int map_cap = std::max(map_n, (int)b->ss_store[0].map_stride);
     score_scratch_free(b);
+    {
+        static bool once = false;
+        if (!once) {
+            once = true;
+            tail_prefer_carveout(), gemm_prefer_carveout(), api_prefer_carveout(), bank_prefer_carveout();
+        }
+    }
     const size_t D = b->dim;
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
     // shared per-slot blocks: queries in, results out (mirrored by a pinned host block)

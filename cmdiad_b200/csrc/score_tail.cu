@@ -1442,6 +1442,28 @@ int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev) {
     return CMDB_OK;
 }
 
+void tail_prefer_carveout() {
+    CMDB_PREFER_MAX_SMEM(refine_kernel);
+    CMDB_PREFER_MAX_SMEM(refine_cert_kernel);
+    CMDB_PREFER_MAX_SMEM(fallback_decide_kernel);
+    CMDB_PREFER_MAX_SMEM(rescan_kernel);
+    CMDB_PREFER_MAX_SMEM(rescan_finish_kernel);
+    CMDB_PREFER_MAX_SMEM(select_kernel);
+    CMDB_PREFER_MAX_SMEM(reweight_cert_kernel);
+    CMDB_PREFER_MAX_SMEM(reweight_lookup_kernel);
+    CMDB_PREFER_MAX_SMEM(merge_top3_kernel);
+    CMDB_PREFER_MAX_SMEM(final_kernel);
+    CMDB_PREFER_MAX_SMEM(shard_lookup_kernel);
+    CMDB_PREFER_MAX_SMEM(shard_final_kernel);
+    CMDB_PREFER_MAX_SMEM(shard_push_keys_kernel);
+    CMDB_PREFER_MAX_SMEM(shard_reduce_keys_kernel);
+    CMDB_PREFER_MAX_SMEM(shard_push_d2_kernel);
+    CMDB_PREFER_MAX_SMEM(shard_sum_d2_kernel);
+    CMDB_PREFER_MAX_SMEM(upsample_hblur_kernel);
+    CMDB_PREFER_MAX_SMEM(vblur_kernel);
+    (void)cudaGetLastError();
+}
+
 int score_merge_top3(cmdb_bank *b, int n_ranks, int B) {
     merge_top3_kernel<<<B, 32, 0, b->stream>>>(b->ss.topk_keys, n_ranks, B, b->ss.top3);
     CMDB_CUDA(cudaGetLastError());
