@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark of the memory-bank anomaly-scoring hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|4|5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4|5]
 
 Default (--config 1, BASELINE cfg 5 headline).  A "step" scores one batch (--batch, default 16) of synthetic 784-patch
 images (DINO ViT-B/8 shaped, 768-d) against an un-subsampled 200 000 x 768 float32 bank through the full path: distance
@@ -12,9 +12,10 @@ GEMM + min/argmin, s*/m*/top-3 re-weighting, bilinear upsample and Gaussian blur
            N > 1 additionally: row-sharded results == single-GPU results, bit for bit, scoring and coreset
   coreset_select_s    projection + greedy selection of 10 % of the same bank
   predict_batch_e2e   the drop-in API (methods.RGBFeatures.predict_batch: normalisation, scoring, late-fusion head on the device)
-  large_bank / configs   the other BASELINE configurations in bounded form (full form: --config 2 / 4 / 5)
+  large_bank / configs   the other BASELINE configurations in bounded form (full form: --config 2 / 3 / 4 / 5;
+                         3 = the ten classes in sequence, class-parallel over the ranks)
 N > 1 (torchrun, one rank per GPU): the bank is row-sharded; every step runs one round of the three-phase sharded
-protocol (two small NCCL collectives) with two rounds in flight (strong scaling: the job is still one 200k bank).
+protocol (two small exchanges over peer-mapped memory fused into the kernels) with two rounds in flight (strong scaling: the job is still one 200k bank).
 `--impl reference` times the CPU restatement of the reference path (oracle/, the one place it may be executed from here)
 on ALL host cores with a bounded sample.
 """
@@ -389,7 +390,7 @@ def large_bank_leg(rank, world, local, pk, steps, rows=1_000_000, picks=10_000, 
     return out
 
 
-def dual_bank_leg(local, pk, n_img=200, score_images=16):
+def dual_bank_leg(local, pk, n_img=200, score_images=16, seed_base=0):
     """BASELINE cfg 2: DINO + Point-MAE dual bank -- XYZ 200 x 3136 x 1152 (627 200 rows, d' = 329, n = 62 720) and RGB
     200 x 784 x 768 (156 800 rows, n = 15 680), 10 % coreset each (multiple_features.py:873-895), then scoring of
     `score_images` test images against both coresets through the device-side late-fusion head (:967-994)."""
@@ -398,7 +399,7 @@ def dual_bank_leg(local, pk, n_img=200, score_images=16):
     dev = torch.device("cuda", local)
     out = {}
     banks = {}
-    for name, Pm, D, seed in (("xyz", 3136, 1152, 21), ("rgb", 784, 768, 22)):
+    for name, Pm, D, seed in (("xyz", 3136, 1152, 21 + seed_base), ("rgb", 784, 768, 22 + seed_base)):
         rows = n_img * Pm
         b = Bank(D, rows, device=local)
         for r0 in range(0, rows, 100_000):
@@ -434,6 +435,48 @@ def dual_bank_leg(local, pk, n_img=200, score_images=16):
     for b, *_ in banks.values():
         b.close()
     return out
+
+
+def ten_class_leg(rank, world, local, pk, n_classes=10):
+    """BASELINE cfg 3: the 10 MVTec-3D-shaped classes, one synthetic dual bank each (the cfg 2 pipeline: 10 % coreset of the
+    XYZ and RGB banks, neighbour tables, scoring through the late-fusion head), handled in sequence as cmdiad_runner.py does
+    per class.  Classes are independent objects: with N GPUs class c runs on rank c % N, no collective on the data path."""
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    mine = [c for c in range(n_classes) if c % world == rank]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    per_class = {}
+    for c in mine:
+        tc = time.perf_counter()
+        r = dual_bank_leg(local, pk, seed_base=40 * (c + 1))
+        torch.cuda.synchronize()
+        per_class[c] = {"rank": rank, "coreset_select_s": r["coreset_select_s"], "us_per_pick_xyz": r["coreset_xyz"]["us_per_pick"],
+                        "us_per_pick_rgb": r["coreset_rgb"]["us_per_pick"], "scoring_value": r["scoring"]["value"],
+                        "scoring_ms_per_step": r["scoring"]["ms_per_step"], "class_wall_s": time.perf_counter() - tc}
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], device=dev, dtype=torch.float64)
+    gathered = [per_class]
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_class)
+    allc = {}
+    for g in gathered:
+        allc.update(g)
+    wall = float(t)
+    n = len(allc)
+    return {"classes": n, "assignment": "class c on rank c % N (independent objects, no data-path collective)",
+            "wall_s_all_classes": wall, "classes_per_s": n / wall,
+            "coreset_select_s_sum": sum(v["coreset_select_s"] for v in allc.values()),
+            "coreset_select_s_mean_per_class": sum(v["coreset_select_s"] for v in allc.values()) / max(1, n),
+            "scoring_value_mean_per_gpu": sum(v["scoring_value"] for v in allc.values()) / max(1, n),
+            "unit_scoring": "patch-NN scores/s (3136 xyz + 784 rgb per image)",
+            "per_class": {str(k): allc[k] for k in sorted(allc)},
+            "note": "wall time covers bank generation on the device, statistics, both coresets (627 200 -> 62 720 and 156 800 -> "
+                    "15 680 rows), gather, finalize, neighbour tables and 6 scoring steps of 16 images per class"}
 
 
 def fused_bank_leg(local, pk, fracs=(0.01,), rows=1_000_000, D=1920):
@@ -753,7 +796,7 @@ def run_ours(args):
         line["large_bank"] = large_bank_leg(rank, world, local, pk, steps=max(5, args.steps // 2), comm=comm)
         if world == 1:
             line["configs"] = {"cfg2_dual_bank": dual_bank_leg(local, pk), "cfg4_fused_bank_1pct": fused_bank_leg(local, pk),
-                               "note": "bounded forms measured in this run; full sweeps: bench.py --config 2 / 4 / 5 "
+                               "note": "bounded forms measured in this run; full sweeps: bench.py --config 2 / 3 / 4 / 5 "
                                        "(logs under profiles/)"}
     if comm is not None:
         comm.close()
@@ -857,7 +900,7 @@ def dropin_leg(bank, imgs, B):
 
 
 def run_config(args):
-    """--config 2 / 4 / 5: the full forms of the other BASELINE configurations (one JSON line each)"""
+    """--config 2 / 3 / 4 / 5: the full forms of the other BASELINE configurations (one JSON line each)"""
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -870,6 +913,8 @@ def run_config(args):
     if args.config == 2:
         assert world == 1
         out["cfg2_dual_bank"] = dual_bank_leg(local, pk)
+    elif args.config == 3:
+        out["cfg3_ten_classes"] = ten_class_leg(rank, world, local, pk)
     elif args.config == 4:
         assert world == 1
         out["cfg4_fused_bank"] = fused_bank_leg(local, pk, fracs=(0.01, 0.10, 0.25))
@@ -898,8 +943,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per step")
-    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 4, 5],
-                    help="1 = headline (default); 2 / 4 / 5 = full form of BASELINE.json configs[1] / [3] / [4]")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4, 5],
+                    help="1 = headline (default); 2 / 3 / 4 / 5 = full form of BASELINE.json configs[1] / [2] / [3] / [4]")
     ap.add_argument("--skip-coreset", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true", help="skip the 1M-row bank and the bounded cfg 2 / cfg 4 legs")

@@ -313,7 +313,7 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
                             unsigned want, int slot, bool host_maps = true) {
 #define CMDB_MARK(i)                                                   \
     do {                                                               \
-        if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[i], b->stream)); \
+        if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[slot][i] : b->ev[i], b->stream)); \
     } while (0)
     ScoreScratch &s = b->ss;
     CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
@@ -337,7 +337,7 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
     CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
     CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_min_val, cudaMemcpyDeviceToHost, b->d2h_stream));
     CMDB_CUDA(cudaEventRecord(b->ev_done[slot], b->d2h_stream));
-    if (b->timing) CMDB_CUDA(cudaEventRecord(b->ev[CMDB_T_COUNT], b->d2h_stream));
+    if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[slot][CMDB_T_COUNT] : b->ev[CMDB_T_COUNT], b->d2h_stream));
 #undef CMDB_MARK
     cmdb_bank::Pending &pd = b->pending[slot];
     pd.active = true, pd.B = bc, pd.P = P, pd.out_hw = out_hw, pd.want = want, pd.host_maps = host_maps;
@@ -349,7 +349,7 @@ static int wait_slot(cmdb_bank *b, int slot, cmdb_score_out *outs) {
     CMDB_CUDA(cudaEventSynchronize(b->ev_done[slot]));
     pd.active = false;
     scatter_outputs(b, b->ss.out_block_host_buf[slot], pd.B, pd.P, pd.out_hw, outs);
-    if (b->timing) b->ev_valid = true;
+    if (b->timing == 1) b->ev_valid = true;
     return CMDB_OK;
 }
 
@@ -727,6 +727,21 @@ int cmdb_debug_exact_min(cmdb_bank *b, const float *patch_host, int P, float *mi
 }
 
 // host-only test hooks (not in the public header): the GEMM's tile-schedule stride and the fallback-tier rule
+// CMDB_OPT_TIMING = 2: milliseconds since the time base of every stage mark of the last batch on each lane
+// (out: float [2][CMDB_T_COUNT + 1]); all submitted batches must have been waited for
+int cmdb_debug_lane_timeline(cmdb_bank *b, float *out) {
+    CMDB_REQUIRE(b && out && b->timing == 2 && b->ev_base, CMDB_ERR_STATE, "cmdb_debug_lane_timeline: set CMDB_OPT_TIMING = 2 first");
+    CMDB_CUDA(cudaSetDevice(b->device));
+    CMDB_CUDA(cudaDeviceSynchronize());
+    for (int l = 0; l < 2; ++l)
+        for (int i = 0; i <= CMDB_T_COUNT; ++i)
+            if (cudaEventElapsedTime(out + l * (CMDB_T_COUNT + 1) + i, b->ev_base, b->ev_tl[l][i]) != cudaSuccess) {
+                (void)cudaGetLastError();
+                out[l * (CMDB_T_COUNT + 1) + i] = -1.f;
+            }
+    return CMDB_OK;
+}
+
 int cmdb_debug_tile_stride(int mt, int G) { return score_tile_stride(mt, G); }
 int cmdb_debug_fallback_use_rescan(int fails, int pairs) { return fallback_use_rescan(fails, pairs) ? 1 : 0; }
 

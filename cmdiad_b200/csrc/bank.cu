@@ -319,6 +319,10 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     cudaFree(b->cert_buf);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &l : b->ev_tl)
+        for (auto &e : l)
+            if (e) cudaEventDestroy(e);
+    if (b->ev_base) cudaEventDestroy(b->ev_base);
     if (b->lane_stream[1] && b->lane_stream[1] != b->lane_stream[0]) cudaStreamDestroy(b->lane_stream[1]);
     if (b->lane_stream[0]) cudaStreamDestroy(b->lane_stream[0]);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
@@ -384,10 +388,20 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
         return CMDB_OK;
     }
     if (option == CMDB_OPT_TIMING) {
-        b->timing = value != 0;
+        b->timing = value == 2 ? 2 : (value != 0);
         if (b->timing && !b->ev[0]) {
             CMDB_CUDA(cudaSetDevice(b->device));
             for (auto &e : b->ev) CMDB_CUDA(cudaEventCreate(&e));
+        }
+        if (b->timing == 2) {  // lane timeline (diagnostics): per-lane events against a common base
+            CMDB_CUDA(cudaSetDevice(b->device));
+            if (!b->ev_base) {
+                CMDB_CUDA(cudaEventCreate(&b->ev_base));
+                for (auto &l : b->ev_tl)
+                    for (auto &e : l) CMDB_CUDA(cudaEventCreate(&e));
+            }
+            CMDB_CUDA(cudaDeviceSynchronize());
+            CMDB_CUDA(cudaEventRecord(b->ev_base, b->lane_stream[0]));
         }
         b->ev_valid = false;
         return CMDB_OK;

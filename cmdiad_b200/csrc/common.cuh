@@ -211,6 +211,11 @@ struct cmdb_bank {
     int timing = 0;
     cudaEvent_t ev[CMDB_T_COUNT + 1] = {};
     bool ev_valid = false;
+    // CMDB_OPT_TIMING = 2 (diagnostics): per-lane copies of the stage events and a common time base, so that the
+    // overlap of the two lanes can be read (cmdb_debug_lane_timeline)
+    cudaEvent_t ev_tl[2][CMDB_T_COUNT + 1] = {};
+    cudaEvent_t ev_base = nullptr;
+    int cur_slot = 0;
     double *stats_buf = nullptr;  // 2 doubles on device
     unsigned int *absmax_buf = nullptr;
 };

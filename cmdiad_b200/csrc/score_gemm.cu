@@ -646,6 +646,7 @@ int score_max_batch(const cmdb_bank *b) {
 void score_select_slot(cmdb_bank *b, int slot) {
     b->ss = b->ss_store[slot];
     b->stream = b->lane_stream[slot];
+    b->cur_slot = slot;
     ScoreScratch &s = b->ss;
     s.q_f32 = s.q_f32_buf[slot];
     s.out_block = s.out_block_buf[slot];

@@ -485,7 +485,7 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     const size_t D = b->dim;
     int n_cand = 0;
     auto mark = [&](int i) -> int {
-        if (b->timing && i >= 0) CMDB_CUDA(cudaEventRecord(b->ev[i], st));
+        if (b->timing && i >= 0) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[b->cur_slot][i] : b->ev[i], st));
         return CMDB_OK;
     };
     const int64_t prev_queries = b->last_queries;
