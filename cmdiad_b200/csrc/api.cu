@@ -141,7 +141,7 @@ static int blur_batch(cmdb_bank *b, int B, int fh, int fw, int out_hw, int img_f
     CMDB_REQUIRE((size_t)out_hw * out_hw <= s.map_stride, CMDB_ERR_INVALID, "scoring: out_hw=%d larger than the scratch maps", out_hw);
     const int n_img = img_first < B ? (B - img_first + img_step - 1) / img_step : 0;
     return upsample_blur_launch(b->stream, n_img, img_first, img_step, s.map_stride, s.min_val, fh, fw, out_hw, s.map_pre,
-                                s.map_out, s.map_u8, s.map_tmp, s.map_max);
+                                s.map_out, s.map_u8, s.map_tmp, s.map_max, s.map_max + s.cap_b);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -971,13 +971,13 @@ int cmdb_upsample_blur(int device, const float *map_host, int fh, int fw, int ou
     unsigned char *u8 = nullptr, *tmp = nullptr;
     cudaError_t e = cudaMalloc(&in, sizeof(float) * fh * fw);
     if (e == cudaSuccess) e = cudaMalloc(&tmp, npix);
-    if (e == cudaSuccess) e = cudaMalloc(&mx, sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&mx, sizeof(float) * 17);
     if (e == cudaSuccess) e = cudaMalloc(&pre, sizeof(float) * npix);
     if (e == cudaSuccess) e = cudaMalloc(&o, sizeof(float) * npix);
     if (e == cudaSuccess) e = cudaMalloc(&u8, npix);
     if (e == cudaSuccess) e = cudaMemcpy(in, map_host, sizeof(float) * fh * fw, cudaMemcpyHostToDevice);
     int rc = CMDB_OK;
-    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, 1, 0, 1, npix, in, fh, fw, out_hw, pre, o, u8, tmp, mx);
+    if (e == cudaSuccess) rc = upsample_blur_launch(nullptr, 1, 0, 1, npix, in, fh, fw, out_hw, pre, o, u8, tmp, mx, mx + 1);
     if (e == cudaSuccess && rc == CMDB_OK) e = cudaMemcpy(out_host, o, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_pre_host) e = cudaMemcpy(out_pre_host, pre, sizeof(float) * npix, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == CMDB_OK && out_u8_host) e = cudaMemcpy(out_u8_host, u8, npix, cudaMemcpyDeviceToHost);

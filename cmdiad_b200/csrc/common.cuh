@@ -328,6 +328,6 @@ int score_merge_top3(cmdb_bank *b, int n_ranks, int B);
 int score_final(cmdb_bank *b, int B);
 int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,
                          int fh, int fw, int out_hw, float *pre_dev, float *out_dev, unsigned char *u8_dev,
-                         unsigned char *tmp_dev, float *mx_dev);
+                         unsigned char *tmp_dev, float *mx_dev, float *mx_part_dev /* [n images][16] band maxima */);
 
 }  // namespace cmdb

@@ -736,7 +736,7 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
             }
         }
         CMDB_CUDA(cudaMalloc(&s.map_tmp, (size_t)map_cap * cap_b));
-        CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b));
+        CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b * 17));  // [cap_b] maxima, then [cap_b][16] band maxima
         CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long) * cap_b));
         CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks * cap_b));
         CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3 * cap_b));

@@ -37,6 +37,35 @@ __device__ __forceinline__ float warp_sqdist(const float *__restrict__ a, const 
     return acc;
 }
 
+// four bank rows against one query at once: per row exactly the accumulation order and shuffle tree of warp_sqdist
+// (bit-identical values), with the loads of all four rows in flight together (the re-checks are latency bound)
+__device__ __forceinline__ void warp_sqdist4(const float *__restrict__ a, const float *__restrict__ b0, const float *__restrict__ b1,
+                                             const float *__restrict__ b2, const float *__restrict__ b3, int dim4, int lane,
+                                             float (&out)[4]) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < dim4; c += 32) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(a) + c);
+        const float4 y0 = __ldg(reinterpret_cast<const float4 *>(b0) + c), y1 = __ldg(reinterpret_cast<const float4 *>(b1) + c);
+        const float4 y2 = __ldg(reinterpret_cast<const float4 *>(b2) + c), y3 = __ldg(reinterpret_cast<const float4 *>(b3) + c);
+        float d;
+        d = x.x - y0.x, acc0 = fmaf(d, d, acc0), d = x.y - y0.y, acc0 = fmaf(d, d, acc0);
+        d = x.z - y0.z, acc0 = fmaf(d, d, acc0), d = x.w - y0.w, acc0 = fmaf(d, d, acc0);
+        d = x.x - y1.x, acc1 = fmaf(d, d, acc1), d = x.y - y1.y, acc1 = fmaf(d, d, acc1);
+        d = x.z - y1.z, acc1 = fmaf(d, d, acc1), d = x.w - y1.w, acc1 = fmaf(d, d, acc1);
+        d = x.x - y2.x, acc2 = fmaf(d, d, acc2), d = x.y - y2.y, acc2 = fmaf(d, d, acc2);
+        d = x.z - y2.z, acc2 = fmaf(d, d, acc2), d = x.w - y2.w, acc2 = fmaf(d, d, acc2);
+        d = x.x - y3.x, acc3 = fmaf(d, d, acc3), d = x.y - y3.y, acc3 = fmaf(d, d, acc3);
+        d = x.z - y3.z, acc3 = fmaf(d, d, acc3), d = x.w - y3.w, acc3 = fmaf(d, d, acc3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o), acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, o), acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
+    }
+    out[0] = acc0, out[1] = acc1, out[2] = acc2, out[3] = acc3;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // refine: one warp per query.  cand[c][q] = (val1, idx1, val2, idx2) from n_cand producers (approximate d^2 up to a
 // per-query constant; idx < 0 = empty).  Takes the 4 best approximate candidates, recomputes their distance exactly
@@ -136,7 +165,37 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
 // this would cost more than a GEMM (fallback_use_rescan; banks full of near-duplicates), the uncertified queries are
 // redone with the FP32-equivalent 3-term GEMM.  Either way min_val / min_idx equal those of an exact scan of the whole bank.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
+// Three passes per warp: (1) smallest first value over all producers' lists -> threshold; (2) the lists again (L1 / L2
+// hits): every kept value inside the band goes to a per-warp row list in shared memory, producers whose SECOND value is
+// inside the band are queued for the rescan; (3) the listed rows are re-checked exactly four at a time (warp_sqdist4).
+// The last warp of the grid to finish also takes the tier decision for the launches behind it (ctl[2..4]).
+// exact re-check of the rows listed by a warp (the smallest (d^2, row) wins: the order of the list does not matter)
+__device__ __forceinline__ void cert_recheck(const int *list, int n_list, const float *__restrict__ qrow, const float *__restrict__ bank,
+                                          int dim, int lane, float &best, int &best_i) {
+    const int dim4 = dim >> 2;
+    __syncwarp();
+    for (int j = 0; j < n_list; j += 4) {
+        const int r0 = list[j], r1 = list[min(j + 1, n_list - 1)], r2 = list[min(j + 2, n_list - 1)], r3 = list[min(j + 3, n_list - 1)];
+        float d[4];
+        if (j + 1 < n_list) {
+            warp_sqdist4(qrow, bank + (size_t)r0 * dim, bank + (size_t)r1 * dim, bank + (size_t)r2 * dim, bank + (size_t)r3 * dim,
+                         dim4, lane, d);
+        } else {
+            d[0] = warp_sqdist(qrow, bank + (size_t)r0 * dim, dim4, lane);
+            d[1] = d[2] = d[3] = d[0];
+        }
+        const int rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // duplicates of the last row (padding of the group) change nothing
+            if (best_i < 0 || d[k] < best || (d[k] == best && rr[k] < best_i)) best = d[k], best_i = rr[k];
+    }
+    __syncwarp();
+}
+
+constexpr int kCertWarps = 4;    // queries per block: 128 threads x <= 64 registers also fit beside a resident GEMM CTA
+constexpr int kCertList = 128;   // rows per warp list; flushed before a chunk of 32 producers could overflow it
+
+__global__ void __launch_bounds__(32 * kCertWarps) refine_cert_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
                                                           const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                           int P, int P_img, long long row_offset,
                                                           const float *__restrict__ q_norm, const float *__restrict__ q_eps,
@@ -145,22 +204,17 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
                                                           long long *__restrict__ min_idx, unsigned long long *s_key,
                                                           int *__restrict__ fail_list, int *__restrict__ ctl,
                                                           int2 *__restrict__ work_list, unsigned long long *__restrict__ best_key) {
-    const int lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (qi >= P) return;
-    // the producers' lists of this query stay in registers (kCertRegs * 32 producers; beyond that they are re-read)
-    constexpr int kCertRegs = 10;
-    const float4 empty = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
-    float4 held[kCertRegs];
+    __shared__ int list_s[kCertWarps][kCertList];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int qi = blockIdx.x * kCertWarps + wib;
+    if (qi >= P) return;   // whole warps leave; only __syncwarp below
+    int *list = list_s[wib];
+    const float4 *col = cand + qi;
+    // pass 1: smallest first value (a producer without any row for this query has idx < 0)
     float v1min = INFINITY;
-#pragma unroll
-    for (int k = 0; k < kCertRegs; ++k) {
-        const int c = lane + 32 * k;
-        held[k] = c < n_cand ? cand[(size_t)c * cand_stride + qi] : empty;
-        if (__float_as_int(held[k].y) >= 0) v1min = fminf(v1min, held[k].x);
-    }
-    for (int c = lane + 32 * kCertRegs; c < n_cand; c += 32) {
-        const float4 t = cand[(size_t)c * cand_stride + qi];
+#pragma unroll 5
+    for (int c = lane; c < n_cand; c += 32) {
+        const float4 t = col[(size_t)c * cand_stride];
         if (__float_as_int(t.y) >= 0) v1min = fminf(v1min, t.x);
     }
 #pragma unroll
@@ -175,41 +229,50 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
     E = __fmaf_ru(__fmul_ru((float)(dim + 16) * 5.9604645e-8f, span), span, E);
     const float thr = __fadd_ru(v1min, __fmul_ru(2.0625f, E));  // 2E plus slack for the float32 evaluation of E itself
     const bool orderable = v1min < INFINITY && thr < INFINITY;  // false for NaN / overflow: never certify those
-    // exact re-check of every kept value inside the band; producers whose SECOND value is inside the band may hide more
     float best = INFINITY;
-    int best_i = -1, n_bad = 0;
-    auto band_step = [&](const float4 t, int c) {
-        const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
-        const bool in1 = i1 >= 0 && (t.x <= thr || !orderable), in2 = i2 >= 0 && (t.z <= thr || !orderable);
-        unsigned int m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
-        const unsigned int bad = m2;
-        n_bad += __popc(bad);
-        while (m1 | m2) {
-            const bool first = m1 != 0;
-            unsigned int &m = first ? m1 : m2;
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int row = __shfl_sync(0xffffffffu, first ? i1 : i2, src);
-            const float d2 = warp_sqdist(q + (size_t)qi * dim, bank + (size_t)row * dim, dim >> 2, lane);
-            if (best_i < 0 || d2 < best || (d2 == best && row < best_i)) best = d2, best_i = row;
+    int best_i = -1, n_bad = 0, n_list = 0;
+    const float *qrow = q + (size_t)qi * dim;
+    auto flush = [&]() {
+        cert_recheck(list, n_list, qrow, bank, dim, lane, best, best_i);
+        n_list = 0;
+    };
+    // pass 2: the lists again, five chunks of 32 producers per round so that the loads of a round are in flight together
+    const float4 empty = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+    const unsigned int below = (1u << lane) - 1u;
+    constexpr int kRound = 5;
+    for (int c0 = 0; c0 < n_cand; c0 += 32 * kRound) {
+        float4 held[kRound];
+#pragma unroll
+        for (int k = 0; k < kRound; ++k) {
+            const int c = c0 + 32 * k + lane;
+            held[k] = c < n_cand ? col[(size_t)c * cand_stride] : empty;
         }
-        if (bad) {  // queue (query, producer) pairs for the exact rescan of the producer's rows
-            int base = 0;
-            if (lane == 0) base = atomicAdd(ctl + 1, __popc(bad));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (in2) {
-                const int slot = base + __popc(bad & ((1u << lane) - 1u));
-                if (slot < kWorkCap) work_list[slot] = make_int2(qi, c);
+#pragma unroll
+        for (int k = 0; k < kRound; ++k) {
+            const float4 t = held[k];
+            const int c = c0 + 32 * k + lane;
+            const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
+            const bool in1 = i1 >= 0 && (t.x <= thr || !orderable), in2 = i2 >= 0 && (t.z <= thr || !orderable);
+            const unsigned int m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
+            if ((m1 | m2) == 0) continue;
+            if (n_list + 64 > kCertList) flush();
+            if (in1) list[n_list + __popc(m1 & below)] = i1;
+            n_list += __popc(m1);
+            if (in2) list[n_list + __popc(m2 & below)] = i2;
+            n_list += __popc(m2);
+            if (m2) {  // a producer whose SECOND value is inside the band may hide more rows: queue (query, producer) for the rescan
+                n_bad += __popc(m2);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(ctl + 1, __popc(m2));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in2) {
+                    const int slot = base + __popc(m2 & below);
+                    if (slot < kWorkCap) work_list[slot] = make_int2(qi, c);
+                }
             }
         }
-    };
-#pragma unroll
-    for (int k = 0; k < kCertRegs; ++k)
-        if (32 * k < n_cand) band_step(held[k], lane + 32 * k);
-    for (int c0 = 32 * kCertRegs; c0 < n_cand; c0 += 32) {
-        const int c = c0 + lane;
-        band_step(c < n_cand ? cand[(size_t)c * cand_stride + qi] : empty, c);
     }
+    flush();
     if (lane != 0) return;
     if (n_bad == 0 && best_i >= 0) {
         const float dv = sqrtf(best);
@@ -221,14 +284,16 @@ __global__ void __launch_bounds__(256) refine_cert_kernel(const float4 *__restri
         fail_list[atomicAdd(ctl + 0, 1)] = qi;
         best_key[qi] = best_i < 0 ? ~0ULL : (((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_i);
     }
-}
-
-// [2] rows of the GEMM fallback, [3] pairs of the rescan, [4] queries the rescan path finishes
-__global__ void fallback_decide_kernel(int *ctl) {
-    const bool rescan = fallback_use_rescan(ctl[0], ctl[1]);
-    ctl[2] = rescan ? 0 : ctl[0];
-    ctl[3] = rescan ? ctl[1] : 0;
-    ctl[4] = rescan ? ctl[0] : 0;
+    // the last query of the grid decides the tier: [2] rows of the GEMM fallback, [3] pairs of the rescan, [4] queries the
+    // rescan path finishes (the launches behind this kernel size themselves from these)
+    __threadfence();
+    if (atomicAdd(ctl + 5, 1) == P - 1) {
+        const int fails = atomicAdd(ctl + 0, 0), pairs = atomicAdd(ctl + 1, 0);
+        const bool rescan = fallback_use_rescan(fails, pairs);
+        ctl[2] = rescan ? 0 : fails;
+        ctl[3] = rescan ? pairs : 0;
+        ctl[4] = rescan ? fails : 0;
+    }
 }
 
 // exact rescan: work item = (query, producer); the producer (CTA c, column group g) saw, for the query's M tile m (counted
@@ -251,8 +316,12 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                      long long rows, int n_units, int cg, int EG, int nt, int chunk_tiles,
                                                      int mt_total, int stride_full, int stride_last, int run_full,
-                                                     int run_last, unsigned long long *best_key) {
+                                                     int run_last, unsigned long long *best_key,
+                                                     const int *__restrict__ fail_list, int *__restrict__ ctl, int P_img,
+                                                     long long row_offset, float *__restrict__ min_val,
+                                                     long long *__restrict__ min_idx, unsigned long long *s_key) {
     __shared__ unsigned long long red[8];
+    __shared__ int last_block;
     const int n_items = min(*n_items_ptr, kWorkCap);
     // n_units scheduling units (CTAs, or CTA pairs when cg == 2) share the runs of N tiles of one M tile (pair); a chunk's
     // schedule deals runs of `run` consecutive N tiles, so a producer's rows are runs_per runs of run tiles each.  Both
@@ -281,13 +350,20 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
         const int n = t < run ? jrun * run + t : nt;
         unsigned long long key = ~0ULL;
         if (n < nt && (long long)jrun * run < nt) {
-            const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows;
-            for (int j = warp; j < kUnitRows; j += 8) {
-                const long long r = r0 + j;
-                if (r >= rows) break;
-                const float d2 = warp_sqdist(q + (size_t)qi * dim, bank + (size_t)r * dim, dim >> 2, lane);
-                const unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)r;
-                key = kk < key ? kk : key;
+            // rows r0 + warp + {0, 8, 16, 24}: four exact distances with all loads in flight together
+            const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows + warp;
+            static_assert(kUnitRows == 32, "four rows per warp");
+            if (r0 < rows) {
+                const long long rl = rows - 1;
+                const float *qrow = q + (size_t)qi * dim;
+                float d[4];
+                warp_sqdist4(qrow, bank + (size_t)r0 * dim, bank + (size_t)min(r0 + 8, rl) * dim, bank + (size_t)min(r0 + 16, rl) * dim,
+                             bank + (size_t)min(r0 + 24, rl) * dim, dim >> 2, lane, d);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // rows clamped to the last one repeat its key: harmless for a minimum
+                    const unsigned long long kk = ((unsigned long long)__float_as_uint(d[k]) << 32) | (unsigned int)min(r0 + 8 * k, rl);
+                    key = kk < key ? kk : key;
+                }
             }
         }
         __syncthreads();
@@ -297,6 +373,24 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
             for (int i = 1; i < 8; ++i) key = red[i] < key ? red[i] : key;
             if (key != ~0ULL) atomicMin(best_key + qi, key);
         }
+    }
+    // the last block to finish publishes min_val / min_idx / the argmax keys of the rescanned queries
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last_block = atomicAdd(ctl + 6, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last_block) return;
+    __threadfence();
+    const int n_fin = ctl[4];
+    for (int i = threadIdx.x; i < n_fin; i += blockDim.x) {
+        const int qi = fail_list[i];
+        const unsigned long long key = __ldcg(best_key + qi);
+        const float dv = sqrtf(__uint_as_float((unsigned int)(key >> 32)));
+        min_val[qi] = dv;
+        min_idx[qi] = key == ~0ULL ? -1 : (long long)(key & 0xffffffffULL) + row_offset;
+        atomicMax(s_key + qi / P_img,
+                  ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
     }
 }
 
@@ -323,21 +417,6 @@ int score_exact_scan(cmdb_bank *b, const float *q_dev, int P, unsigned long long
     exact_scan_kernel<<<dim3(gx, (P + 7) / 8), 256, 0, b->stream>>>(q_dev, P, b->data, b->fin_rows, b->dim, chunk, keys_dev);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
-}
-
-__global__ void rescan_finish_kernel(const int *__restrict__ fail_list, const int *__restrict__ count_ptr,
-                                     const unsigned long long *__restrict__ best_key, int P_img, long long row_offset,
-                                     float *__restrict__ min_val, long long *__restrict__ min_idx, unsigned long long *s_key) {
-    const int n = *count_ptr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int qi = fail_list[i];
-        const unsigned long long key = best_key[qi];
-        const float dv = sqrtf(__uint_as_float((unsigned int)(key >> 32)));
-        min_val[qi] = dv;
-        min_idx[qi] = key == ~0ULL ? -1 : (long long)(key & 0xffffffffULL) + row_offset;
-        atomicMax(s_key + qi / P_img,
-                  ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -446,13 +525,11 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     cudaStream_t st = b->stream;
     CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
     CMDB_CUDA(cudaMemsetAsync(s.fail_ctl, 0, 8 * sizeof(int), st));
-    // 4 queries per block: 128 threads x 80 registers fit beside a resident GEMM CTA of the other lane (384 x 120 registers)
-    refine_cert_kernel<<<(P + 3) / 4, 128, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img, b->row_offset,
+    // 4 queries per block: 128 threads fit beside a resident GEMM CTA of the other lane (384 x 120 registers)
+    refine_cert_kernel<<<(P + kCertWarps - 1) / kCertWarps, 32 * kCertWarps, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img, b->row_offset,
                                                     s.q_norm, s.q_eps, b->cert_bmax, b->cert_eb_max,
                                                     (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f, s.min_val, s.min_idx, s.s_key,
                                                     s.fail_list, s.fail_ctl, s.work_list, s.best_key);
-    CMDB_CUDA(cudaGetLastError());
-    fallback_decide_kernel<<<1, 1, 0, st>>>(s.fail_ctl);
     CMDB_CUDA(cudaGetLastError());
     // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
     const int cg = s.sched_pair ? 2 : 1, n_units = b->num_sms / cg, EG = score_gemm_groups();
@@ -463,10 +540,8 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
                                                   score_tile_stride((s.chunk_tiles + cg - 1) / cg, n_units),
                                                   score_tile_stride((last_tiles + cg - 1) / cg, n_units),
                                                   score_gemm_run(nt, (s.chunk_tiles + cg - 1) / cg, n_units),
-                                                  score_gemm_run(nt, (last_tiles + cg - 1) / cg, n_units), s.best_key);
-    CMDB_CUDA(cudaGetLastError());
-    rescan_finish_kernel<<<8, 256, 0, st>>>(s.fail_list, s.fail_ctl + 4, s.best_key, P_img, b->row_offset, s.min_val, s.min_idx,
-                                            s.s_key);
+                                                  score_gemm_run(nt, (last_tiles + cg - 1) / cg, n_units), s.best_key,
+                                                  s.fail_list, s.fail_ctl, P_img, b->row_offset, s.min_val, s.min_idx, s.s_key);
     CMDB_CUDA(cudaGetLastError());
     return CMDB_OK;
 }
@@ -1178,8 +1253,9 @@ __global__ void __launch_bounds__(64) final_kernel(const unsigned long long *__r
 
 // ---------------------------------------------------------------------------------------------------------------
 // upsample + blur in two small multi-CTA kernels (the image is split into 16 row bands, then 16 column bands):
-//   K1  every CTA recomputes the global max of the upsampled map (needed before the 8-bit quantisation; 50k pixels, cheaper
-//       than a grid barrier), upsamples + quantises its row band and runs the 3 horizontal box passes in shared memory;
+//   K0  every CTA takes the max of its row band of the upsampled map (the global max is needed before the 8-bit
+//       quantisation; round 1 recomputed all 50k pixels in every CTA of K1, which was two thirds of K1's time);
+//   K1  folds the 16 band maxima, upsamples + quantises its row band and runs the 3 horizontal box passes in shared memory;
 //   K2  every CTA loads its column band of K1's result and runs the 3 vertical passes (Pillow transposes instead), then
 //       applies ToTensor (/255) and * max.
 // ---------------------------------------------------------------------------------------------------------------
@@ -1224,36 +1300,62 @@ __device__ __forceinline__ void box_pass(const unsigned char *__restrict__ src, 
     }
 }
 
+constexpr int kMaxThreads = 256;
+__global__ void __launch_bounds__(kMaxThreads) upsample_max_kernel(const float *__restrict__ map_in, int fh, int fw_, int out_hw,
+                                                                   int band, float *__restrict__ mx_part, int img_first, int img_step) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const size_t img = img_first + (size_t)blockIdx.y * img_step;
+    map_in += img * fh * fw_;
+    float *in_s = reinterpret_cast<float *>(sm);
+    __shared__ float red[kMaxThreads / 32];
+    // only the input rows this band interpolates from
+    const float sh = (float)fh / (float)out_hw, sw = (float)fw_ / (float)out_hw;
+    const int y0 = blockIdx.x * band, rows = min(band, out_hw - y0);
+    float mx = -INFINITY;  // fmaxf ignores NaN and is order independent: the fold of the band maxima equals one global pass
+    if (rows > 0) {
+        int r_lo, r_hi, t0, t1;
+        float w0, w1;
+        bilinear_coeff(y0, sh, fh, r_lo, t1, w0, w1);
+        bilinear_coeff(y0 + rows - 1, sh, fh, t0, r_hi, w0, w1);
+        for (int i = threadIdx.x + r_lo * fw_; i < (r_hi + 1) * fw_; i += kMaxThreads) in_s[i] = map_in[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * out_hw; i += kMaxThreads)
+            mx = fmaxf(mx, bilinear_at(in_s, fh, fw_, sh, sw, y0 + i / out_hw, i % out_hw));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kMaxThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+        mx_part[img * kBlurBands + blockIdx.x] = mx;
+    }
+}
+
 __global__ void __launch_bounds__(kBlurThreads) upsample_hblur_kernel(const float *__restrict__ map_in, int fh, int fw_,
                                                                       int out_hw, int band, float *__restrict__ pre,
                                                                       unsigned char *__restrict__ u8_out,
                                                                       unsigned char *__restrict__ tmp, float *__restrict__ mx_out,
+                                                                      const float *__restrict__ mx_part,
                                                                       int radius, unsigned int ww, unsigned int fwt, int img_first,
                                                                       int img_step, size_t map_stride) {
     extern __shared__ __align__(16) unsigned char sm[];
     {  // image of the batch handled by this CTA
         const size_t img = img_first + (size_t)blockIdx.y * img_step;
-        map_in += img * fh * fw_, tmp += img * map_stride, mx_out += img;
+        map_in += img * fh * fw_, tmp += img * map_stride, mx_out += img, mx_part += img * kBlurBands;
         if (pre) pre += img * map_stride;
         if (u8_out) u8_out += img * map_stride;
     }
     float *in_s = reinterpret_cast<float *>(sm);                    // [fh*fw]
     unsigned char *A = sm + sizeof(float) * ((fh * fw_ + 3) & ~3);  // [band][out_hw]
     unsigned char *B = A + ((band * out_hw + 15) & ~15);
-    __shared__ float red[kBlurThreads / 32];
     for (int i = threadIdx.x; i < fh * fw_; i += kBlurThreads) in_s[i] = map_in[i];
     __syncthreads();
     const float sh = (float)fh / (float)out_hw, sw = (float)fw_ / (float)out_hw;
-    const int npix = out_hw * out_hw;
-    float mx = -INFINITY;  // map_max = img.max() over the WHOLE upsampled image (utils/utils.py:81)
-    for (int i = threadIdx.x; i < npix; i += kBlurThreads) mx = fmaxf(mx, bilinear_at(in_s, fh, fw_, sh, sw, i / out_hw, i % out_hw));
+    float mx = mx_part[0];  // map_max = img.max() over the WHOLE upsampled image (utils/utils.py:81): fold of K0's band maxima
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-#pragma unroll
-    for (int w = 1; w < kBlurThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+    for (int w = 1; w < kBlurBands; ++w) mx = fmaxf(mx, mx_part[w]);
     if (blockIdx.x == 0 && threadIdx.x == 0) *mx_out = mx;
     const int y0 = blockIdx.x * band, rows = min(band, out_hw - y0);
     if (rows <= 0) return;
@@ -1445,9 +1547,7 @@ int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev) {
 void tail_prefer_carveout() {
     CMDB_PREFER_MAX_SMEM(refine_kernel);
     CMDB_PREFER_MAX_SMEM(refine_cert_kernel);
-    CMDB_PREFER_MAX_SMEM(fallback_decide_kernel);
     CMDB_PREFER_MAX_SMEM(rescan_kernel);
-    CMDB_PREFER_MAX_SMEM(rescan_finish_kernel);
     CMDB_PREFER_MAX_SMEM(select_kernel);
     CMDB_PREFER_MAX_SMEM(reweight_cert_kernel);
     CMDB_PREFER_MAX_SMEM(reweight_lookup_kernel);
@@ -1459,6 +1559,7 @@ void tail_prefer_carveout() {
     CMDB_PREFER_MAX_SMEM(shard_reduce_keys_kernel);
     CMDB_PREFER_MAX_SMEM(shard_push_d2_kernel);
     CMDB_PREFER_MAX_SMEM(shard_sum_d2_kernel);
+    CMDB_PREFER_MAX_SMEM(upsample_max_kernel);
     CMDB_PREFER_MAX_SMEM(upsample_hblur_kernel);
     CMDB_PREFER_MAX_SMEM(vblur_kernel);
     (void)cudaGetLastError();
@@ -1480,7 +1581,7 @@ int score_final(cmdb_bank *b, int B) {
 // images img_first, img_first + img_step, ... (n_img of them); per-image stride of the map buffers = map_stride pixels
 int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_step, size_t map_stride, const float *map_dev,
                          int fh, int fw, int out_hw, float *pre_dev, float *out_dev, unsigned char *u8_dev,
-                         unsigned char *tmp_dev, float *mx_dev) {
+                         unsigned char *tmp_dev, float *mx_dev, float *mx_part_dev) {
     if (n_img <= 0) return CMDB_OK;
     CMDB_REQUIRE(fh > 0 && fw > 0 && out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID,
                  "upsample_blur: need out_hw in [8,256] (got %d) and positive map dims", out_hw);
@@ -1500,8 +1601,11 @@ int upsample_blur_launch(cudaStream_t stream, int n_img, int img_first, int img_
     const size_t smem1 = sizeof(float) * ((fh * fw + 3) & ~3) + 2 * tile;
     CMDB_REQUIRE(smem1 <= 200 * 1024, CMDB_ERR_UNSUPPORTED, "upsample_blur: map too large for shared memory");
     CMDB_CUDA(cudaFuncSetAttribute(upsample_hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    CMDB_CUDA(cudaFuncSetAttribute(upsample_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * fh * fw)));
+    upsample_max_kernel<<<dim3(kBlurBands, n_img), kMaxThreads, sizeof(float) * fh * fw, stream>>>(map_dev, fh, fw, out_hw, band,
+                                                                                                   mx_part_dev, img_first, img_step);
     upsample_hblur_kernel<<<dim3(kBlurBands, n_img), kBlurThreads, smem1, stream>>>(
-        map_dev, fh, fw, out_hw, band, pre_dev, u8_dev, tmp_dev, mx_dev, radius, ww, fwt, img_first, img_step, map_stride);
+        map_dev, fh, fw, out_hw, band, pre_dev, u8_dev, tmp_dev, mx_dev, mx_part_dev, radius, ww, fwt, img_first, img_step, map_stride);
     vblur_kernel<<<dim3(kBlurBands, n_img), kBlurThreads, 2 * tile, stream>>>(tmp_dev, out_hw, band, mx_dev, out_dev, radius, ww,
                                                                              fwt, img_first, img_step, map_stride);
     CMDB_CUDA(cudaGetLastError());

@@ -63,6 +63,24 @@ def _check_against_oracle(env, r, ref, P):
     _check_map(env, r, ref["s_map"])
 
 
+def _diagnose(b, patch, bank_rows, r, ref, what):
+    """printed when a parity assertion fails: which queries, against the exact device scan, a float64 brute force and a
+    second scoring call of the same patch"""
+    P = patch.shape[0]
+    ex_val, ex_idx = np.empty(P, np.float32), np.empty(P, np.int64)
+    q = np.ascontiguousarray(patch)
+    b._lib.cmdb_debug_exact_min(b._h, q.ctypes.data, P, ex_val.ctypes.data, ex_idx.ctypes.data)
+    d64 = np.sqrt(((patch.astype(np.float64)[:, None, :] - bank_rows.astype(np.float64)[None]) ** 2).sum(-1))
+    tv, ti = d64.min(1), d64.argmin(1)
+    again = b.score(patch, (int(np.sqrt(P)),) * 2, 224, full=True)
+    w = np.nonzero(np.abs(r.min_val - tv) > 2e-5 * tv)[0]
+    print(f"DIAG {what}: stats {b.score_stats()}; {len(w)} queries off the float64 brute force: {w.tolist()}")
+    print(f"DIAG bank rows on the device equal the host rows: {np.array_equal(b.read().numpy(), bank_rows)}")
+    for i in w[:40]:
+        print(f"DIAG   q {i}: ours {r.min_val[i]!r} row {r.min_idx[i]} | second call {again.min_val[i]!r} row {again.min_idx[i]} | "
+              f"exact scan {ex_val[i]!r} row {ex_idx[i]} | torch {ref['min_val'][i]!r} row {ref['min_idx'][i]} | f64 {tv[i]!r} row {ti[i]}")
+
+
 @pytest.mark.parametrize("impl", ["tcgen05", "simt"])
 def test_score_golden_rgb_case(env, golden, impl):
     """the reference's own outputs (frozen in tests/golden/rgb_case.npz) for 2 test images against a 784-row coreset"""
@@ -75,7 +93,11 @@ def test_score_golden_rgb_case(env, golden, impl):
         patch = ((torch.from_numpy(cases.rgb_test_patch(t)) - torch.tensor(g["rgb_mean"])) / torch.tensor(g["rgb_std"])).numpy()
         r = b.score(patch, (28, 28), 224, full=True)
         ref = O.score_restated(patch, bank_rows, (28, 28), 224)
-        _check_against_oracle(env, r, ref, 784)
+        try:
+            _check_against_oracle(env, r, ref, 784)
+        except AssertionError:
+            _diagnose(b, patch, bank_rows, r, ref, f"golden rgb image {t} ({impl})")
+            raise
         assert (r.min_idx == g[f"t{t}_min_idx"]).mean() >= 0.998
         np.testing.assert_allclose(r.min_val, g[f"t{t}_min_val"], rtol=1e-4)
         np.testing.assert_allclose(r.s[0], g[f"t{t}_s"], rtol=1e-4)
@@ -510,6 +532,21 @@ def test_upsample_blur_bit_exact(env):
         assert (u8 == ref_u8).all() and (out == ref).all()
         t = torch.nn.functional.interpolate(torch.from_numpy(m).view(1, 1, h, h), size=(224, 224), mode="bilinear")
         assert (pre == t[0, 0].numpy()).all()
+    # non-square maps, output sizes that leave row bands empty or ragged, the maximum in the first / last band: the
+    # global max is folded from per-band maxima and has to equal the max of the whole upsampled map bit for bit
+    for (fh, fw, hw) in ((7, 13, 8), (28, 28, 100), (14, 56, 250), (3, 3, 256), (56, 56, 17)):
+        for peak in ("first", "last", "none"):
+            m = (np.abs(g.standard_normal((fh, fw))) * 2 + 1).astype(np.float32)
+            if peak == "first":
+                m[0, fw // 2] = 40.0
+            elif peak == "last":
+                m[fh - 1, 0] = 40.0
+            out, pre, u8 = env["upsample_blur"](m, hw)
+            t = torch.nn.functional.interpolate(torch.from_numpy(m).view(1, 1, fh, fw), size=(hw, hw), mode="bilinear")
+            # (bit-exactness of the bilinear weights is pinned for the reference's 28 / 56 -> 224 only)
+            np.testing.assert_allclose(pre, t[0, 0].numpy(), rtol=2e-6, atol=1e-6, err_msg=str((fh, fw, hw, peak)))
+            ref, ref_u8 = O.knn_blur_restated(pre)
+            assert (u8 == ref_u8).all() and (out == ref).all(), (fh, fw, hw, peak)
 
 
 def test_score_errors(env):
