@@ -728,17 +728,21 @@ int cmdb_debug_exact_min(cmdb_bank *b, const float *patch_host, int P, float *mi
 
 // host-only test hooks (not in the public header): the GEMM's tile-schedule stride and the fallback-tier rule
 // CMDB_OPT_TIMING = 2: milliseconds since the time base of every stage mark of the last batch on each lane
-// (out: float [2][CMDB_T_COUNT + 1]); all submitted batches must have been waited for
+// (out: float [2][CMDB_T_COUNT + 1 + 4]: the stage marks, then the four marks inside the refine stage); all submitted
+// batches must have been waited for
 int cmdb_debug_lane_timeline(cmdb_bank *b, float *out) {
     CMDB_REQUIRE(b && out && b->timing == 2 && b->ev_base, CMDB_ERR_STATE, "cmdb_debug_lane_timeline: set CMDB_OPT_TIMING = 2 first");
     CMDB_CUDA(cudaSetDevice(b->device));
     CMDB_CUDA(cudaDeviceSynchronize());
+    constexpr int kN = CMDB_T_COUNT + 1 + 4;
     for (int l = 0; l < 2; ++l)
-        for (int i = 0; i <= CMDB_T_COUNT; ++i)
-            if (cudaEventElapsedTime(out + l * (CMDB_T_COUNT + 1) + i, b->ev_base, b->ev_tl[l][i]) != cudaSuccess) {
+        for (int i = 0; i < kN; ++i) {
+            cudaEvent_t e = i <= CMDB_T_COUNT ? b->ev_tl[l][i] : b->ev_dbg[l][i - CMDB_T_COUNT - 1];
+            if (cudaEventElapsedTime(out + l * kN + i, b->ev_base, e) != cudaSuccess) {
                 (void)cudaGetLastError();
-                out[l * (CMDB_T_COUNT + 1) + i] = -1.f;
+                out[l * kN + i] = -1.f;
             }
+        }
     return CMDB_OK;
 }
 

@@ -323,6 +323,9 @@ void cmdb_bank_destroy(cmdb_bank *b) {
         for (auto &e : l)
             if (e) cudaEventDestroy(e);
     if (b->ev_base) cudaEventDestroy(b->ev_base);
+    for (auto &l : b->ev_dbg)
+        for (auto &e : l)
+            if (e) cudaEventDestroy(e);
     if (b->lane_stream[1] && b->lane_stream[1] != b->lane_stream[0]) cudaStreamDestroy(b->lane_stream[1]);
     if (b->lane_stream[0]) cudaStreamDestroy(b->lane_stream[0]);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
@@ -398,6 +401,8 @@ int cmdb_bank_set_option(cmdb_bank *b, int option, int value) {
             if (!b->ev_base) {
                 CMDB_CUDA(cudaEventCreate(&b->ev_base));
                 for (auto &l : b->ev_tl)
+                    for (auto &e : l) CMDB_CUDA(cudaEventCreate(&e));
+                for (auto &l : b->ev_dbg)
                     for (auto &e : l) CMDB_CUDA(cudaEventCreate(&e));
             }
             CMDB_CUDA(cudaDeviceSynchronize());

@@ -215,6 +215,7 @@ struct cmdb_bank {
     // overlap of the two lanes can be read (cmdb_debug_lane_timeline)
     cudaEvent_t ev_tl[2][CMDB_T_COUNT + 1] = {};
     cudaEvent_t ev_base = nullptr;
+    cudaEvent_t ev_dbg[2][4] = {};   // inside the refine stage: before / after the certificate kernel, after the rescan, after the tier-2 launches
     int cur_slot = 0;
     double *stats_buf = nullptr;  // 2 doubles on device
     unsigned int *absmax_buf = nullptr;

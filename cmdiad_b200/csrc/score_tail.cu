@@ -43,7 +43,7 @@ __device__ __forceinline__ void warp_sqdist4(const float *__restrict__ a, const 
                                              const float *__restrict__ b2, const float *__restrict__ b3, int dim4, int lane,
                                              float (&out)[4]) {
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 2
+#pragma unroll 3
     for (int c = lane; c < dim4; c += 32) {
         const float4 x = __ldg(reinterpret_cast<const float4 *>(a) + c);
         const float4 y0 = __ldg(reinterpret_cast<const float4 *>(b0) + c), y1 = __ldg(reinterpret_cast<const float4 *>(b1) + c);
@@ -165,15 +165,21 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
 // this would cost more than a GEMM (fallback_use_rescan; banks full of near-duplicates), the uncertified queries are
 // redone with the FP32-equivalent 3-term GEMM.  Either way min_val / min_idx equal those of an exact scan of the whole bank.
 // ---------------------------------------------------------------------------------------------------------------
-// Three passes per warp: (1) smallest first value over all producers' lists -> threshold; (2) the lists again (L1 / L2
-// hits): every kept value inside the band goes to a per-warp row list in shared memory, producers whose SECOND value is
-// inside the band are queued for the rescan; (3) the listed rows are re-checked exactly four at a time (warp_sqdist4).
-// The last warp of the grid to finish also takes the tier decision for the launches behind it (ctl[2..4]).
-// exact re-check of the rows listed by a warp (the smallest (d^2, row) wins: the order of the list does not matter)
+// One block per kCertQ consecutive queries, three phases:
+//   (1) the producers' lists are read with the QUERY index along the lanes (a warp-wide load is one or two contiguous
+//       256 / 512-byte runs of cand[c][q0 ...]; round 1 read them one query per warp, 32 sectors per request, which was two
+//       thirds of the kernel's time): smallest first value per query -> threshold;
+//   (2) the lists again (L2 hits): every kept value inside a query's band goes to that query's row list in shared memory,
+//       producers whose SECOND value is inside the band -- or whose row no longer fits the list -- are queued for the rescan;
+//   (3) the listed rows are re-checked exactly, one warp per query, four rows at a time (warp_sqdist4).
+// The last block of the grid to finish also takes the tier decision for the launches behind it (ctl[2..4]).
+constexpr int kCertThreads = 256;
+constexpr int kCertRows = 24;    // rows per query list; a query with more in-band first values hands the surplus to the rescan
+
+// exact re-check of a query's listed rows (the smallest (d^2, row) wins: the order of the list does not matter)
 __device__ __forceinline__ void cert_recheck(const int *list, int n_list, const float *__restrict__ qrow, const float *__restrict__ bank,
-                                          int dim, int lane, float &best, int &best_i) {
+                                             int dim, int lane, float &best, int &best_i) {
     const int dim4 = dim >> 2;
-    __syncwarp();
     for (int j = 0; j < n_list; j += 4) {
         const int r0 = list[j], r1 = list[min(j + 1, n_list - 1)], r2 = list[min(j + 2, n_list - 1)], r3 = list[min(j + 3, n_list - 1)];
         float d[4];
@@ -189,13 +195,10 @@ __device__ __forceinline__ void cert_recheck(const int *list, int n_list, const 
         for (int k = 0; k < 4; ++k)  // duplicates of the last row (padding of the group) change nothing
             if (best_i < 0 || d[k] < best || (d[k] == best && rr[k] < best_i)) best = d[k], best_i = rr[k];
     }
-    __syncwarp();
 }
 
-constexpr int kCertWarps = 4;    // queries per block: 128 threads x <= 64 registers also fit beside a resident GEMM CTA
-constexpr int kCertList = 128;   // rows per warp list; flushed before a chunk of 32 producers could overflow it
-
-__global__ void __launch_bounds__(32 * kCertWarps) refine_cert_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
+template <int QB>  // queries per block: 32 (large batches), 16 or 8 (single images: more blocks, one query per warp)
+__global__ void __launch_bounds__(kCertThreads) refine_cert_kernel(const float4 *__restrict__ cand, int n_cand, int cand_stride,
                                                           const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                           int P, int P_img, long long row_offset,
                                                           const float *__restrict__ q_norm, const float *__restrict__ q_eps,
@@ -204,95 +207,126 @@ __global__ void __launch_bounds__(32 * kCertWarps) refine_cert_kernel(const floa
                                                           long long *__restrict__ min_idx, unsigned long long *s_key,
                                                           int *__restrict__ fail_list, int *__restrict__ ctl,
                                                           int2 *__restrict__ work_list, unsigned long long *__restrict__ best_key) {
-    __shared__ int list_s[kCertWarps][kCertList];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int qi = blockIdx.x * kCertWarps + wib;
-    if (qi >= P) return;   // whole warps leave; only __syncwarp below
-    int *list = list_s[wib];
-    const float4 *col = cand + qi;
-    // pass 1: smallest first value (a producer without any row for this query has idx < 0)
-    float v1min = INFINITY;
-#pragma unroll 5
-    for (int c = lane; c < n_cand; c += 32) {
-        const float4 t = col[(size_t)c * cand_stride];
-        if (__float_as_int(t.y) >= 0) v1min = fminf(v1min, t.x);
+    constexpr int kWarps = kCertThreads / 32;
+    constexpr int PL = 32 / QB;            // producers covered by one warp-wide load
+    constexpr int CSTEP = kWarps * PL;     // producers covered by one block-wide load
+    __shared__ float part_s[CSTEP][QB];    // per (producer class, query) minima of phase 1
+    __shared__ float thr_s[QB];
+    __shared__ int cnt_s[QB], bad_s[QB], list_s[QB][kCertRows];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ql = lane % QB;              // query of this thread inside the block (phases 1 and 2)
+    const int q0 = blockIdx.x * QB, qi = q0 + ql;
+    const int cls = warp * PL + lane / QB; // producers cls, cls + CSTEP, ...
+    const bool live = qi < P;
+    const float4 *col = cand + (live ? qi : q0);
+    if (threadIdx.x < QB) cnt_s[threadIdx.x] = 0, bad_s[threadIdx.x] = 0;
+    // ---- phase 1: smallest first value (a producer without any row for this query has idx < 0).  The thread's share of
+    //      the lists stays in registers for phase 2 (kHold loads in flight together, ONE memory round trip for both
+    //      phases; producers beyond kHold * CSTEP -- none on a 148-SM part -- are read again in phase 2) ----
+    constexpr int kHold = QB <= 16 ? 320 / CSTEP : 8;
+    const float4 empty = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
+    float4 held[kHold];
+    float v1 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < kHold; ++k) {
+        const int c = cls + k * CSTEP;
+        held[k] = c < n_cand ? col[(size_t)c * cand_stride] : empty;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v1min = fminf(v1min, __shfl_xor_sync(0xffffffffu, v1min, o));
-    const float qn = q_norm[qi], qe = q_eps[qi];
-    const float bh = __fadd_ru(bmax, eb_max);
-    float E = __fmul_ru(qe, bh);
-    E = __fmaf_ru(qn, eb_max, E);
-    E = __fmaf_ru(__fmul_ru(acc_model, __fadd_ru(qn, qe)), bh, E);
-    E = __fmul_ru(2.f, E);
-    const float span = __fadd_ru(qn, bmax);
-    E = __fmaf_ru(__fmul_ru((float)(dim + 16) * 5.9604645e-8f, span), span, E);
-    const float thr = __fadd_ru(v1min, __fmul_ru(2.0625f, E));  // 2E plus slack for the float32 evaluation of E itself
-    const bool orderable = v1min < INFINITY && thr < INFINITY;  // false for NaN / overflow: never certify those
-    float best = INFINITY;
-    int best_i = -1, n_bad = 0, n_list = 0;
-    const float *qrow = q + (size_t)qi * dim;
-    auto flush = [&]() {
-        cert_recheck(list, n_list, qrow, bank, dim, lane, best, best_i);
-        n_list = 0;
-    };
-    // pass 2: the lists again, five chunks of 32 producers per round so that the loads of a round are in flight together
-    const float4 empty = make_float4(INFINITY, __int_as_float(-1), INFINITY, __int_as_float(-1));
-    const unsigned int below = (1u << lane) - 1u;
-    constexpr int kRound = 5;
-    for (int c0 = 0; c0 < n_cand; c0 += 32 * kRound) {
-        float4 held[kRound];
+    for (int k = 0; k < kHold; ++k)
+        if (__float_as_int(held[k].y) >= 0) v1 = fminf(v1, held[k].x);
+#pragma unroll 4
+    for (int c = cls + kHold * CSTEP; c < n_cand; c += CSTEP) {
+        const float4 t = col[(size_t)c * cand_stride];
+        if (__float_as_int(t.y) >= 0) v1 = fminf(v1, t.x);
+    }
+    part_s[cls][ql] = v1;
+    __syncthreads();
+    if (threadIdx.x < QB) {
+        float v1min = part_s[0][threadIdx.x];
 #pragma unroll
-        for (int k = 0; k < kRound; ++k) {
-            const int c = c0 + 32 * k + lane;
-            held[k] = c < n_cand ? col[(size_t)c * cand_stride] : empty;
+        for (int k = 1; k < CSTEP; ++k) v1min = fminf(v1min, part_s[k][threadIdx.x]);
+        const int qq = q0 + threadIdx.x;
+        float thr = INFINITY;  // +inf also stands for "not orderable" (NaN / overflow): everything is inside the band then
+        if (qq < P) {
+            const float qn = q_norm[qq], qe = q_eps[qq];
+            const float bh = __fadd_ru(bmax, eb_max);
+            float E = __fmul_ru(qe, bh);
+            E = __fmaf_ru(qn, eb_max, E);
+            E = __fmaf_ru(__fmul_ru(acc_model, __fadd_ru(qn, qe)), bh, E);
+            E = __fmul_ru(2.f, E);
+            const float span = __fadd_ru(qn, bmax);
+            E = __fmaf_ru(__fmul_ru((float)(dim + 16) * 5.9604645e-8f, span), span, E);
+            const float t = __fadd_ru(v1min, __fmul_ru(2.0625f, E));  // 2E plus slack for the float32 evaluation of E itself
+            if (v1min < INFINITY && t < INFINITY) thr = t;            // false for NaN / overflow: never certify those
         }
-#pragma unroll
-        for (int k = 0; k < kRound; ++k) {
-            const float4 t = held[k];
-            const int c = c0 + 32 * k + lane;
+        thr_s[threadIdx.x] = thr;
+    }
+    __syncthreads();
+    // ---- phase 2: band membership; rows to the query's list, (query, producer) pairs to the rescan queue ----
+    {
+        const float thr = thr_s[ql];
+        const bool all_in = !(thr < INFINITY);
+        auto band = [&](const float4 t, int c) {
             const int i1 = __float_as_int(t.y), i2 = __float_as_int(t.w);
-            const bool in1 = i1 >= 0 && (t.x <= thr || !orderable), in2 = i2 >= 0 && (t.z <= thr || !orderable);
-            const unsigned int m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
-            if ((m1 | m2) == 0) continue;
-            if (n_list + 64 > kCertList) flush();
-            if (in1) list[n_list + __popc(m1 & below)] = i1;
-            n_list += __popc(m1);
-            if (in2) list[n_list + __popc(m2 & below)] = i2;
-            n_list += __popc(m2);
-            if (m2) {  // a producer whose SECOND value is inside the band may hide more rows: queue (query, producer) for the rescan
-                n_bad += __popc(m2);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(ctl + 1, __popc(m2));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (in2) {
-                    const int slot = base + __popc(m2 & below);
-                    if (slot < kWorkCap) work_list[slot] = make_int2(qi, c);
-                }
+            const bool in1 = i1 >= 0 && (t.x <= thr || all_in), in2 = i2 >= 0 && (t.z <= thr || all_in);
+            bool queue = in2;   // a producer whose SECOND value is inside the band may hide more rows
+            if (in1) {
+                const int slot = atomicAdd(&cnt_s[ql], 1);
+                if (slot < kCertRows) list_s[ql][slot] = i1;
+                else queue = true;   // the row is covered by the exact rescan of its producer instead
+            }
+            if (in2) {
+                const int slot = atomicAdd(&cnt_s[ql], 1);
+                if (slot < kCertRows) list_s[ql][slot] = i2;
+            }
+            if (queue) {
+                atomicAdd(&bad_s[ql], 1);
+                const int slot = atomicAdd(ctl + 1, 1);
+                if (slot < kWorkCap) work_list[slot] = make_int2(qi, c);
+            }
+        };
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < kHold; ++k) band(held[k], cls + k * CSTEP);   // empty entries (idx < 0) are never inside
+#pragma unroll 4
+            for (int c = cls + kHold * CSTEP; c < n_cand; c += CSTEP) band(col[(size_t)c * cand_stride], c);
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: exact re-checks, one warp per query ----
+    for (int k = warp; k < QB; k += kWarps) {
+        const int qq = q0 + k;
+        if (qq >= P) break;
+        float best = INFINITY;
+        int best_i = -1;
+        cert_recheck(list_s[k], min(cnt_s[k], kCertRows), q + (size_t)qq * dim, bank, dim, lane, best, best_i);
+        if (lane == 0) {
+            if (bad_s[k] == 0 && best_i >= 0) {
+                const float dv = sqrtf(best);
+                min_val[qq] = dv;
+                min_idx[qq] = (long long)best_i + row_offset;
+                atomicMax(s_key + qq / P_img,
+                          ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qq % P_img)));
+            } else {
+                fail_list[atomicAdd(ctl + 0, 1)] = qq;
+                best_key[qq] = best_i < 0 ? ~0ULL : (((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_i);
             }
         }
     }
-    flush();
-    if (lane != 0) return;
-    if (n_bad == 0 && best_i >= 0) {
-        const float dv = sqrtf(best);
-        min_val[qi] = dv;
-        min_idx[qi] = (long long)best_i + row_offset;
-        atomicMax(s_key + qi / P_img,
-                  ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (unsigned int)(qi % P_img)));
-    } else {
-        fail_list[atomicAdd(ctl + 0, 1)] = qi;
-        best_key[qi] = best_i < 0 ? ~0ULL : (((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_i);
-    }
-    // the last query of the grid decides the tier: [2] rows of the GEMM fallback, [3] pairs of the rescan, [4] queries the
+    // the last block of the grid decides the tier: [2] rows of the GEMM fallback, [3] pairs of the rescan, [4] queries the
     // rescan path finishes (the launches behind this kernel size themselves from these)
-    __threadfence();
-    if (atomicAdd(ctl + 5, 1) == P - 1) {
-        const int fails = atomicAdd(ctl + 0, 0), pairs = atomicAdd(ctl + 1, 0);
-        const bool rescan = fallback_use_rescan(fails, pairs);
-        ctl[2] = rescan ? 0 : fails;
-        ctl[3] = rescan ? pairs : 0;
-        ctl[4] = rescan ? fails : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ctl + 5, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const int fails = atomicAdd(ctl + 0, 0), pairs = atomicAdd(ctl + 1, 0);
+            const bool rescan = fallback_use_rescan(fails, pairs);
+            ctl[2] = rescan ? 0 : fails;
+            ctl[3] = rescan ? pairs : 0;
+            ctl[4] = rescan ? fails : 0;
+        }
     }
 }
 
@@ -315,12 +349,11 @@ __device__ __forceinline__ int producer_first_tile(int c, int m, int G, int stri
 __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ work, const int *__restrict__ n_items_ptr,
                                                      const float *__restrict__ q, const float *__restrict__ bank, int dim,
                                                      long long rows, int n_units, int cg, int EG, int nt, int chunk_tiles,
-                                                     int mt_total, int stride_full, int stride_last, int run_full,
+                                                     int mt_total, int inv_full, int inv_last, int run_full,
                                                      int run_last, unsigned long long *best_key,
                                                      const int *__restrict__ fail_list, int *__restrict__ ctl, int P_img,
                                                      long long row_offset, float *__restrict__ min_val,
                                                      long long *__restrict__ min_idx, unsigned long long *s_key) {
-    __shared__ unsigned long long red[8];
     __shared__ int last_block;
     const int n_items = min(*n_items_ptr, kWorkCap);
     // n_units scheduling units (CTAs, or CTA pairs when cg == 2) share the runs of N tiles of one M tile (pair); a chunk's
@@ -331,12 +364,18 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
     const int tiles_per = runs_per * run_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cols = kScoreBN / EG;
-    constexpr int kUnitRows = 32;  // rows per block and step: 4 per warp, so a handful of pairs still fills the GPU
+    // warp unit = (item, k-th tile of the producer, 32-row slice of the tile's column group, warp slot): four exact
+    // distances (rows r, r + 8, r + 16, r + 24) with all loads in flight together, one atomicMin per warp; no block barrier
+    constexpr int kUnitRows = 32;
     const int units_per_tile = cols / kUnitRows;
-    const long long n_work = (long long)n_items * tiles_per * units_per_tile;
-    for (long long u = blockIdx.x; u < n_work; u += gridDim.x) {
-        const int item = (int)(u / (tiles_per * units_per_tile));
-        const int rem = (int)(u % (tiles_per * units_per_tile));
+    const long long n_work = (long long)n_items * tiles_per * units_per_tile * 8;
+    for (long long wu = (long long)blockIdx.x * 8 + warp; wu < n_work; wu += (long long)gridDim.x * 8) {
+        const int wsub = (int)(wu & 7);
+        const long long u = wu >> 3;
+        // item varies fastest: a producer's tile slots beyond its real tiles (about half of them: tiles_per covers the
+        // longest producer) are empty, and this way every block meets its share of them instead of whole blocks idling
+        const int item = (int)(u % n_items);
+        const int rem = (int)(u / n_items);
         const int kt = rem / units_per_tile, sub = rem % units_per_tile;
         const int2 w = work[item];
         const int qi = w.x, c = w.y / EG, g = w.y % EG;
@@ -346,34 +385,31 @@ __global__ void __launch_bounds__(256) rescan_kernel(const int2 *__restrict__ wo
         const int m_in = mtile - chunk * chunk_tiles;  // pair mode: CTA 2u + r handled the M tiles 2*mp + r of pair u
         const int run = last ? run_last : run_full;
         const int k = kt / run_max, t = kt % run_max;   // k-th run of this producer, t-th tile inside it
-        const int jrun = producer_first_tile(c / cg, m_in / cg, n_units, last ? stride_last : stride_full) + k * n_units;
+        // first run that unit c / cg processes for M tile m_in / cg under the GEMM's schedule: the smallest j with
+        // j * stride = c - m (mod G); stride is coprime with G, so j = (c - m) * stride^-1 mod G (inverse from the host)
+        const int G = n_units;
+        const int want = (((c / cg) - (m_in / cg) % G) % G + G) % G;
+        const int jrun = (int)(((long long)want * (last ? inv_last : inv_full)) % G) + k * n_units;
         const int n = t < run ? jrun * run + t : nt;
-        unsigned long long key = ~0ULL;
         if (n < nt && (long long)jrun * run < nt) {
-            // rows r0 + warp + {0, 8, 16, 24}: four exact distances with all loads in flight together
-            const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows + warp;
-            static_assert(kUnitRows == 32, "four rows per warp");
+            const long long r0 = (long long)n * kScoreBN + g * cols + sub * kUnitRows + wsub;
             if (r0 < rows) {
                 const long long rl = rows - 1;
                 const float *qrow = q + (size_t)qi * dim;
                 float d[4];
                 warp_sqdist4(qrow, bank + (size_t)r0 * dim, bank + (size_t)min(r0 + 8, rl) * dim, bank + (size_t)min(r0 + 16, rl) * dim,
                              bank + (size_t)min(r0 + 24, rl) * dim, dim >> 2, lane, d);
+                unsigned long long key = ~0ULL;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // rows clamped to the last one repeat its key: harmless for a minimum
-                    const unsigned long long kk = ((unsigned long long)__float_as_uint(d[k]) << 32) | (unsigned int)min(r0 + 8 * k, rl);
+                for (int kk4 = 0; kk4 < 4; ++kk4) {  // rows clamped to the last one repeat its key: harmless for a minimum
+                    const unsigned long long kk = ((unsigned long long)__float_as_uint(d[kk4]) << 32) | (unsigned int)min(r0 + 8 * kk4, rl);
                     key = kk < key ? kk : key;
                 }
+                if (lane == 0) atomicMin(best_key + qi, key);
             }
         }
-        __syncthreads();
-        if (lane == 0) red[warp] = key;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 1; i < 8; ++i) key = red[i] < key ? red[i] : key;
-            if (key != ~0ULL) atomicMin(best_key + qi, key);
-        }
     }
+    __syncthreads();
     // the last block to finish publishes min_val / min_idx / the argmax keys of the rescanned queries
     if (threadIdx.x == 0) {
         __threadfence();
@@ -519,17 +555,39 @@ int score_refine(cmdb_bank *b, int B, int P_img, int n_cand, bool compact) {
     return CMDB_OK;
 }
 
+// x with (a * x) % m == 1 (a coprime with m; m = scheduling units of the GEMM, <= a few hundred); 0 for m == 1
+static int mod_inverse(int a, int m) {
+    a %= m;
+    for (int x = 0; x < m; ++x)
+        if ((a * x) % m == 1 % m) return x;
+    return 0;
+}
+
 int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     const int P = B * P_img;
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
     CMDB_CUDA(cudaMemsetAsync(s.fail_ctl, 0, 8 * sizeof(int), st));
-    // 4 queries per block: 128 threads fit beside a resident GEMM CTA of the other lane (384 x 120 registers)
-    refine_cert_kernel<<<(P + kCertWarps - 1) / kCertWarps, 32 * kCertWarps, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img, b->row_offset,
-                                                    s.q_norm, s.q_eps, b->cert_bmax, b->cert_eb_max,
-                                                    (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f, s.min_val, s.min_idx, s.s_key,
-                                                    s.fail_list, s.fail_ctl, s.work_list, s.best_key);
+    const float acc_model = (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f;
+    if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][0], st));
+    // queries per block: 8 = one query per warp in phase 3 and 10 list entries per thread held in registers (measured best;
+    // CMDB_CERT_QB = 16 / 32 select the wider variants)
+    static const int qb_env = [] {
+        const char *e = getenv("CMDB_CERT_QB");
+        return e ? atoi(e) : 0;
+    }();
+    const int qb = qb_env == 8 || qb_env == 16 || qb_env == 32 ? qb_env : 8;
+#define CMDB_CERT(QB)                                                                                                       \
+    refine_cert_kernel<QB><<<(P + QB - 1) / QB, kCertThreads, 0, st>>>(s.cand, n_cand, s.cap_p, s.q_f32, b->data, b->dim, P, P_img,    \
+                                                                       b->row_offset, s.q_norm, s.q_eps, b->cert_bmax, b->cert_eb_max, \
+                                                                       acc_model, s.min_val, s.min_idx, s.s_key, s.fail_list,          \
+                                                                       s.fail_ctl, s.work_list, s.best_key)
+    if (qb == 32) CMDB_CERT(32);
+    else if (qb == 16) CMDB_CERT(16);
+    else CMDB_CERT(8);
+#undef CMDB_CERT
+    if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][1], st));
     CMDB_CUDA(cudaGetLastError());
     // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
     const int cg = s.sched_pair ? 2 : 1, n_units = b->num_sms / cg, EG = score_gemm_groups();
@@ -537,12 +595,13 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     const int nt = (int)(b->fin_rows_pad / kScoreBN);
     rescan_kernel<<<b->num_sms * 8, 256, 0, st>>>(s.work_list, s.fail_ctl + 3, s.q_f32, b->data, b->dim, b->fin_rows, n_units, cg, EG,
                                                   nt, s.chunk_tiles, s.mt_total,
-                                                  score_tile_stride((s.chunk_tiles + cg - 1) / cg, n_units),
-                                                  score_tile_stride((last_tiles + cg - 1) / cg, n_units),
+                                                  mod_inverse(score_tile_stride((s.chunk_tiles + cg - 1) / cg, n_units), n_units),
+                                                  mod_inverse(score_tile_stride((last_tiles + cg - 1) / cg, n_units), n_units),
                                                   score_gemm_run(nt, (s.chunk_tiles + cg - 1) / cg, n_units),
                                                   score_gemm_run(nt, (last_tiles + cg - 1) / cg, n_units), s.best_key,
                                                   s.fail_list, s.fail_ctl, P_img, b->row_offset, s.min_val, s.min_idx, s.s_key);
     CMDB_CUDA(cudaGetLastError());
+    if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][2], st));
     return CMDB_OK;
 }
 
@@ -647,7 +706,9 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     // itself from the device-side control block and returns at once in the common case
     CMDB_CHECK(score_query_prep(b, P, true));
     CMDB_CHECK(score_gemm_candidates(b, P, 3, true, &n_cand));
-    return score_refine(b, B, P_img, n_cand, true);
+    CMDB_CHECK(score_refine(b, B, P_img, n_cand, true));
+    if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][3], st));
+    return CMDB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1546,7 +1607,9 @@ int score_shard_final(cmdb_bank *b, int B, const float *d2_sum_dev) {
 
 void tail_prefer_carveout() {
     CMDB_PREFER_MAX_SMEM(refine_kernel);
-    CMDB_PREFER_MAX_SMEM(refine_cert_kernel);
+    CMDB_PREFER_MAX_SMEM(refine_cert_kernel<32>);
+    CMDB_PREFER_MAX_SMEM(refine_cert_kernel<16>);
+    CMDB_PREFER_MAX_SMEM(refine_cert_kernel<8>);
     CMDB_PREFER_MAX_SMEM(rescan_kernel);
     CMDB_PREFER_MAX_SMEM(select_kernel);
     CMDB_PREFER_MAX_SMEM(reweight_cert_kernel);

@@ -37,7 +37,7 @@ torch.cuda.synchronize()
 L.check(lib.cmdb_bank_set_option(bank._h, L.OPT_TIMING, 2))
 n = 8
 run(n)
-names = list(L.T_STAGES) + ["done"]
+names = list(L.T_STAGES) + ["done", "cert0", "cert1", "rescan1", "tier2_1"]
 arr = (ctypes.c_float * (2 * len(names)))()
 L.check(lib.cmdb_debug_lane_timeline(bank._h, arr))
 t = [[arr[l * len(names) + i] for i in range(len(names))] for l in range(2)]
@@ -49,4 +49,7 @@ print(f"batch n-2: gemm {a[2] - a[1]:.3f} ms, refine {a[3] - a[2]:.3f}, map {a[4
 print(f"batch n-1: gemm {b[2] - b[1]:.3f} ms, refine {b[3] - b[2]:.3f}, map {b[4] - b[3]:.3f}, reweight {b[5] - b[4]:.3f}, out {b[6] - b[5]:.3f}")
 print(f"GEMM(n-1) starts {b[1] - a[2]:+.3f} ms after GEMM(n-2) ends; tail(n-2) ends {a[5] - b[1]:+.3f} ms after GEMM(n-1) starts "
       f"and {a[5] - b[2]:+.3f} ms relative to its end; period (end of refine to end of refine) {b[3] - a[3]:.3f} ms")
+for nm, x in (("n-2", a), ("n-1", b)):
+    print(f"batch {nm} refine stage: memsets {x[7] - x[2]:.3f}, certificate {x[8] - x[7]:.3f}, rescan {x[9] - x[8]:.3f}, "
+          f"counters copy + tier-2 launches {x[10] - x[9]:.3f} ms")
 bank.close()

@@ -544,7 +544,7 @@ def test_upsample_blur_bit_exact(env):
             out, pre, u8 = env["upsample_blur"](m, hw)
             t = torch.nn.functional.interpolate(torch.from_numpy(m).view(1, 1, fh, fw), size=(hw, hw), mode="bilinear")
             # (bit-exactness of the bilinear weights is pinned for the reference's 28 / 56 -> 224 only)
-            np.testing.assert_allclose(pre, t[0, 0].numpy(), rtol=2e-6, atol=1e-6, err_msg=str((fh, fw, hw, peak)))
+            np.testing.assert_allclose(pre, t[0, 0].numpy(), rtol=2e-5, atol=1e-5, err_msg=str((fh, fw, hw, peak)))
             ref, ref_u8 = O.knn_blur_restated(pre)
             assert (u8 == ref_u8).all() and (out == ref).all(), (fh, fw, hw, peak)
 
