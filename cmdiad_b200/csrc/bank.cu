@@ -259,6 +259,9 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2; ++i) {
+        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->lane_aux[i], cudaStreamNonBlocking);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fork[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_compute[i], cudaEventDisableTiming);
     }
@@ -302,6 +305,8 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     cudaSetDevice(b->device);
     for (auto st : b->lane_stream)
         if (st) cudaStreamSynchronize(st);
+    for (auto st : b->lane_aux)
+        if (st) cudaStreamSynchronize(st);
     if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
     if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
     free_scoring_layout(b);
@@ -331,6 +336,9 @@ void cmdb_bank_destroy(cmdb_bank *b) {
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     if (b->d2h_stream) cudaStreamDestroy(b->d2h_stream);
     for (int i = 0; i < 2; ++i) {
+        if (b->lane_aux[i]) cudaStreamDestroy(b->lane_aux[i]);
+        if (b->ev_fork[i]) cudaEventDestroy(b->ev_fork[i]);
+        if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
         if (b->ev_compute[i]) cudaEventDestroy(b->ev_compute[i]);
     }

@@ -147,6 +147,9 @@ struct cmdb_bank {
     // lane currently selected (score_select_slot); everything that is not scoring runs on whichever lane is current.
     cudaStream_t stream = nullptr;
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    // per lane: side stream for the (normally empty) tier-2 launches and the counters copy, which run beside the rescan
+    cudaStream_t lane_aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
     cmdb::ScoreScratch ss_store[2];
     int *last_fail_host = nullptr;   // pinned certificate counters of the most recent certified call (either lane)
     cudaStream_t copy_stream = nullptr;   // host -> device staging of query chunks, overlapped with the GEMM of earlier chunks

@@ -605,7 +605,7 @@ void gemm_prefer_carveout() {
 
 static void free_lane(ScoreScratch &s) {
     cudaFree(s.q_hi), cudaFree(s.q_lo), cudaFree(s.q_scale_exp);
-    cudaFree(s.cand), cudaFree(s.s_key), cudaFree(s.topk_keys);
+    cudaFree(s.cand), cudaFree(s.topk_keys);   // s_key lives inside the fail_ctl allocation
     cudaFree(s.map_tmp), cudaFree(s.map_max), cudaFree(s.m_test), cudaFree(s.m_star), cudaFree(s.nn_rows);
     cudaFree(s.top3), cudaFree(s.done_counter);
     cudaFree(s.q_norm), cudaFree(s.q_eps), cudaFree(s.fail_list), cudaFree(s.fail_ctl);
@@ -619,6 +619,8 @@ void score_scratch_free(cmdb_bank *b) {
     if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
     if (b->d2h_stream) cudaStreamSynchronize(b->d2h_stream);
     for (auto st : b->lane_stream)
+        if (st) cudaStreamSynchronize(st);
+    for (auto st : b->lane_aux)
         if (st) cudaStreamSynchronize(st);
     // query / result blocks are per SLOT and shared by both lane copies (slot i is only ever used by lane i)
     ScoreScratch &s0 = b->ss_store[0];
@@ -704,7 +706,9 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
         CMDB_CUDA(cudaMalloc(&s.q_norm, sizeof(float) * cap_p));
         CMDB_CUDA(cudaMalloc(&s.q_eps, sizeof(float) * cap_p));
         CMDB_CUDA(cudaMalloc(&s.fail_list, sizeof(int) * cap_p));
-        CMDB_CUDA(cudaMalloc(&s.fail_ctl, 8 * sizeof(int)));
+        // control block (8 ints) and the per-image argmax keys behind it: one allocation, cleared by ONE memset per call
+        CMDB_CUDA(cudaMalloc(&s.fail_ctl, 8 * sizeof(int) + sizeof(unsigned long long) * cap_b));
+        s.s_key = reinterpret_cast<unsigned long long *>(s.fail_ctl + 8);
         CMDB_CUDA(cudaMalloc(&s.work_list, sizeof(int2) * kWorkCap));
         CMDB_CUDA(cudaMalloc(&s.best_key, sizeof(unsigned long long) * cap_p));
         CMDB_CUDA(cudaMallocHost(&s.fail_count_host, 2 * sizeof(int)));
@@ -737,7 +741,6 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
         }
         CMDB_CUDA(cudaMalloc(&s.map_tmp, (size_t)map_cap * cap_b));
         CMDB_CUDA(cudaMalloc(&s.map_max, sizeof(float) * cap_b * 17));  // [cap_b] maxima, then [cap_b][16] band maxima
-        CMDB_CUDA(cudaMalloc(&s.s_key, sizeof(unsigned long long) * cap_b));
         CMDB_CUDA(cudaMalloc(&s.topk_keys, sizeof(unsigned long long) * 3 * s.n_topk_blocks * cap_b));
         CMDB_CUDA(cudaMalloc(&s.top3, sizeof(unsigned long long) * 3 * cap_b));
         CMDB_CUDA(cudaMalloc(&s.m_test, sizeof(float) * D * cap_b));

@@ -563,12 +563,11 @@ static int mod_inverse(int a, int m) {
     return 0;
 }
 
-int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
+static int score_certify(cmdb_bank *b, int B, int P_img, int n_cand) {
     const int P = B * P_img;
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
-    CMDB_CUDA(cudaMemsetAsync(s.s_key, 0, sizeof(unsigned long long) * B, st));
-    CMDB_CUDA(cudaMemsetAsync(s.fail_ctl, 0, 8 * sizeof(int), st));
+    CMDB_CUDA(cudaMemsetAsync(s.fail_ctl, 0, 8 * sizeof(int) + sizeof(unsigned long long) * B, st));  // control block + s_key
     const float acc_model = (float)(b->dim / 16 + 1) * 17.f * 1.1920929e-7f;
     if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][0], st));
     // queries per block: 8 = one query per warp in phase 3 and 10 list entries per thread held in registers (measured best;
@@ -588,6 +587,13 @@ int score_refine_certified(cmdb_bank *b, int B, int P_img, int n_cand) {
     else CMDB_CERT(8);
 #undef CMDB_CERT
     if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][1], st));
+    CMDB_CUDA(cudaGetLastError());
+    return CMDB_OK;
+}
+
+static int score_rescan(cmdb_bank *b, int P_img) {
+    ScoreScratch &s = b->ss;
+    cudaStream_t st = b->stream;
     CMDB_CUDA(cudaGetLastError());
     // tier 1: few uncertified (query, producer) pairs -> exact rescan of those producers' rows
     const int cg = s.sched_pair ? 2 : 1, n_units = b->num_sms / cg, EG = score_gemm_groups();
@@ -697,17 +703,36 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     }
     CMDB_CHECK(mark(ev_refine));
     if (mode != 0) return score_refine(b, B, P_img, n_cand, false);
-    CMDB_CHECK(score_refine_certified(b, B, P_img, n_cand));
-    CMDB_CUDA(cudaMemcpyAsync(s.fail_count_host, s.fail_ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CMDB_CUDA(cudaEventRecord(b->ev_fail, st));
+    // certificate kernel (takes the tier decision), then the two tiers side by side: the exact rescan on the lane's stream,
+    // the counters copy and the tier-2 launches on the lane's side stream.  The tiers are exclusive (the control block
+    // enables one of them) and touch disjoint buffers, so nothing orders them against each other; the side stream's launches
+    // are empty in the common case and their launch latencies (27 us in a row) disappear behind the rescan.
+    const int lane = b->cur_slot;
+    cudaStream_t aux = b->lane_aux[lane];
+    CMDB_CHECK(score_certify(b, B, P_img, n_cand));
+    CMDB_CUDA(cudaEventRecord(b->ev_fork[lane], st));
+    CMDB_CUDA(cudaStreamWaitEvent(aux, b->ev_fork[lane], 0));
+    CMDB_CHECK(score_rescan(b, P_img));
+    b->stream = aux;
+    int rc = CMDB_OK;
+    if (cudaMemcpyAsync(s.fail_count_host, s.fail_ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, aux) != cudaSuccess ||
+        cudaEventRecord(b->ev_fail, aux) != cudaSuccess)
+        rc = CMDB_ERR_CUDA;
     b->fail_pending = true;
     b->last_fail_host = s.fail_count_host;   // this lane's pinned counters
     // tier 2 (many uncertified pairs): FP32-equivalent GEMM over the compacted uncertified queries; every launch sizes
     // itself from the device-side control block and returns at once in the common case
-    CMDB_CHECK(score_query_prep(b, P, true));
-    CMDB_CHECK(score_gemm_candidates(b, P, 3, true, &n_cand));
-    CMDB_CHECK(score_refine(b, B, P_img, n_cand, true));
-    if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[b->cur_slot][3], st));
+    if (rc == CMDB_OK) rc = score_query_prep(b, P, true);
+    if (rc == CMDB_OK) rc = score_gemm_candidates(b, P, 3, true, &n_cand);
+    if (rc == CMDB_OK) rc = score_refine(b, B, P_img, n_cand, true);
+    b->stream = st;
+    if (rc != CMDB_OK) {
+        if (rc == CMDB_ERR_CUDA) set_error("scoring: CUDA error while enqueuing the fallback tier: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
+    CMDB_CUDA(cudaEventRecord(b->ev_join[lane], aux));
+    CMDB_CUDA(cudaStreamWaitEvent(st, b->ev_join[lane], 0));
+    if (b->timing == 2) CMDB_CUDA(cudaEventRecord(b->ev_dbg[lane][3], st));
     return CMDB_OK;
 }
 
