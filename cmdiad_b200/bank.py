@@ -439,15 +439,15 @@ class Bank:
 
     def score_batch_async(self, patches, feature_map_dims, out_hw=224, full=False):
         """Pipelined score_batch: enqueues the batch (at most max_shard_batch() images) and returns a ticket at once;
-        ticket.wait() returns the list of ScoreResult.  Two batches may be outstanding per bank, so the result copy of
-        batch k and the staging of batch k+1 overlap the kernels of the other batch:
+        ticket.wait() returns the list of ScoreResult.  Three batches may be outstanding per bank, so the result copy of
+        batch k and the staging of batch k+1 overlap the kernels of the other compute lane, and the host's enqueue time
+        never delays the next distance GEMM:
 
-            pending = None
+            pending = []
             for batch in batches:
-                t = bank.score_batch_async(batch, dims)
-                if pending is not None: consume(pending.wait())
-                pending = t
-            consume(pending.wait())
+                pending.append(bank.score_batch_async(batch, dims))
+                if len(pending) == 3: consume(pending.pop(0).wait())
+            while pending: consume(pending.pop(0).wait())
         """
         patches = _as_f32(patches)
         assert patches.dim() == 3 and patches.shape[2] == self.dim, f"expected [B,P,{self.dim}], got {tuple(patches.shape)}"
@@ -500,8 +500,8 @@ class Bank:
                             img_base=0, phase_events=None):
         """One pipelined round (<= max_shard_batch() images) of row-sharded scoring with the replicated neighbour table
         (build_knn_sharded): min -> MIN all-reduce -> lookup -> SUM all-reduce -> finish, all enqueued on the handle's
-        stream without waiting.  Returns a ticket; ticket.wait() -> BatchResult.  Two rounds may be outstanding, so the
-        caller submits round k + 1 before waiting for round k.  Collective: every rank calls it with the same images.
+        stream without waiting.  Returns a ticket; ticket.wait() -> BatchResult.  Three rounds may be outstanding, so the
+        caller submits rounds k + 1 and k + 2 before waiting for round k.  Collective: every rank calls it with the same images.
         distribute: rank r runs the blur and the device->host copy only for the images i with (img_base + i) % world == r
         (the scalars of all images are replicated)."""
         import torch.distributed as dist
@@ -511,7 +511,7 @@ class Bank:
         assert B <= self.max_shard_batch()
         fh, fw = feature_map_dims
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        slot = self.__dict__.setdefault("_shard_round", 0) & 1
+        slot = self.__dict__.setdefault("_shard_round", 0) % 3   # staging buffers: one set per outstanding round
         self._shard_round += 1
         evs = phase_events
         lane = self.stream()   # the lane this round runs on (the finish call below hands the handle to the other lane)

@@ -309,19 +309,31 @@ int cmdb_coreset_rownorms(int device, const void *z_host, const void *last_host,
 
 // Enqueue one sub-batch (<= score_max_batch images) on buffer slot `slot`: staging, GEMM + certificate, maps, re-weighting
 // and the device->host copies of the results (on the d2h stream, the maps as soon as the blur is done).  No host sync.
+// A submitted call takes the next result slot (kResultSlots of them) and the next compute lane (two, alternating).
+struct SlotPick {
+    int lane, rslot;
+};
+static SlotPick take_slot(cmdb_bank *b) {
+    const SlotPick p{b->next_lane, b->next_slot};
+    b->next_lane ^= 1;
+    b->next_slot = (b->next_slot + 1) % kResultSlots;
+    return p;
+}
+
 static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int bc, int P, int fh, int fw, int out_hw,
-                            unsigned want, int slot, bool host_maps = true) {
+                            unsigned want, SlotPick pick, bool host_maps = true) {
+    const int slot = pick.rslot, lane = pick.lane;
 #define CMDB_MARK(i)                                                   \
     do {                                                               \
-        if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[slot][i] : b->ev[i], b->stream)); \
+        if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[lane][i] : b->ev[i], b->stream)); \
     } while (0)
     ScoreScratch &s = b->ss;
     CMDB_CHECK(stage_alloc(b, bc, P, out_hw));
-    score_select_slot(b, slot);
-    cudaStream_t st = b->stream;  // the slot's lane (only valid after the selection)
+    score_select_slot(b, lane, slot);
+    cudaStream_t st = b->stream;  // the lane's stream (only valid after the selection)
     CMDB_MARK(CMDB_T_STAGE_IN);
-    // this slot's q_f32 was last read by the batch submitted two calls ago
-    CMDB_CHECK(score_local_min(b, src, is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE, b->ev_compute[slot]));
+    // this lane's q_f32 was last read by the batch submitted two calls ago
+    CMDB_CHECK(score_local_min(b, src, is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE, b->ev_compute[lane]));
     CMDB_MARK(CMDB_T_MAP);
     CMDB_CHECK(blur_batch(b, bc, fh, fw, out_hw));
     // min_val / min_idx / maps do not depend on the re-weighting: their copy overlaps it
@@ -333,11 +345,11 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
     CMDB_MARK(CMDB_T_REWEIGHT);
     CMDB_CHECK(score_reweight(b, bc, P, true));
     CMDB_MARK(CMDB_T_OUT);
-    CMDB_CUDA(cudaEventRecord(b->ev_compute[slot], st));
-    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
+    CMDB_CUDA(cudaEventRecord(b->ev_compute[lane], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[lane], 0));
     CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_min_val, cudaMemcpyDeviceToHost, b->d2h_stream));
     CMDB_CUDA(cudaEventRecord(b->ev_done[slot], b->d2h_stream));
-    if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[slot][CMDB_T_COUNT] : b->ev[CMDB_T_COUNT], b->d2h_stream));
+    if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[lane][CMDB_T_COUNT] : b->ev[CMDB_T_COUNT], b->d2h_stream));
 #undef CMDB_MARK
     cmdb_bank::Pending &pd = b->pending[slot];
     pd.active = true, pd.B = bc, pd.P = P, pd.out_hw = out_hw, pd.want = want, pd.host_maps = host_maps;
@@ -359,7 +371,7 @@ static int check_batch_args(cmdb_bank *b, const float *patches, int B, int P, in
     CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "%s: out_hw=%d not in [8,256]", fn, out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
     if (b->ss.map_stride && (size_t)out_hw * out_hw != b->ss.map_stride) {  // map stride is fixed per scratch
-        CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
+        CMDB_REQUIRE(!b->any_pending(), CMDB_ERR_STATE,
                      "%s: out_hw changes while a submitted batch is outstanding; wait for it first", fn);
         score_scratch_free(b);
     }
@@ -375,11 +387,12 @@ int cmdb_score_batch(cmdb_bank *b, const float *patches, int B, int P, int fh, i
     int prev_slot = -1, prev_b0 = 0;
     for (int b0 = 0; b0 < B; b0 += bc_max) {
         const int bc = std::min(bc_max, B - b0);
-        const int slot = b->next_slot;
-        CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE, "cmdb_score_batch: two submitted batches are outstanding; wait for one first");
-        b->next_slot ^= 1;
+        CMDB_REQUIRE(!b->pending[b->next_slot].active, CMDB_ERR_STATE,
+                     "cmdb_score_batch: all result slots hold submitted batches; wait for one first");
+        const SlotPick pick = take_slot(b);
+        const int slot = pick.rslot;
         CMDB_CHECK(submit_sub_batch(b, patches + (size_t)b0 * P * b->dim, patch_is_device, bc, P, fh, fw, out_hw,
-                                    want_mask_of(outs + b0, bc), slot));
+                                    want_mask_of(outs + b0, bc), pick));
         if (prev_slot >= 0) CMDB_CHECK(wait_slot(b, prev_slot, outs + prev_b0));
         prev_slot = slot, prev_b0 = b0;
     }
@@ -393,11 +406,11 @@ int cmdb_score_batch_submit(cmdb_bank *b, const float *patches, int B, int P, in
     CMDB_CHECK(check_batch_args(b, patches, B, P, fh, fw, out_hw, "cmdb_score_batch_submit"));
     CMDB_REQUIRE(B <= score_max_batch(b), CMDB_ERR_INVALID, "cmdb_score_batch_submit: batch=%d exceeds the per-call limit %d", B,
                  score_max_batch(b));
-    const int slot = b->next_slot;
-    CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
-                 "cmdb_score_batch_submit: two batches are already outstanding; call cmdb_score_batch_wait first");
-    CMDB_CHECK(submit_sub_batch(b, patches, patch_is_device, B, P, fh, fw, out_hw, want_maps & 3u, slot));
-    b->next_slot ^= 1;
+    CMDB_REQUIRE(!b->pending[b->next_slot].active, CMDB_ERR_STATE,
+                 "cmdb_score_batch_submit: three batches are already outstanding; call cmdb_score_batch_wait first");
+    const SlotPick pick = take_slot(b);
+    const int slot = pick.rslot;
+    CMDB_CHECK(submit_sub_batch(b, patches, patch_is_device, B, P, fh, fw, out_hw, want_maps & 3u, pick));
     b->pending[slot].ticket = ++b->ticket_counter;
     *out_ticket = b->pending[slot].ticket;
     return CMDB_OK;
@@ -405,7 +418,7 @@ int cmdb_score_batch_submit(cmdb_bank *b, const float *patches, int B, int P, in
 
 int cmdb_score_batch_wait(cmdb_bank *b, int64_t ticket, cmdb_score_out *outs) {
     CMDB_REQUIRE(b && outs, CMDB_ERR_INVALID, "cmdb_score_batch_wait: NULL argument");
-    for (int slot = 0; slot < 2; ++slot)
+    for (int slot = 0; slot < kResultSlots; ++slot)
         if (b->pending[slot].active && b->pending[slot].ticket == ticket) {
             CMDB_CUDA(cudaSetDevice(b->device));
             return wait_slot(b, slot, outs);
@@ -435,17 +448,17 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     {
         // the round runs on lane / result slot next_slot (what cmdb_bank_stream returns before this call); with the submit /
         // wait finish two rounds may be in flight, one per lane
-        const bool busy = b->pending[0].active || b->pending[1].active;
+        const bool busy = b->any_pending();
         CMDB_REQUIRE(!busy || (size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
                      "cmdb_score_shard_min: out_hw changes while a submitted round is outstanding; wait for it first");
         if (!busy && (size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
-        const int slot = b->next_slot;
+        const int slot = b->next_slot, lane = b->next_lane;   // advanced by the finish call of the round
         CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
-                     "cmdb_score_shard_min: two submitted rounds are outstanding on this handle; wait for one first");
+                     "cmdb_score_shard_min: all result slots hold submitted rounds; wait for one first");
         CMDB_CHECK(stage_alloc(b, B, P, out_hw));  // fails with CMDB_ERR_STATE if the scratch would have to grow
-        score_select_slot(b, slot);
-        b->shard_slot = slot;
-        CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
+        score_select_slot(b, lane, slot);
+        b->shard_slot = slot, b->shard_lane = lane;
+        CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[lane]));
     }
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
@@ -541,15 +554,15 @@ static int shard_finish_enqueue(cmdb_bank *b, const float *knn_d2_sum_device, in
     CMDB_REQUIRE((size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_INVALID,
                  "cmdb_score_shard_finish_submit: out_hw differs from cmdb_score_shard_min");
     CMDB_REQUIRE(img_first >= 0 && img_step >= 1, CMDB_ERR_INVALID, "cmdb_score_shard_finish_submit: bad image subset");
-    const int slot = b->shard_slot;
+    const int slot = b->shard_slot, lane = b->shard_lane;
     CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE, "cmdb_score_shard_finish_submit: this round's slot is still outstanding");
     CMDB_CUDA(cudaSetDevice(b->device));
     ScoreScratch &s = b->ss;
     cudaStream_t st = b->stream;
     CMDB_CHECK(score_shard_final(b, B, knn_d2_sum_device));
     CMDB_CHECK(blur_batch(b, B, fh, fw, out_hw, img_first, img_step));
-    CMDB_CUDA(cudaEventRecord(b->ev_compute[slot], st));
-    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
+    CMDB_CUDA(cudaEventRecord(b->ev_compute[lane], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[lane], 0));
     // scalar / per-patch prefix of ALL images in one copy, then the maps of the images this rank finished
     const size_t npix = (size_t)out_hw * out_hw;
     want_maps &= 3u;
@@ -570,7 +583,7 @@ static int shard_finish_enqueue(cmdb_bank *b, const float *knn_d2_sum_device, in
     pd.active = true, pd.B = B, pd.P = P, pd.out_hw = out_hw, pd.want = want_maps, pd.host_maps = true;
     pd.img_first = img_first, pd.img_step = img_step;
     pd.ticket = ++b->ticket_counter;
-    b->next_slot = slot ^ 1;
+    b->next_slot = (slot + 1) % kResultSlots, b->next_lane = lane ^ 1;
     *out_ticket = pd.ticket;
     return CMDB_OK;
 }
@@ -579,7 +592,7 @@ static int shard_finish_enqueue(cmdb_bank *b, const float *knn_d2_sum_device, in
 
 int cmdb_bank_attach_comm(cmdb_bank *b, cmdb_comm *comm) {
     CMDB_REQUIRE(b, CMDB_ERR_INVALID, "cmdb_bank_attach_comm: bank is NULL");
-    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "cmdb_bank_attach_comm: a submitted round is outstanding");
+    CMDB_REQUIRE(!b->any_pending(), CMDB_ERR_STATE, "cmdb_bank_attach_comm: a submitted round is outstanding");
     b->comm = comm;
     if (!comm) return CMDB_OK;
     int rank = 0, world = 1;
@@ -615,17 +628,17 @@ int cmdb_score_shard_round_submit(cmdb_bank *b, const float *patches, int B, int
     PeerPtrs peers{};
     CMDB_CHECK(comm_info(b->comm, &rank, &world, &local, peers.p, &bytes));
     CMDB_CUDA(cudaSetDevice(b->device));
-    const bool busy = b->pending[0].active || b->pending[1].active;
+    const bool busy = b->any_pending();
     if (!busy && (size_t)out_hw * out_hw != b->ss.map_stride) score_scratch_free(b);
     CMDB_REQUIRE(!busy || (size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
                  "cmdb_score_shard_round_submit: out_hw changes while a submitted round is outstanding; wait for it first");
-    const int slot = b->next_slot;
+    const int slot = b->next_slot, lane = b->next_lane;   // advanced by shard_finish_enqueue
     CMDB_REQUIRE(!b->pending[slot].active, CMDB_ERR_STATE,
-                 "cmdb_score_shard_round_submit: two submitted rounds are outstanding on this handle; wait for one first");
+                 "cmdb_score_shard_round_submit: three submitted rounds are outstanding on this handle; wait for one first");
     CMDB_CHECK(stage_alloc(b, B, P, out_hw));
-    score_select_slot(b, slot);
-    b->shard_slot = slot;
-    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
+    score_select_slot(b, lane, slot);
+    b->shard_slot = slot, b->shard_lane = lane;
+    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[lane]));
     const unsigned long long epoch = comm_next_score_epoch(b->comm);  // per buffer, not per bank: several banks may share it
     const int xslot = (int)(epoch % kShardSlots);
     CMDB_CHECK(score_shard_exchange_keys(b, B, P, peers, world, rank, xslot, epoch));
@@ -638,7 +651,7 @@ int cmdb_score_shard_round_submit(cmdb_bank *b, const float *patches, int B, int
 
 int cmdb_score_shard_wait(cmdb_bank *b, int64_t ticket, cmdb_score_out *outs) {
     CMDB_REQUIRE(b && outs, CMDB_ERR_INVALID, "cmdb_score_shard_wait: NULL argument");
-    for (int slot = 0; slot < 2; ++slot) {
+    for (int slot = 0; slot < kResultSlots; ++slot) {
         cmdb_bank::Pending &pd = b->pending[slot];
         if (!pd.active || pd.ticket != ticket) continue;
         CMDB_CUDA(cudaSetDevice(b->device));
@@ -803,8 +816,9 @@ int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *p
     cmdb_bank::Fused &f = b0->fused;
     CMDB_CUDA(cudaSetDevice(b0->device));
     CMDB_CHECK(fused_alloc(b0, out_hw));
-    const int fs = b0->next_slot;  // the fused block shares the slot parity of modality 0
-    CMDB_REQUIRE(!f.active[fs], CMDB_ERR_STATE, "cmdb_score_fused_batch_submit: fused slot still outstanding");
+    const int fs = f.next_fs;   // two fused blocks: at most two fused batches are outstanding
+    CMDB_REQUIRE(!f.active[fs], CMDB_ERR_STATE, "cmdb_score_fused_batch_submit: two fused batches are already outstanding; wait for one first");
+    f.next_fs ^= 1;
     const int npix = out_hw * out_hw;
     const bool keep = (flags & CMDB_FUSED_KEEP_ON_DEVICE) != 0, host_maps = (flags & CMDB_FUSED_NO_HOST_MAPS) == 0;
     if (keep) {
@@ -816,9 +830,9 @@ int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *p
     fp.n_modal = M, fp.B = B, fp.npix = npix;
     for (int m = 0; m < M; ++m) {
         cmdb_bank *bm = banks[m];
-        const int slot = bm->next_slot;
-        bm->next_slot ^= 1;
-        CMDB_CHECK(submit_sub_batch(bm, patches[m], patch_is_device, B, P[m], fh[m], fw[m], out_hw, 0u, slot, false));
+        const SlotPick pick = take_slot(bm);
+        const int slot = pick.rslot;
+        CMDB_CHECK(submit_sub_batch(bm, patches[m], patch_is_device, B, P[m], fh[m], fw[m], out_hw, 0u, pick, false));
         bm->pending[slot].ticket = ++bm->ticket_counter;
         f.banks[fs][m] = bm, f.slots[fs][m] = slot;
         fp.maps[m] = reinterpret_cast<const float *>(bm->ss.out_block_buf[slot] + bm->ss.off_map_out);
@@ -826,7 +840,7 @@ int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *p
         fp.tails[m] = reinterpret_cast<const TailResult *>(bm->ss.out_block_buf[slot]);
         fp.s_lambda[m] = head->s_lambda[m], fp.smap_lambda[m] = head->smap_lambda[m];
         fp.det_coef[m] = head->detect_coef[m], fp.seg_coef[m] = head->seg_coef[m];
-        if (m > 0) CMDB_CUDA(cudaStreamWaitEvent(b0->stream, bm->ev_compute[slot], 0));
+        if (m > 0) CMDB_CUDA(cudaStreamWaitEvent(b0->stream, bm->ev_compute[pick.lane], 0));
     }
     fp.det_off = head->detect_offset, fp.seg_off = head->seg_offset;
     unsigned char *blk = f.dev[fs];

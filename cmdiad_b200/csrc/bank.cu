@@ -262,9 +262,10 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
         if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->lane_aux[i], cudaStreamNonBlocking);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fork[i], cudaEventDisableTiming);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_compute[i], cudaEventDisableTiming);
     }
+    for (auto &e : b->ev_done)
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fail, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_stage, cudaEventDisableTiming);
     for (auto &e : b->ev_chunk)
@@ -339,9 +340,10 @@ void cmdb_bank_destroy(cmdb_bank *b) {
         if (b->lane_aux[i]) cudaStreamDestroy(b->lane_aux[i]);
         if (b->ev_fork[i]) cudaEventDestroy(b->ev_fork[i]);
         if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
-        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
         if (b->ev_compute[i]) cudaEventDestroy(b->ev_compute[i]);
     }
+    for (auto &e : b->ev_done)
+        if (e) cudaEventDestroy(e);
     if (b->ev_fail) cudaEventDestroy(b->ev_fail);
     if (b->ev_stage) cudaEventDestroy(b->ev_stage);
     for (auto &e : b->ev_chunk)
@@ -434,7 +436,7 @@ int cmdb_bank_set_query_norm(cmdb_bank *b, float mean, float stdv, int enabled) 
 
 int cmdb_bank_stream(cmdb_bank *b, void **out_stream) {
     CMDB_REQUIRE(b && out_stream, CMDB_ERR_INVALID, "cmdb_bank_stream: bad arguments");
-    *out_stream = (void *)b->lane_stream[b->next_slot];  // the lane the NEXT scoring call of this handle runs on
+    *out_stream = (void *)b->lane_stream[b->next_lane];  // the lane the NEXT scoring call of this handle runs on
     return CMDB_OK;
 }
 
@@ -458,7 +460,7 @@ static int build_knn_checks(cmdb_bank *b, const char *fn) {
     CMDB_REQUIRE(b->row_offset == 0, CMDB_ERR_UNSUPPORTED,
                  "%s: the table is computed on a handle that holds every bank row (row-sharded handles install a replicated "
                  "table with cmdb_bank_set_knn_table)", fn);
-    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "%s: a submitted batch is outstanding", fn);
+    CMDB_REQUIRE(!b->any_pending(), CMDB_ERR_STATE, "%s: a submitted batch is outstanding", fn);
     CMDB_CUDA(cudaSetDevice(b->device));
     return CMDB_OK;
 }
@@ -493,7 +495,7 @@ int cmdb_bank_set_knn_table(cmdb_bank *b, const uint64_t *keys, int64_t n_rows_t
     CMDB_REQUIRE(b->row_offset + b->fin_rows <= n_rows_total, CMDB_ERR_INVALID,
                  "cmdb_bank_set_knn_table: the table must cover all GLOBAL rows (this shard ends at %lld, table has %lld)",
                  (long long)(b->row_offset + b->fin_rows), (long long)n_rows_total);
-    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE, "cmdb_bank_set_knn_table: a submitted batch is outstanding");
+    CMDB_REQUIRE(!b->any_pending(), CMDB_ERR_STATE, "cmdb_bank_set_knn_table: a submitted batch is outstanding");
     CMDB_CUDA(cudaSetDevice(b->device));
     CMDB_CUDA(cudaStreamSynchronize(b->stream));
     cudaFree(b->knn_table);

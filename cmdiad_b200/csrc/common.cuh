@@ -42,6 +42,7 @@ constexpr int kNumSMsDefault = 148;
 constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch box
 constexpr int kScoreBN = 256;        // bank rows per GEMM tile
 constexpr int kScoreBM = 128;        // query rows per GEMM tile
+constexpr int kResultSlots = 3;      // result blocks / outstanding submitted calls per handle (the compute lanes stay two)
 constexpr int kMaxStageChunks = 4;   // host query batches are staged and multiplied in up to this many chunks
 constexpr int kWorkCap = 16384;      // capacity of ScoreScratch::work_list
 // Fallback tiers of the certified pre-filter.  Tier 1, exact rescan: ~R/296 rows x D x 4 B per (query, producer) pair, HBM
@@ -63,7 +64,7 @@ struct ScoreScratch {
     int cap_p = 0;                  // padded query-row capacity of a sub-batch (multiple of 128)
     int cap_b = 0;                  // image capacity of a sub-batch
     float *q_f32 = nullptr;         // [cap_p, D]  normalised query patches (the slot selected by score_select_slot)
-    float *q_f32_buf[2] = {nullptr, nullptr};   // double-buffered: batch k+1 is staged while batch k is still scored
+    float *q_f32_buf[2] = {nullptr, nullptr};   // per LANE: batch k+1 is staged while batch k is still scored
     __half *q_hi = nullptr;         // [cap_p, D]  split-fp16 query operand
     __half *q_lo = nullptr;
     int *q_scale_exp = nullptr;     // device [cap_p]: per-row exponent e_q with q_hi + q_lo = q * 2^e_q
@@ -101,8 +102,10 @@ struct ScoreScratch {
     // host block, so a scoring call ends with a single device->host copy
     unsigned char *out_block = nullptr;       // (current slot)
     unsigned char *out_block_host = nullptr;  // cudaMallocHost
-    unsigned char *out_block_buf[2] = {nullptr, nullptr};       // double-buffered: the results of batch k travel to the
-    unsigned char *out_block_host_buf[2] = {nullptr, nullptr};  // host while batch k+1 is scored
+    // per RESULT SLOT (kResultSlots of them, cycled independently of the two lanes): the results of batches k - 1 and k
+    // travel to the host / wait for the caller while batch k + 1 is already enqueued behind batch k - 1 on its lane
+    unsigned char *out_block_buf[kResultSlots] = {};
+    unsigned char *out_block_host_buf[kResultSlots] = {};
     size_t off_min_val = 0, off_min_idx = 0, off_map_out = 0, off_map_pre = 0, off_map_u8 = 0, out_block_bytes = 0;
     size_t map_stride = 0;  // pixels reserved per image in the map sections
     float *map_pre = nullptr;       // [out_hw^2]
@@ -155,8 +158,8 @@ struct cmdb_bank {
     cudaStream_t copy_stream = nullptr;   // host -> device staging of query chunks, overlapped with the GEMM of earlier chunks
     cudaEvent_t ev_chunk[cmdb::kMaxStageChunks] = {};
     cudaStream_t d2h_stream = nullptr;    // device -> host copies of the results
-    cudaEvent_t ev_done[2] = {};          // slot's results are in the pinned host block
-    cudaEvent_t ev_compute[2] = {};       // slot's kernels are done (its q_f32 may be overwritten)
+    cudaEvent_t ev_done[cmdb::kResultSlots] = {};   // result slot's block is in the pinned host memory
+    cudaEvent_t ev_compute[2] = {};       // lane's kernels are done (its q_f32 may be overwritten)
     cudaEvent_t ev_fail = nullptr;        // the certificate counters of the last certified call are on the host
     cudaEvent_t ev_stage = nullptr;       // cmdb_bank_stage_h2d: the staged bytes are on the device
     struct Pending {
@@ -166,7 +169,12 @@ struct cmdb_bank {
         bool host_maps = true;   // false: the per-modality maps stay in HBM (fused late-fusion head), only scalars travel
         int img_first = 0, img_step = 1;  // sharded rounds: the images whose maps this rank finished
         long long ticket = 0;
-    } pending[2];
+    } pending[cmdb::kResultSlots];
+    bool any_pending() const {
+        for (const auto &p : pending)
+            if (p.active) return true;
+        return false;
+    }
     // queries are normalised on the device right after staging: (q - q_mean) / q_std, one IEEE subtract + one IEEE divide
     // like the reference's torch expression (multiple_features.py:90, 976-977); cmdb_bank_set_query_norm
     bool q_norm_enabled = false;
@@ -179,6 +187,7 @@ struct cmdb_bank {
         size_t cap_bytes = 0;
         cudaEvent_t ev_done[2] = {};
         bool active[2] = {false, false};
+        int next_fs = 0;   // fused block of the next fused call (two fused batches may be outstanding)
         int n_modal[2] = {0, 0}, B[2] = {0, 0}, out_hw[2] = {0, 0};
         cmdb_bank *banks[2][3] = {};
         int slots[2][3] = {};
@@ -190,7 +199,9 @@ struct cmdb_bank {
         int acc_npix = 0;
     } fused;
     long long ticket_counter = 0;
-    int next_slot = 0;
+    int next_slot = 0;    // result slot of the next submitted call (cycles through kResultSlots)
+    int next_lane = 0;    // compute lane of the next submitted call (alternates)
+    int shard_lane = 0;   // lane of the sharded round in progress
     int shard_slot = 0;   // result slot of the sharded round in progress (cmdb_score_shard_min .. finish)
     cmdb_comm *comm = nullptr;             // peer buffers for NCCL-free sharded rounds (cmdb_bank_attach_comm; not owned)
     unsigned int *shard_ctr = nullptr;     // [0] device: last-block counter of the push kernels
@@ -276,7 +287,7 @@ int coreset_rownorms(int device, const void *z_host, const void *last_host, int6
 
 // score_gemm.cu
 int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw);
-void score_select_slot(cmdb_bank *b, int slot);  // point ss.q_f32 / ss.out_block / result pointers at buffer `slot`
+void score_select_slot(cmdb_bank *b, int lane, int rslot);  // lane's stream / scratch / q_f32, result pointers at block `rslot`
 int score_max_batch(const cmdb_bank *b);  // images per internal sub-batch (shared-memory bound of reweight_kernel)
 void score_scratch_free(cmdb_bank *b);
 int score_make_tensor_maps(cmdb_bank *b);

@@ -624,8 +624,9 @@ void score_scratch_free(cmdb_bank *b) {
         if (st) cudaStreamSynchronize(st);
     // query / result blocks are per SLOT and shared by both lane copies (slot i is only ever used by lane i)
     ScoreScratch &s0 = b->ss_store[0];
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(s0.q_f32_buf[i]), cudaFree(s0.out_block_buf[i]);
+    for (int i = 0; i < 2; ++i) cudaFree(s0.q_f32_buf[i]);
+    for (int i = 0; i < kResultSlots; ++i) {
+        cudaFree(s0.out_block_buf[i]);
         if (s0.out_block_host_buf[i]) cudaFreeHost(s0.out_block_host_buf[i]);
         b->pending[i].active = false;
     }
@@ -645,14 +646,14 @@ int score_max_batch(const cmdb_bank *b) {
 }
 
 // lane == slot: points b->ss / b->stream at that lane's scratch copy and stream, and at the slot's query / result blocks
-void score_select_slot(cmdb_bank *b, int slot) {
-    b->ss = b->ss_store[slot];
-    b->stream = b->lane_stream[slot];
-    b->cur_slot = slot;
+void score_select_slot(cmdb_bank *b, int lane, int rslot) {
+    b->ss = b->ss_store[lane];
+    b->stream = b->lane_stream[lane];
+    b->cur_slot = lane;
     ScoreScratch &s = b->ss;
-    s.q_f32 = s.q_f32_buf[slot];
-    s.out_block = s.out_block_buf[slot];
-    s.out_block_host = s.out_block_host_buf[slot];
+    s.q_f32 = s.q_f32_buf[lane];
+    s.out_block = s.out_block_buf[rslot];
+    s.out_block_host = s.out_block_host_buf[rslot];
     s.tail = s.out_block;
     s.min_val = reinterpret_cast<float *>(s.out_block + s.off_min_val);
     s.min_idx = reinterpret_cast<long long *>(s.out_block + s.off_min_idx);
@@ -668,7 +669,7 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
         const ScoreScratch &cur = b->ss_store[0];
         if (cur.cap_p >= p_pad && cur.cap_b >= B && (int)cur.map_stride >= map_n) return CMDB_OK;
     }
-    CMDB_REQUIRE(!b->pending[0].active && !b->pending[1].active, CMDB_ERR_STATE,
+    CMDB_REQUIRE(!b->any_pending(), CMDB_ERR_STATE,
                  "scoring: the scratch buffers have to grow while a submitted batch is outstanding; wait for it first");
     const int cap_p = std::max(p_pad, b->ss_store[0].cap_p), cap_b = std::max(B, b->ss_store[0].cap_b);
     const int map_cap = std::max(map_n, (int)b->ss_store[0].map_stride);
@@ -691,8 +692,8 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     shared.off_map_pre = shared.off_map_out + up(sizeof(float) * map_cap * cap_b);
     shared.off_map_u8 = shared.off_map_pre + up(sizeof(float) * map_cap * cap_b);
     shared.out_block_bytes = shared.off_map_u8 + up((size_t)map_cap * cap_b);
-    for (int i = 0; i < 2; ++i) {
-        CMDB_CUDA(cudaMalloc(&shared.q_f32_buf[i], sizeof(float) * cap_p * D));
+    for (int i = 0; i < 2; ++i) CMDB_CUDA(cudaMalloc(&shared.q_f32_buf[i], sizeof(float) * cap_p * D));
+    for (int i = 0; i < kResultSlots; ++i) {
         CMDB_CUDA(cudaMalloc(&shared.out_block_buf[i], shared.out_block_bytes));
         CMDB_CUDA(cudaMallocHost(&shared.out_block_host_buf[i], shared.out_block_bytes));
     }
@@ -751,7 +752,7 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
         CMDB_CHECK(make_map(&s.tmap_qlo, s.q_lo, cap_p, b->dim, BM));
     }
     b->fail_pending = false;
-    score_select_slot(b, 0);
+    score_select_slot(b, 0, 0);
     return CMDB_OK;
 }
 

@@ -664,7 +664,7 @@ int score_local_min(cmdb_bank *b, const float *src, int src_is_device, int B, in
     }();
     // another batch in flight on this handle (submit / wait pipeline): the whole copy already overlaps that batch's
     // kernels, so one chunk -- and one GEMM launch -- is best
-    const bool overlapped = b->pending[0].active || b->pending[1].active;
+    const bool overlapped = b->any_pending();
     const bool via_copy_stream = !src_is_device && (overlapped || mt_total >= 16);
     int n_chunks = 1;
     if (via_copy_stream && !overlapped) n_chunks = env_chunks > 0 ? env_chunks : (mt_total >= 64 ? 4 : 2);
@@ -1539,7 +1539,7 @@ int score_build_knn_table(cmdb_bank *b, long long row_first, long long row_count
     const int chunk = 64 * kScoreBM;  // 8192 rows: 64 M tiles per GEMM launch
     // scratch for `chunk` query rows; sized like a 32-image batch so that later scoring calls do not have to grow it
     CMDB_CHECK(score_scratch_alloc(b, 32, chunk / 32, s.map_stride ? (int)lround(sqrt((double)s.map_stride)) : 224));
-    score_select_slot(b, 0);
+    score_select_slot(b, 0, 0);
     cudaStream_t st = b->stream;  // lane 0 (only valid after the selection)
     if (!b->knn_table || b->knn_rows != b->fin_rows) {
         cudaFree(b->knn_table);

@@ -220,8 +220,9 @@ int cmdb_score(cmdb_bank *bank, const float *patch, int P, int fh, int fw, int o
 /* Pipelined form of cmdb_score_batch.  submit enqueues everything for one batch (B <= 32 images, <= 160 KB of m_star rows:
  * the limit cmdb_score_batch splits larger batches by) -- host->device staging, scoring, device->host copies into an
  * internal pinned block -- and returns without waiting; wait blocks until that batch is complete and fills outs[B].
- * Up to two batches may be outstanding per handle (double-buffered query and result blocks), so the result copy of
- * batch k and the staging of batch k+1 overlap the kernels of the other batch.  `patches` must stay valid until the
+ * Up to three batches may be outstanding per handle (three result blocks, two compute lanes with their own query blocks
+ * and scratch): the result copy of batch k and the staging of batch k+1 overlap the kernels of the other lane, and with two
+ * calls queued behind the running one the host's enqueue time never delays the next distance GEMM.  `patches` must stay valid until the
  * matching wait returns.  want_maps: bit 0 = outs[].s_map_pre will be requested, bit 1 = outs[].s_map_u8.
  * Results are identical to cmdb_score_batch.  Not combined with the sharded phases on the same handle. */
 int cmdb_score_batch_submit(cmdb_bank *bank, const float *patches, int batch, int P, int fh, int fw, int out_hw,
@@ -331,8 +332,8 @@ int cmdb_eval_read(cmdb_bank *bank, int64_t first, int64_t n, double *maps_host 
 
 /*
  * Row-sharded scoring with the replicated neighbour table (cmdb_bank_set_knn_table): three phases and TWO small collectives
- * per round, and a submit / wait finish so that two rounds can be in flight per handle (the result copy of round k and the
- * host work for round k + 1 overlap the kernels of the other round; nothing synchronises the host between the phases):
+ * per round, and a submit / wait finish so that three rounds can be outstanding per handle (the result copy of round k and
+ * the host work for the next rounds overlap the kernels of the other lane; nothing synchronises the host between the phases):
  *   1. cmdb_score_shard_min            as above                                                     -> all-reduce MIN (int64[B*P])
  *   2. cmdb_score_shard_lookup         decodes the reduced keys (min_val, min_idx, s*, s_idx, m_star row), reads the three
  *      nearest rows of m_star from the table and writes, per image, the exact SQUARED distances ||m_test - bank[nn_k]||^2

@@ -73,6 +73,16 @@ for mode in ("five-phase", "table/nccl", "table/peer-memory"):
     for t in range(2):
         a = shard.score_sharded(pb[t], (28, 28), 224, full=True)
         report(f"[{tag}] single image {t}", same(a, bb[t]))
+    if table:  # three rounds outstanding (three result slots on two compute lanes), 8 rounds of 8 images
+        for src_name, src in (("host", torch.from_numpy(pb).pin_memory()), ("device", torch.from_numpy(pb).cuda())):
+            pending, got = [], []
+            for k in range(8):
+                pending.append(shard.score_sharded_async(src[8 * k:8 * k + 8], (28, 28), 224, full=True))
+                if len(pending) == 3:
+                    got.extend(pending.pop(0).wait())
+            while pending:
+                got.extend(pending.pop(0).wait())
+            report(f"[{tag}] 8 rounds, three outstanding, {src_name} queries", all(same(got[t], bb[t]) for t in range(64)))
 t = torch.tensor([bad], device="cuda")
 dist.all_reduce(t)
 if rank == 0:

@@ -195,37 +195,41 @@ def test_bank_knn_table(env, R, D, dist):
 
 
 def test_async_submit_wait_pipeline(env):
-    """cmdb_score_batch_submit / _wait: two batches outstanding (double-buffered query / result blocks); results equal
-    the synchronous call, in submission order and out of order, host and device inputs; a third submit is refused."""
+    """cmdb_score_batch_submit / _wait: three batches outstanding (three result blocks, two compute lanes); results equal
+    the synchronous call, in submission order and out of order, host and device inputs, pipeline depth 2 and 3; a fourth
+    submit is refused."""
     from cmdiad_b200 import synth
     cent = synth.centroids(768, 128)
     lib = synth.patches(20000, 768, seed=71, cent=cent)
     b = _bank(env, lib)
     batches = [np.stack([synth.patches(784, 768, seed=500 + 10 * k + i, anomalous_frac=0.01, cent=cent) for i in range(6)])
-               for k in range(5)]
+               for k in range(7)]
     ref = [b.score_batch(x, (28, 28), 224, full=True) for x in batches]
     for dev in (False, True):
         xs = [torch.from_numpy(x).cuda() if dev else torch.from_numpy(x).pin_memory() for x in batches]
-        got, pending = [], None
-        for x in xs:
-            t = b.score_batch_async(x, (28, 28), 224, full=True)
-            if pending is not None:
-                got.append(pending.wait())
-            pending = t
-        got.append(pending.wait())
-        for k in range(5):
-            _assert_same_results(ref[k], got[k], f"async batch {k} dev={dev}")
+        for depth in (2, 3):
+            got, pending = [], []
+            for x in xs:
+                pending.append(b.score_batch_async(x, (28, 28), 224, full=True))
+                if len(pending) == depth:
+                    got.append(pending.pop(0).wait())
+            while pending:
+                got.append(pending.pop(0).wait())
+            for k in range(len(batches)):
+                _assert_same_results(ref[k], got[k], f"async batch {k} dev={dev} depth={depth}")
     t0 = b.score_batch_async(batches[0], (28, 28), 224)
     t1 = b.score_batch_async(batches[1], (28, 28), 224)
+    t2 = b.score_batch_async(batches[2], (28, 28), 224)
     with pytest.raises(RuntimeError):
-        b.score_batch_async(batches[2], (28, 28), 224)
+        b.score_batch_async(batches[3], (28, 28), 224)
     with pytest.raises(RuntimeError):
-        b.score_batch(batches[2], (28, 28), 224)
-    r1, r0 = t1.wait(), t0.wait()   # out of order
+        b.score_batch(batches[3], (28, 28), 224)
+    r1, r2, r0 = t1.wait(), t2.wait(), t0.wait()   # out of order
     for name in ("min_idx", "min_val", "s", "nn_idx", "s_map"):
         assert all((getattr(r0[i], name) == getattr(ref[0][i], name)).all() for i in range(6))
         assert all((getattr(r1[i], name) == getattr(ref[1][i], name)).all() for i in range(6))
-    assert all((a.s_map == c.s_map).all() for a, c in zip(b.score_batch(batches[2], (28, 28), 224), ref[2]))
+        assert all((getattr(r2[i], name) == getattr(ref[2][i], name)).all() for i in range(6))
+    assert all((a.s_map == c.s_map).all() for a, c in zip(b.score_batch(batches[3], (28, 28), 224), ref[3]))
     b.close()
 
 
