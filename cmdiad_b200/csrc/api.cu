@@ -332,8 +332,8 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
     score_select_slot(b, lane, slot);
     cudaStream_t st = b->stream;  // the lane's stream (only valid after the selection)
     CMDB_MARK(CMDB_T_STAGE_IN);
-    // this lane's q_f32 was last read by the batch submitted two calls ago
-    CMDB_CHECK(score_local_min(b, src, is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE, b->ev_compute[lane]));
+    // this slot's q_f32 was last read by the batch submitted three calls ago
+    CMDB_CHECK(score_local_min(b, src, is_device, bc, P, CMDB_T_GEMM, CMDB_T_REFINE, b->ev_compute[slot]));
     CMDB_MARK(CMDB_T_MAP);
     CMDB_CHECK(blur_batch(b, bc, fh, fw, out_hw));
     // min_val / min_idx / maps do not depend on the re-weighting: their copy overlaps it
@@ -345,8 +345,8 @@ static int submit_sub_batch(cmdb_bank *b, const float *src, int is_device, int b
     CMDB_MARK(CMDB_T_REWEIGHT);
     CMDB_CHECK(score_reweight(b, bc, P, true));
     CMDB_MARK(CMDB_T_OUT);
-    CMDB_CUDA(cudaEventRecord(b->ev_compute[lane], st));
-    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[lane], 0));
+    CMDB_CUDA(cudaEventRecord(b->ev_compute[slot], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
     CMDB_CUDA(cudaMemcpyAsync(s.out_block_host, s.out_block, s.off_min_val, cudaMemcpyDeviceToHost, b->d2h_stream));
     CMDB_CUDA(cudaEventRecord(b->ev_done[slot], b->d2h_stream));
     if (b->timing) CMDB_CUDA(cudaEventRecord(b->timing == 2 ? b->ev_tl[lane][CMDB_T_COUNT] : b->ev[CMDB_T_COUNT], b->d2h_stream));
@@ -458,7 +458,7 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
         CMDB_CHECK(stage_alloc(b, B, P, out_hw));  // fails with CMDB_ERR_STATE if the scratch would have to grow
         score_select_slot(b, lane, slot);
         b->shard_slot = slot, b->shard_lane = lane;
-        CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[lane]));
+        CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
     }
     pack_keys_kernel<<<(B * P + 255) / 256, 256, 0, b->stream>>>(b->ss.min_val, b->ss.min_idx, B * P, (long long *)keys_device);
     CMDB_CUDA(cudaGetLastError());
@@ -561,8 +561,8 @@ static int shard_finish_enqueue(cmdb_bank *b, const float *knn_d2_sum_device, in
     cudaStream_t st = b->stream;
     CMDB_CHECK(score_shard_final(b, B, knn_d2_sum_device));
     CMDB_CHECK(blur_batch(b, B, fh, fw, out_hw, img_first, img_step));
-    CMDB_CUDA(cudaEventRecord(b->ev_compute[lane], st));
-    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[lane], 0));
+    CMDB_CUDA(cudaEventRecord(b->ev_compute[slot], st));
+    CMDB_CUDA(cudaStreamWaitEvent(b->d2h_stream, b->ev_compute[slot], 0));
     // scalar / per-patch prefix of ALL images in one copy, then the maps of the images this rank finished
     const size_t npix = (size_t)out_hw * out_hw;
     want_maps &= 3u;
@@ -638,7 +638,7 @@ int cmdb_score_shard_round_submit(cmdb_bank *b, const float *patches, int B, int
     CMDB_CHECK(stage_alloc(b, B, P, out_hw));
     score_select_slot(b, lane, slot);
     b->shard_slot = slot, b->shard_lane = lane;
-    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[lane]));
+    CMDB_CHECK(score_local_min(b, patches, patch_is_device, B, P, -1, -1, b->ev_compute[slot]));
     const unsigned long long epoch = comm_next_score_epoch(b->comm);  // per buffer, not per bank: several banks may share it
     const int xslot = (int)(epoch % kShardSlots);
     CMDB_CHECK(score_shard_exchange_keys(b, B, P, peers, world, rank, xslot, epoch));
@@ -840,7 +840,7 @@ int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *p
         fp.tails[m] = reinterpret_cast<const TailResult *>(bm->ss.out_block_buf[slot]);
         fp.s_lambda[m] = head->s_lambda[m], fp.smap_lambda[m] = head->smap_lambda[m];
         fp.det_coef[m] = head->detect_coef[m], fp.seg_coef[m] = head->seg_coef[m];
-        if (m > 0) CMDB_CUDA(cudaStreamWaitEvent(b0->stream, bm->ev_compute[pick.lane], 0));
+        if (m > 0) CMDB_CUDA(cudaStreamWaitEvent(b0->stream, bm->ev_compute[slot], 0));
     }
     fp.det_off = head->detect_offset, fp.seg_off = head->seg_offset;
     unsigned char *blk = f.dev[fs];

@@ -262,9 +262,10 @@ int cmdb_bank_create(int device, int dim, int64_t capacity_rows, cmdb_bank **out
         if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->lane_aux[i], cudaStreamNonBlocking);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fork[i], cudaEventDisableTiming);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_compute[i], cudaEventDisableTiming);
     }
     for (auto &e : b->ev_done)
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : b->ev_compute)
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_fail, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_stage, cudaEventDisableTiming);
@@ -340,9 +341,10 @@ void cmdb_bank_destroy(cmdb_bank *b) {
         if (b->lane_aux[i]) cudaStreamDestroy(b->lane_aux[i]);
         if (b->ev_fork[i]) cudaEventDestroy(b->ev_fork[i]);
         if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
-        if (b->ev_compute[i]) cudaEventDestroy(b->ev_compute[i]);
     }
     for (auto &e : b->ev_done)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : b->ev_compute)
         if (e) cudaEventDestroy(e);
     if (b->ev_fail) cudaEventDestroy(b->ev_fail);
     if (b->ev_stage) cudaEventDestroy(b->ev_stage);

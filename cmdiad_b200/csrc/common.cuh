@@ -64,7 +64,7 @@ struct ScoreScratch {
     int cap_p = 0;                  // padded query-row capacity of a sub-batch (multiple of 128)
     int cap_b = 0;                  // image capacity of a sub-batch
     float *q_f32 = nullptr;         // [cap_p, D]  normalised query patches (the slot selected by score_select_slot)
-    float *q_f32_buf[2] = {nullptr, nullptr};   // per LANE: batch k+1 is staged while batch k is still scored
+    float *q_f32_buf[kResultSlots] = {};   // per result slot: batches k+1 and k+2 are staged while batch k is still scored
     __half *q_hi = nullptr;         // [cap_p, D]  split-fp16 query operand
     __half *q_lo = nullptr;
     int *q_scale_exp = nullptr;     // device [cap_p]: per-row exponent e_q with q_hi + q_lo = q * 2^e_q
@@ -159,7 +159,7 @@ struct cmdb_bank {
     cudaEvent_t ev_chunk[cmdb::kMaxStageChunks] = {};
     cudaStream_t d2h_stream = nullptr;    // device -> host copies of the results
     cudaEvent_t ev_done[cmdb::kResultSlots] = {};   // result slot's block is in the pinned host memory
-    cudaEvent_t ev_compute[2] = {};       // lane's kernels are done (its q_f32 may be overwritten)
+    cudaEvent_t ev_compute[cmdb::kResultSlots] = {};   // the kernels of the call that used the slot are done (its q_f32 may be overwritten)
     cudaEvent_t ev_fail = nullptr;        // the certificate counters of the last certified call are on the host
     cudaEvent_t ev_stage = nullptr;       // cmdb_bank_stage_h2d: the staged bytes are on the device
     struct Pending {

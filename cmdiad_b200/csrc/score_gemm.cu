@@ -624,9 +624,8 @@ void score_scratch_free(cmdb_bank *b) {
         if (st) cudaStreamSynchronize(st);
     // query / result blocks are per SLOT and shared by both lane copies (slot i is only ever used by lane i)
     ScoreScratch &s0 = b->ss_store[0];
-    for (int i = 0; i < 2; ++i) cudaFree(s0.q_f32_buf[i]);
     for (int i = 0; i < kResultSlots; ++i) {
-        cudaFree(s0.out_block_buf[i]);
+        cudaFree(s0.q_f32_buf[i]), cudaFree(s0.out_block_buf[i]);
         if (s0.out_block_host_buf[i]) cudaFreeHost(s0.out_block_host_buf[i]);
         b->pending[i].active = false;
     }
@@ -651,7 +650,7 @@ void score_select_slot(cmdb_bank *b, int lane, int rslot) {
     b->stream = b->lane_stream[lane];
     b->cur_slot = lane;
     ScoreScratch &s = b->ss;
-    s.q_f32 = s.q_f32_buf[lane];
+    s.q_f32 = s.q_f32_buf[rslot];
     s.out_block = s.out_block_buf[rslot];
     s.out_block_host = s.out_block_host_buf[rslot];
     s.tail = s.out_block;
@@ -692,8 +691,8 @@ int score_scratch_alloc(cmdb_bank *b, int B, int P_img, int out_hw) {
     shared.off_map_pre = shared.off_map_out + up(sizeof(float) * map_cap * cap_b);
     shared.off_map_u8 = shared.off_map_pre + up(sizeof(float) * map_cap * cap_b);
     shared.out_block_bytes = shared.off_map_u8 + up((size_t)map_cap * cap_b);
-    for (int i = 0; i < 2; ++i) CMDB_CUDA(cudaMalloc(&shared.q_f32_buf[i], sizeof(float) * cap_p * D));
     for (int i = 0; i < kResultSlots; ++i) {
+        CMDB_CUDA(cudaMalloc(&shared.q_f32_buf[i], sizeof(float) * cap_p * D));
         CMDB_CUDA(cudaMalloc(&shared.out_block_buf[i], shared.out_block_bytes));
         CMDB_CUDA(cudaMallocHost(&shared.out_block_host_buf[i], shared.out_block_bytes));
     }
