@@ -72,12 +72,18 @@ if __name__ == "__main__":
     g = "gpurun_out"
     if os.path.exists(f"{g}/launches.csv"):
         launches(f"{g}/launches.csv", f"profiles/{TAG}_launches_bench.txt",
-                 "ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 python bench.py --steps 2 --warmup 3 --skip-cpu")
-    for rep, title in (("prof_gemm", "ncu --set full --clock-control none, score_gemm_kernel, batch of 16 images x 784 patches vs 200k x 768 bank"),
-                       ("prof_coreset", "ncu --set full --clock-control none, coreset_kernel<__half,3>, 200k x 301, 300 picks"),
-                       ("prof_reweight", "ncu --set full --clock-control none, reweight_kernel<6>, batch of 16, 200k x 768 bank")):
-        if os.path.exists(f"{g}/{rep}.ncu-rep"):
-            m = full(f"{g}/{rep}.ncu-rep", f"profiles/{TAG}_{rep}.txt", title)
-            if rep == "prof_gemm":
-                gemm_traffic(m, 16, f"profiles/{TAG}_prof_gemm.txt (gpurun_out/prof_gemm.ncu-rep: ncu --set full --clock-control none "
-                                    f"-k regex:score_gemm -s 1 -c 1 python scripts/profile_target.py score 16)")
+                 "ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 python bench.py --steps 2 --warmup 3 --skip-cpu "
+                 "--skip-extras --skip-dropin   (scripts/final_check.sh)")
+    cap = "ncu --set full --clock-control none --import-source on -k regex:%s -s 1 -c 1 python scripts/profile_target.py score 16"
+    for rep, out, title in (
+            ("prof_score_gemm", "prof_gemm", "score_gemm_kernel<1,2,1>, batch of 16 images x 784 patches vs 200k x 768 bank"),
+            ("prof_gemm", "prof_gemm", "score_gemm_kernel<1,2,1>, batch of 16 images x 784 patches vs 200k x 768 bank"),
+            ("prof_refine_cert", "prof_refine_cert", "refine_cert_kernel<8>, 12 544 queries x 296 producers, 200k x 768 bank"),
+            ("prof_rescan_kernel", "prof_rescan", "rescan_kernel, ~100 (query, producer) pairs of a 16-image batch, 200k x 768 bank"),
+            ("prof_upsample_hblur", "prof_hblur", "upsample_hblur_kernel, 16 images 28x28 -> 224x224"),
+            ("prof_coreset", "prof_coreset", "coreset_kernel<__half,3>, 200k x 301, 300 picks"),
+            ("prof_reweight", "prof_reweight", "reweight_kernel<6>, batch of 16, 200k x 768 bank")):
+        if os.path.exists(f"{g}/{rep}.ncu-rep") and not (rep == "prof_gemm" and os.path.exists(f"{g}/prof_score_gemm.ncu-rep")):
+            m = full(f"{g}/{rep}.ncu-rep", f"profiles/{TAG}_{out}.txt", (cap % rep[5:]) + " -- " + title)
+            if out == "prof_gemm":
+                gemm_traffic(m, 16, f"profiles/{TAG}_prof_gemm.txt (gpurun_out/{rep}.ncu-rep: " + (cap % "score_gemm") + ")")
