@@ -476,24 +476,34 @@ class Bank:
             t = cache[key] = torch.empty(shape, dtype=dtype, device=torch.device("cuda", self.device))
         return t
 
-    def _stage_sharded(self, chunk, slot, world, rank, group):
-        """Host queries of a sharded round: every rank copies only its 1/world slice of the rows over PCIe (on the
-        handle's copy stream) and the slices are all-gathered over NVLink -- every rank needs all queries, but NVLink is
-        ~10x the host link.  The buffers are double-buffered per result slot."""
+    def _stage_sharded(self, chunk, slot, world, rank, group, lane):
+        """Host queries of a sharded round: every rank copies only its 1/world slice of the rows over PCIe and the slices
+        are all-gathered over NVLink -- every rank needs all queries, but NVLink is ~10x the host link.  Copy and
+        all-gather run on a staging stream of their own, so that with several rounds outstanding they overlap the kernels
+        of the earlier rounds instead of sitting in front of this round's GEMM on its lane; the lane only waits for the
+        event behind the all-gather.  One set of buffers per outstanding round (slot = round % 3): a set is rewritten
+        three rounds later, after the caller has waited for the round that read it."""
         import torch.distributed as dist
         from .sharding import stage_slice
         B, P, D = chunk.shape
         rows = B * P
         flat = chunk.reshape(rows, D)
         per, lo, hi = stage_slice(rows, world, rank)
+        dev = torch.device("cuda", self.device)
+        ss = self.__dict__.get("_stage_stream")
+        if ss is None:
+            ss = self._stage_stream = torch.cuda.Stream(device=dev)
         part = self._shard_buf("part", slot, (per, D), torch.float32)
-        if hi > lo:
-            src = flat[lo:hi]
-            L.check(self._lib.cmdb_bank_stage_h2d(self._h, _ptr(part), _ptr(src), src.numel() * 4))
-        if hi - lo < per:
-            part[hi - lo:].zero_()
         full = self._shard_buf("full", slot, (per * world, D), torch.float32)
-        dist.all_gather_into_tensor(full, part, group=group)
+        with torch.cuda.stream(ss):
+            if hi > lo:
+                part[:hi - lo].copy_(flat[lo:hi], non_blocking=True)
+            if hi - lo < per:
+                part[hi - lo:].zero_()
+            dist.all_gather_into_tensor(full, part, group=group)
+            ev = torch.cuda.Event()
+            ev.record(ss)
+        lane.wait_event(ev)
         return full[:rows].view(B, P, D)
 
     def score_sharded_async(self, patches, feature_map_dims, out_hw=224, full=False, group=None, distribute=False,
@@ -530,7 +540,7 @@ class Bank:
             mark()
             chunk = patches
             if not chunk.is_cuda and world > 1 and B * P >= 1024:
-                chunk = self._stage_sharded(chunk, slot, world, rank, group)
+                chunk = self._stage_sharded(chunk, slot, world, rank, group, lane)
             mark()
             first, stride = ((rank - img_base) % world, world) if distribute else (0, 1)
             if getattr(self, "_comm", None) is not None:
@@ -601,7 +611,7 @@ class Bank:
                 slot = k & 1
                 res, outs, _ = self._alloc_out(B, P, out_hw, full)
                 if not chunk.is_cuda and world > 1 and B * P >= 1024:
-                    chunk = self._stage_sharded(chunk, slot, world, rank, group)
+                    chunk = self._stage_sharded(chunk, slot, world, rank, group, torch.cuda.current_stream(chunk.device if chunk.is_cuda else torch.device('cuda', self.device)))
                 keys = self._shard_buf("keys", slot, (B * P,), torch.int64)
                 L.check(self._lib.cmdb_score_shard_min(self._h, _ptr(chunk), B, P, int(chunk.is_cuda), int(out_hw), _ptr(keys)))
                 dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
