@@ -446,8 +446,8 @@ int cmdb_score_shard_min(cmdb_bank *b, const float *patches, int B, int P, int p
     CMDB_REQUIRE(out_hw >= 8 && out_hw <= 256, CMDB_ERR_INVALID, "cmdb_score_shard_min: out_hw=%d not in [8,256]", out_hw);
     CMDB_CUDA(cudaSetDevice(b->device));
     {
-        // the round runs on lane / result slot next_slot (what cmdb_bank_stream returns before this call); with the submit /
-        // wait finish two rounds may be in flight, one per lane
+        // the round runs on lane next_lane (what cmdb_bank_stream returns before this call) with result slot next_slot; with
+        // the submit / wait finish up to three rounds may be outstanding (three result slots on the two lanes)
         const bool busy = b->any_pending();
         CMDB_REQUIRE(!busy || (size_t)out_hw * out_hw == b->ss.map_stride, CMDB_ERR_STATE,
                      "cmdb_score_shard_min: out_hw changes while a submitted round is outstanding; wait for it first");
