@@ -165,11 +165,12 @@ __global__ void __launch_bounds__(256) refine_kernel(const float4 *__restrict__ 
 // this would cost more than a GEMM (fallback_use_rescan; banks full of near-duplicates), the uncertified queries are
 // redone with the FP32-equivalent 3-term GEMM.  Either way min_val / min_idx equal those of an exact scan of the whole bank.
 // ---------------------------------------------------------------------------------------------------------------
-// One block per kCertQ consecutive queries, three phases:
-//   (1) the producers' lists are read with the QUERY index along the lanes (a warp-wide load is one or two contiguous
-//       256 / 512-byte runs of cand[c][q0 ...]; round 1 read them one query per warp, 32 sectors per request, which was two
-//       thirds of the kernel's time): smallest first value per query -> threshold;
-//   (2) the lists again (L2 hits): every kept value inside a query's band goes to that query's row list in shared memory,
+// One block per QB consecutive queries (QB = 8 by default), three phases:
+//   (1) the producers' lists are read with the QUERY index along the lanes (a warp-wide load is 32 / QB contiguous runs of
+//       QB x 16 bytes of cand[c][q0 ...]; round 1 read them one query per warp, 32 sectors of 32 producers per request,
+//       which was two thirds of the kernel's time); every thread keeps its share in registers; smallest first value per
+//       query through shared memory -> threshold;
+//   (2) from the registers: every kept value inside a query's band goes to that query's row list in shared memory;
 //       producers whose SECOND value is inside the band -- or whose row no longer fits the list -- are queued for the rescan;
 //   (3) the listed rows are re-checked exactly, one warp per query, four rows at a time (warp_sqdist4).
 // The last block of the grid to finish also takes the tier decision for the launches behind it (ctl[2..4]).
