@@ -640,11 +640,12 @@ def run_ours(args):
                          "h2d_bytes_per_step": B * P * DIM * 4 // world if world > 1 else B * P * DIM * 4,
                          "d2h_bytes_per_step": maps_d2h * OUT_HW * OUT_HW * 4 + B * (P * 12 + 64),
                          "note": "per rank" if world > 1 else "pinned host block in, results out, inside the timed region"},
-                 # per step (N = 1): q_split, GEMM, certified refine, decide, rescan, rescan-finish, GEMM-fallback chain
-                 # (q_split, GEMM, refine: sized on the device, empty unless many certificates fail), select + neighbour-table
-                 # lookup, 2 blur kernels = 13; sharded round: the same 9 of local_min, pack, unpack, select, lookup, final,
-                 # 2 blur kernels = 16.  Two timed loops (device-resident and host inputs).
-                 "gpu_launches": args.steps * 2 * (13 if world == 1 else 16),
+                 # kernels per step (N = 1): q_split, GEMM, certificate (takes the tier decision), rescan (publishes its
+                 # results), tier-2 chain on the side stream (q_split, GEMM, refine: sized on the device, empty unless very many
+                 # certificates fail), select + neighbour-table lookup, 3 map kernels (band maxima, horizontal, vertical) = 12;
+                 # sharded round: the same 7 of local_min, push / reduce keys, select, lookup, push / sum of the neighbour
+                 # distances, final, 3 map kernels = 17.  Two timed loops (device-resident and host inputs).
+                 "gpu_launches": args.steps * 2 * (12 if world == 1 else 17),
                  "clocks": clk.summary(), "sync_call": sync_call})
     flop = 2.0 * B * P * BANK_ROWS * DIM
     if world == 1:
