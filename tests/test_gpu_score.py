@@ -437,13 +437,13 @@ def test_prefilter_error_model(env):
     b.close()
 
 
-def _adversarial(kind, R, P, D, seed):
+def _adversarial(kind, R, P, D, seed, range_bits=14, dup=8):
     """inputs built to stress the certificate: the accumulation model is empirical, so it is probed
     where alignment / truncation inside the tensor core hurts most"""
     g = np.random.Generator(np.random.PCG64(seed))
     if kind == "wide_range":      # 2^-14 .. 1 inside every row: small addends are aligned against large partial sums
-        lib = g.standard_normal((R, D), dtype=np.float32) * np.exp2(-14 * g.random((R, D), dtype=np.float32))
-        patch = g.standard_normal((P, D), dtype=np.float32) * np.exp2(-14 * g.random((P, D), dtype=np.float32))
+        lib = g.standard_normal((R, D), dtype=np.float32) * np.exp2(-range_bits * g.random((R, D), dtype=np.float32))
+        patch = g.standard_normal((P, D), dtype=np.float32) * np.exp2(-range_bits * g.random((P, D), dtype=np.float32))
     elif kind == "subnormal_residue":  # one spike per row: everything else lands in fp16's subnormal range after scaling
         lib = g.standard_normal((R, D), dtype=np.float32) * np.float32(3e-8)
         patch = g.standard_normal((P, D), dtype=np.float32) * np.float32(3e-8)
@@ -458,9 +458,9 @@ def _adversarial(kind, R, P, D, seed):
         patch = np.ascontiguousarray(patch, dtype=np.float32)
         lib = np.ascontiguousarray(lib, dtype=np.float32)
     elif kind == "near_duplicates":   # many rows within float32 noise of each other: the band never empties
-        base = g.standard_normal((R // 8, D), dtype=np.float32)
-        lib = np.repeat(base, 8, 0) * (1 + 1e-6 * g.standard_normal((R, 1), dtype=np.float32))
-        patch = base[g.integers(0, R // 8, P)] + 1e-3 * g.standard_normal((P, D), dtype=np.float32)
+        base = g.standard_normal((R // dup, D), dtype=np.float32)
+        lib = np.repeat(base, dup, 0) * (1 + 1e-6 * g.standard_normal((R // dup * dup, 1), dtype=np.float32))
+        patch = base[g.integers(0, R // dup, P)] + 1e-3 * g.standard_normal((P, D), dtype=np.float32)
     else:
         raise ValueError(kind)
     return np.ascontiguousarray(lib, np.float32), np.ascontiguousarray(patch, np.float32)
@@ -496,6 +496,32 @@ def test_certificate_under_adversarial_inputs(env, kind, D):
     if kind in ("wide_range", "cancelling"):   # no engineered near-ties: mode 3 must agree as well
         assert n3 == 0
     b.close()
+
+
+def test_certificate_hypothesis_sweep(env):
+    """a property sweep over the adversarial families -- bank size (ragged against the 256-row tile),
+    dimension, query count, dynamic range inside the rows, duplication factor (up to 40-fold: far more in-band rows than the
+    certificate kernel's 24-row query lists, so the surplus goes through the rescan queue) and seed are drawn by hypothesis
+    (derandomised: the same examples in every run).  Property: the default mode equals the exact scan of the whole bank,
+    value and row, on every query."""
+    from hypothesis import given, settings, HealthCheck, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(kind=st.sampled_from(["wide_range", "subnormal_residue", "cancelling", "near_duplicates"]),
+           D=st.sampled_from([256, 768, 1152, 1920]), n=st.integers(8, 220), side=st.sampled_from([8, 10, 16]),
+           range_bits=st.integers(2, 20), dup=st.sampled_from([2, 8, 40]), seed=st.integers(0, 10_000))
+    def prop(kind, D, n, side, range_bits, dup, seed):
+        R, P = n * dup, side * side
+        lib, patch = _adversarial(kind, R, P, D, seed, range_bits=range_bits, dup=dup)
+        b = _bank(env, lib)
+        cert = b.score(patch, (side, side), 64)
+        stats = b.score_stats()
+        ex_val, ex_idx = _exact_scan(b, patch)
+        bad = np.nonzero((cert.min_idx != ex_idx) | (cert.min_val != ex_val))[0]
+        b.close()
+        assert bad.size == 0, (kind, D, R, P, range_bits, dup, seed, stats, bad[:5], cert.min_idx[bad[:5]], ex_idx[bad[:5]])
+
+    prop()
 
 
 def test_score_duplicate_rows_lowest_index(env):
