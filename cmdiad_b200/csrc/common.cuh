@@ -73,7 +73,9 @@ struct ScoreScratch {
     int *fail_list = nullptr;       // [cap_p] query rows whose pre-filter result could not be certified
     // device control block of the fallback: [0] uncertified queries, [1] (query, producer) pairs to rescan,
     // [2] rows of the 3-term GEMM fallback, [3] pairs of the exact rescan, [4] queries the rescan finishes
-    // ([2..4] are derived from [0..1] by fallback_decide_kernel: few pairs -> rescan, many -> GEMM)
+    // ([2..4] are derived from [0..1] by the last block of refine_cert_kernel: pairs that fit the work list -> rescan, more ->
+    // GEMM), [5] / [6] last-block tickets of the certificate / rescan kernels; the per-image argmax keys (s_key) follow at
+    // fail_ctl + 8 in the same allocation so that one memset clears both
     int *fail_ctl = nullptr;
     int *fail_count_host = nullptr; // pinned copy of [0..1] (statistics / adaptive mode)
     bool sched_pair = false;            // the last first-pass GEMM ran on CTA pairs (cta_group::2)

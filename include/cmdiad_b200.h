@@ -306,8 +306,8 @@ typedef struct cmdb_fused_out {
 /*
  * Scores B images against n_modal banks (one handle per modality, all on the same GPU; patches[m]: float32
  * [B, P[m], dim_m]) and applies the late-fusion head.  The per-modality maps never leave HBM; per image one float64 map
- * and one float64 score travel to the host.  submit / wait follow cmdb_score_batch_submit / _wait (two batches may be in
- * flight; B <= the per-call limit of every bank); cmdb_score_fused_batch = submit + wait, any B.
+ * and one float64 score travel to the host.  submit / wait follow cmdb_score_batch_submit / _wait (two FUSED batches may be
+ * outstanding; B <= the per-call limit of every bank); cmdb_score_fused_batch = submit + wait, any B.
  * The ticket belongs to banks[0].
  */
 int cmdb_score_fused_batch_submit(cmdb_bank *const *banks, const float *const *patches, const int *P, const int *fh,
