@@ -15,7 +15,7 @@ GEMM + min/argmin, s*/m*/top-3 re-weighting, bilinear upsample and Gaussian blur
   large_bank / configs   the other BASELINE configurations in bounded form (full form: --config 2 / 3 / 4 / 5;
                          3 = the ten classes in sequence, class-parallel over the ranks)
 N > 1 (torchrun, one rank per GPU): the bank is row-sharded; every step runs one round of the three-phase sharded
-protocol (two small exchanges over peer-mapped memory fused into the kernels) with two rounds in flight (strong scaling: the job is still one 200k bank).
+protocol (two small exchanges over peer-mapped memory fused into the kernels) with three rounds outstanding on two compute lanes (strong scaling: the job is still one 200k bank).
 `--impl reference` times the CPU restatement of the reference path (oracle/, the one place it may be executed from here)
 on ALL host cores with a bounded sample.
 """
